@@ -1,0 +1,150 @@
+/* ivgpt_b200 -- C ABI of the B200-native iVideoGPT next-frame-prediction hot path.
+ *
+ * The reference (thuml/iVideoGPT) has no native boundary of its own: its hot path is Python calling
+ * torch / diffusers / transformers library kernels.  This header is the boundary a maintainer binds with
+ * ctypes from the reference's Python modules; every entry point names the reference
+ * call site(s) whose arithmetic it replaces.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success; non-zero on failure, with a thread-local message available from
+ *     ivgpt_last_error().  Nothing ever calls exit()/abort().
+ *   - all pointers are DEVICE pointers on the current CUDA device unless stated; `stream` is a cudaStream_t.
+ *     Work is enqueued asynchronously on that stream; the library holds no global state besides per-kernel
+ *     attribute caches, so calls are re-entrant per (device, stream).
+ *   - activations are NHWC ([frames, H, W, C], C fastest), dtype IVGPT_F32 (fed to tensor cores as TF32) or
+ *     IVGPT_BF16; accumulation is always fp32.
+ *   - integer results (token ids) are int64, matching torch.argmin / generate outputs of the reference.
+ */
+#ifndef IVGPT_B200_H
+#define IVGPT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVGPT_F32 0
+#define IVGPT_BF16 1
+
+#define IVGPT_ACT_NONE 0
+#define IVGPT_ACT_SILU 1
+#define IVGPT_ACT_SWIGLU 2 /* interleaved (gate, up) column pairs -> silu(gate)*up, N/2 output columns */
+
+const char* ivgpt_last_error(void);
+unsigned long long ivgpt_launch_count(void); /* kernels launched by this library since load */
+int ivgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- VQ codebook lookup -------------------------------------------------------------------------
+ * Replaces diffusers VectorQuantizer.forward's `argmin(cdist(z, E))`, called at
+ * ivideogpt/vq_model/compressive_vq_model.py:199 (context codebook) and :202 (dynamics codebook).
+ * z [N, D] fp32, codebook [K, D] fp32, idx [N] int64.  D must be 64.
+ * Workspaces: enorm_ws [K] fp32, packed_ws [N] uint64.  Ties resolve to the lowest index. */
+int ivgpt_vq_argmin(const float* z, const float* codebook, float* enorm_ws, unsigned long long* packed_ws,
+                    long long* idx, int N, int K, int D, void* stream);
+
+/* ---- tensor-core GEMM --------------------------------------------------------------------------
+ * out = epilogue(alpha * A . B^T): A [a_rows, a_cols] (lda), B [b_rows, b_cols] (ldb), K contiguous in both.
+ * Replaces nn.Linear / 1x1 nn.Conv2d / torch.bmm call sites: Llama q,k,v,o,gate,up,down,lm_head
+ * (transformers modeling_llama via inference/predict.py:64, train_gpt.py:792), quant_conv / post_quant_conv /
+ * quant_linear / post_quant_linear (compressive_vq_model.py:188,196,241,245), nn.MultiheadAttention
+ * projections and score/value products (conditional_vae.py:49), mid-block attention (diffusers Attention).
+ * grid-z index bz in [0, batch): outer = bz / heads, h = bz % heads; *_bsel: 0 -> batch 0, 1 -> outer / *_bdiv,
+ * 2 -> bz.  A columns start at a_kbase + h*a_khead; B columns at b_kbase + h*b_khead, B rows at n + h*b_nhead;
+ * output columns at n + h*o_nhead. */
+typedef struct ivgpt_gemm_desc {
+  int dtype; /* operand dtype of A and B */
+  int bn;    /* N tile: 32, 64, 128 or 256; 0 = choose */
+  const void* a; long long lda, a_bstride; int a_rows, a_cols, a_batches;
+  const void* b; long long ldb, b_bstride; int b_rows, b_cols, b_batches;
+  int M, N, K;
+  int batch, heads;
+  int a_bsel, a_bdiv, b_bsel, b_bdiv, o_bsel;
+  int a_kbase, a_khead, b_kbase, b_khead, b_nhead, o_nhead;
+  int causal_skip;
+  void* out; long long ldo, out_bstride; int out_dtype;
+  const float* bias; int bias_along_m;
+  const void* residual; long long ldr, res_bstride; int res_dtype;
+  int act;
+  float alpha;
+} ivgpt_gemm_desc;
+int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream);
+
+/* ---- 3x3 convolution as implicit GEMM -----------------------------------------------------------
+ * Replaces nn.Conv2d(k=3) inside diffusers ResnetBlock2D / Downsample2D / Upsample2D and the conv_in(64->C) /
+ * conv_out(C->64) layers built at ivideogpt/vq_model/vae.py:86-137,236-294.
+ * x NHWC [N, Hin, Win, Cin]; stride 1 => pad 1, stride 2 => pad (0,1,0,1) (diffusers downsample_padding=0).
+ * w packed [Cout][9*Cin + C2], k index = (ky*3+kx)*Cin + c, then the C2 channels of the optional fused 1x1
+ * source x2 (NHWC at the OUTPUT resolution) -- the ResnetBlock2D conv_shortcut.
+ * out/residual NHWC [N, Hout, Wout, Cout]. */
+typedef struct ivgpt_conv_desc {
+  int dtype; int bn;
+  const void* x; int N, Hin, Win, Cin; int stride;
+  const void* w; int Cout;
+  const void* x2; int C2;
+  const float* bias;
+  const void* residual; int res_dtype;
+  int act;
+  void* out; int out_dtype;
+} ivgpt_conv_desc;
+int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream);
+
+/* ---- GroupNorm (nn.GroupNorm in ResnetBlock2D / conv_norm_out / CrossAttentionBlock) --------------
+ * x [N, rows, C]; stats [N, G, 2] = (mean, rstd); part_ws [N * ceil(rows/64) * G * 2] fp32. */
+int ivgpt_groupnorm_stats(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G,
+                          float eps, void* stream);
+/* y = (x-mean)*rstd*gamma+beta, optional SiLU, optional + pos[row % pos_rows][C] (conditional_vae.py:44-47). */
+int ivgpt_groupnorm_apply(int dtype, const void* x, void* y, const float* stats, const float* gamma,
+                          const float* beta, const float* pos, long long total_rows, int rows_per_sample, int C,
+                          int G, int silu, int pos_rows, void* stream);
+
+/* conv_in: 3x3 conv 3 -> Cout on NCHW fp32 pixels -> NHWC (vae.py:86,149).  w [Cout][27], b [Cout].
+ * Frame n of the N processed frames is read from slot (n / frames_per_clip) * clip_frames + frame_offset +
+ * n % frames_per_clip of the caller's [B, T, 3, H, W] clip tensor (the context / future split of
+ * compressive_vq_model.py:170-171 without a copy). */
+int ivgpt_conv_in(int dtype, const float* x_nchw, const float* w, const float* b, void* y, int N, int H, int W,
+                  int Cout, int frames_per_clip, int clip_frames, int frame_offset, void* stream);
+/* decoder head: GroupNorm -> SiLU -> 3x3 conv C -> 3, NHWC in, NCHW fp32 out (vae.py:292-294,363-369).
+ * w [3][9][C] (tap-major, channel fastest), b [3].  Output frames are scattered into [B, T, 3, H, W] with the
+ * same slot mapping as ivgpt_conv_in (the torch.cat of compressive_vq_model.py:274-277 without a copy). */
+int ivgpt_conv_out3(int dtype, const void* x, const float* stats, const float* gamma, const float* beta,
+                    const float* w, const float* b, float* y_nchw, int N, int H, int W, int C, int G,
+                    int frames_per_clip, int clip_frames, int frame_offset, void* stream);
+/* nearest 2x upsample, NHWC (diffusers Upsample2D). */
+int ivgpt_upsample2x(int dtype, const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* (de)patchify, compressive_vq_model.py:192-195 / :247-250.  inverse=0: [F,R,R,C] -> [F*(R/P)^2, P*P*C]. */
+int ivgpt_patchify(int dtype, const void* x, void* y, int F, int R, int C, int P, int inverse, void* stream);
+int ivgpt_convert(int src_dtype, const void* x, int dst_dtype, void* y, long long n, void* stream);
+
+/* token (de)serialisation, compressive_vq_model.py:205-220 / :227-245 */
+int ivgpt_tokens_serialise(const long long* idx_ctx, const long long* idx_dyn, long long* tokens, long long* labels,
+                           int B, int t, int f, int cr, int dr, long long n_vq, long long n_dyn, void* stream);
+int ivgpt_tokens_gather(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* q_ctx,
+                        void* q_dyn, int B, int t, int f, int cr, int dr, int D, long long n_vq, long long n_dyn,
+                        int L, void* stream);
+
+/* ---- Llama pieces (transformers LlamaForCausalLM as used by predict.py:64 / train_gpt.py:792) ----- */
+int ivgpt_embed(const long long* ids, long long ids_stride, int L, const int* dpos, const float* table, float* x,
+                long long M, int hidden, long long vocab, void* stream);
+int ivgpt_add_rows(float* x, const float* e, long long n, void* stream);
+int ivgpt_rmsnorm(int dtype, const float* x, const float* w, void* y, long long M, int hidden, float eps,
+                  void* stream);
+int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, int B, int Lq, int heads,
+                  int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, void* stream);
+int ivgpt_softmax(int dtype, const float* S, void* P, long long rows, int Lq, int Lk, long long lds, long long ldp,
+                  int causal, int causal_off, void* stream);
+int ivgpt_decode_attn(int dtype, const void* q, const void* k_cache, const void* v_cache_t, void* out, int B,
+                      int heads, int Lmax, int Lcur, const int* dpos, float scale, void* stream);
+int ivgpt_argmax(const float* logits, long long ld, int rows, int V, long long* out, long long out_stride,
+                 const int* dpos, void* stream);
+int ivgpt_topk_sample(const float* logits, long long ld, int rows, int V, int k, float temperature,
+                      unsigned long long seed, unsigned long long step, long long* out, long long out_stride,
+                      const int* dpos, void* stream);
+/* shifted CE of LlamaForCausalLM.forward(labels=...): logits [B,L,ld] fp32, labels [B,L] int64 (-100 ignored);
+ * loss_rows / valid_ws [B*(L-1)] fp32 workspaces; loss_out[0] = mean over labelled positions, [1] = their count. */
+int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const long long* labels, float* loss_rows,
+                  float* valid_ws, float* loss_out, void* stream);
+int ivgpt_incr(int* p, int by, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVGPT_B200_H */

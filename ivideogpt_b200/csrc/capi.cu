@@ -1,0 +1,338 @@
+// extern "C" entry points of libivgpt_b200.so (declared in include/ivgpt_b200.h) + host-side plumbing:
+// thread-local error string, tensor-map construction through the driver entry point, GEMM/conv descriptors.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ivgpt_b200.h"
+#include "common.cuh"
+#include "gemm_params.cuh"
+
+namespace ivg {
+
+static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ---- tensor maps ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  IVG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  IVG_CHECK(((uintptr_t)base & 15) == 0, "tensor map: base pointer %p not 16-byte aligned", base);
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) {
+    gs[i] = strides_bytes[i];
+    IVG_CHECK(gs[i] % 16 == 0, "tensor map: stride %d = %llu bytes is not a multiple of 16", i,
+              (unsigned long long)gs[i]);
+  }
+  CUresult r = fn(out, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IVG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)",
+            (int)r, rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+            (unsigned long long)(rank > 2 ? gd[2] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ---- forward declarations of launchers defined in the other translation units -----------------
+int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream);
+int vq_argmin_launch(const float*, const float*, float*, unsigned long long*, long long*, int, int, int, int,
+                     cudaStream_t);
+int gn_stats_launch(int, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
+int gn_apply_launch(int, const void*, void*, const float*, const float*, const float*, const float*, long long, int,
+                    int, int, int, int, cudaStream_t);
+int conv_in_launch(int, const float*, const float*, const float*, void*, int, int, int, int, int, int, int,
+                   cudaStream_t);
+int conv_out3_launch(int, const void*, const float*, const float*, const float*, const float*, const float*, float*,
+                     int, int, int, int, int, int, int, int, cudaStream_t);
+int upsample2x_launch(int, const void*, void*, int, int, int, int, cudaStream_t);
+int patchify_launch(int, const void*, void*, int, int, int, int, int, cudaStream_t);
+int convert_launch(int, const void*, int, void*, long long, cudaStream_t);
+int serialise_launch(const long long*, const long long*, long long*, long long*, int, int, int, int, int, long long,
+                     long long, cudaStream_t);
+int detok_gather_launch(int, const long long*, const float*, const float*, void*, void*, int, int, int, int, int, int,
+                        long long, long long, int, cudaStream_t);
+int embed_launch(const long long*, long long, int, const int*, const float*, float*, long long, int, long long,
+                 cudaStream_t);
+int add_rows_launch(float*, const float*, long long, cudaStream_t);
+int rmsnorm_launch(int, const float*, const float*, void*, long long, int, float, cudaStream_t);
+int rope_kv_launch(int, const void*, void*, void*, void*, int, int, int, int, int, const int*, const float*,
+                   const float*, cudaStream_t);
+int softmax_launch(int, const float*, void*, long long, int, int, long long, long long, int, int, cudaStream_t);
+int decode_attn_launch(int, const void*, const void*, const void*, void*, int, int, int, int, const int*, float,
+                       cudaStream_t);
+int argmax_launch(const float*, long long, int, int, long long*, long long, const int*, cudaStream_t);
+int topk_sample_launch(const float*, long long, int, int, int, float, unsigned long long, unsigned long long,
+                       long long*, long long, const int*, cudaStream_t);
+int ce_loss_launch(const float*, long long, int, int, int, const long long*, float*, float*, float*, cudaStream_t);
+int incr_launch(int*, int, cudaStream_t);
+
+}  // namespace ivg
+
+
+using namespace ivg;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int esize(int dt) { return dt == DT_BF16 ? 2 : 4; }
+
+extern "C" {
+
+const char* ivgpt_last_error(void) { return ivg::last_error(); }
+unsigned long long ivgpt_launch_count(void) { return ivg::g_launches; }
+
+int ivgpt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  IVG_CUDA(cudaGetDevice(&dev));
+  IVG_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  IVG_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  IVG_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+int ivgpt_vq_argmin(const float* z, const float* codebook, float* enorm_ws, unsigned long long* packed_ws,
+                    long long* idx, int N, int K, int D, void* stream) {
+  return vq_argmin_launch(z, codebook, enorm_ws, packed_ws, idx, N, K, D, num_sms(), S(stream));
+}
+
+static int pick_bn(int N, long long tiles_m_times_batch) {
+  // widest tile (<= 128) that still gives every SM a CTA; skinny problems (decode steps) get narrow tiles so
+  // that more CTAs stream the weight matrix concurrently.
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  const int sms = num_sms();
+  const int cands[3] = {128, 64, 32};
+  for (int i = 0; i < 3; ++i)
+    if (tiles_m_times_batch * ((N + cands[i] - 1) / cands[i]) >= sms) return cands[i];
+  return 32;
+}
+
+int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream) {
+  IVG_CHECK(d != nullptr, "gemm: null descriptor");
+  IVG_CHECK(d->dtype == DT_F32 || d->dtype == DT_BF16, "gemm: bad dtype %d", d->dtype);
+  if (d->M <= 0 || d->N <= 0 || d->batch <= 0) return 0;
+  IVG_CHECK(d->K > 0, "gemm: K must be positive");
+  const int es = esize(d->dtype);
+  const int BK = 128 / es;
+  const int heads = d->heads > 0 ? d->heads : 1;
+  IVG_CHECK(d->batch % heads == 0, "gemm: batch %d not a multiple of heads %d", d->batch, heads);
+  IVG_CHECK(heads == 1 || d->K % BK == 0 || (d->a_khead == 0 && d->b_khead == 0),
+            "gemm: per-head K offsets need K %% %d == 0 (K=%d)", BK, d->K);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const long long tiles_m = (d->M + GEMM_BM - 1) / GEMM_BM;
+  int bn = d->bn ? d->bn : pick_bn(d->N, tiles_m * d->batch);
+  IVG_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad bn %d", bn);
+  {
+    uint64_t dims[3] = {(uint64_t)d->a_cols, (uint64_t)d->a_rows, (uint64_t)(d->a_batches > 0 ? d->a_batches : 1)};
+    uint64_t str[2] = {(uint64_t)d->lda * es, (uint64_t)(d->a_batches > 1 ? d->a_bstride : (long long)d->a_rows * d->lda) * es};
+    uint32_t box[3] = {(uint32_t)BK, GEMM_BM, 1};
+    if (make_tensor_map(&maps.a[0], d->dtype, d->a, 3, dims, str, box, 1)) return 1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->b_cols, (uint64_t)d->b_rows, (uint64_t)(d->b_batches > 0 ? d->b_batches : 1)};
+    uint64_t str[2] = {(uint64_t)d->ldb * es, (uint64_t)(d->b_batches > 1 ? d->b_bstride : (long long)d->b_rows * d->ldb) * es};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)bn, 1};
+    if (make_tensor_map(&maps.b, d->dtype, d->b, 3, dims, str, box, 1)) return 1;
+  }
+  p.M = d->M; p.N = d->N; p.num_kb = (d->K + BK - 1) / BK;
+  p.mode = 0;
+  p.batch = d->batch; p.heads = heads;
+  p.a_bsel = d->a_bsel; p.a_bdiv = d->a_bdiv > 0 ? d->a_bdiv : 1;
+  p.b_bsel = d->b_bsel; p.b_bdiv = d->b_bdiv > 0 ? d->b_bdiv : 1;
+  p.o_bsel = d->o_bsel;
+  p.a_kbase = d->a_kbase; p.a_khead = d->a_khead; p.b_kbase = d->b_kbase; p.b_khead = d->b_khead;
+  p.b_nhead = d->b_nhead; p.o_nhead = d->o_nhead;
+  p.causal_skip = d->causal_skip;
+  p.out = d->out; p.ldo = d->ldo; p.out_bstride = d->out_bstride; p.out_dtype = d->out_dtype;
+  p.bias = d->bias; p.bias_along_m = d->bias_along_m;
+  p.residual = d->residual; p.ldr = d->ldr; p.res_bstride = d->res_bstride; p.res_dtype = d->res_dtype;
+  p.act = d->act; p.alpha = d->alpha;
+  p.tiles_m = (int)tiles_m; p.tiles_n = (d->N + bn - 1) / bn;
+  IVG_CHECK(d->act != IVGPT_ACT_SWIGLU || (d->N % 2 == 0 && d->residual == nullptr), "gemm: SwiGLU needs even N, no residual");
+  return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
+}
+
+int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
+  IVG_CHECK(d != nullptr, "conv3x3: null descriptor");
+  IVG_CHECK(d->dtype == DT_F32 || d->dtype == DT_BF16, "conv3x3: bad dtype %d", d->dtype);
+  IVG_CHECK(d->stride == 1 || d->stride == 2, "conv3x3: stride must be 1 or 2");
+  if (d->N <= 0) return 0;
+  const int es = esize(d->dtype);
+  const int BK = 128 / es;
+  IVG_CHECK(d->Cin % BK == 0 && d->C2 % BK == 0, "conv3x3: Cin=%d / C2=%d must be multiples of %d", d->Cin, d->C2, BK);
+  const int Hout = d->Hin / d->stride, Wout = d->Win / d->stride;
+  IVG_CHECK(d->Hin % d->stride == 0 && d->Win % d->stride == 0, "conv3x3: odd input size for stride 2");
+  const int tw = Wout < 128 ? Wout : 128;
+  IVG_CHECK(tw > 0 && 128 % tw == 0, "conv3x3: output width %d must divide 128 or be a multiple of it", Wout);
+  const int th = 128 / tw;
+  IVG_CHECK(Wout % tw == 0 && Hout % th == 0, "conv3x3: output %dx%d not tileable by %dx%d", Hout, Wout, th, tw);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const uint32_t box[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, 1};
+  const long long C = d->Cin;
+  if (d->stride == 1) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)C * es, (uint64_t)d->Win * C * es, (uint64_t)d->Hin * d->Win * C * es};
+    if (make_tensor_map(&maps.a[0], d->dtype, d->x, 4, dims, str, box, 1)) return 1;
+    for (int t = 0; t < 9; ++t) { p.tap_map[t] = 0; p.tap_dy[t] = (signed char)(t / 3 - 1); p.tap_dx[t] = (signed char)(t % 3 - 1); }
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const char* base = reinterpret_cast<const char*>(d->x) + ((long long)py * d->Win + px) * C * es;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)(d->Win / 2), (uint64_t)(d->Hin / 2), (uint64_t)d->N};
+        uint64_t str[3] = {(uint64_t)2 * C * es, (uint64_t)2 * d->Win * C * es, (uint64_t)d->Hin * d->Win * C * es};
+        if (make_tensor_map(&maps.a[py * 2 + px], d->dtype, base, 4, dims, str, box, 1)) return 1;
+      }
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      p.tap_map[t] = (signed char)((ky & 1) * 2 + (kx & 1));
+      p.tap_dy[t] = (signed char)(ky >> 1);
+      p.tap_dx[t] = (signed char)(kx >> 1);
+    }
+  }
+  if (d->C2 > 0) {
+    IVG_CHECK(d->x2 != nullptr, "conv3x3: C2 > 0 but x2 is null");
+    uint64_t dims[4] = {(uint64_t)d->C2, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->C2 * es, (uint64_t)Wout * d->C2 * es, (uint64_t)Hout * Wout * d->C2 * es};
+    if (make_tensor_map(&maps.a[4], d->dtype, d->x2, 4, dims, str, box, 1)) return 1;
+  }
+  const long long Ktot = 9LL * C + d->C2;
+  const long long tiles_m = (long long)d->N * (Hout / th) * (Wout / tw);
+  int bn = d->bn ? d->bn : pick_bn(d->Cout, tiles_m);
+  IVG_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv3x3: bad bn %d", bn);
+  {
+    uint64_t dims[3] = {(uint64_t)Ktot, (uint64_t)d->Cout, 1};
+    uint64_t str[2] = {(uint64_t)Ktot * es, (uint64_t)Ktot * d->Cout * es};
+    uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)bn, 1};
+    if (make_tensor_map(&maps.b, d->dtype, d->w, 3, dims, str, bbox, 1)) return 1;
+  }
+  p.M = (int)((long long)d->N * Hout * Wout);
+  IVG_CHECK((long long)d->N * Hout * Wout < 0x7fffffffLL, "conv3x3: too many output pixels for one launch");
+  p.N = d->Cout; p.num_kb = (int)(Ktot / BK);
+  p.mode = 1; p.H = Hout; p.W = Wout; p.tw = tw; p.th = th; p.cpb = d->Cin / BK; p.ntaps = 9; p.extra_kb = d->C2 / BK;
+  p.batch = 1; p.heads = 1; p.a_bdiv = 1; p.b_bdiv = 1;
+  p.out = d->out; p.ldo = d->Cout; p.out_dtype = d->out_dtype;
+  p.bias = d->bias;
+  p.residual = d->residual; p.ldr = d->Cout; p.res_dtype = d->res_dtype;
+  p.act = d->act; p.alpha = 1.0f;
+  p.tiles_m = (int)tiles_m; p.tiles_n = (d->Cout + bn - 1) / bn;
+  return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
+}
+
+int ivgpt_groupnorm_stats(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G,
+                          float eps, void* stream) {
+  return gn_stats_launch(dtype, x, part_ws, stats, N, rows, C, G, eps, S(stream));
+}
+int ivgpt_groupnorm_apply(int dtype, const void* x, void* y, const float* stats, const float* gamma,
+                          const float* beta, const float* pos, long long total_rows, int rows_per_sample, int C,
+                          int G, int silu, int pos_rows, void* stream) {
+  return gn_apply_launch(dtype, x, y, stats, gamma, beta, pos, total_rows, rows_per_sample, C, G, silu, pos_rows,
+                         S(stream));
+}
+int ivgpt_conv_in(int dtype, const float* x, const float* w, const float* b, void* y, int N, int H, int W, int Cout,
+                  int frames_per_clip, int clip_frames, int frame_offset, void* stream) {
+  return conv_in_launch(dtype, x, w, b, y, N, H, W, Cout, frames_per_clip, clip_frames, frame_offset, S(stream));
+}
+int ivgpt_conv_out3(int dtype, const void* x, const float* stats, const float* gamma, const float* beta,
+                    const float* w, const float* b, float* y, int N, int H, int W, int C, int G, int frames_per_clip,
+                    int clip_frames, int frame_offset, void* stream) {
+  return conv_out3_launch(dtype, x, stats, gamma, beta, w, b, y, N, H, W, C, G, frames_per_clip, clip_frames,
+                          frame_offset, S(stream));
+}
+int ivgpt_upsample2x(int dtype, const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  return upsample2x_launch(dtype, x, y, N, H, W, C, S(stream));
+}
+int ivgpt_patchify(int dtype, const void* x, void* y, int F, int R, int C, int P, int inverse, void* stream) {
+  return patchify_launch(dtype, x, y, F, R, C, P, inverse, S(stream));
+}
+int ivgpt_convert(int src_dtype, const void* x, int dst_dtype, void* y, long long n, void* stream) {
+  return convert_launch(src_dtype, x, dst_dtype, y, n, S(stream));
+}
+int ivgpt_tokens_serialise(const long long* ic, const long long* id, long long* tokens, long long* labels, int B,
+                           int t, int f, int cr, int dr, long long n_vq, long long n_dyn, void* stream) {
+  return serialise_launch(ic, id, tokens, labels, B, t, f, cr, dr, n_vq, n_dyn, S(stream));
+}
+int ivgpt_tokens_gather(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* qc,
+                        void* qd, int B, int t, int f, int cr, int dr, int D, long long n_vq, long long n_dyn, int L,
+                        void* stream) {
+  return detok_gather_launch(dtype, tokens, cb_ctx, cb_dyn, qc, qd, B, t, f, cr, dr, D, n_vq, n_dyn, L, S(stream));
+}
+int ivgpt_embed(const long long* ids, long long ids_stride, int L, const int* dpos, const float* table, float* x,
+                long long M, int hidden, long long vocab, void* stream) {
+  return embed_launch(ids, ids_stride, L, dpos, table, x, M, hidden, vocab, S(stream));
+}
+int ivgpt_add_rows(float* x, const float* e, long long n, void* stream) { return add_rows_launch(x, e, n, S(stream)); }
+int ivgpt_rmsnorm(int dtype, const float* x, const float* w, void* y, long long M, int hidden, float eps,
+                  void* stream) {
+  return rmsnorm_launch(dtype, x, w, y, M, hidden, eps, S(stream));
+}
+int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, int B, int Lq, int heads,
+                  int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, void* stream) {
+  return rope_kv_launch(dtype, qkv, q_out, k_cache, v_cache_t, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab,
+                        S(stream));
+}
+int ivgpt_softmax(int dtype, const float* Sm, void* P, long long rows, int Lq, int Lk, long long lds, long long ldp,
+                  int causal, int causal_off, void* stream) {
+  return softmax_launch(dtype, Sm, P, rows, Lq, Lk, lds, ldp, causal, causal_off, S(stream));
+}
+int ivgpt_decode_attn(int dtype, const void* q, const void* k_cache, const void* v_cache_t, void* out, int B,
+                      int heads, int Lmax, int Lcur, const int* dpos, float scale, void* stream) {
+  return decode_attn_launch(dtype, q, k_cache, v_cache_t, out, B, heads, Lmax, Lcur, dpos, scale, S(stream));
+}
+int ivgpt_argmax(const float* logits, long long ld, int rows, int V, long long* out, long long out_stride,
+                 const int* dpos, void* stream) {
+  return argmax_launch(logits, ld, rows, V, out, out_stride, dpos, S(stream));
+}
+int ivgpt_topk_sample(const float* logits, long long ld, int rows, int V, int k, float temperature,
+                      unsigned long long seed, unsigned long long step, long long* out, long long out_stride,
+                      const int* dpos, void* stream) {
+  return topk_sample_launch(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos, S(stream));
+}
+int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const long long* labels, float* loss_rows,
+                  float* valid_ws, float* loss_out, void* stream) {
+  return ce_loss_launch(logits, ld, B, L, V, labels, loss_rows, valid_ws, loss_out, S(stream));
+}
+int ivgpt_incr(int* p, int by, void* stream) { return incr_launch(p, by, S(stream)); }
+
+}  // extern "C"

@@ -1,0 +1,452 @@
+// Memory-bound kernels of the ctx_vqgan tokenizer path: GroupNorm statistics / apply (+SiLU, +pos-emb),
+// first/last 3-channel convolutions on CUDA cores, nearest-2x upsample, (de)patchify, codebook gathers and
+// token (de)serialisation.  All activations are NHWC ([N, H, W, C], C fastest) in fp32 or bf16.
+// Reference call sites are cited per kernel.
+#include "common.cuh"
+
+namespace ivg {
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm (torch.nn.GroupNorm semantics; eps 1e-6 in ResnetBlock2D/mid/out norms, vae.py:110,133,
+// eps 1e-5 in CrossAttentionBlock q/kv norms, conditional_vae.py:26-27).
+// Two deterministic stages: per-(sample, slab) partial sums in fp32 -> per-(sample, group) mean/rstd
+// combined in fp64.  "sample" may span several frames (kv_norm normalises both context frames jointly,
+// conditional_vae.py:41-44) -- the caller just passes rows = frames*H*W.
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_SLAB_ROWS = 64;  // pixels per partial-sum CTA
+
+template <typename T>
+__global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int rows, int C, int G,
+                                  int slabs) {
+  // grid: (slabs, N).  part layout [N][slabs][G][2]
+  extern __shared__ float gn_sm[];  // [G][2] accumulators
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gn_sm[i] = 0.f;
+  __syncthreads();
+  const int r0 = slab * GN_SLAB_ROWS;
+  const int r1 = min(rows, r0 + GN_SLAB_ROWS);
+  const T* base = x + ((size_t)n * rows) * C;
+  // each thread owns a fixed channel pair position -> walks rows
+  const int vecC = C / 2;
+  for (int cv = threadIdx.x; cv < vecC; cv += blockDim.x) {
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    const int c = cv * 2;
+    for (int r = r0; r < r1; ++r) {
+      float a = to_f32(base[(size_t)r * C + c]);
+      float b = to_f32(base[(size_t)r * C + c + 1]);
+      s0 += a; q0 = fmaf(a, a, q0);
+      s1 += b; q1 = fmaf(b, b, q1);
+    }
+    const int g0 = c / cpg, g1 = (c + 1) / cpg;
+    atomicAdd(&gn_sm[2 * g0], s0); atomicAdd(&gn_sm[2 * g0 + 1], q0);
+    atomicAdd(&gn_sm[2 * g1], s1); atomicAdd(&gn_sm[2 * g1 + 1], q1);
+  }
+  __syncthreads();
+  float* dst = part + ((size_t)n * slabs + slab) * G * 2;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = gn_sm[i];
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int slabs, int G,
+                                   double count, float eps) {
+  // grid: N, block: G threads (G <= 64).  stats layout [N][G][2] = (mean, rstd)
+  const int n = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < slabs; ++i) {
+    const float* p = part + ((size_t)n * slabs + i) * G * 2 + 2 * g;
+    s += (double)p[0]; q += (double)p[1];
+  }
+  double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[((size_t)n * G + g) * 2] = (float)mean;
+  stats[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y = (x - mean) * rstd * gamma + beta ; optional SiLU ; optional + pos[(row % pos_rows)][C]
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ pos, long long total_rows, int rows_per_sample, int C, int G,
+                                int silu, int pos_rows) {
+  const int cpg = C / G;
+  const int vecC = C / 2;
+  const long long total = total_rows * vecC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vecC;
+    const int c = (int)(i - row * vecC) * 2;
+    const int n = (int)(row / rows_per_sample);
+    float v0 = to_f32(x[row * C + c]), v1 = to_f32(x[row * C + c + 1]);
+    const float* st0 = stats + ((size_t)n * G + c / cpg) * 2;
+    const float* st1 = stats + ((size_t)n * G + (c + 1) / cpg) * 2;
+    v0 = (v0 - st0[0]) * st0[1] * gamma[c] + beta[c];
+    v1 = (v1 - st1[0]) * st1[1] * gamma[c + 1] + beta[c + 1];
+    if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
+    if (pos) {
+      const long long pr = row % pos_rows;
+      v0 += pos[pr * C + c]; v1 += pos[pr * C + c + 1];
+    }
+    y[row * C + c] = from_f32<T>(v0);
+    y[row * C + c + 1] = from_f32<T>(v1);
+  }
+}
+
+template <typename T>
+int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows, int C, int G, float eps,
+                      cudaStream_t st) {
+  const int slabs = cdiv(rows, GN_SLAB_ROWS);
+  dim3 grid(slabs, N);
+  gn_partial_kernel<T><<<grid, 128, 2 * G * sizeof(float), st>>>(x, part_ws, rows, C, G, slabs);
+  gn_finalize_kernel<<<N, 64, 0, st>>>(part_ws, stats, slabs, G, (double)rows * (C / G), eps);
+  count_launch(2);
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+int gn_stats_launch(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G, float eps,
+                    cudaStream_t st) {
+  IVG_CHECK(C % G == 0 && C % 2 == 0 && G <= 64, "groupnorm: bad C=%d G=%d", C, G);
+  if (N == 0) return 0;
+  if (dtype == DT_BF16) return gn_stats_launch_t((const __nv_bfloat16*)x, part_ws, stats, N, rows, C, G, eps, st);
+  return gn_stats_launch_t((const float*)x, part_ws, stats, N, rows, C, G, eps, st);
+}
+
+int gn_apply_launch(int dtype, const void* x, void* y, const float* stats, const float* gamma, const float* beta,
+                    const float* pos, long long total_rows, int rows_per_sample, int C, int G, int silu, int pos_rows,
+                    cudaStream_t st) {
+  if (total_rows == 0) return 0;
+  long long work = total_rows * (C / 2);
+  int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  if (dtype == DT_BF16)
+    gn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats, gamma,
+                                                           beta, pos, total_rows, rows_per_sample, C, G, silu,
+                                                           pos_rows);
+  else
+    gn_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, stats, gamma, beta, pos, total_rows,
+                                                   rows_per_sample, C, G, silu, pos_rows);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_in: 3x3, pad 1, Cin=3 -> Cout (vae.py:86,149).  Reads the caller's NCHW fp32 pixels, writes NHWC T.
+// K = 27 is far too small for a tensor-core tile; the kernel is bound by the output write.
+// Thread = (pixel, 8 output channels); weights [Cout][27] + bias staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                               T* __restrict__ y, int N, int H, int W, int Cout, int fpc, int clipT, int foff) {
+  extern __shared__ float cw[];  // [Cout*27] + [Cout]
+  for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) cw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) cw[Cout * 27 + i] = b[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long long total = (long long)N * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    const size_t nf = (size_t)(n / fpc) * clipT + foff + (n % fpc);  // frame slot inside the caller's [B,T,3,H,W]
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = yh + ky - 1, xx = xw + kx - 1;
+          in[c * 9 + ky * 3 + kx] =
+              (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((nf * 3 + c) * H + yy) * W + xx) : 0.f;
+        }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wj = cw + (g * 8 + j) * 27;
+      float a = cw[Cout * 27 + g * 8 + j];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) a = fmaf(in[t], wj[t], a);
+      o[j] = a;
+    }
+    T* dst = y + pix * Cout + g * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = from_f32<T>(o[j]);
+  }
+}
+
+int conv_in_launch(int dtype, const float* x, const float* w, const float* b, void* y, int N, int H, int W, int Cout,
+                   int fpc, int clipT, int foff, cudaStream_t st) {
+  IVG_CHECK(fpc > 0, "conv_in: frames-per-clip must be positive");
+  IVG_CHECK(Cout % 8 == 0, "conv_in: Cout %% 8 != 0");
+  if (N == 0) return 0;
+  size_t smem = (size_t)Cout * 28 * sizeof(float);
+  long long work = (long long)N * H * W * (Cout / 8);
+  int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
+  if (dtype == DT_BF16)
+    conv_in_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(x, w, b, (__nv_bfloat16*)y, N, H, W, Cout, fpc, clipT, foff);
+  else
+    conv_in_kernel<float><<<blocks, 256, smem, st>>>(x, w, b, (float*)y, N, H, W, Cout, fpc, clipT, foff);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_out of the decoders: GroupNorm -> SiLU -> 3x3 conv C -> 3 (vae.py:292-294,363-369), fused.
+// One warp per output pixel: lanes split the channels, 9 taps x (C/32) channels each, 3 warp reductions.
+// Reads raw NHWC T activations + GN stats, writes the caller-visible NCHW fp32 frame.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_out3_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ b,
+                                 float* __restrict__ y, int N, int H, int W, int C, int G, int fpc, int clipT, int foff) {
+  extern __shared__ float ws[];  // [27*C] weights, then gamma[C], beta[C]
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { ws[27 * C + i] = gamma[i]; ws[28 * C + i] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = (long long)N * H * W;
+  const int cpg = C / G;
+  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < total;
+       pix += (long long)gridDim.x * warps_per_block) {
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = lane * 2; c < C; c += 64) {
+      const float* st0 = stats + ((size_t)n * G + c / cpg) * 2;
+      const float* st1 = stats + ((size_t)n * G + (c + 1) / cpg) * 2;
+      const float m0 = st0[0], r0 = st0[1] * ws[27 * C + c], bb0 = ws[28 * C + c];
+      const float m1 = st1[0], r1 = st1[1] * ws[27 * C + c + 1], bb1 = ws[28 * C + c + 1];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const T* px = x + (((size_t)n * H + yy) * W + xx) * C + c;
+        float v0 = silu_f((to_f32(px[0]) - m0) * r0 + bb0);
+        float v1 = silu_f((to_f32(px[1]) - m1) * r1 + bb1);
+        a0 = fmaf(v0, ws[(0 * 9 + t) * C + c], a0); a0 = fmaf(v1, ws[(0 * 9 + t) * C + c + 1], a0);
+        a1 = fmaf(v0, ws[(1 * 9 + t) * C + c], a1); a1 = fmaf(v1, ws[(1 * 9 + t) * C + c + 1], a1);
+        a2 = fmaf(v0, ws[(2 * 9 + t) * C + c], a2); a2 = fmaf(v1, ws[(2 * 9 + t) * C + c + 1], a2);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) {
+      const size_t plane = (size_t)H * W;
+      const size_t nf = (size_t)(n / fpc) * clipT + foff + (n % fpc);
+      float* dst = y + nf * 3 * plane + (size_t)yh * W + xw;
+      dst[0] = a0 + b[0]; dst[plane] = a1 + b[1]; dst[2 * plane] = a2 + b[2];
+    }
+  }
+}
+
+int conv_out3_launch(int dtype, const void* x, const float* stats, const float* gamma, const float* beta,
+                     const float* w, const float* b, float* y, int N, int H, int W, int C, int G, int fpc, int clipT,
+                     int foff, cudaStream_t st) {
+  IVG_CHECK(fpc > 0, "conv_out3: frames-per-clip must be positive");
+  IVG_CHECK(C % 2 == 0 && C % G == 0, "conv_out3: bad C");
+  if (N == 0) return 0;
+  size_t smem = (size_t)29 * C * sizeof(float);
+  long long pixels = (long long)N * H * W;
+  int blocks = (int)((pixels + 7) / 8 < 148 * 8 ? (pixels + 7) / 8 : 148 * 8);
+  if (dtype == DT_BF16)
+    conv_out3_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>((const __nv_bfloat16*)x, stats, gamma, beta, w, b, y,
+                                                               N, H, W, C, G, fpc, clipT, foff);
+  else
+    conv_out3_kernel<float><<<blocks, 256, smem, st>>>((const float*)x, stats, gamma, beta, w, b, y, N, H, W, C, G, fpc, clipT, foff);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest-neighbour 2x upsample, NHWC (diffusers Upsample2D -> F.interpolate(scale_factor=2, 'nearest'))
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void upsample2x_kernel(const V* __restrict__ x, V* __restrict__ y, int N, int H, int W, int CV) {
+  const long long total = (long long)N * (2 * H) * (2 * W) * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV);
+    long long p = i / CV;
+    const int xo = (int)(p % (2 * W)); p /= (2 * W);
+    const int yo = (int)(p % (2 * H));
+    const int n = (int)(p / (2 * H));
+    y[i] = x[(((size_t)n * H + (yo >> 1)) * W + (xo >> 1)) * CV + c];
+  }
+}
+
+int upsample2x_launch(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {
+  const int esz = dtype == DT_BF16 ? 2 : 4;
+  IVG_CHECK((C * esz) % 16 == 0, "upsample2x: C*elsize must be a multiple of 16 bytes");
+  if (N == 0) return 0;
+  const int CV = C * esz / 16;
+  long long work = (long long)N * 4 * H * W * CV;
+  int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  upsample2x_kernel<uint4><<<blocks, 256, 0, st>>>((const uint4*)x, (uint4*)y, N, H, W, CV);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// patchify (compressive_vq_model.py:192-195): NHWC [F,16,16,C] -> [F*16, p*p*C], feature order (py,px,c);
+// depatchify (:247-250, einsum nhwpqc->nchpwq) is the inverse.  p = 4.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, T* __restrict__ y, int F, int R, int C, int P, int inverse) {
+  const int PR = R / P;  // patches per side
+  const long long total = (long long)F * R * R * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int xx = (int)(p % R); p /= R;
+    const int yy = (int)(p % R);
+    const int f = (int)(p / R);
+    const long long patch_row = ((long long)f * PR + yy / P) * PR + xx / P;
+    const long long j = patch_row * ((long long)P * P * C) + ((yy % P) * P + (xx % P)) * C + c;
+    if (inverse) y[i] = x[j]; else y[j] = x[i];
+  }
+}
+
+int patchify_launch(int dtype, const void* x, void* y, int F, int R, int C, int P, int inverse, cudaStream_t st) {
+  if (F == 0) return 0;
+  long long work = (long long)F * R * R * C;
+  int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  if (dtype == DT_BF16)
+    patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, F, R, C, P, inverse);
+  else
+    patchify_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, F, R, C, P, inverse);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dtype conversion (fp32 <-> T), used at API boundaries (latents to fp32 for the exact VQ stage)
+// ---------------------------------------------------------------------------------------------
+template <typename A, typename B>
+__global__ void convert_kernel(const A* __restrict__ x, B* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f32<B>(to_f32(x[i]));
+}
+
+int convert_launch(int src_dtype, const void* x, int dst_dtype, void* y, long long n, cudaStream_t st) {
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (src_dtype == DT_F32 && dst_dtype == DT_BF16)
+    convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else if (src_dtype == DT_BF16 && dst_dtype == DT_F32)
+    convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+  else if (src_dtype == DT_F32 && dst_dtype == DT_F32)
+    convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, n);
+  else
+    convert_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Token (de)serialisation, compressive_vq_model.py:205-220 and :227-236.  int64 throughout.
+// Sequence layout for t context frames / f future frames (cr = 256 ctx tokens, dr = 16 dyn tokens):
+//   c0[256] scf c1[256] ... | sdf d0[16] sdf d1[16] ...      length L = t*257 - 1 + f*17
+// ---------------------------------------------------------------------------------------------
+__global__ void serialise_kernel(const long long* __restrict__ ic, const long long* __restrict__ id,
+                                 long long* __restrict__ tokens, long long* __restrict__ labels, int B, int t, int f,
+                                 int cr, int dr, long long nvq, long long ndyn) {
+  const int L = t * (cr + 1) - 1 + f * (dr + 1);
+  const long long total = (long long)B * L;
+  const long long scf = nvq + ndyn, sdf = nvq + ndyn + 1;
+  const int ctx_len = t * (cr + 1) - 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / L), pos = (int)(i % L);
+    long long tok, lab;
+    if (pos < ctx_len) {
+      const int fr = pos / (cr + 1), k = pos % (cr + 1);
+      tok = (k == cr) ? scf : ic[((size_t)b * t + fr) * cr + k];
+      lab = -100;
+    } else {
+      const int q = pos - ctx_len;
+      const int fr = q / (dr + 1), k = q % (dr + 1);
+      tok = (k == 0) ? sdf : id[((size_t)b * f + fr) * dr + (k - 1)] + nvq;
+      lab = (q == 0) ? -100 : tok;
+    }
+    tokens[i] = tok;
+    if (labels) labels[i] = lab;
+  }
+}
+
+int serialise_launch(const long long* ic, const long long* id, long long* tokens, long long* labels, int B, int t,
+                     int f, int cr, int dr, long long nvq, long long ndyn, cudaStream_t st) {
+  if (B == 0) return 0;
+  const long long total = (long long)B * (t * (cr + 1) - 1 + f * (dr + 1));
+  serialise_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ic, id, tokens, labels, B, t, f, cr, dr, nvq, ndyn);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// tokens[B, L] -> gathered codebook rows: ctx latents [B*t*cr, D] and dyn latents [B*f*dr, D] (T)
+template <typename T>
+__global__ void detok_gather_kernel(const long long* __restrict__ tokens, const float* __restrict__ cb_ctx,
+                                    const float* __restrict__ cb_dyn, T* __restrict__ qc, T* __restrict__ qd, int B,
+                                    int t, int f, int cr, int dr, int D, long long nvq, long long ndyn, int L) {
+  const long long nctx = (long long)B * t * cr, ndy = (long long)B * f * dr;
+  const int ctx_len = t * (cr + 1) - 1;
+  const long long total = (nctx + ndy) * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long row = i / D;
+    if (row < nctx) {
+      const int b = (int)(row / ((long long)t * cr));
+      const int r = (int)(row % ((long long)t * cr));
+      const int fr = r / cr, k = r % cr;
+      long long id = tokens[(size_t)b * L + fr * (cr + 1) + k];
+      id = id < 0 ? 0 : (id >= nvq ? nvq - 1 : id);  // the reference would raise on out-of-range ctx ids
+      qc[row * D + d] = from_f32<T>(cb_ctx[id * D + d]);
+    } else {
+      const long long r2 = row - nctx;
+      const int b = (int)(r2 / ((long long)f * dr));
+      const int r = (int)(r2 % ((long long)f * dr));
+      const int fr = r / dr, k = r % dr;
+      long long id = tokens[(size_t)b * L + ctx_len + fr * (dr + 1) + 1 + k] - nvq;
+      id = id < 0 ? 0 : (id > ndyn - 1 ? ndyn - 1 : id);  // clamp, compressive_vq_model.py:236
+      qd[r2 * D + d] = from_f32<T>(cb_dyn[id * D + d]);
+    }
+  }
+}
+
+int detok_gather_launch(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* qc,
+                        void* qd, int B, int t, int f, int cr, int dr, int D, long long nvq, long long ndyn, int L,
+                        cudaStream_t st) {
+  if (B == 0) return 0;
+  const long long total = ((long long)B * t * cr + (long long)B * f * dr) * D;
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (dtype == DT_BF16)
+    detok_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, cb_ctx, cb_dyn, (__nv_bfloat16*)qc,
+                                                               (__nv_bfloat16*)qd, B, t, f, cr, dr, D, nvq, ndyn, L);
+  else
+    detok_gather_kernel<float><<<blocks, 256, 0, st>>>(tokens, cb_ctx, cb_dyn, (float*)qc, (float*)qd, B, t, f, cr, dr,
+                                                       D, nvq, ndyn, L);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ivg

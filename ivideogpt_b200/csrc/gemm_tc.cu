@@ -1,0 +1,327 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )          fp32 accumulation in TMEM
+//
+// One kernel covers every dense contraction on the iVideoGPT hot path:
+//   * mode 0 (plain / batched): Llama q/k/v/o/gate/up/down/lm_head projections
+//     (transformers LlamaAttention / LlamaMLP, called from reference inference/predict.py:64 via generate),
+//     1x1 convs and Linear layers of the tokenizer (compressive_vq_model.py:188,196,241,245),
+//     Q.K^T and P.V of the cross/self attention blocks (conditional_vae.py:49), with per-head column offsets
+//     so that no head split/merge copies are ever made.
+//   * mode 1 (conv taps): 3x3 convolutions of the ctx_vqgan encoder/decoder (vae.py:86-137,236-294) as an
+//     implicit GEMM over NHWC activations: the A operand of k-block (tap, channel-chunk) is a 4-D TMA box
+//     of th x tw output pixels shifted by the tap; TMA out-of-bounds zero fill *is* the conv padding.
+//     Stride-2 convs (diffusers Downsample2D, pad (0,1,0,1)) read one of four parity views of the input.
+//     A trailing "extra" segment of k-blocks reads a second tensor at tap (0,0): the fused 1x1 shortcut of
+//     ResnetBlock2D.
+//
+// Structure (per CTA, 192 threads, 1 CTA/SM, grid = min(#tiles, #SMs), static tile striding):
+//   warp 0 (one elected lane) : TMA producer       -> smem ring of S stages {A 128x128B, B BNx128B}, SWIZZLE_128B
+//   warp 1 (one elected lane) : tcgen05.mma issuer -> 2 TMEM accumulator stages of BN fp32 columns each
+//   warps 2-5                 : epilogue, tcgen05.ld 32 lanes x 16 columns, bias/residual/activation, global stores
+// Operands are bf16 (kind::f16) or fp32 read as tf32 (kind::tf32); a k-block is always 128 bytes of K.
+#include "common.cuh"
+#include "gemm_params.cuh"
+
+namespace ivg {
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_ROWB;
+  static constexpr int B_BYTES = BN * GEMM_ROWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barrier block + alignment slack
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  using SM = GemmSmem<BN>;
+  constexpr bool TF32 = (sizeof(T) == 4);
+  constexpr int BK = GEMM_ROWB / (int)sizeof(T);  // elements of K per k-block
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, GEMM_BM, BN);
+
+  extern __shared__ uint8_t gemm_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + SM::STAGES;
+  uint64_t* tfull_bar = empty_bar + SM::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < SM::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_holder, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.batch;
+  const int num_kb = p.num_kb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =============================== TMA producer ===============================
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int bz = tile / tiles_mn;
+        const int rem = tile - bz * tiles_mn;
+        const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
+        const int m0 = tm * GEMM_BM, n0 = tn * BN;
+        if (p.causal_skip && n0 > m0 + GEMM_BM - 1) continue;
+        const int outer = bz / p.heads, h = bz - outer * p.heads;
+        const int a_b = p.a_bsel == 0 ? 0 : (p.a_bsel == 1 ? outer / p.a_bdiv : bz);
+        const int b_b = p.b_bsel == 0 ? 0 : (p.b_bsel == 1 ? outer / p.b_bdiv : bz);
+        const int a_k0 = p.a_kbase + h * p.a_khead, b_k0 = p.b_kbase + h * p.b_khead;
+        const int b_n0 = n0 + h * p.b_nhead;
+        int img = 0, y0 = 0, x0 = 0;
+        if (p.mode == 1) {
+          const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
+          img = tm / tiles_img;
+          const int r2 = tm - img * tiles_img;
+          y0 = (r2 / tiles_x) * p.th;
+          x0 = (r2 % tiles_x) * p.tw;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * SM::STAGE_BYTES;
+          uint8_t* sb = sa + SM::A_BYTES;
+          mbar_expect_tx(full_bar + stage, SM::STAGE_BYTES);
+          if (p.mode == 0) {
+            tma_load_3d(sa, &maps.a[0], full_bar + stage, a_k0 + kb * BK, m0, a_b);
+          } else {
+            int tap = kb / p.cpb;
+            int chunk = kb - tap * p.cpb;
+            if (tap < p.ntaps) {
+              tma_load_4d(sa, &maps.a[p.tap_map[tap]], full_bar + stage, chunk * BK, x0 + p.tap_dx[tap],
+                          y0 + p.tap_dy[tap], img);
+            } else {
+              chunk = kb - p.ntaps * p.cpb;
+              tma_load_4d(sa, &maps.a[4], full_bar + stage, chunk * BK, x0, y0, img);
+            }
+          }
+          tma_load_3d(sb, &maps.b, full_bar + stage, b_k0 + kb * BK, b_n0, b_b);
+          if (++stage == SM::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // =============================== MMA issuer ===============================
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (p.causal_skip) {
+          const int rem = tile % tiles_mn;
+          const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
+          if (tn * BN > tm * GEMM_BM + GEMM_BM - 1) continue;
+        }
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        ++local;
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per k-block
+            umma_ss<TF32>(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
+          if (++stage == SM::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + acc);      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;        // row of the 128-row tile owned by this thread
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int bz = tile / tiles_mn;
+      const int rem = tile - bz * tiles_mn;
+      const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
+      const int m0 = tm * GEMM_BM, n0 = tn * BN;
+      if (p.causal_skip && n0 > m0 + GEMM_BM - 1) continue;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      ++local;
+      const int outer = bz / p.heads, h = bz - outer * p.heads;
+      const int o_b = p.o_bsel == 0 ? 0 : (p.o_bsel == 1 ? outer : bz);
+
+      // logical output row of this thread
+      long long orow;
+      bool row_ok;
+      if (p.mode == 0) {
+        orow = m0 + row;
+        row_ok = (m0 + row) < p.M;
+      } else {
+        const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
+        const int img = tm / tiles_img;
+        const int r2 = tm - img * tiles_img;
+        const int y = (r2 / tiles_x) * p.th + row / p.tw;
+        const int x = (r2 % tiles_x) * p.tw + row % p.tw;
+        orow = ((long long)img * p.H + y) * p.W + x;
+        row_ok = orow < (long long)p.M;
+      }
+      const int ocol0 = n0 + h * p.o_nhead;  // column in the output matrix (before SwiGLU halving)
+
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[(p.mode == 0 ? (m0 + row) : 0)] : 0.f;
+
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        if (n0 + c >= p.N) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias) {
+          if (p.bias_along_m) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += bias_m;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += (n0 + c + j < p.N) ? __ldg(p.bias + h * p.o_nhead + n0 + c + j) : 0.f;
+          }
+        }
+        if (p.act == 2) {
+          // interleaved (gate, up) pairs -> 8 outputs
+          const long long ooff = (long long)o_b * p.out_bstride + orow * p.ldo + ((ocol0 + c) >> 1);
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = silu_f(v[2 * j]) * v[2 * j + 1];
+          const bool full = (n0 + c + 16 <= p.N);
+          if (p.out_dtype == DT_BF16) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
+            if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              uint4 w = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                   pack_bf16x2(o[6], o[7]));
+              *reinterpret_cast<uint4*>(op) = w;
+            } else {
+              for (int j = 0; j < 8; ++j) if (n0 + c + 2 * j + 1 < p.N) op[j] = __float2bfloat16_rn(o[j]);
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + ooff;
+            for (int j = 0; j < 8; ++j) if (n0 + c + 2 * j + 1 < p.N) op[j] = o[j];
+          }
+          continue;
+        }
+        if (p.residual) {
+          const long long roff = (long long)o_b * p.res_bstride + orow * p.ldr + ocol0 + c;
+          if (p.res_dtype == DT_BF16) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + c + j < p.N) v[j] += __bfloat162float(rp[j]);
+          } else {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + c + j < p.N) v[j] += rp[j];
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        }
+        const long long ooff = (long long)o_b * p.out_bstride + orow * p.ldo + ocol0 + c;
+        const bool full = (n0 + c + 16 <= p.N);
+        if (p.out_dtype == DT_BF16) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
+          if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+            uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            reinterpret_cast<uint4*>(op)[0] = w0;
+            reinterpret_cast<uint4*>(op)[1] = w1;
+          } else {
+            for (int j = 0; j < 16; ++j) if (n0 + c + j < p.N) op[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* op = reinterpret_cast<float*>(p.out) + ooff;
+          if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 16; ++j) if (n0 + c + j < p.N) op[j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T, int BN>
+static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using SM = GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IVG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
+  int grid = (int)(total < num_sms ? total : num_sms);
+  if (grid < 1) return 0;
+  gemm_tc_kernel<T, BN><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(maps, p);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (dtype == DT_BF16) {
+    switch (bn) {
+      case 32: return launch_one<__nv_bfloat16, 32>(maps, p, num_sms, stream);
+      case 64: return launch_one<__nv_bfloat16, 64>(maps, p, num_sms, stream);
+      case 128: return launch_one<__nv_bfloat16, 128>(maps, p, num_sms, stream);
+      case 256: return launch_one<__nv_bfloat16, 256>(maps, p, num_sms, stream);
+    }
+  } else if (dtype == DT_F32) {
+    switch (bn) {
+      case 32: return launch_one<float, 32>(maps, p, num_sms, stream);
+      case 64: return launch_one<float, 64>(maps, p, num_sms, stream);
+      case 128: return launch_one<float, 128>(maps, p, num_sms, stream);
+      case 256: return launch_one<float, 256>(maps, p, num_sms, stream);
+    }
+  }
+  set_error("gemm_tc: unsupported dtype=%d / BN=%d", dtype, bn);
+  return 1;
+}
+
+}  // namespace ivg

@@ -1,0 +1,323 @@
+"""Thin torch-tensor front end over the C ABI (ivideogpt_b200/_lib.py).
+
+torch is used here only as the owner of device memory and streams: every function checks that its tensors
+live on a CUDA device, allocates the output with torch.empty and enqueues one or more of OUR kernels on
+torch.cuda.current_stream().  Nothing in this file computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, ACT_SWIGLU, BF16, F32, ConvDesc, GemmDesc
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"ivideogpt_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.B200LibraryError("ivideogpt_b200 runs on CUDA (sm_100a) only; got a tensor on "
+                                        f"{t.device}.  There is no CPU fallback.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def torch_dtype(code: int):
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# VQ argmin
+# ------------------------------------------------------------------------------------------------
+def vq_argmin(z: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """idx[n] = argmin_k ||z_n - e_k||  (int64).  z [N,64] fp32, codebook [K,64] fp32."""
+    _cuda(z, codebook)
+    assert z.dtype == torch.float32 and codebook.dtype == torch.float32
+    z = z.contiguous()
+    codebook = codebook.contiguous()
+    N, D = z.shape
+    K = codebook.shape[0]
+    idx = torch.empty(N, dtype=torch.int64, device=z.device)
+    enorm = torch.empty(K, dtype=torch.float32, device=z.device)
+    packed = torch.empty(max(N, 1), dtype=torch.int64, device=z.device)
+    lib = _lib.load()
+    _lib.check(lib.ivgpt_vq_argmin(z.data_ptr(), codebook.data_ptr(), enorm.data_ptr(), packed.data_ptr(),
+                                   idx.data_ptr(), N, K, D, _stream()), "vq_argmin")
+    return idx
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM family
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out_dtype: Optional[torch.dtype] = None,
+         out: Optional[torch.Tensor] = None, alpha: float = 1.0, bn: int = 0) -> torch.Tensor:
+    """out[M,N] = act(alpha * a[M,K] @ w[N,K]^T + bias + residual).  a, w share dtype (fp32->TF32, or bf16)."""
+    _cuda(a, w, bias, residual, out)
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    assert a.dtype == w.dtype
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, dtype=out_dtype or a.dtype, device=a.device)
+    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == n_out
+    d = GemmDesc()
+    d.dtype = _dt(a); d.bn = bn
+    d.a = a.data_ptr(); d.lda = a.stride(0); d.a_rows = M; d.a_cols = K; d.a_batches = 1
+    d.b = w.data_ptr(); d.ldb = w.stride(0); d.b_rows = N; d.b_cols = K; d.b_batches = 1
+    d.M, d.N, d.K = M, N, K
+    d.batch = 1; d.heads = 1; d.a_bdiv = 1; d.b_bdiv = 1
+    d.out = out.data_ptr(); d.ldo = out.stride(0); d.out_dtype = _dt(out)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        d.bias = bias.data_ptr()
+    if residual is not None:
+        assert residual.shape == out.shape and residual.stride(1) == 1
+        d.residual = residual.data_ptr(); d.ldr = residual.stride(0); d.res_dtype = _dt(residual)
+    d.act = act; d.alpha = alpha
+    _lib.check(_lib.load().ivgpt_gemm(C.byref(d), _stream()), "gemm")
+    return out
+
+
+def gemm_desc(**kw) -> GemmDesc:
+    d = GemmDesc()
+    d.batch = 1; d.heads = 1; d.a_bdiv = 1; d.b_bdiv = 1; d.alpha = 1.0
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def gemm_raw(d: GemmDesc):
+    _lib.check(_lib.load().ivgpt_gemm(C.byref(d), _stream()), "gemm")
+
+
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1,
+            x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+            out_dtype: Optional[torch.dtype] = None, bn: int = 0) -> torch.Tensor:
+    """3x3 conv over NHWC x [N,H,W,Cin] with packed weights [Cout, 9*Cin (+C2)]; optional fused 1x1 source x2."""
+    _cuda(x, w_packed, bias, x2, residual)
+    assert x.is_contiguous() and w_packed.is_contiguous() and x.dtype == w_packed.dtype
+    N, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert w_packed.shape[1] == 9 * Cin + C2, (w_packed.shape, Cin, C2)
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty(N, Ho, Wo, Cout, dtype=out_dtype or x.dtype, device=x.device)
+    d = ConvDesc()
+    d.dtype = _dt(x); d.bn = bn
+    d.x = x.data_ptr(); d.N, d.Hin, d.Win, d.Cin, d.stride = N, H, W, Cin, stride
+    d.w = w_packed.data_ptr(); d.Cout = Cout
+    if x2 is not None:
+        assert x2.is_contiguous() and x2.shape[:3] == (N, Ho, Wo) and x2.dtype == x.dtype
+        d.x2 = x2.data_ptr(); d.C2 = C2
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cout
+        d.bias = bias.data_ptr()
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == out.shape
+        d.residual = residual.data_ptr(); d.res_dtype = _dt(residual)
+    d.act = act
+    d.out = out.data_ptr(); d.out_dtype = _dt(out)
+    _lib.check(_lib.load().ivgpt_conv3x3(C.byref(d), _stream()), "conv3x3")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm and friends
+# ------------------------------------------------------------------------------------------------
+def groupnorm_stats(x: torch.Tensor, samples: int, groups: int, eps: float) -> torch.Tensor:
+    """x is any contiguous [..., C] tensor viewed as [samples, rows, C]; returns (mean, rstd) [samples, G, 2]."""
+    _cuda(x)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // (samples * Cc)
+    slabs = (rows + 63) // 64
+    part = torch.empty(samples * slabs * groups * 2, dtype=torch.float32, device=x.device)
+    stats = torch.empty(samples, groups, 2, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_groupnorm_stats(_dt(x), x.data_ptr(), part.data_ptr(), stats.data_ptr(), samples,
+                                                 rows, Cc, groups, eps, _stream()), "groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,
+                    pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, stats, gamma, beta, pos)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    samples, groups = stats.shape[0], stats.shape[1]
+    total_rows = x.numel() // Cc
+    y = torch.empty_like(x)
+    pos_rows = 0
+    if pos is not None:
+        assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[1] == Cc
+        pos_rows = pos.shape[0]
+    _lib.check(_lib.load().ivgpt_groupnorm_apply(_dt(x), x.data_ptr(), y.data_ptr(), stats.data_ptr(),
+                                                 gamma.data_ptr(), beta.data_ptr(), _ptr(pos), total_rows,
+                                                 total_rows // samples, Cc, groups, int(silu), pos_rows, _stream()),
+               "groupnorm_apply")
+    return y
+
+
+def conv_in(clips: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype, frame_offset: int,
+            frames_per_clip: int) -> torch.Tensor:
+    """clips [B,T,3,H,W] fp32 contiguous; processes frames [frame_offset, frame_offset+frames_per_clip) of each clip."""
+    _cuda(clips, w27, bias)
+    assert clips.dtype == torch.float32 and clips.is_contiguous() and clips.dim() == 5 and clips.shape[2] == 3
+    B, T, _, H, W = clips.shape
+    N = B * frames_per_clip
+    Cout = w27.shape[0]
+    y = torch.empty(N, H, W, Cout, dtype=dtype, device=clips.device)
+    _lib.check(_lib.load().ivgpt_conv_in(_dt(y), clips.data_ptr(), w27.data_ptr(), bias.data_ptr(), y.data_ptr(), N,
+                                         H, W, Cout, frames_per_clip, T, frame_offset, _stream()), "conv_in")
+    return y
+
+
+def conv_out3(x: torch.Tensor, stats: torch.Tensor, gamma, beta, w_packed: torch.Tensor, bias: torch.Tensor,
+              out_clips: torch.Tensor, frame_offset: int, frames_per_clip: int):
+    """Writes frames into out_clips [B,T,3,H,W] fp32 at slots [frame_offset, frame_offset+frames_per_clip)."""
+    _cuda(x, stats, gamma, beta, w_packed, bias, out_clips)
+    N, H, W, Cc = x.shape
+    assert out_clips.is_contiguous() and out_clips.dtype == torch.float32
+    _lib.check(_lib.load().ivgpt_conv_out3(_dt(x), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                           w_packed.data_ptr(), bias.data_ptr(), out_clips.data_ptr(), N, H, W, Cc,
+                                           stats.shape[1], frames_per_clip, out_clips.shape[1], frame_offset,
+                                           _stream()), "conv_out3")
+    return out_clips
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x)
+    N, H, W, Cc = x.shape
+    y = torch.empty(N, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().ivgpt_upsample2x(_dt(x), x.data_ptr(), y.data_ptr(), N, H, W, Cc, _stream()), "upsample2x")
+    return y
+
+
+def patchify(x: torch.Tensor, p: int, inverse: bool = False, frames: int = 0, res: int = 0, ch: int = 0):
+    _cuda(x)
+    assert x.is_contiguous()
+    if not inverse:
+        F_, R, _, Cc = x.shape
+        y = torch.empty(F_ * (R // p) ** 2, p * p * Cc, dtype=x.dtype, device=x.device)
+    else:
+        F_, R, Cc = frames, res, ch
+        y = torch.empty(F_, R, R, Cc, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().ivgpt_patchify(_dt(x), x.data_ptr(), y.data_ptr(), F_, R, Cc, p, int(inverse), _stream()),
+               "patchify")
+    return y
+
+
+def convert(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _cuda(x)
+    if x.dtype == dtype:
+        return x
+    assert x.is_contiguous()
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _lib.check(_lib.load().ivgpt_convert(_dt(x), x.data_ptr(), _dt(y), y.data_ptr(), x.numel(), _stream()), "convert")
+    return y
+
+
+def tokens_serialise(idx_ctx, idx_dyn, B, t, f, cr, dr, n_vq, n_dyn, want_labels=True):
+    _cuda(idx_ctx, idx_dyn)
+    L = t * (cr + 1) - 1 + f * (dr + 1)
+    tokens = torch.empty(B, L, dtype=torch.int64, device=idx_ctx.device)
+    labels = torch.empty(B, L, dtype=torch.int64, device=idx_ctx.device) if want_labels else None
+    _lib.check(_lib.load().ivgpt_tokens_serialise(idx_ctx.data_ptr(), idx_dyn.data_ptr(), tokens.data_ptr(),
+                                                  _ptr(labels), B, t, f, cr, dr, n_vq, n_dyn, _stream()),
+               "tokens_serialise")
+    return tokens, labels
+
+
+def tokens_gather(tokens, cb_ctx, cb_dyn, t, f, cr, dr, dtype):
+    _cuda(tokens, cb_ctx, cb_dyn)
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous()
+    B, L = tokens.shape
+    D = cb_ctx.shape[1]
+    qc = torch.empty(B * t * cr, D, dtype=dtype, device=tokens.device)
+    qd = torch.empty(B * f * dr, D, dtype=dtype, device=tokens.device)
+    _lib.check(_lib.load().ivgpt_tokens_gather(_dt(qc), tokens.data_ptr(), cb_ctx.data_ptr(), cb_dyn.data_ptr(),
+                                               qc.data_ptr(), qd.data_ptr(), B, t, f, cr, dr, D, cb_ctx.shape[0],
+                                               cb_dyn.shape[0], L, _stream()), "tokens_gather")
+    return qc, qd
+
+
+# ------------------------------------------------------------------------------------------------
+# Llama pieces (raw-pointer style: the engine in transformer/engine.py owns the buffers)
+# ------------------------------------------------------------------------------------------------
+def embed(ids, ids_stride, L, dpos, table, x, M):
+    _lib.check(_lib.load().ivgpt_embed(ids.data_ptr(), ids_stride, L, _ptr(dpos), table.data_ptr(), x.data_ptr(), M,
+                                       table.shape[1], table.shape[0], _stream()), "embed")
+
+
+def add_rows(x, e):
+    _lib.check(_lib.load().ivgpt_add_rows(x.data_ptr(), e.data_ptr(), x.numel(), _stream()), "add_rows")
+
+
+def rmsnorm(x, w, y, M, eps):
+    _lib.check(_lib.load().ivgpt_rmsnorm(_dt(y), x.data_ptr(), w.data_ptr(), y.data_ptr(), M, x.shape[-1], eps,
+                                         _stream()), "rmsnorm")
+
+
+def rope_kv(qkv, q_out, k_cache, v_cache_t, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab):
+    _lib.check(_lib.load().ivgpt_rope_kv(_dt(qkv), qkv.data_ptr(), q_out.data_ptr(), k_cache.data_ptr(),
+                                         v_cache_t.data_ptr(), B, Lq, heads, Lmax, pos0, _ptr(dpos),
+                                         cos_tab.data_ptr(), sin_tab.data_ptr(), _stream()), "rope_kv")
+
+
+def softmax(S, P, rows, Lq, Lk, lds, ldp, causal, causal_off=0):
+    _lib.check(_lib.load().ivgpt_softmax(_dt(P), S.data_ptr(), P.data_ptr(), rows, Lq, Lk, lds, ldp, int(causal),
+                                         causal_off, _stream()), "softmax")
+
+
+def decode_attn(q, k_cache, v_cache_t, out, B, heads, Lmax, Lcur, dpos, scale):
+    _lib.check(_lib.load().ivgpt_decode_attn(_dt(q), q.data_ptr(), k_cache.data_ptr(), v_cache_t.data_ptr(),
+                                             out.data_ptr(), B, heads, Lmax, Lcur, _ptr(dpos), scale, _stream()),
+               "decode_attn")
+
+
+def argmax(logits, ld, rows, V, out, out_stride, dpos=None, out_offset=0):
+    _lib.check(_lib.load().ivgpt_argmax(logits.data_ptr(), ld, rows, V, out.data_ptr() + 8 * out_offset, out_stride,
+                                        _ptr(dpos), _stream()), "argmax")
+
+
+def topk_sample(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos=None, out_offset=0):
+    _lib.check(_lib.load().ivgpt_topk_sample(logits.data_ptr(), ld, rows, V, k, temperature, seed, step,
+                                             out.data_ptr() + 8 * out_offset, out_stride, _ptr(dpos), _stream()),
+               "topk_sample")
+
+
+def ce_loss(logits, ld, B, L, V, labels):
+    """Shifted cross-entropy over logits [B,L,ld] fp32 / labels [B,L] int64; returns (mean loss 0-d, per-row)."""
+    _cuda(logits, labels)
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    rows = B * (L - 1)
+    loss_rows = torch.empty(max(rows, 1), dtype=torch.float32, device=logits.device)
+    valid = torch.empty(max(rows, 1), dtype=torch.float32, device=logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().ivgpt_ce_loss(logits.data_ptr(), ld, B, L, V, labels.data_ptr(), loss_rows.data_ptr(),
+                                         valid.data_ptr(), out.data_ptr(), _stream()), "ce_loss")
+    return out[0], loss_rows[:rows]
+
+
+def incr(p, by=1):
+    _lib.check(_lib.load().ivgpt_incr(p.data_ptr(), by, _stream()), "incr")

@@ -1,0 +1,266 @@
+"""Kernel plan for the Llama-style autoregressive transformer over frame tokens.
+
+Replaces transformers' LlamaModel / LlamaAttention / LlamaMLP / GenerationMixin arithmetic that the reference
+reaches through `model.generate(...)` (inference/predict.py:64-69, ivideogpt/transformer/action_model.py:86-110)
+and `model(input_ids=, labels=)` (train_gpt.py:792).
+
+B200-first layout:
+  * weights are packed once per parameter version: [q;k;v] fused to one [3h,h] operand, gate/up interleaved
+    row-wise into [2*inter,h] so SwiGLU is a GEMM epilogue, all in the compute dtype (bf16, or fp32->TF32);
+  * the residual stream stays fp32; every projection is one tcgen05 GEMM launch with bias-free epilogues that
+    add the residual in place;
+  * static KV cache, K as [B,heads,Lmax,64] and V transposed [B,heads,64,Lmax]: prefill attention is
+    Q.K^T -> causal softmax -> P.V^T^T on the tensor cores straight out of the cache, decode attention is a
+    single HBM-streaming kernel over the same buffers;
+  * one decode step (embed -> 12/24 layers -> lm_head -> sample -> append) is captured once into a CUDA graph
+    whose kernels read the current position from device memory, and replayed max_new_tokens-1 times.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import ops
+from .._lib import ACT_SWIGLU, BF16, F32
+
+
+def _round_tf32(w: torch.Tensor) -> torch.Tensor:
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _pack(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    w = w.detach().float()
+    return _round_tf32(w).contiguous() if dtype == torch.float32 else w.to(dtype).contiguous()
+
+
+class LlamaWeights:
+    """Kernel-layout copy of an HF LlamaForCausalLM's parameters (cached per parameter version)."""
+
+    def __init__(self, hf_model, dtype: torch.dtype):
+        cfg = hf_model.config
+        self.dtype = dtype
+        self.hidden = cfg.hidden_size
+        self.inter = cfg.intermediate_size
+        self.heads = cfg.num_attention_heads
+        self.layers_n = cfg.num_hidden_layers
+        self.vocab = cfg.vocab_size
+        self.eps = float(cfg.rms_norm_eps)
+        if cfg.num_key_value_heads != cfg.num_attention_heads:
+            raise NotImplementedError("grouped-query attention is not used by iVideoGPT configs and not implemented")
+        if self.hidden // self.heads != 64:
+            raise NotImplementedError("head_dim must be 64 (both iVideoGPT Llama configs)")
+        if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
+            raise NotImplementedError("attention/mlp biases are not part of the iVideoGPT Llama configs")
+        m = hf_model.model
+        self.embed = m.embed_tokens.weight.detach().float().contiguous()
+        self.layers = []
+        for lyr in m.layers:
+            a, mlp = lyr.self_attn, lyr.mlp
+            wqkv = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], dim=0)
+            wgu = torch.stack([mlp.gate_proj.weight, mlp.up_proj.weight], dim=1).reshape(2 * self.inter, self.hidden)
+            self.layers.append(dict(
+                wqkv=_pack(wqkv, dtype), wo=_pack(a.o_proj.weight, dtype), wgu=_pack(wgu, dtype),
+                wd=_pack(mlp.down_proj.weight, dtype),
+                n1=lyr.input_layernorm.weight.detach().float().contiguous(),
+                n2=lyr.post_attention_layernorm.weight.detach().float().contiguous()))
+        self.norm = m.norm.weight.detach().float().contiguous()
+        self.lm_head = _pack(hf_model.lm_head.weight, dtype)
+        # RoPE tables exactly as LlamaRotaryEmbedding computes them (fp32, theta from config)
+        theta = float(getattr(cfg, "rope_theta", None) or (getattr(cfg, "rope_parameters", None) or {}).get("rope_theta", 10000.0))
+        dev = self.embed.device
+        inv_freq = 1.0 / (theta ** (torch.arange(0, 64, 2, dtype=torch.int64, device=dev).float() / 64))
+        pos = torch.arange(cfg.max_position_embeddings, device=dev, dtype=torch.float32)
+        freqs = pos[:, None] * inv_freq[None, :]
+        self.cos, self.sin = freqs.cos().contiguous(), freqs.sin().contiguous()
+        self.max_pos = cfg.max_position_embeddings
+
+    @staticmethod
+    def signature(hf_model, dtype):
+        return (dtype,) + tuple((p.data_ptr(), p._version) for p in hf_model.parameters())
+
+
+class LlamaEngine:
+    def __init__(self, weights: LlamaWeights):
+        self.w = weights
+        self.dtype = weights.dtype
+        self.code = BF16 if self.dtype == torch.bfloat16 else F32
+        self._buf: Dict[tuple, torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+
+    # ---- buffers ------------------------------------------------------------------------------------
+    def buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = torch.empty(*shape, dtype=dtype, device=self.w.embed.device)
+            self._buf[key] = t
+        return t
+
+    def kv_cache(self, B, Lmax):
+        w = self.w
+        k = self.buf("kcache", (w.layers_n, B, w.heads, Lmax, 64), self.dtype)
+        v = self.buf("vcache_t", (w.layers_n, B, w.heads, 64, Lmax), self.dtype)
+        return k, v
+
+    # ---- one transformer layer over M = B*Lq rows -----------------------------------------------------
+    def _layer(self, li, x, B, Lq, kc, vc, Lmax, pos0, dpos, prefill: bool):
+        w, dt, code = self.w, self.dtype, self.code
+        lw = w.layers[li]
+        M = B * Lq
+        h, H = w.hidden, w.heads
+        xn = self.buf("xn", (M, h), dt)
+        ops.rmsnorm(x, lw["n1"], xn, M, w.eps)
+        qkv = self.buf("qkv", (M, 3 * h), dt)
+        ops.gemm(xn, lw["wqkv"], out=qkv)
+        q = self.buf("q", (B, H, Lq, 64), dt)
+        ops.rope_kv(qkv, q, kc[li], vc[li], B, Lq, H, Lmax, pos0, dpos, w.cos, w.sin)
+        ao = self.buf("attn_out", (M, h), dt)
+        if prefill:
+            Lk = pos0 + Lq
+            ld = (Lk + 7) // 8 * 8
+            s = self.buf("scores", (B * H, Lq, ld), torch.float32)
+            ops.gemm_raw(ops.gemm_desc(
+                dtype=code, a=q.data_ptr(), lda=64, a_bstride=Lq * 64, a_rows=Lq, a_cols=64, a_batches=B * H,
+                b=kc[li].data_ptr(), ldb=64, b_bstride=Lmax * 64, b_rows=Lk, b_cols=64, b_batches=B * H,
+                M=Lq, N=Lk, K=64, batch=B * H, heads=1, a_bsel=2, b_bsel=2, o_bsel=2, causal_skip=1 if pos0 == 0 else 0,
+                out=s.data_ptr(), ldo=ld, out_bstride=Lq * ld, out_dtype=F32, alpha=0.125))
+            p = self.buf("probs", (B * H, Lq, ld), dt)
+            ops.softmax(s, p, B * H * Lq, Lq, Lk, ld, ld, True, pos0)
+            ops.gemm_raw(ops.gemm_desc(
+                dtype=code, a=p.data_ptr(), lda=ld, a_bstride=Lq * ld, a_rows=Lq, a_cols=Lk, a_batches=B * H,
+                b=vc[li].data_ptr(), ldb=Lmax, b_bstride=64 * Lmax, b_rows=64, b_cols=Lk, b_batches=B * H,
+                M=Lq, N=64, K=Lk, batch=B * H, heads=H, a_bsel=2, b_bsel=2, o_bsel=1, o_nhead=64,
+                out=ao.data_ptr(), ldo=h, out_bstride=Lq * h, out_dtype=code))
+        else:
+            ops.decode_attn(q, kc[li], vc[li], ao, B, H, Lmax, pos0 + 1, dpos, 0.125)
+        ops.gemm(ao, lw["wo"], residual=x, out=x)                      # x += attn @ Wo^T   (fp32, in place)
+        ops.rmsnorm(x, lw["n2"], xn, M, w.eps)
+        act = self.buf("act", (M, w.inter), dt)
+        ops.gemm(xn, lw["wgu"], act=ACT_SWIGLU, out=act)               # silu(gate) * up
+        ops.gemm(act, lw["wd"], residual=x, out=x)                     # x += act @ Wd^T
+
+    # ---- prefill ------------------------------------------------------------------------------------------
+    def prefill(self, B, L, Lmax, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], all_logits: bool,
+                logits_out: Optional[torch.Tensor] = None, want_hidden: bool = False):
+        """Runs L prompt positions, fills the KV cache.  Returns logits: [B, V] of the last position, or
+        [B, L, Vpad] of every position when all_logits."""
+        w = self.w
+        M = B * L
+        h = w.hidden
+        if Lmax > w.max_pos:
+            raise ValueError(f"sequence length {Lmax} exceeds max_position_embeddings {w.max_pos}")
+        x = self.buf("x", (M, h), torch.float32)
+        if embeds is not None:
+            assert embeds.shape == (B, L, h)
+            x.copy_(embeds.reshape(M, h).to(torch.float32))
+        else:
+            assert ids.dtype == torch.int64 and ids.is_contiguous()
+            ops.embed(ids, ids.stride(0), L, None, w.embed, x, M)
+        kc, vc = self.kv_cache(B, Lmax)
+        for li in range(w.layers_n):
+            self._layer(li, x, B, L, kc, vc, Lmax, 0, None, True)
+        xn = self.buf("xn", (M, h), self.dtype)
+        ops.rmsnorm(x, w.norm, xn, M, w.eps)
+        V = w.vocab
+        if all_logits:
+            vpad = (V + 3) // 4 * 4
+            logits = logits_out if logits_out is not None else torch.empty(B, L, vpad, dtype=torch.float32,
+                                                                           device=x.device)
+            ops.gemm(xn, w.lm_head, out=logits.view(M, vpad)[:, :V])
+            hidden = xn.view(B, L, h) if want_hidden else None
+            return logits, hidden
+        logits = self.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)
+        last = xn.view(B, L, h)[:, L - 1, :]                         # strided view: lda = L*h, no copy
+        ops.gemm(last, w.lm_head, out=logits[:, :V])
+        return logits, None
+
+    # ---- one decode step, position read from device memory ----------------------------------------------------
+    def _decode_step(self, B, Lmax, tokens, dpos, sample_cfg):
+        w = self.w
+        h = w.hidden
+        x = self.buf("xd", (B, h), torch.float32)
+        ops.embed(tokens, tokens.stride(0), 1, dpos, w.embed, x, B)
+        kc, vc = self.kv_cache(B, Lmax)
+        for li in range(w.layers_n):
+            self._layer_decode(li, x, B, kc, vc, Lmax, dpos)
+        xn = self.buf("xnd", (B, h), self.dtype)
+        ops.rmsnorm(x, w.norm, xn, B, w.eps)
+        V = w.vocab
+        logits = self.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)
+        ops.gemm(xn, w.lm_head, out=logits[:, :V])
+        self._sample(logits, B, tokens, dpos, sample_cfg, 0)
+        ops.incr(dpos, 1)
+
+    def _layer_decode(self, li, x, B, kc, vc, Lmax, dpos):
+        w, dt = self.w, self.dtype
+        lw = w.layers[li]
+        h, H = w.hidden, w.heads
+        xn = self.buf("xnd", (B, h), dt)
+        ops.rmsnorm(x, lw["n1"], xn, B, w.eps)
+        qkv = self.buf("qkvd", (B, 3 * h), dt)
+        ops.gemm(xn, lw["wqkv"], out=qkv)
+        q = self.buf("qd", (B, H, 1, 64), dt)
+        ops.rope_kv(qkv, q, kc[li], vc[li], B, 1, H, Lmax, 0, dpos, w.cos, w.sin)
+        ao = self.buf("aod", (B, h), dt)
+        ops.decode_attn(q, kc[li], vc[li], ao, B, H, Lmax, 1, dpos, 0.125)
+        ops.gemm(ao, lw["wo"], residual=x, out=x)
+        ops.rmsnorm(x, lw["n2"], xn, B, w.eps)
+        act = self.buf("actd", (B, w.inter), dt)
+        ops.gemm(xn, lw["wgu"], act=ACT_SWIGLU, out=act)
+        ops.gemm(act, lw["wd"], residual=x, out=x)
+
+    def _sample(self, logits, B, tokens, dpos, sample_cfg, out_offset):
+        """Writes the next token of every row to tokens[b, (*dpos + 1 if dpos else 0) + out_offset]."""
+        V = self.w.vocab
+        ld = logits.stride(0)
+        if sample_cfg is None:
+            ops.argmax(logits, ld, B, V, tokens, tokens.stride(0), dpos, out_offset)
+        else:
+            k, temp, seed = sample_cfg
+            ops.topk_sample(logits, ld, B, V, k, temp, seed, 0, tokens, tokens.stride(0), dpos, out_offset)
+
+    # ---- generation ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], max_new_tokens: int,
+                 do_sample: bool, top_k: int, temperature: float, seed: int, use_graph: bool = True) -> torch.Tensor:
+        """Returns the full token buffer [B, L + max_new_tokens] (prompt slots hold ids, or zeros for embeds)."""
+        src = ids if ids is not None else embeds
+        B, L = src.shape[0], src.shape[1]
+        dev = src.device
+        total = L + max_new_tokens
+        Lmax = (total + 7) // 8 * 8
+        tokens = torch.zeros(B, total, dtype=torch.int64, device=dev)
+        if ids is not None:
+            tokens[:, :L].copy_(ids)
+        if max_new_tokens <= 0:
+            return tokens
+        V = self.w.vocab
+        k = min(int(top_k), V) if (top_k is not None and top_k > 0) else V
+        sample_cfg = (k, float(temperature), int(seed)) if do_sample else None
+        logits, _ = self.prefill(B, L, Lmax, ids.contiguous() if ids is not None else None, embeds, False)
+        # first new token from the prefill logits -> tokens[:, L]
+        self._sample(logits, B, tokens, None, sample_cfg, L)
+        if max_new_tokens == 1:
+            return tokens
+        dpos = torch.full((1,), L, dtype=torch.int32, device=dev)    # position of the token fed next
+        steps = max_new_tokens - 1
+        if use_graph:
+            stream = torch.cuda.Stream(device=dev)
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(stream):
+                self._decode_step(B, Lmax, tokens, dpos, sample_cfg)            # warm-up (also step 1)
+            torch.cuda.current_stream(dev).wait_stream(stream)
+            if steps > 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg)
+                # capture does not execute: steps-1 replays remain
+                for _ in range(steps - 1):
+                    g.replay()
+        else:
+            for _ in range(steps):
+                self._decode_step(B, Lmax, tokens, dpos, sample_cfg)
+        return tokens

@@ -1,0 +1,135 @@
+"""Tokenizer half: B200 CompressiveVQModel vs the CPU fp32 oracle restatement on shared seeded weights."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, rel_err
+
+
+def _pair(cfg, cuda=None, dtype=torch.float32, codebook="normal"):
+    from oracle.vq_model_ref import RefCompressiveVQModel, seeded_init_
+    from ivideogpt_b200.vq_model import CompressiveVQModel
+    ref = seeded_init_(RefCompressiveVQModel(**cfg).eval(), codebook=codebook)
+    mine = CompressiveVQModel.from_config(cfg)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    if cuda is not None:
+        mine = mine.to(cuda).eval().set_compute_dtype(dtype)
+    return ref, mine
+
+
+def _cfg(name):
+    with open(os.path.join(ROOT, "configs", name + ".json")) as fh:
+        return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+
+
+def test_state_dict_layout_and_param_counts():
+    """Key names / shapes equal the oracle's (which mirror the reference module tree) and the README counts."""
+    for name, want in (("ctx_vae64", 114.2), ("ctx_vae256", 310.5)):
+        ref, mine = _pair(_cfg(name))
+        a, b = mine.state_dict(), ref.state_dict()
+        assert set(a) == set(b)
+        assert all(a[k].shape == b[k].shape for k in a)
+        assert abs(sum(p.numel() for p in mine.parameters()) / 1e6 - want) < 0.06
+    assert mine.context_length == 2 and mine.num_vq_embeddings == 8192 and mine.num_dyn_embeddings == 8192
+    assert any("quantize" in n for n, _ in mine.named_parameters())        # train_tokenizer.py:424 name filter
+    assert mine.cond_decoder.conv_out.weight.shape == (3, 128, 3, 3)        # train_tokenizer.py:714 attribute path
+
+
+def test_save_load_roundtrip_and_cpu_refusal(tmp_path):
+    from ivideogpt_b200.vq_model import CompressiveVQModel
+    from oracle.vq_model_ref import TINY_CFG
+    _, mine = _pair(TINY_CFG)
+    mine.save_pretrained(str(tmp_path / "tokenizer"))
+    again = CompressiveVQModel.from_pretrained(str(tmp_path), subfolder="tokenizer", low_cpu_mem_usage=False)
+    assert all(torch.equal(v, again.state_dict()[k]) for k, v in mine.state_dict().items())
+    assert again.config["context_length"] == 2 and again.config.patch_size == 4
+    with pytest.raises(RuntimeError):
+        again.tokenize(torch.rand(1, 4, 3, 32, 32), 2)                      # CPU: loud failure, no fallback
+    again.set_context_length(1)
+    assert again.cond_encoder.cross_att_blocks[0].kv_pos_emb.shape[0] == 256
+
+
+def test_oracle_golden_vectors():
+    """The committed golden fixture (made by tests/golden/make_golden.py from the oracle) still reproduces."""
+    from oracle.vq_model_ref import TINY_CFG
+    path = os.path.join(ROOT, "tests", "golden", "tokenizer_tiny.npz")
+    gold = np.load(path)
+    ref, _ = _pair(TINY_CFG)
+    px = torch.from_numpy(gold["pixels"])
+    tok, lab = ref.tokenize(px, 2)
+    # BLAS summation order differs between hosts: allow isolated near-tie flips, nothing structural
+    assert (tok.numpy() == gold["tokens"]).mean() > 0.99
+    assert np.array_equal(lab.numpy() == -100, gold["labels"] == -100)
+    rec = ref.detokenize(torch.from_numpy(gold["tokens"]), 2)
+    assert rel_err(rec, torch.from_numpy(gold["recon"])) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol_lat,tol_px,min_match", [(torch.float32, 2e-3, 3e-3, 0.97),
+                                                            (torch.bfloat16, 3e-2, 4e-2, 0.80)])
+def test_tiny_tokenizer_vs_oracle(cuda, dtype, tol_lat, tol_px, min_match):
+    from oracle.vq_model_ref import TINY_CFG
+    ref, mine = _pair(TINY_CFG, cuda, dtype)
+    px = torch.rand(2, 6, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    zc_ref, zd_ref = ref.encode_latents(px)
+    zc, zd = mine.encode_latents(px.to(cuda))
+    assert rel_err(zc, zc_ref) < tol_lat and rel_err(zd, zd_ref) < tol_lat
+    tok_ref, lab_ref = ref.tokenize(px, 2)
+    tok, lab = mine.tokenize(px.to(cuda), 2)
+    assert tok.shape == tok_ref.shape and tok.dtype == torch.int64
+    match = (tok.cpu() == tok_ref).float().mean().item()
+    assert match >= min_match, f"token agreement {match:.4f}"
+    # structural positions (separators, -100 labels) are exact regardless of float noise
+    sep = tok_ref >= 1024
+    assert torch.equal(tok.cpu()[sep], tok_ref[sep]) and torch.equal(lab.cpu() == -100, lab_ref == -100)
+    # detokenize from the ORACLE's tokens so both sides decode the same ids
+    rec_ref = ref.detokenize(tok_ref, 2)
+    rec = mine.detokenize(tok_ref.to(cuda), 2)
+    assert rec.shape == rec_ref.shape and rec.dtype == torch.float32
+    assert rel_err(rec, rec_ref) < tol_px
+    # golden fixture
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_tiny.npz"))
+    rec_g = mine.detokenize(torch.from_numpy(gold["tokens"]).to(cuda), 2)
+    assert rel_err(rec_g, torch.from_numpy(gold["recon"])) < tol_px
+
+
+@pytest.mark.gpu
+def test_cfg64_tokenizer_vs_oracle(cuda):
+    """BASELINE config ctx_vae64 (114 M), one 64x64x16 clip, TF32 path."""
+    ref, mine = _pair(_cfg("ctx_vae64"), cuda, torch.float32)
+    px = torch.rand(1, 16, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    zc_ref, zd_ref = ref.encode_latents(px)
+    zc, zd = mine.encode_latents(px.to(cuda))
+    assert rel_err(zc, zc_ref) < 3e-3 and rel_err(zd, zd_ref) < 3e-3
+    tok_ref, _ = ref.tokenize(px, 2)
+    tok, _ = mine.tokenize(px.to(cuda), 2)
+    assert tok.shape == (1, 751)
+    assert (tok.cpu() == tok_ref).float().mean().item() > 0.95
+    rec_ref = ref.detokenize(tok_ref, 2)
+    rec = mine.detokenize(tok_ref.to(cuda), 2)
+    assert rec.shape == (1, 16, 3, 64, 64)
+    assert rel_err(rec, rec_ref) < 5e-3
+    ctx_only = mine.tokenize_context(px.to(cuda))
+    assert torch.equal(ctx_only, tok[:, :514])
+
+
+@pytest.mark.gpu
+def test_detokenize_batch_independence_and_cache(cuda):
+    """Size-independent properties: clips are independent units (batching must not change any clip), and the
+    cached-context path reproduces the uncached frames."""
+    from oracle.vq_model_ref import TINY_CFG
+    _, mine = _pair(TINY_CFG, cuda, torch.float32)
+    g = torch.Generator().manual_seed(4)
+    tok = torch.cat([torch.randint(0, 512, (3, 513), generator=g), torch.randint(512, 1024, (3, 68), generator=g)], 1)
+    tok[:, 256] = 1024
+    tok[:, 513::17] = 1025
+    tok = tok.to(cuda)
+    full = mine.detokenize(tok, 2)
+    one = mine.detokenize(tok[1:2].contiguous(), 2)
+    assert rel_err(one, full[1:2]) < 1e-6
+    rec, cache = mine.detokenize(tok, 2, return_cache=True)
+    again = mine.detokenize(tok, 2, cache=cache)
+    assert torch.equal(rec, full) and rel_err(again, full) < 1e-6
