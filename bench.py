@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- predicted frames/sec of the iVideoGPT next-frame-prediction hot path on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic clips (the body of reference
+inference/predict.py:53-73): tokenize the context frames -> autoregressive rollout of the future-frame tokens
+(top-k 100 sampling, predict.py:58-63) -> detokenize all frames.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1: independent replicas, weak scaling)
+    python bench.py --impl reference ...                      (the reference algorithm's CPU path: oracle + HF Llama)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job predicted frames/s with inputs resident in HBM;
+`e2e` = the same metric through the reference-facing Python API exactly as predict.py drives it
+(tokenize(all 16 frames) / generate / detokenize) with pinned-host pixels copied H2D and the frames copied D2H
+inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (tokenizer config, llama config, resolution, per-GPU batch)
+    "cfg64": ("ctx_vae64", "llama_138m", 64, 64),
+    "cfg256": ("ctx_vae256", "llama_138m", 256, 16),
+    "cfg64-medium": ("ctx_vae64", "llama_436m", 64, 32),
+    "tiny": (None, None, 64, 2),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg64", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU clips (default: the workload's)")
+    ap.add_argument("--context-length", type=int, default=2)
+    ap.add_argument("--segment-length", type=int, default=16)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--greedy", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=1)
+    ap.add_argument("--quick", action="store_true", help="profiling aid: exact --warmup, no e2e / cpu legs")
+    return ap.parse_args()
+
+
+def load_json_cfg(name):
+    with open(os.path.join(ROOT, "configs", name + ".json")) as fh:
+        return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return p.get("bf16_tflops_sustained", 1391.4), p.get("hbm_gbs", 6566.7), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# model construction (seeded random weights in the reference state-dict layout; no checkpoints offline)
+# ----------------------------------------------------------------------------------------------------
+def build_oracle_models(workload):
+    import torch
+    from oracle.llama_ref import TINY_LLAMA, build_hf_llama, config_path as llama_cfg_path
+    from oracle.vq_model_ref import TINY_CFG, RefCompressiveVQModel, seeded_init_
+    tok_name, llm_name, _, _ = WORKLOADS[workload]
+    tok_cfg = TINY_CFG if tok_name is None else load_json_cfg(tok_name)
+    tok_cfg = {k: v for k, v in tok_cfg.items() if k not in ("down_block_types", "up_block_types")}
+    ref_tok = seeded_init_(RefCompressiveVQModel(**tok_cfg).eval())
+    llm_cfg = dict(TINY_LLAMA, vocab_size=tok_cfg["num_vq_embeddings"] + tok_cfg["num_dyn_embeddings"] + 2) \
+        if llm_name is None else llama_cfg_path(llm_name)
+    ref_llm = build_hf_llama(llm_cfg)
+    return tok_cfg, ref_tok, ref_llm
+
+
+def build_b200_models(workload, dev, dtype):
+    """Same seeded weights as the oracle, loaded through the product classes' state-dict interface."""
+    import torch
+    from ivideogpt_b200.transformer import B200LlamaForCausalLM
+    from ivideogpt_b200.vq_model import CompressiveVQModel
+    tok_cfg, ref_tok, ref_llm = build_oracle_models(workload)
+    tok = CompressiveVQModel.from_config(tok_cfg)
+    tok.load_state_dict(ref_tok.state_dict(), strict=True)
+    tok = tok.to(dev).eval().set_compute_dtype(dtype)
+    llm = B200LlamaForCausalLM(ref_llm.config)
+    llm.load_state_dict(ref_llm.state_dict(), strict=True)
+    llm = llm.to(dev).eval().set_compute_dtype(dtype)
+    return tok, llm, ref_tok, ref_llm
+
+
+def synthetic_clips(B, T, res, seed=0):
+    import torch
+    return torch.rand(B, T, 3, res, res, generator=torch.Generator().manual_seed(seed))
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm on host cores (oracle tokenizer + genuine HF Llama)
+# ----------------------------------------------------------------------------------------------------
+def cpu_rollout(ref_tok, ref_llm, clips, ctx, seg, greedy=True):
+    import torch
+    fut = seg - ctx
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        tokens, _ = ref_tok.tokenize(clips, ctx)          # predict.py:53 tokenizes all frames
+        prompt = tokens[:, : ctx * 257]
+        out = ref_llm.generate(prompt, do_sample=not greedy, top_k=100, temperature=1.0,
+                               max_new_tokens=17 * fut - 1, pad_token_id=50256)
+        frames = ref_tok.detokenize(out, ctx).clamp(0.0, 1.0)
+    return time.perf_counter() - t0, frames
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, _, res, _ = WORKLOADS[args.workload]
+    tok_cfg, ref_tok, ref_llm = build_oracle_models(args.workload)
+    ctx, seg = args.context_length, args.segment_length
+    clips = synthetic_clips(args.cpu_clips, seg, res)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_rollout(ref_tok, ref_llm, clips, ctx, seg)
+    times = [cpu_rollout(ref_tok, ref_llm, clips, ctx, seg)[0] for _ in range(max(args.steps, 1))]
+    t = statistics.median(times)
+    fps = args.cpu_clips * (seg - ctx) / t
+    sample = f"{args.cpu_clips} clip(s) {res}x{res}x{seg}, greedy, fp32, {cores} threads (oracle tokenizer + HF Llama)"
+    print(json.dumps({
+        "impl": "reference", "metric": "predicted_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.cpu_clips, res),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, batch, res):
+    ctx, seg = args.context_length, args.segment_length
+    return {"workload": f"{args.workload}: {batch} synthetic {res}x{res}x{seg} clips per GPU, context {ctx}, "
+                        f"{seg - ctx} predicted frames, {ctx * 257 + 17 * (seg - ctx) - 1} tokens/clip "
+                        f"(predict.py defaults; pass --segment-length 17 for the 15-frame variant)",
+            "tokenizer": WORKLOADS[args.workload][0], "transformer": WORKLOADS[args.workload][1],
+            "per_gpu_batch": batch, "context": ctx, "segment": seg, "predicted": seg - ctx,
+            "sampling": "greedy" if args.greedy else "top_k=100,T=1", "parallelism": f"replicas x{args.gpus}",
+            "l2_policy": "inputs+weights+activations per step exceed the 126 MB L2 (no explicit flush)"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ivideogpt_b200 import _lib
+    lib = _lib.load()
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    _, _, res, default_b = WORKLOADS[args.workload]
+    B = args.batch or default_b
+    ctx, seg = args.context_length, args.segment_length
+    fut = seg - ctx
+    max_new = 17 * fut - 1
+    tok, llm, ref_tok, ref_llm = build_b200_models(args.workload, dev, dtype)
+    clips_host = synthetic_clips(B, seg, res, seed=rank).pin_memory()
+    clips_dev = clips_host.to(dev)
+    gen_kw = dict(do_sample=not args.greedy, temperature=1.0, top_k=100, max_new_tokens=max_new, pad_token_id=50256)
+
+    def step_resident():
+        prompt = tok.tokenize_context(clips_dev)                      # prediction-minimal tokenisation
+        out = llm.generate(prompt, **gen_kw)
+        return tok.detokenize(out, ctx)
+
+    def step_e2e():
+        px = clips_host.to(dev, non_blocking=True)                    # H2D from pinned memory
+        tokens, _ = tok.tokenize(px, ctx)                             # predict.py:53 (all frames)
+        out = llm.generate(tokens[:, : ctx * 257], **gen_kw)          # predict.py:54-69
+        frames = tok.detokenize(out, ctx).clamp_(0.0, 1.0)            # predict.py:72-73
+        return frames.to("cpu", non_blocking=False)                   # D2H of the result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        n0 = _lib.launch_count()
+        if profile:
+            lib.ivgpt_profile_enable(1)
+        e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_all0.record()
+        for i in range(steps):
+            ev[i][0].record()
+            fn()
+            ev[i][1].record()
+        e_all1.record()
+        barrier()
+        if profile:
+            lib.ivgpt_profile_enable(0)
+        total_ms = e_all0.elapsed_time(e_all1)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), [a.elapsed_time(b) for a, b in ev], _lib.launch_count() - n0
+
+    for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    total_ms, per_step, launches = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.finish() if sampler else None
+    # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), measured in the timed region above
+    prof = {}
+    for bucket, name in ((1, "conv"), (0, "gemm")):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+        lib.ivgpt_profile_collect(bucket, C.byref(ms), C.byref(fl), C.byref(n))
+        prof[name] = (ms.value, fl.value, n.value)
+    # end-to-end arm through the reference-facing API
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_ms = float("nan")
+    if not args.quick:
+        step_e2e()
+        e2e_ms, _, _ = timed(step_e2e, e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames_per_step = world * B * fut
+    ms_per_step = total_ms / args.steps
+    value = frames_per_step / (ms_per_step / 1e3)
+    peak_tf, peak_gbs, peak_src = measured_peaks()
+    conv_ms, conv_fl, conv_n = prof["conv"]
+    gemm_ms, gemm_fl, gemm_n = prof["gemm"]
+    dom = "conv" if conv_ms >= gemm_ms else "gemm"
+    dms, dfl, dn = prof[dom]
+    achieved = dfl / (dms * 1e-3) / 1e12 if dms > 0 else 0.0
+    dense_peak = peak_tf if args.dtype == "bf16" else peak_tf / 2.0    # tf32 runs at half the bf16 rate
+    roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{args.dtype}> ({'implicit-GEMM 3x3 conv' if dom == 'conv' else 'plain/batched GEMM'})",
+                "achieved": achieved, "peak": dense_peak, "unit": "TFLOP/s", "frac": achieved / dense_peak,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})" + ("" if args.dtype == "bf16" else " / 2 for tf32"),
+                "launches_per_step": dn / args.steps, "kernel_ms_per_step": dms / args.steps,
+                "share_of_step": dms / total_ms, "traffic": None,
+                "other": {"gemm" if dom == "conv" else "conv": {
+                    "ms_per_step": (gemm_ms if dom == "conv" else conv_ms) / args.steps,
+                    "tflops": ((gemm_fl / (gemm_ms * 1e-3) / 1e12) if dom == "conv" and gemm_ms > 0 else
+                               (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else 0.0)}}}
+    px_bytes = clips_host.numel() * 4
+    out = {
+        "metric": "predicted_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (U[0,1) pixels, seeded random weights in the reference state-dict layout)",
+        "config": workload_config(args, B, res),
+        "per_step_ms": per_step, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "e2e": {"value": frames_per_step / (e2e_ms / e2e_steps / 1e3), "unit": "frames/s",
+                "h2d_bytes_per_step": px_bytes, "d2h_bytes_per_step": px_bytes, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "CompressiveVQModel.tokenize(all frames) -> B200LlamaForCausalLM.generate -> detokenize -> .cpu()"},
+    }
+    if not args.no_cpu_baseline and not args.quick and world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        clips = synthetic_clips(args.cpu_clips, seg, res)
+        t_cpu, _ = cpu_rollout(ref_tok, ref_llm, clips, ctx, seg)
+        out["cpu_baseline"] = {"value": args.cpu_clips * fut / t_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"{args.cpu_clips} clip {res}x{res}x{seg}, greedy, fp32 (oracle tokenizer + HF Llama), {t_cpu:.1f} s"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

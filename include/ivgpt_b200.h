@@ -32,6 +32,12 @@ extern "C" {
 const char* ivgpt_last_error(void);
 unsigned long long ivgpt_launch_count(void); /* kernels launched by this library since load */
 int ivgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Measurement hooks (bench.py): when enabled, every tensor-core GEMM (bucket 0) / conv (bucket 1) launch issued
+ * outside stream capture is bracketed by CUDA events on its own stream; collect() synchronises them and returns the
+ * summed device time, the summed algorithmic FLOPs (2*M*N*K, causal tiles excluded) and the launch count. */
+int ivgpt_profile_enable(int on);
+int ivgpt_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches);
+int ivgpt_count_add(long long n); /* account for kernels replayed through a CUDA graph */
 
 /* ---- VQ codebook lookup -------------------------------------------------------------------------
  * Replaces diffusers VectorQuantizer.forward's `argmin(cdist(z, E))`, called at

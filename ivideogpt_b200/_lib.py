@@ -55,6 +55,9 @@ SIGNATURES = {
     "ivgpt_last_error": [],
     "ivgpt_launch_count": [],
     "ivgpt_device_info": [C.POINTER(C.c_int)] * 3,
+    "ivgpt_profile_enable": [_I],
+    "ivgpt_profile_collect": [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
+    "ivgpt_count_add": [_L],
     "ivgpt_vq_argmin": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ivgpt_gemm": [C.POINTER(GemmDesc), _P],
     "ivgpt_conv3x3": [C.POINTER(ConvDesc), _P],

@@ -73,6 +73,8 @@ static int num_sms() {
 
 // ---- forward declarations of launchers defined in the other translation units -----------------
 int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream);
+void gemm_profile_enable(int on);
+int gemm_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches);
 int vq_argmin_launch(const float*, const float*, float*, unsigned long long*, long long*, int, int, int, int,
                      cudaStream_t);
 int gn_stats_launch(int, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
@@ -116,6 +118,12 @@ extern "C" {
 
 const char* ivgpt_last_error(void) { return ivg::last_error(); }
 unsigned long long ivgpt_launch_count(void) { return ivg::g_launches; }
+
+int ivgpt_profile_enable(int on) { gemm_profile_enable(on); return 0; }
+int ivgpt_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches) {
+  return gemm_profile_collect(bucket, ms_total, flops_total, launches);
+}
+int ivgpt_count_add(long long n) { ivg::g_launches += (unsigned long long)n; return 0; }
 
 int ivgpt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

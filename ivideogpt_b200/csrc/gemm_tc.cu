@@ -20,6 +20,9 @@
 //   warp 1 (one elected lane) : tcgen05.mma issuer -> 2 TMEM accumulator stages of BN fp32 columns each
 //   warps 2-5                 : epilogue, tcgen05.ld 32 lanes x 16 columns, bias/residual/activation, global stores
 // Operands are bf16 (kind::f16) or fp32 read as tf32 (kind::tf32); a k-block is always 128 bytes of K.
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 #include "gemm_params.cuh"
 
@@ -304,7 +307,32 @@ static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cu
   return 0;
 }
 
-int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+// ---- optional per-launch event timing (bench.py roofline leg) -----------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; double flops; int bucket; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+
+void gemm_profile_enable(int on) { g_prof_on = on != 0; }
+
+int gemm_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches) {
+  double ms = 0.0, fl = 0.0; long long n = 0;
+  std::vector<ProfRec> keep;
+  for (auto& r : g_prof) {
+    if (r.bucket != bucket) { keep.push_back(r); continue; }
+    IVG_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    IVG_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t; fl += r.flops; ++n;
+    g_prof_pool.push_back({r.e0, r.e1});
+  }
+  g_prof.swap(keep);
+  *ms_total = ms; *flops_total = fl; *launches = n;
+  return 0;
+}
+
+static int dispatch_inner(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms,
+                          cudaStream_t stream) {
   if (dtype == DT_BF16) {
     switch (bn) {
       case 32: return launch_one<__nv_bfloat16, 32>(maps, p, num_sms, stream);
@@ -322,6 +350,34 @@ int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& 
   }
   set_error("gemm_tc: unsupported dtype=%d / BN=%d", dtype, bn);
   return 1;
+}
+
+int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  bool prof = g_prof_on;
+  if (prof) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) prof = false;
+  }
+  if (!prof) return dispatch_inner(dtype, bn, maps, p, num_sms, stream);
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r.e0 = g_prof_pool.back().first; r.e1 = g_prof_pool.back().second; g_prof_pool.pop_back(); }
+  else { IVG_CUDA(cudaEventCreate(&r.e0)); IVG_CUDA(cudaEventCreate(&r.e1)); }
+  const int BK = 128 / (dtype == DT_BF16 ? 2 : 4);
+  double frac = 1.0;
+  if (p.causal_skip) {  // only tiles on or below the diagonal are computed
+    long long done = 0, all = (long long)p.tiles_m * p.tiles_n;
+    for (int tm = 0; tm < p.tiles_m; ++tm)
+      for (int tn = 0; tn < p.tiles_n; ++tn) done += (tn * bn <= tm * GEMM_BM + GEMM_BM - 1);
+    frac = all ? (double)done / (double)all : 1.0;
+  }
+  r.flops = 2.0 * (double)p.M * (double)p.N * ((double)p.num_kb * BK) * (double)p.batch * frac;
+  r.bucket = p.mode;
+  IVG_CUDA(cudaEventRecord(r.e0, stream));
+  int rc = dispatch_inner(dtype, bn, maps, p, num_sms, stream);
+  IVG_CUDA(cudaEventRecord(r.e1, stream));
+  g_prof.push_back(r);
+  return rc;
 }
 
 }  // namespace ivg

@@ -254,12 +254,15 @@ class LlamaEngine:
                 self._decode_step(B, Lmax, tokens, dpos, sample_cfg)            # warm-up (also step 1)
             torch.cuda.current_stream(dev).wait_stream(stream)
             if steps > 1:
+                from .. import _lib
                 g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
                 with torch.cuda.graph(g):
                     self._decode_step(B, Lmax, tokens, dpos, sample_cfg)
-                # capture does not execute: steps-1 replays remain
+                per_step = _lib.launch_count() - n0      # kernels recorded in the graph (capture does not run them)
                 for _ in range(steps - 1):
                     g.replay()
+                _lib.load().ivgpt_count_add(per_step * (steps - 2))   # replays launch the recorded kernels again
         else:
             for _ in range(steps):
                 self._decode_step(B, Lmax, tokens, dpos, sample_cfg)

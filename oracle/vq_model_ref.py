@@ -430,10 +430,11 @@ def seeded_init_(model: nn.Module, seed: int = 1234, codebook: str = "normal") -
     return model
 
 
-TINY_CFG = dict(  # a structurally complete miniature used for fast CPU/GPU parity tests
-    in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+TINY_CFG = dict(  # a structurally complete miniature (shortcut convs, stride-2, cross-attention in both the
+    # encoder and the decoder, head_dim 64) used for fast CPU/GPU parity tests
+    in_channels=3, out_channels=3, block_out_channels=(128, 256, 256), layers_per_block=1,
     latent_channels=64, num_vq_embeddings=512, norm_num_groups=32, mid_block_add_attention=False,
-    num_dyn_embeddings=512, context_length=2, max_att_resolution=16, resolution=32, patch_size=4)
+    num_dyn_embeddings=512, context_length=2, max_att_resolution=16, resolution=64, patch_size=4)
 
 
 def config_path(name: str) -> str:

@@ -13,7 +13,7 @@ from oracle.vq_model_ref import TINY_CFG, RefCompressiveVQModel, seeded_init_  #
 
 torch.set_num_threads(1)   # summation order of the CPU kernels must not depend on the thread count
 ref = seeded_init_(RefCompressiveVQModel(**TINY_CFG).eval())
-px = torch.rand(1, 5, 3, 32, 32, generator=torch.Generator().manual_seed(11))
+px = torch.rand(1, 5, 3, 64, 64, generator=torch.Generator().manual_seed(11))
 tok, lab = ref.tokenize(px, 2)
 rec = ref.detokenize(tok, 2)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tokenizer_tiny.npz"), pixels=px.numpy(),

@@ -47,7 +47,7 @@ def test_save_load_roundtrip_and_cpu_refusal(tmp_path):
     assert all(torch.equal(v, again.state_dict()[k]) for k, v in mine.state_dict().items())
     assert again.config["context_length"] == 2 and again.config.patch_size == 4
     with pytest.raises(RuntimeError):
-        again.tokenize(torch.rand(1, 4, 3, 32, 32), 2)                      # CPU: loud failure, no fallback
+        again.tokenize(torch.rand(1, 4, 3, 64, 64), 2)                      # CPU: loud failure, no fallback
     again.set_context_length(1)
     assert again.cond_encoder.cross_att_blocks[0].kv_pos_emb.shape[0] == 256
 
@@ -73,7 +73,7 @@ def test_oracle_golden_vectors():
 def test_tiny_tokenizer_vs_oracle(cuda, dtype, tol_lat, tol_px, min_match):
     from oracle.vq_model_ref import TINY_CFG
     ref, mine = _pair(TINY_CFG, cuda, dtype)
-    px = torch.rand(2, 6, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    px = torch.rand(2, 6, 3, 64, 64, generator=torch.Generator().manual_seed(0))
     zc_ref, zd_ref = ref.encode_latents(px)
     zc, zd = mine.encode_latents(px.to(cuda))
     assert rel_err(zc, zc_ref) < tol_lat and rel_err(zd, zd_ref) < tol_lat
