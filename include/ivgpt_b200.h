@@ -143,12 +143,21 @@ int ivgpt_argmax(const float* logits, long long ld, int rows, int V, long long* 
                  const int* dpos, void* stream);
 int ivgpt_topk_sample(const float* logits, long long ld, int rows, int V, int k, float temperature,
                       unsigned long long seed, unsigned long long step, long long* out, long long out_stride,
-                      const int* dpos, void* stream);
+                      const int* dpos, const unsigned long long* dseed /* added to seed when non-NULL */,
+                      void* stream);
 /* shifted CE of LlamaForCausalLM.forward(labels=...): logits [B,L,ld] fp32, labels [B,L] int64 (-100 ignored);
  * loss_rows / valid_ws [B*(L-1)] fp32 workspaces; loss_out[0] = mean over labelled positions, [1] = their count. */
 int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const long long* labels, float* loss_rows,
                   float* valid_ws, float* loss_out, void* stream);
 int ivgpt_incr(int* p, int by, void* stream);
+/* One decode step of attention for the newest token (HF generate's per-token forward with a KV cache): RoPE on q/k,
+ * append k / v to the caches at position pos (= *dpos when dpos != NULL), attention over positions [0, pos].
+ * qkv [B, 3*hidden], k_cache [B,heads,Lmax,64], v_cache_t [B,heads,64,Lmax], out [B, hidden]. */
+int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_cache_t, void* out, int B, int heads,
+                            int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
+                            float scale, void* stream);
+/* Programmatic dependent launch for the kernels of the decode step (prologue overlap inside CUDA graphs). */
+int ivgpt_set_pdl(int on);
 
 #ifdef __cplusplus
 }

@@ -77,9 +77,11 @@ SIGNATURES = {
     "ivgpt_softmax": [_I, _P, _P, _L, _I, _I, _L, _L, _I, _I, _P],
     "ivgpt_decode_attn": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _P],
     "ivgpt_argmax": [_P, _L, _I, _I, _P, _L, _P, _P],
-    "ivgpt_topk_sample": [_P, _L, _I, _I, _I, _F, _U, _U, _P, _L, _P, _P],
+    "ivgpt_topk_sample": [_P, _L, _I, _I, _I, _F, _U, _U, _P, _L, _P, _P, _P],
     "ivgpt_ce_loss": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P],
     "ivgpt_incr": [_P, _I, _P],
+    "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],
+    "ivgpt_set_pdl": [_I],
 }
 _RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong}
 

@@ -12,6 +12,7 @@ namespace ivg {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
+bool g_pdl = false;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -102,9 +103,11 @@ int decode_attn_launch(int, const void*, const void*, const void*, void*, int, i
                        cudaStream_t);
 int argmax_launch(const float*, long long, int, int, long long*, long long, const int*, cudaStream_t);
 int topk_sample_launch(const float*, long long, int, int, int, float, unsigned long long, unsigned long long,
-                       long long*, long long, const int*, cudaStream_t);
+                       long long*, long long, const int*, const unsigned long long*, cudaStream_t);
 int ce_loss_launch(const float*, long long, int, int, int, const long long*, float*, float*, float*, cudaStream_t);
 int incr_launch(int*, int, cudaStream_t);
+int decode_attn_fused_launch(int, const void*, void*, void*, void*, int, int, int, int, const int*, const float*,
+                             const float*, float, cudaStream_t);
 
 }  // namespace ivg
 
@@ -334,13 +337,20 @@ int ivgpt_argmax(const float* logits, long long ld, int rows, int V, long long* 
 }
 int ivgpt_topk_sample(const float* logits, long long ld, int rows, int V, int k, float temperature,
                       unsigned long long seed, unsigned long long step, long long* out, long long out_stride,
-                      const int* dpos, void* stream) {
-  return topk_sample_launch(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos, S(stream));
+                      const int* dpos, const unsigned long long* dseed, void* stream) {
+  return topk_sample_launch(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos, dseed, S(stream));
 }
 int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const long long* labels, float* loss_rows,
                   float* valid_ws, float* loss_out, void* stream) {
   return ce_loss_launch(logits, ld, B, L, V, labels, loss_rows, valid_ws, loss_out, S(stream));
 }
 int ivgpt_incr(int* p, int by, void* stream) { return incr_launch(p, by, S(stream)); }
+int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_cache_t, void* out, int B, int heads,
+                            int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
+                            float scale, void* stream) {
+  return decode_attn_fused_launch(dtype, qkv, k_cache, v_cache_t, out, B, heads, Lmax, pos, dpos, cos_tab, sin_tab, scale,
+                                  S(stream));
+}
+int ivgpt_set_pdl(int on) { ivg::g_pdl = on != 0; return 0; }
 
 }  // extern "C"

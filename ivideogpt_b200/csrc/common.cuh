@@ -41,6 +41,24 @@ inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 // dtype codes shared with include/ivgpt_b200.h
 enum : int { DT_F32 = 0, DT_BF16 = 1 };
 
+// PDL switch (ivgpt_set_pdl): when on, the kernels of the decode step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so their prologues overlap the predecessor's tail.
+extern bool g_pdl;
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }
 
@@ -60,6 +78,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// Programmatic dependent launch: a kernel launched with the PDL attribute may start while its predecessor in the
+// stream is still running; it must not touch global memory before pdl_wait() (which returns once the predecessor
+// has completed and flushed).  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -70,6 +70,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();               // everything above overlaps the predecessor kernel's tail under PDL
+  pdl_launch_dependents();
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_mn * p.batch;
@@ -301,7 +303,7 @@ static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cu
   long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
   int grid = (int)(total < num_sms ? total : num_sms);
   if (grid < 1) return 0;
-  gemm_tc_kernel<T, BN><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(maps, p);
+  IVG_CUDA(launch_k(gemm_tc_kernel<T, BN>, dim3(grid), dim3(GEMM_THREADS), (size_t)SM::TOTAL, stream, maps, p));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;

@@ -13,6 +13,8 @@ namespace ivg {
 __global__ void embed_kernel(const long long* __restrict__ ids, long long ids_stride, int L,
                              const int* __restrict__ dpos, const float* __restrict__ table,
                              float* __restrict__ x, long long M, int Hd, long long vocab) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int hv = Hd / 4;
   const long long total = M * hv;
   const int off = dpos ? *dpos : 0;
@@ -32,7 +34,7 @@ int embed_launch(const long long* ids, long long ids_stride, int L, const int* d
   if (M == 0) return 0;
   long long work = M * (Hd / 4);
   int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
-  embed_kernel<<<blocks, 256, 0, st>>>(ids, ids_stride, L, dpos, table, x, M, Hd, vocab);
+  IVG_CUDA(launch_k(embed_kernel, dim3(blocks), dim3(256), 0, st, ids, ids_stride, L, dpos, table, x, M, Hd, vocab));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
@@ -44,6 +46,8 @@ int embed_launch(const long long* ids, long long ids_stride, int L, const int* d
 template <typename T>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                                long long M, int Hd, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -73,8 +77,10 @@ int rmsnorm_launch(int dtype, const float* x, const float* w, void* y, long long
   IVG_CHECK(Hd % 4 == 0, "rmsnorm: hidden %% 4 != 0");
   if (M == 0) return 0;
   int blocks = (int)((M + 7) / 8);
-  if (dtype == DT_BF16) rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, w, (__nv_bfloat16*)y, M, Hd, eps);
-  else rmsnorm_kernel<float><<<blocks, 256, 0, st>>>(x, w, (float*)y, M, Hd, eps);
+  if (dtype == DT_BF16)
+    IVG_CUDA(launch_k(rmsnorm_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, x, w, (__nv_bfloat16*)y, M, Hd, eps));
+  else
+    IVG_CUDA(launch_k(rmsnorm_kernel<float>, dim3(blocks), dim3(256), 0, st, x, w, (float*)y, M, Hd, eps));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
@@ -248,13 +254,152 @@ int decode_attn_launch(int dtype, const void* q, const void* kcache, const void*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused decode-step attention: RoPE(q,k) + KV-cache append + attention over the cache, one CTA per (batch, head).
+// This is the per-token rollout step of HF generate (predict.py:64) with an incremental KV cache.  HBM-bound:
+// K rows [Lcur,64] and V^T rows [64,Lcur] of the (b,h) slab are streamed exactly once with 16-byte coalesced
+// loads (8 lanes per K row; a full warp per V^T row), everything else lives in shared memory.
+//   qkv [B, 3*hidden] (T) for the current token, position pos = *dpos (or pos_arg), Lcur = pos + 1.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[16 / sizeof(T)]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  if constexpr (sizeof(T) == 2) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+  } else {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_attn_fused_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
+                         T* __restrict__ out, int heads, int Lmax, int pos_arg, const int* __restrict__ dpos,
+                         const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, float scale) {
+  constexpr int VN = Vec16<T>::N;            // elements per 16-byte load (8 bf16 / 4 fp32)
+  constexpr int LPR = 64 / VN;               // lanes per K row (8 / 16)
+  extern __shared__ float fa_sm[];           // [Lmax + VN] probabilities, then q[64], red[16]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pos = dpos ? *dpos : pos_arg;
+  const int Lcur = pos + 1;
+  float* sc = fa_sm;
+  float* qs = fa_sm + Lmax + VN;
+  float* red = qs + 64;
+  const int bh = blockIdx.x;
+  const int b = bh / heads, hh = bh - b * heads;
+  const int Hd = heads * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T* kslab = kcache + (size_t)bh * Lmax * 64;
+  T* vslab = vcache + (size_t)bh * 64 * Lmax;
+
+  if (tid < 32) {                            // RoPE + append (one warp: pair (i, i+32))
+    const T* row = qkv + (size_t)b * 3 * Hd;
+    const float cs = __ldg(cos_tab + (size_t)pos * 32 + tid), sn = __ldg(sin_tab + (size_t)pos * 32 + tid);
+    const float q0 = to_f32(row[hh * 64 + tid]), q1 = to_f32(row[hh * 64 + tid + 32]);
+    const float k0 = to_f32(row[Hd + hh * 64 + tid]), k1 = to_f32(row[Hd + hh * 64 + tid + 32]);
+    // q is rounded to T exactly like the unfused path (rope_kv_kernel) so both decode paths agree bit for bit
+    qs[tid] = to_f32(from_f32<T>(q0 * cs - q1 * sn)) * scale;
+    qs[tid + 32] = to_f32(from_f32<T>(q1 * cs + q0 * sn)) * scale;
+    kslab[(size_t)pos * 64 + tid] = from_f32<T>(k0 * cs - k1 * sn);
+    kslab[(size_t)pos * 64 + tid + 32] = from_f32<T>(k1 * cs + k0 * sn);
+    vslab[(size_t)tid * Lmax + pos] = row[2 * Hd + hh * 64 + tid];
+    vslab[(size_t)(tid + 32) * Lmax + pos] = row[2 * Hd + hh * 64 + tid + 32];
+  }
+  __syncthreads();                           // orders the global K/V writes above for this CTA, publishes qs
+
+  // ---- scores: LPR lanes per cache row ----
+  const int sub = tid % LPR, rslot = tid / LPR;
+  constexpr int ROWS_PER_PASS = 256 / LPR;
+  float qreg[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) qreg[i] = qs[sub * VN + i];
+  for (int l0 = 0; l0 < Lcur; l0 += ROWS_PER_PASS) {
+    const int l = l0 + rslot;
+    float part = 0.f;
+    if (l < Lcur) {
+      float kv[VN];
+      load8<T>(kslab + (size_t)l * 64 + sub * VN, kv);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) part = fmaf(qreg[i], kv[i], part);
+    }
+#pragma unroll
+    for (int off = LPR / 2; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (sub == 0 && l < Lcur) sc[l] = part;
+  }
+  __syncthreads();
+  // ---- softmax over sc[0..Lcur) ----
+  float mx = -INFINITY;
+  for (int l = tid; l < Lcur; l += 256) mx = fmaxf(mx, sc[l]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  float sum = 0.f;
+  for (int l = tid; l < Lcur + VN; l += 256) {
+    const float e = l < Lcur ? __expf(sc[l] - mx) : 0.f;
+    sc[l] = e;                               // zero tail so the vector loop below can run past Lcur
+    sum += e;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (lane == 0) red[8 + warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[8 + i];
+  const float inv = 1.0f / tot;
+  // ---- out[d] = sum_l p[l] * V^T[d][l] : warp per row, 16-byte loads along l ----
+  for (int d = warp; d < 64; d += 8) {
+    const T* vr = vslab + (size_t)d * Lmax;
+    float a = 0.f;
+    for (int l = lane * VN; l < Lcur; l += 32 * VN) {
+      float vv[VN];
+      load8<T>(vr + l, vv);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) a += (l + i < Lcur) ? sc[l + i] * vv[i] : 0.f;   // cache past Lcur is uninitialised
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) out[(size_t)b * Hd + hh * 64 + d] = from_f32<T>(a * inv);
+  }
+}
+
+int decode_attn_fused_launch(int dtype, const void* qkv, void* kcache, void* vcache, void* out, int B, int heads,
+                             int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
+                             float scale, cudaStream_t st) {
+  IVG_CHECK(dpos || (pos >= 0 && pos < Lmax), "decode_attn_fused: pos=%d out of range (Lmax=%d)", pos, Lmax);
+  IVG_CHECK(Lmax % 8 == 0, "decode_attn_fused: Lmax must be a multiple of 8");
+  if (B == 0) return 0;
+  size_t smem = (size_t)(Lmax + 8 + 64 + 16) * sizeof(float);
+  if (dtype == DT_BF16)
+    IVG_CUDA(launch_k(decode_attn_fused_kernel<__nv_bfloat16>, dim3(B * heads), dim3(256), smem, st,
+                      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, (__nv_bfloat16*)out,
+                      heads, Lmax, pos, dpos, cos_tab, sin_tab, scale));
+  else
+    IVG_CUDA(launch_k(decode_attn_fused_kernel<float>, dim3(B * heads), dim3(256), smem, st, (const float*)qkv,
+                      (float*)kcache, (float*)vcache, (float*)out, heads, Lmax, pos, dpos, cos_tab, sin_tab, scale));
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Greedy argmax over fp32 logits rows (first maximal index, torch.argmax rule).  One CTA per row.
 // ---------------------------------------------------------------------------------------------
 __global__ void argmax_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ out,
                               long long out_stride, const int* __restrict__ dpos) {
   __shared__ float sv[32];
-  if (dpos) out += *dpos + 1;
   __shared__ int si[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  if (dpos) out += *dpos + 1;
   const float* row = logits + (size_t)blockIdx.x * ld;
   float bv = -INFINITY; int bi = 0x7fffffff;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
@@ -286,7 +431,7 @@ __global__ void argmax_kernel(const float* __restrict__ logits, long long ld, in
 int argmax_launch(const float* logits, long long ld, int rows, int V, long long* out, long long out_stride,
                   const int* dpos, cudaStream_t st) {
   if (rows == 0) return 0;
-  argmax_kernel<<<rows, 256, 0, st>>>(logits, ld, V, out, out_stride, dpos);
+  IVG_CUDA(launch_k(argmax_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, out, out_stride, dpos));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
@@ -313,9 +458,13 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 __global__ void __launch_bounds__(512)
 topk_sample_kernel(const float* __restrict__ logits, long long ld, int V, int k, float inv_temp,
                    unsigned long long seed, unsigned long long step, long long* __restrict__ out,
-                   long long out_stride, const int* __restrict__ dpos) {
+                   long long out_stride, const int* __restrict__ dpos,
+                   const unsigned long long* __restrict__ dseed) {
   extern __shared__ uint32_t tk_sm[];
-  if (dpos) { out += *dpos + 1; step += (unsigned long long)*dpos; }  // [V] keys, then 256 hist, then scratch
+  pdl_wait();
+  pdl_launch_dependents();
+  if (dpos) { out += *dpos + 1; step += (unsigned long long)*dpos; }
+  if (dseed) seed += *dseed;  // [V] keys, then 256 hist, then scratch
   uint32_t* keys = tk_sm;
   uint32_t* hist = tk_sm + V;
   __shared__ uint32_t s_prefix, s_remaining;
@@ -360,28 +509,62 @@ topk_sample_kernel(const float* __restrict__ logits, long long ld, int V, int k,
   mx = -INFINITY;
   for (int i = 0; i < nw; ++i) mx = fmaxf(mx, s_red[i]);
   __syncthreads();
-  // total mass, computed by thread 0 in index order together with the inverse-CDF walk (k ~ 100 survivors:
-  // a serial walk over V = 16386 keys in shared memory is ~16k LDS, negligible next to the lm_head GEMM).
-  if (threadIdx.x == 0) {
-    float total = 0.f;
-    for (int c = 0; c < V; ++c) if (keys[c] >= kth) total += __expf(row[c] * inv_temp - mx);
-    const float u = hash_uniform(seed, step, blockIdx.x) * total;
-    float acc = 0.f;
-    int pick = -1, last = 0;
-    for (int c = 0; c < V; ++c) {
-      if (keys[c] >= kth) {
-        acc += __expf(row[c] * inv_temp - mx);
-        last = c;
-        if (acc >= u) { pick = c; break; }
+  // Inverse-CDF draw over the survivors, in index order, parallel and deterministic: thread t owns the contiguous
+  // index chunk [t*cpt, (t+1)*cpt); block-wide inclusive scan of the chunk masses; the FIRST thread whose cumulative
+  // mass reaches u (block-wide min) walks its <= cpt elements.  Values are recovered from the shared-memory keys.
+  {
+    __shared__ float s_hi[512];
+    __shared__ int s_win, s_lastmass;
+    if (threadIdx.x == 0) { s_win = 0x7fffffff; s_lastmass = 0; }
+    const int cpt = (V + blockDim.x - 1) / blockDim.x;
+    const int c0 = threadIdx.x * cpt, c1 = min(V, c0 + cpt);
+    float local = 0.f;
+    for (int c = c0; c < c1; ++c) {
+      const uint32_t kk = keys[c];
+      if (kk >= kth) {
+        const float f = __uint_as_float((kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk);
+        local += __expf(f - mx);
       }
     }
-    out[(size_t)blockIdx.x * out_stride] = pick >= 0 ? pick : last;
+    float incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_red[warp] = incl;
+    __syncthreads();
+    float wbase = 0.f, total = 0.f;
+    for (int i = 0; i < nw; ++i) { const float v = s_red[i]; if (i < warp) wbase += v; total += v; }
+    const float hi = wbase + incl;
+    s_hi[threadIdx.x] = hi;
+    const float u = hash_uniform(seed, step, blockIdx.x) * total;
+    if (local > 0.f) {
+      atomicMax(&s_lastmass, (int)threadIdx.x);
+      if (hi >= u) atomicMin(&s_win, (int)threadIdx.x);
+    }
+    __syncthreads();
+    const int win = (s_win == 0x7fffffff) ? s_lastmass : s_win;
+    if ((int)threadIdx.x == win) {
+      float acc = win > 0 ? s_hi[win - 1] : 0.f;
+      int pick = -1, last = c0;
+      for (int c = c0; c < c1; ++c) {
+        const uint32_t kk = keys[c];
+        if (kk >= kth) {
+          const float f = __uint_as_float((kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk);
+          acc += __expf(f - mx);
+          last = c;
+          if (acc >= u) { pick = c; break; }
+        }
+      }
+      out[(size_t)blockIdx.x * out_stride] = pick >= 0 ? pick : last;
+    }
   }
 }
 
 int topk_sample_launch(const float* logits, long long ld, int rows, int V, int k, float temperature,
                        unsigned long long seed, unsigned long long step, long long* out, long long out_stride,
-                       const int* dpos, cudaStream_t st) {
+                       const int* dpos, const unsigned long long* dseed, cudaStream_t st) {
   IVG_CHECK(k >= 1 && temperature > 0.f, "topk_sample: bad k=%d / temperature=%f", k, temperature);
   if (rows == 0) return 0;
   size_t smem = (size_t)(V + 256) * sizeof(uint32_t);
@@ -391,7 +574,8 @@ int topk_sample_launch(const float* logits, long long ld, int rows, int V, int k
     attr_set = true;
   }
   IVG_CHECK(smem <= 200 * 1024, "topk_sample: vocab %d too large for the shared-memory select", V);
-  topk_sample_kernel<<<rows, 512, smem, st>>>(logits, ld, V, k, 1.0f / temperature, seed, step, out, out_stride, dpos);
+  IVG_CUDA(launch_k(topk_sample_kernel, dim3(rows), dim3(512), smem, st, logits, ld, V, k, 1.0f / temperature, seed, step,
+                    out, out_stride, dpos, dseed));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
@@ -479,9 +663,13 @@ int add_rows_launch(float* x, const float* e, long long n, cudaStream_t st) {
   return 0;
 }
 
-__global__ void incr_kernel(int* p, int by) { *p += by; }
+__global__ void incr_kernel(int* p, int by) {
+  pdl_wait();
+  pdl_launch_dependents();
+  *p += by;
+}
 int incr_launch(int* p, int by, cudaStream_t st) {
-  incr_kernel<<<1, 1, 0, st>>>(p, by);
+  IVG_CUDA(launch_k(incr_kernel, dim3(1), dim3(1), 0, st, p, by));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;

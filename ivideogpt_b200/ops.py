@@ -295,15 +295,25 @@ def decode_attn(q, k_cache, v_cache_t, out, B, heads, Lmax, Lcur, dpos, scale):
                "decode_attn")
 
 
+def decode_attn_fused(qkv, k_cache, v_cache_t, out, B, heads, Lmax, pos, dpos, cos_tab, sin_tab, scale):
+    _lib.check(_lib.load().ivgpt_decode_attn_fused(_dt(qkv), qkv.data_ptr(), k_cache.data_ptr(), v_cache_t.data_ptr(),
+                                                   out.data_ptr(), B, heads, Lmax, pos, _ptr(dpos), cos_tab.data_ptr(),
+                                                   sin_tab.data_ptr(), scale, _stream()), "decode_attn_fused")
+
+
+def set_pdl(on: bool):
+    _lib.load().ivgpt_set_pdl(int(on))
+
+
 def argmax(logits, ld, rows, V, out, out_stride, dpos=None, out_offset=0):
     _lib.check(_lib.load().ivgpt_argmax(logits.data_ptr(), ld, rows, V, out.data_ptr() + 8 * out_offset, out_stride,
                                         _ptr(dpos), _stream()), "argmax")
 
 
-def topk_sample(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos=None, out_offset=0):
+def topk_sample(logits, ld, rows, V, k, temperature, seed, step, out, out_stride, dpos=None, out_offset=0, dseed=None):
     _lib.check(_lib.load().ivgpt_topk_sample(logits.data_ptr(), ld, rows, V, k, temperature, seed, step,
-                                             out.data_ptr() + 8 * out_offset, out_stride, _ptr(dpos), _stream()),
-               "topk_sample")
+                                             out.data_ptr() + 8 * out_offset, out_stride, _ptr(dpos), _ptr(dseed),
+                                             _stream()), "topk_sample")
 
 
 def ce_loss(logits, ld, B, L, V, labels):

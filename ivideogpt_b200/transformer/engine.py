@@ -178,7 +178,7 @@ class LlamaEngine:
         return logits, None
 
     # ---- one decode step, position read from device memory ----------------------------------------------------
-    def _decode_step(self, B, Lmax, tokens, dpos, sample_cfg):
+    def _decode_step(self, B, Lmax, tokens, dpos, sample_cfg, dseed=None):
         w = self.w
         h = w.hidden
         x = self.buf("xd", (B, h), torch.float32)
@@ -191,7 +191,7 @@ class LlamaEngine:
         V = w.vocab
         logits = self.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)
         ops.gemm(xn, w.lm_head, out=logits[:, :V])
-        self._sample(logits, B, tokens, dpos, sample_cfg, 0)
+        self._sample(logits, B, tokens, dpos, sample_cfg, 0, dseed)
         ops.incr(dpos, 1)
 
     def _layer_decode(self, li, x, B, kc, vc, Lmax, dpos):
@@ -202,68 +202,90 @@ class LlamaEngine:
         ops.rmsnorm(x, lw["n1"], xn, B, w.eps)
         qkv = self.buf("qkvd", (B, 3 * h), dt)
         ops.gemm(xn, lw["wqkv"], out=qkv)
-        q = self.buf("qd", (B, H, 1, 64), dt)
-        ops.rope_kv(qkv, q, kc[li], vc[li], B, 1, H, Lmax, 0, dpos, w.cos, w.sin)
         ao = self.buf("aod", (B, h), dt)
-        ops.decode_attn(q, kc[li], vc[li], ao, B, H, Lmax, 1, dpos, 0.125)
+        ops.decode_attn_fused(qkv, kc[li], vc[li], ao, B, H, Lmax, 0, dpos, w.cos, w.sin, 0.125)
         ops.gemm(ao, lw["wo"], residual=x, out=x)
         ops.rmsnorm(x, lw["n2"], xn, B, w.eps)
         act = self.buf("actd", (B, w.inter), dt)
         ops.gemm(xn, lw["wgu"], act=ACT_SWIGLU, out=act)
         ops.gemm(act, lw["wd"], residual=x, out=x)
 
-    def _sample(self, logits, B, tokens, dpos, sample_cfg, out_offset):
+    def _sample(self, logits, B, tokens, dpos, sample_cfg, out_offset, dseed=None):
         """Writes the next token of every row to tokens[b, (*dpos + 1 if dpos else 0) + out_offset]."""
         V = self.w.vocab
         ld = logits.stride(0)
         if sample_cfg is None:
             ops.argmax(logits, ld, B, V, tokens, tokens.stride(0), dpos, out_offset)
         else:
-            k, temp, seed = sample_cfg
-            ops.topk_sample(logits, ld, B, V, k, temp, seed, 0, tokens, tokens.stride(0), dpos, out_offset)
+            k, temp = sample_cfg
+            ops.topk_sample(logits, ld, B, V, k, temp, 0, 0, tokens, tokens.stride(0), dpos, out_offset, dseed)
 
     # ---- generation ---------------------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], max_new_tokens: int,
-                 do_sample: bool, top_k: int, temperature: float, seed: int, use_graph: bool = True) -> torch.Tensor:
-        """Returns the full token buffer [B, L + max_new_tokens] (prompt slots hold ids, or zeros for embeds)."""
+                 do_sample: bool, top_k: int, temperature: float, seed: int, use_graph: bool = True,
+                 use_pdl: bool = True) -> torch.Tensor:
+        """Returns the token buffer [B, L + max_new_tokens] (prompt slots hold ids, or zeros for embeds).
+
+        The decode step is captured ONCE per (batch, length, sampling mode) into a CUDA graph: position and RNG seed
+        live in device memory, the token buffer is a persistent engine buffer, so later calls only replay."""
         src = ids if ids is not None else embeds
         B, L = src.shape[0], src.shape[1]
         dev = src.device
         total = L + max_new_tokens
         Lmax = (total + 7) // 8 * 8
-        tokens = torch.zeros(B, total, dtype=torch.int64, device=dev)
+        tokens = self.buf("tokens", (B, total), torch.int64)
         if ids is not None:
             tokens[:, :L].copy_(ids)
+        else:
+            tokens[:, :L].zero_()
         if max_new_tokens <= 0:
-            return tokens
+            return tokens.clone()
         V = self.w.vocab
         k = min(int(top_k), V) if (top_k is not None and top_k > 0) else V
-        sample_cfg = (k, float(temperature), int(seed)) if do_sample else None
+        sample_cfg = (k, float(temperature)) if do_sample else None
+        dseed = self.buf("dseed", (1,), torch.int64)
+        dseed.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        dpos = self.buf("dpos", (1,), torch.int32)
         logits, _ = self.prefill(B, L, Lmax, ids.contiguous() if ids is not None else None, embeds, False)
-        # first new token from the prefill logits -> tokens[:, L]
-        self._sample(logits, B, tokens, None, sample_cfg, L)
-        if max_new_tokens == 1:
-            return tokens
-        dpos = torch.full((1,), L, dtype=torch.int32, device=dev)    # position of the token fed next
+        self._sample(logits, B, tokens, None, sample_cfg, L, dseed)       # first new token -> tokens[:, L]
         steps = max_new_tokens - 1
-        if use_graph:
-            stream = torch.cuda.Stream(device=dev)
-            stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(stream):
-                self._decode_step(B, Lmax, tokens, dpos, sample_cfg)            # warm-up (also step 1)
-            torch.cuda.current_stream(dev).wait_stream(stream)
-            if steps > 1:
-                from .. import _lib
+        if steps == 0:
+            return tokens.clone()
+        dpos.fill_(L)                                                     # position of the token fed next
+        if not use_graph:
+            ops.set_pdl(use_pdl)
+            try:
+                for _ in range(steps):
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)
+            finally:
+                ops.set_pdl(False)
+            return tokens.clone()
+        from .. import _lib
+        key = ("decode", B, Lmax, total, sample_cfg, use_pdl)
+        entry = self._graphs.get(key)
+        done = 0
+        if entry is None:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            ops.set_pdl(use_pdl)
+            try:
+                with torch.cuda.stream(side):
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)   # warm-up run (is decode step 1)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                done = 1
                 g = torch.cuda.CUDAGraph()
                 n0 = _lib.launch_count()
                 with torch.cuda.graph(g):
-                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg)
-                per_step = _lib.launch_count() - n0      # kernels recorded in the graph (capture does not run them)
-                for _ in range(steps - 1):
-                    g.replay()
-                _lib.load().ivgpt_count_add(per_step * (steps - 2))   # replays launch the recorded kernels again
-        else:
-            for _ in range(steps):
-                self._decode_step(B, Lmax, tokens, dpos, sample_cfg)
-        return tokens
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)
+                per_step = _lib.launch_count() - n0
+                _lib.load().ivgpt_count_add(-per_step)        # capture records kernels without running them
+            finally:
+                ops.set_pdl(False)
+            entry = (g, per_step)
+            self._graphs[key] = entry
+        g, per_step = entry
+        for _ in range(steps - done):
+            g.replay()
+        _lib.load().ivgpt_count_add(per_step * (steps - done))
+        return tokens.clone()

@@ -77,8 +77,9 @@ def test_generate_graph_equals_eager_and_embeds_path(cuda):
     ids = torch.randint(0, 1026, (2, 21), generator=torch.Generator().manual_seed(2)).to(cuda)
     eng = mine.b200_engine()
     a = eng.generate(ids, None, 12, False, 0, 1.0, 0, use_graph=True)
-    b = eng.generate(ids, None, 12, False, 0, 1.0, 0, use_graph=False)
-    assert torch.equal(a, b)
+    b = eng.generate(ids, None, 12, False, 0, 1.0, 0, use_graph=False, use_pdl=False)
+    a2 = eng.generate(ids, None, 12, False, 0, 1.0, 0, use_graph=True)      # cached graph replay
+    assert torch.equal(a, b) and torch.equal(a, a2)
     emb = mine.get_input_embeddings()(ids)
     c = mine.generate(inputs_embeds=emb, do_sample=False, max_new_tokens=12)
     assert c.shape == (2, 12) and torch.equal(c, a[:, 21:])
