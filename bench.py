@@ -142,6 +142,13 @@ def build_b200_models(workload, dev, dtype):
     return tok, llm, ref_tok, ref_llm
 
 
+def host_threads():
+    """Threads for the CPU arm.  torch's intra-op pool stops scaling (and then regresses badly) on the small GEMMs
+    of a batch-1 rollout well before the 128 hardware threads of the GPU host (the 128-thread run took 322 s for
+    one clip); the count actually used is reported as `cores`."""
+    return min(os.cpu_count() or 1, int(os.environ.get("IVGPT_CPU_THREADS", "32")))
+
+
 def synthetic_clips(B, T, res, seed=0):
     import torch
     return torch.rand(B, T, 3, res, res, generator=torch.Generator().manual_seed(seed))
@@ -168,7 +175,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     _, _, res, _ = WORKLOADS[args.workload]
     tok_cfg, ref_tok, ref_llm = build_oracle_models(args.workload)
@@ -322,7 +329,7 @@ def run_b200(args):
                 "api": "CompressiveVQModel.tokenize(all frames) -> B200LlamaForCausalLM.generate -> detokenize -> .cpu()"},
     }
     if not args.no_cpu_baseline and not args.quick and world == 1:
-        cores = os.cpu_count() or 1
+        cores = host_threads()
         torch.set_num_threads(cores)
         clips = synthetic_clips(args.cpu_clips, seg, res)
         t_cpu, _ = cpu_rollout(ref_tok, ref_llm, clips, ctx, seg)
