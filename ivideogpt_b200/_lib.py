@@ -49,6 +49,26 @@ class ConvDesc(C.Structure):
     ]
 
 
+class MegaDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+        ("vocab", C.c_int), ("Lmax", C.c_int), ("steps", C.c_int),
+        ("o_splits", C.c_int), ("d_splits", C.c_int),
+        ("eps", C.c_float),
+        ("x", C.c_void_p), ("xn", C.c_void_p), ("qkv", C.c_void_p), ("ao", C.c_void_p), ("act", C.c_void_p),
+        ("part", C.c_void_p), ("logits", C.c_void_p),
+        ("ldl", C.c_longlong),
+        ("kcache", C.c_void_p), ("vcache", C.c_void_p),
+        ("embed", C.c_void_p), ("norm_f", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
+        ("tokens", C.c_void_p), ("tok_stride", C.c_longlong),
+        ("dpos", C.c_void_p),
+        ("do_sample", C.c_int), ("topk", C.c_int), ("inv_temp", C.c_float),
+        ("dseed", C.c_void_p),
+        ("barrier", C.c_void_p), ("error", C.c_void_p),
+        ("layers_dev", C.c_void_p), ("lm_head_map_dev", C.c_void_p),
+    ]
+
+
 # name -> argtypes (return type is always int unless listed in _RESTYPES)
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 SIGNATURES = {
@@ -82,6 +102,10 @@ SIGNATURES = {
     "ivgpt_incr": [_P, _I, _P],
     "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],
     "ivgpt_set_pdl": [_I],
+    "ivgpt_mega_layer_bytes": [],
+    "ivgpt_mega_fill_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I],
+    "ivgpt_mega_fill_map": [_P, _P, _I, _I],
+    "ivgpt_decode_mega": [C.POINTER(MegaDesc), _P],
 }
 _RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong}
 

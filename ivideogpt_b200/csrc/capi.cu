@@ -7,6 +7,7 @@
 #include "../../include/ivgpt_b200.h"
 #include "common.cuh"
 #include "gemm_params.cuh"
+#include "decode_mega.cuh"
 
 namespace ivg {
 
@@ -352,5 +353,49 @@ int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_c
                                   S(stream));
 }
 int ivgpt_set_pdl(int on) { ivg::g_pdl = on != 0; return 0; }
+
+// ---- persistent decode megakernel -------------------------------------------------------------------
+int ivgpt_mega_layer_bytes(void) { return (int)sizeof(ivg::MegaLayer); }
+
+static int mega_weight_map(CUtensorMap* m, const void* w, int rows, int cols) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)cols * 2};
+  uint32_t box[2] = {64, (uint32_t)ivg::MEGA_BN};
+  return make_tensor_map(m, DT_BF16, w, 2, dims, str, box, 1);
+}
+
+int ivgpt_mega_fill_map(void* host_map, const void* w, int rows, int cols) {
+  return mega_weight_map(reinterpret_cast<CUtensorMap*>(host_map), w, rows, cols);
+}
+
+int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,
+                          const float* n1, const float* n2, int hidden, int inter) {
+  ivg::MegaLayer* L = reinterpret_cast<ivg::MegaLayer*>(host_layer);
+  if (mega_weight_map(&L->wqkv, wqkv, 3 * hidden, hidden)) return 1;
+  if (mega_weight_map(&L->wo, wo, hidden, hidden)) return 1;
+  if (mega_weight_map(&L->wgu, wgu, 2 * inter, hidden)) return 1;
+  if (mega_weight_map(&L->wd, wd, hidden, inter)) return 1;
+  L->n1 = n1; L->n2 = n2;
+  return 0;
+}
+
+int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
+  IVG_CHECK(d != nullptr, "decode_mega: null descriptor");
+  ivg::MegaParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.hidden = d->hidden; p.inter = d->inter; p.heads = d->heads; p.layers = d->layers; p.vocab = d->vocab;
+  p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps; p.o_splits = d->o_splits; p.d_splits = d->d_splits;
+  p.x = (float*)d->x; p.xn = (__nv_bfloat16*)d->xn; p.qkv = (__nv_bfloat16*)d->qkv; p.ao = (__nv_bfloat16*)d->ao;
+  p.act = (__nv_bfloat16*)d->act; p.part = (float*)d->part; p.logits = (float*)d->logits; p.ldl = d->ldl;
+  p.kcache = (__nv_bfloat16*)d->kcache; p.vcache = (__nv_bfloat16*)d->vcache;
+  p.embed = d->embed; p.norm_f = d->norm_f; p.cos_tab = d->cos_tab; p.sin_tab = d->sin_tab;
+  p.tokens = d->tokens; p.tok_stride = d->tok_stride; p.dpos = d->dpos;
+  p.do_sample = d->do_sample; p.topk = d->topk; p.inv_temp = d->inv_temp; p.dseed = d->dseed;
+  p.barrier = d->barrier; p.error = d->error;
+  p.lw = reinterpret_cast<const ivg::MegaLayer*>(d->layers_dev);
+  p.lm_head = reinterpret_cast<const CUtensorMap*>(d->lm_head_map_dev);
+  if (p.steps <= 0) return 0;
+  return ivg::decode_mega_launch(p, num_sms(), S(stream));
+}
 
 }  // extern "C"

@@ -1,0 +1,53 @@
+// Parameter blocks of the persistent decode megakernel, shared by decode_mega.cu (device) and capi.cu (host).
+#pragma once
+#include "common.cuh"
+
+namespace ivg {
+
+constexpr int MEGA_THREADS = 256;
+constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
+constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
+constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
+constexpr int MEGA_B_BYTES = MEGA_BN * MEGA_MAXK * 2;   // 32 KB per slab
+constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MEGA_MAX_SPLITS = 8;
+
+struct MegaLayer {
+  CUtensorMap wqkv, wo, wgu, wd;   // B operands, box {64 k, 16 rows}, SWIZZLE_128B
+  const float* n1;
+  const float* n2;
+};
+
+struct MegaParams {
+  int B, hidden, inter, heads, layers, vocab, Lmax, steps;
+  int o_splits, d_splits;   // split-K factors of the o-proj (K = hidden) and down-proj (K = inter) phases
+  float eps;
+  float* x;                 // [B, hidden] fp32 residual stream
+  __nv_bfloat16* xn;        // [B, hidden]
+  __nv_bfloat16* qkv;       // [B, 3*hidden]
+  __nv_bfloat16* ao;        // [B, hidden]
+  __nv_bfloat16* act;       // [B, inter]
+  float* part;              // [max(o_splits, d_splits)][B][hidden]
+  float* logits;            // [B, ldl]
+  long long ldl;
+  __nv_bfloat16* kcache;    // [layers][B][heads][Lmax][64]
+  __nv_bfloat16* vcache;    // [layers][B][heads][64][Lmax]
+  const float* embed;       // [vocab, hidden] fp32
+  const float* norm_f;      // final RMSNorm weight
+  const float* cos_tab;     // [max_pos, 32]
+  const float* sin_tab;
+  long long* tokens;        // [B, tok_stride]
+  long long tok_stride;
+  int* dpos;                // in: position of the token fed at step 0; out: advanced by `steps`
+  int do_sample, topk;
+  float inv_temp;
+  const unsigned long long* dseed;
+  unsigned int* barrier;    // zero-initialised
+  int* error;               // zero-initialised; 1 = barrier timeout
+  const MegaLayer* lw;      // device array [layers]
+  const CUtensorMap* lm_head;   // device pointer (box {64, 16})
+};
+
+int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);
+
+}  // namespace ivg

@@ -55,7 +55,9 @@ __global__ void vq_unpack_kernel(const unsigned long long* __restrict__ packed, 
   if (i < N) idx[i] = (long long)(packed[i] & 0xFFFFFFFFull);
 }
 
-// thread (ty, tx): rows  n = ty*4 + {0..3} and 64 + ty*4 + {0..3};  codes k = tx*4 + {0..3} and 64 + tx*4 + {0..3}
+// thread (ty, tx): rows n = i*16 + ty, codes k = j*16 + tx (i, j = 0..7).  Lanes of a warp therefore read 16
+// CONSECUTIVE codebook rows per LDS.128: row pitch 68 words -> bank offset 4*tx, conflict-free per quarter-warp
+// (the first version used k = tx*4 + j: lane stride 272 words = 16 banks -> 8-way conflicts, ncu: 2.0e8 conflicts).
 __global__ void __launch_bounds__(VQ_THREADS, 2)
 vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e, const float* __restrict__ enorm,
                  unsigned long long* __restrict__ packed, int N, int K, int tiles_per_split) {
@@ -118,12 +120,12 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e, const
       float4 zv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+        int r = i * 16 + ty;
         zv[i] = *reinterpret_cast<const float4*>(zs + r * VQ_PITCH + d);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        int c = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4);
+        int c = j * 16 + tx;
         float4 ev = *reinterpret_cast<const float4*>(eb + c * VQ_PITCH + d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -140,7 +142,7 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e, const
     const int kbase = (ktile0 + t) * VQ_TK;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int c = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4);
+      int c = j * 16 + tx;
       float en = ns[buf * VQ_TK + c];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -161,7 +163,7 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e, const
       p = (q < p) ? q : p;
     }
     if (tx == 0) {
-      int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+      int r = i * 16 + ty;
       if (n0 + r < N) atomicMin(packed + n0 + r, p);
     }
   }

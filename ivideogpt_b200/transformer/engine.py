@@ -220,11 +220,94 @@ class LlamaEngine:
             k, temp = sample_cfg
             ops.topk_sample(logits, ld, B, V, k, temp, 0, 0, tokens, tokens.stride(0), dpos, out_offset, dseed)
 
+    # ---- persistent decode megakernel (bf16, B <= 64 with these widths) --------------------------------------
+    def mega_supported(self, B: int, Lmax: int) -> bool:
+        w = self.w
+        if self.dtype != torch.bfloat16 or B < 1:
+            return False
+        a_rows = 64 if B <= 64 else 128
+        if B > 128:
+            return False
+        o_s, d_s = self._mega_splits()
+        if o_s is None:
+            return False
+        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024
+                and (w.vocab + 256) * 4 <= 128 * 1024 and (Lmax + 88) * 4 <= 128 * 1024)
+
+    def _mega_splits(self):
+        w = self.w
+        o_s = next((s for s in (3, 2, 4, 1) if w.hidden % (64 * s) == 0), None)
+        d_s = next((s for s in range(1, 9) if w.inter % (64 * s) == 0 and w.inter // s <= 1024), None)
+        if o_s is None or d_s is None:
+            return None, None
+        return o_s, d_s
+
+    def _mega_tables(self):
+        """Device-resident array of per-layer weight tensor maps (+ the lm_head map), built once per engine."""
+        if getattr(self, "_mega_dev", None) is not None:
+            return self._mega_dev
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.load()
+        w = self.w
+        nbytes = lib.ivgpt_mega_layer_bytes()
+        host = (C.c_uint8 * (nbytes * w.layers_n + 128 + 64))()
+        base = C.addressof(host)
+        base_al = (base + 63) // 64 * 64
+        for i, lw in enumerate(w.layers):
+            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, lw["wqkv"].data_ptr(), lw["wo"].data_ptr(),
+                                                 lw["wgu"].data_ptr(), lw["wd"].data_ptr(), lw["n1"].data_ptr(),
+                                                 lw["n2"].data_ptr(), w.hidden, w.inter), "mega_fill_layer")
+        _lib.check(lib.ivgpt_mega_fill_map(base_al + w.layers_n * nbytes, w.lm_head.data_ptr(), w.vocab, w.hidden),
+                   "mega_fill_map")
+        total = nbytes * w.layers_n + 128
+        raw = bytes((C.c_uint8 * total).from_address(base_al))
+        dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.w.embed.device)
+        assert dev.data_ptr() % 64 == 0
+        self._mega_dev = (dev, nbytes)
+        return self._mega_dev
+
+    def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps):
+        import ctypes as C
+        from .. import _lib
+        w = self.w
+        h = w.hidden
+        dev_tab, nbytes = self._mega_tables()
+        o_s, d_s = self._mega_splits()
+        kc, vc = self.kv_cache(B, Lmax)
+        logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
+        sync = self.buf("mega_sync", (2,), torch.int32)
+        sync.zero_()
+        d = _lib.MegaDesc()
+        d.B, d.hidden, d.inter, d.heads, d.layers, d.vocab, d.Lmax, d.steps = B, h, w.inter, w.heads, w.layers_n, w.vocab, Lmax, steps
+        d.o_splits, d.d_splits = o_s, d_s
+        d.eps = w.eps
+        d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
+        d.xn = self.buf("xnd", (B, h), self.dtype).data_ptr()
+        d.qkv = self.buf("qkvd", (B, 3 * h), self.dtype).data_ptr()
+        d.ao = self.buf("aod", (B, h), self.dtype).data_ptr()
+        d.act = self.buf("actd", (B, w.inter), self.dtype).data_ptr()
+        d.part = self.buf("mega_part", (max(o_s, d_s), B, h), torch.float32).data_ptr()
+        d.logits = logits.data_ptr(); d.ldl = logits.stride(0)
+        d.kcache = kc.data_ptr(); d.vcache = vc.data_ptr()
+        d.embed = w.embed.data_ptr(); d.norm_f = w.norm.data_ptr(); d.cos_tab = w.cos.data_ptr(); d.sin_tab = w.sin.data_ptr()
+        d.tokens = tokens.data_ptr(); d.tok_stride = tokens.stride(0)
+        d.dpos = dpos.data_ptr()
+        if sample_cfg is None:
+            d.do_sample, d.topk, d.inv_temp = 0, 1, 1.0
+        else:
+            d.do_sample, d.topk, d.inv_temp = 1, sample_cfg[0], 1.0 / sample_cfg[1]
+        d.dseed = dseed.data_ptr()
+        d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
+        d.layers_dev = dev_tab.data_ptr(); d.lm_head_map_dev = dev_tab.data_ptr() + w.layers_n * nbytes
+        _lib.check(_lib.load().ivgpt_decode_mega(C.byref(d), torch.cuda.current_stream().cuda_stream), "decode_mega")
+        return sync
+
     # ---- generation ---------------------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], max_new_tokens: int,
                  do_sample: bool, top_k: int, temperature: float, seed: int, use_graph: bool = True,
-                 use_pdl: bool = True) -> torch.Tensor:
+                 use_pdl: bool = True, use_mega: Optional[bool] = None) -> torch.Tensor:
         """Returns the token buffer [B, L + max_new_tokens] (prompt slots hold ids, or zeros for embeds).
 
         The decode step is captured ONCE per (batch, length, sampling mode) into a CUDA graph: position and RNG seed
@@ -253,6 +336,17 @@ class LlamaEngine:
         if steps == 0:
             return tokens.clone()
         dpos.fill_(L)                                                     # position of the token fed next
+        if use_mega is None:
+            use_mega = self.mega_supported(B, Lmax)
+        if use_mega:
+            if not self.mega_supported(B, Lmax):
+                raise ValueError(f"decode megakernel does not support B={B}, dtype={self.dtype}, widths "
+                                 f"{self.w.hidden}/{self.w.inter}")
+            sync = self._decode_mega(B, Lmax, tokens, dpos, sample_cfg, dseed, steps)
+            out = tokens.clone()
+            if int(sync[1].item()) != 0:
+                raise RuntimeError("decode megakernel: device-wide barrier timed out (a CTA was not co-resident?)")
+            return out
         if not use_graph:
             ops.set_pdl(use_pdl)
             try:
