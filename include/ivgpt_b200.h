@@ -176,6 +176,8 @@ typedef struct ivgpt_mega_desc {
   const unsigned long long* dseed;
   unsigned int* barrier; int* error;
   const void* layers_dev; const void* lm_head_map_dev;
+  long long* prof; /* optional device [16]: SM-cycle totals of CTA 0 per phase kind (norm, qkv, attention, o, gate/up,
+                      down, lm_head, sample, barriers); NULL to disable */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,

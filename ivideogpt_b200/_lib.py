@@ -66,6 +66,7 @@ class MegaDesc(C.Structure):
         ("dseed", C.c_void_p),
         ("barrier", C.c_void_p), ("error", C.c_void_p),
         ("layers_dev", C.c_void_p), ("lm_head_map_dev", C.c_void_p),
+        ("prof", C.c_void_p),
     ]
 
 

@@ -394,6 +394,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.barrier = d->barrier; p.error = d->error;
   p.lw = reinterpret_cast<const ivg::MegaLayer*>(d->layers_dev);
   p.lm_head = reinterpret_cast<const CUtensorMap*>(d->lm_head_map_dev);
+  p.prof = d->prof;
   if (p.steps <= 0) return 0;
   return ivg::decode_mega_launch(p, num_sms(), S(stream));
 }

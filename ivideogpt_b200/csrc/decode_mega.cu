@@ -52,19 +52,18 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-// device-wide barrier; returns false when it timed out (error flag is set, every CTA leaves the kernel)
+// device-wide barrier; returns false when it timed out (error flag is set, every CTA leaves the kernel).
+// Arrival is a release-reduction, the wait an acquire-load: no full sc fences (v1 used __threadfence() on both sides
+// and cost ~2.8 us per barrier, 87 barriers per decode step).
 __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
   __syncthreads();
   if (threadIdx.x == 0) {
     c.epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(p.barrier, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier) : "memory");
     const long long t0 = clock64();
     while (ld_acquire_u32(p.barrier) < c.epoch) {
       if (clock64() - t0 > (1ll << 32)) { *p.error = 1; break; }   // ~2 s: never hang the GPU
-      if (*reinterpret_cast<volatile int*>(p.error)) break;
     }
-    __threadfence();
   }
   __syncthreads();
   return *reinterpret_cast<volatile int*>(p.error) == 0;
@@ -86,15 +85,21 @@ __device__ __forceinline__ void load_a(const MegaParams& p, MegaCtx& c, const __
                                        int Kc, int a_rows) {
   const int nkb = Kc / 64;
   const int chunks = nkb * a_rows * 8;            // 16-byte chunks
+  // cp.async (LDGSTS): every thread fires all of its 16-byte copies back to back -- no register staging, the whole
+  // slab is in flight at once (one CTA owns the SM, so memory-level parallelism must come from within the thread;
+  // v1 issued one load at a time: L2-latency bound, v2 staged 8 in registers).  Rows >= B are left untouched: their
+  // TMEM lanes are never read.
   for (int i = threadIdx.x; i < chunks; i += MEGA_THREADS) {
     const int ch = i & 7;
     const int r = (i >> 3) % a_rows;
     const int j = (i >> 3) / a_rows;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < p.B) v = *reinterpret_cast<const uint4*>(A + (size_t)r * lda + k0 + j * 64 + ch * 8);
-    uint8_t* dst = c.sm.a + (size_t)j * a_rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(dst) = v;
+    if (r < p.B) {
+      uint8_t* dst = c.sm.a + (size_t)j * a_rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+      cp_async16(dst, A + (size_t)r * lda + k0 + j * 64 + ch * 8);
+    }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core's async proxy
   __syncthreads();
 }
@@ -167,7 +172,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
       umma_commit(c.sm.mma_done);
     }
     // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3 ----
-    if (warp >= 4) {
+    if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
       mbar_wait(c.sm.mma_done, c.mphase);
@@ -209,11 +214,13 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
 }
 
 // ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
+// One row per CTA, one float4 per thread (hidden <= 1024): every load of the row is in flight at once.
 __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col) {
+  __shared__ float s_ss[MEGA_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (MEGA_THREADS / 32) + warp;
   const int H = p.hidden;
-  for (int m = gw; m < p.B; m += gridDim.x * (MEGA_THREADS / 32)) {
+  const int i = threadIdx.x * 4;
+  for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
     float* xr = p.x + (size_t)m * H;
     const float* src = xr;
     if (tok_row0) {
@@ -221,119 +228,172 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
       id = id < 0 ? 0 : (id >= p.vocab ? p.vocab - 1 : id);
       src = p.embed + (size_t)id * H;
     }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     float ss = 0.f;
-    for (int i = lane * 4; i < H; i += 128) {
-      float4 v = *reinterpret_cast<const float4*>(src + i);
-      for (int s = 0; s < nparts; ++s) {
-        const float4 q = *reinterpret_cast<const float4*>(p.part + ((size_t)s * p.B + m) * H + i);
-        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-      }
+    if (i < H) {
+      v = *reinterpret_cast<const float4*>(src + i);
+      float4 q[MEGA_MAX_SPLITS];
+#pragma unroll
+      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+        if (s < nparts) q[s] = *reinterpret_cast<const float4*>(p.part + ((size_t)s * p.B + m) * H + i);
+#pragma unroll
+      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+        if (s < nparts) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }   // fixed order: reproducible
       *reinterpret_cast<float4*>(xr + i) = v;
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    const float r = rsqrtf(ss / (float)H + p.eps);
-    __nv_bfloat16* yr = p.xn + (size_t)m * H;
-    for (int i = lane * 4; i < H; i += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    if (lane == 0) s_ss[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MEGA_THREADS / 32; ++k) tot += s_ss[k];
+    const float r = rsqrtf(tot / (float)H + p.eps);
+    if (i < H) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
       uint2 o;
       o.x = pack_bf16x2(g.x * (v.x * r), g.y * (v.y * r));
       o.y = pack_bf16x2(g.z * (v.z * r), g.w * (v.w * r));
-      *reinterpret_cast<uint2*>(yr + i) = o;
+      *reinterpret_cast<uint2*>(p.xn + (size_t)m * H + i) = o;
     }
+    __syncthreads();
   }
 }
 
-// ---- RoPE + KV append + attention over the cache for one (b, head); same arithmetic as decode_attn_fused_kernel ----
-__device__ void attention_item(const MegaParams& p, int layer, int bh, int pos, float* smem_f) {
+// ---- RoPE + KV append + attention over the cache: a PAIR of warps per (b, head) item ----
+// v1 gave each item a whole CTA: with one CTA per SM an item's loads form a latency chain (~10 us/item, 2.5 TB/s).
+// v2 used one warp per item (6 of 8 warps busy).  v3: 16 warps per CTA, each item split along the sequence between two
+// warps (flash-decoding style partial softmax, combined through shared memory): ~11 warps per SM keep 12-16
+// independent 16-byte loads per lane in flight.  Arithmetic per position equals decode_attn_fused_kernel.
+constexpr int ATT_QB = 12;    // K rows in flight per 8-lane group (4 rows per pass)
+constexpr int ATT_DB = 8;     // V^T rows in flight per lane (register budget: 128 / thread at 512 threads)
+constexpr int ATT_WS = 64 + 64 + 4;   // per-pair combine scratch: acc[2][64] ... laid out as [half][66]
+
+__device__ __forceinline__ void pair_barrier(int pair) {   // named barrier 1 + pair, 64 threads
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+__device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, float* psm, int half, int pair) {
+  // psm: per-PAIR scratch: sc[Lmax + 16] | q[64] | comb[2][66]
   const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
   const int Lcur = pos + 1;
-  float* sc = smem_f;
-  float* qs = smem_f + Lmax + 8;
-  float* red = qs + 64;
+  const int Lh = min(Lcur, ((Lcur / 2 + 7) / 8) * 8);          // split point, multiple of 8 (vector loads on V^T)
+  const int lbeg = half == 0 ? 0 : Lh, lend = half == 0 ? Lh : Lcur;
+  float* sc = psm;
+  float* qs = psm + Lmax + 16;
+  float* comb = qs + 64;                                        // [2][66]: m, s, acc[64]
   const int b = bh / heads, hh = bh - b * heads;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31;
   __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
   __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
-  if (tid < 32) {
+  if (half == 1) {   // the warp that owns position `pos` appends K/V (it is the one that reads them back) and stages q
     const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
-    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + tid), sn = __ldg(p.sin_tab + (size_t)pos * 32 + tid);
-    const float q0 = __bfloat162float(row[hh * 64 + tid]), q1 = __bfloat162float(row[hh * 64 + tid + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + tid]), k1 = __bfloat162float(row[Hd + hh * 64 + tid + 32]);
-    qs[tid] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
-    qs[tid + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
-    kslab[(size_t)pos * 64 + tid] = __float2bfloat16_rn(k0 * cs - k1 * sn);
-    kslab[(size_t)pos * 64 + tid + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
-    vslab[(size_t)tid * Lmax + pos] = row[2 * Hd + hh * 64 + tid];
-    vslab[(size_t)(tid + 32) * Lmax + pos] = row[2 * Hd + hh * 64 + tid + 32];
+    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
+    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
+    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
+    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
+    qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
+    qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
+    kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
+    kslab[(size_t)pos * 64 + lane + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
+    vslab[(size_t)lane * Lmax + pos] = v0;
+    vslab[(size_t)(lane + 32) * Lmax + pos] = v1;
   }
-  __syncthreads();
-  const int sub = tid & 7, rslot = tid >> 3;
+  pair_barrier(pair);                 // q visible to both warps; K/V writes ordered before the owner warp's reads
+  const int sub = lane & 7, rslot = lane >> 3;
   float qreg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) qreg[i] = qs[sub * 8 + i];
-  for (int l0 = 0; l0 < Lcur; l0 += 32) {
-    const int l = l0 + rslot;
-    float part = 0.f;
-    if (l < Lcur) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kslab + (size_t)l * 64 + sub * 8);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float mx = -INFINITY;
+  for (int l0 = lbeg; l0 < lend; l0 += 4 * ATT_QB) {
+    uint4 kv[ATT_QB];
+#pragma unroll
+    for (int u = 0; u < ATT_QB; ++u) {
+      const int l = l0 + u * 4 + rslot;
+      kv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (l < lend) kv[u] = *reinterpret_cast<const uint4*>(kslab + (size_t)l * 64 + sub * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < ATT_QB; ++u) {
+      const int l = l0 + u * 4 + rslot;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
+      float part = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __bfloat1622float2(h2[i]);
         part = fmaf(qreg[2 * i], f.x, part);
         part = fmaf(qreg[2 * i + 1], f.y, part);
       }
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (l < lend) {
+        mx = fmaxf(mx, part);
+        if (sub == 0) sc[l] = part;
+      }
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    if (sub == 0 && l < Lcur) sc[l] = part;
   }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int l = tid; l < Lcur; l += MEGA_THREADS) mx = fmaxf(mx, sc[l]);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncwarp();
   float sum = 0.f;
-  for (int l = tid; l < Lcur + 8; l += MEGA_THREADS) {
-    const float e = l < Lcur ? __expf(sc[l] - mx) : 0.f;
+  const int lend8 = half == 0 ? lend : lend + 8;                // owner of the tail clears 8 entries past Lcur
+  for (int l = lbeg + lane; l < lend8; l += 32) {
+    const float e = l < lend ? __expf(sc[l] - mx) : 0.f;
     sc[l] = e;
     sum += e;
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  if (lane == 0) red[8 + warp] = sum;
-  __syncthreads();
-  float tot = 0.f;
+  __syncwarp();
+  float* my = comb + half * 66;
+  if (lane == 0) { my[0] = mx; my[1] = sum; }
+  for (int d0 = 0; d0 < 64; d0 += ATT_DB) {
+    float acc[ATT_DB];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[8 + i];
-  const float inv = 1.0f / tot;
-  for (int d = warp; d < 64; d += 8) {
-    const __nv_bfloat16* vr = vslab + (size_t)d * Lmax;
-    float a = 0.f;
-    for (int l = lane * 8; l < Lcur; l += 256) {
-      const uint4 u = *reinterpret_cast<const uint4*>(vr + l);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int r = 0; r < ATT_DB; ++r) acc[r] = 0.f;
+    for (int l = lbeg + lane * 8; l < lend; l += 256) {
+      uint4 vv[ATT_DB];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h2[i]);
-        a += (l + 2 * i < Lcur) ? sc[l + 2 * i] * f.x : 0.f;
-        a += (l + 2 * i + 1 < Lcur) ? sc[l + 2 * i + 1] * f.y : 0.f;
+      for (int r = 0; r < ATT_DB; ++r) vv[r] = *reinterpret_cast<const uint4*>(vslab + (size_t)(d0 + r) * Lmax + l);
+      float pr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pr[i] = sc[l + i];
+      const int nvalid = lend - l;    // beyond the range: other half's entries / uninitialised cache -> select, never multiply
+#pragma unroll
+      for (int r = 0; r < ATT_DB; ++r) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[r]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          acc[r] += (2 * i < nvalid) ? pr[2 * i] * f.x : 0.f;
+          acc[r] += (2 * i + 1 < nvalid) ? pr[2 * i + 1] * f.y : 0.f;
+        }
       }
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if (lane == 0) p.ao[(size_t)b * Hd + hh * 64 + d] = __float2bfloat16_rn(a * inv);
+    for (int r = 0; r < ATT_DB; ++r) {
+      float a = acc[r];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == r) my[2 + d0 + r] = a;
+    }
   }
-  __syncthreads();   // smem scratch reused by the next item
+  pair_barrier(pair);
+  if (half == 0) {                    // combine the two partial softmaxes: lanes own output dims lane, lane + 32
+    const float m0 = comb[0], s0 = comb[1], m1 = comb[66], s1 = comb[67];
+    const float M = fmaxf(m0, m1);
+    const float e0 = (s0 > 0.f) ? __expf(m0 - M) : 0.f, e1 = (s1 > 0.f) ? __expf(m1 - M) : 0.f;
+    const float inv = 1.0f / (s0 * e0 + s1 * e1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int d = lane + 32 * k;
+      const float o = (comb[2 + d] * e0 + comb[66 + 2 + d] * e1) * inv;
+      p.ao[(size_t)b * Hd + hh * 64 + d] = __float2bfloat16_rn(o);
+    }
+  }
+  pair_barrier(pair);                 // scratch reusable by the pair's next item
 }
 
 // ---- sampling of one logits row by one CTA (argmax, or top-k radix select + inverse CDF as topk_sample_kernel) ----
@@ -354,10 +414,12 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   const int V = p.vocab;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long* out = p.tokens + (size_t)b * p.tok_stride + pos + 1;
-  __shared__ float s_redf[8];
-  __shared__ int s_redi[8];
+  constexpr int NW = MEGA_THREADS / 32;
+  __shared__ float s_redf[NW];
+  __shared__ int s_redi[NW];
   if (!p.do_sample) {
     float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 8
     for (int c = tid; c < V; c += MEGA_THREADS) { const float v = row[c]; if (v > bv || (v == bv && c < bi)) { bv = v; bi = c; } }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -368,7 +430,7 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
     if (lane == 0) { s_redf[warp] = bv; s_redi[warp] = bi; }
     __syncthreads();
     if (tid == 0) {
-      for (int i = 1; i < 8; ++i) if (s_redf[i] > bv || (s_redf[i] == bv && s_redi[i] < bi)) { bv = s_redf[i]; bi = s_redi[i]; }
+      for (int i = 1; i < NW; ++i) if (s_redf[i] > bv || (s_redf[i] == bv && s_redi[i] < bi)) { bv = s_redf[i]; bi = s_redi[i]; }
       *out = bi;
     }
     __syncthreads();
@@ -379,6 +441,7 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ float s_hi[MEGA_THREADS];
   __shared__ int s_win, s_lastmass;
+#pragma unroll 8
   for (int c = tid; c < V; c += MEGA_THREADS) keys[c] = mega_fkey(row[c] * p.inv_temp);
   if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)(p.topk < V ? p.topk : V); s_win = 0x7fffffff; s_lastmass = 0; }
   __syncthreads();
@@ -409,7 +472,7 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   for (int off = 16; off >= 1; off >>= 1) mk = max(mk, __shfl_xor_sync(0xffffffffu, mk, off));
   if (lane == 0) s_redi[warp] = (int)mk;
   __syncthreads();
-  for (int i = 0; i < 8; ++i) mk = max(mk, (uint32_t)s_redi[i]);
+  for (int i = 0; i < NW; ++i) mk = max(mk, (uint32_t)s_redi[i]);
   const float mx = __uint_as_float((mk & 0x80000000u) ? (mk ^ 0x80000000u) : ~mk);
   const int cpt = (V + MEGA_THREADS - 1) / MEGA_THREADS;
   const int c0 = tid * cpt, c1 = min(V, c0 + cpt);
@@ -427,7 +490,7 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   if (lane == 31) s_redf[warp] = incl;
   __syncthreads();
   float wbase = 0.f, total = 0.f;
-  for (int i = 0; i < 8; ++i) { const float v = s_redf[i]; if (i < warp) wbase += v; total += v; }
+  for (int i = 0; i < NW; ++i) { const float v = s_redf[i]; if (i < warp) wbase += v; total += v; }
   const float hi = wbase + incl;
   s_hi[tid] = hi;
   const unsigned long long seed = p.dseed ? *p.dseed : 0ull;
@@ -481,50 +544,73 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   float* smem_f = reinterpret_cast<float*>(c.sm.a);
   uint32_t* smem_u = reinterpret_cast<uint32_t*>(c.sm.a);
   bool ok = true;
+  // phase timing (CTA 0, thread 0): slots 0 norm, 1 qkv, 2 attention, 3 o-proj, 4 gate/up, 5 down, 6 lm_head,
+  // 7 sample, 8 barriers
+  long long tprof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool profiling = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tmark = clock64();
+#define MEGA_MARK(slot) do { if (profiling) { const long long _t = clock64(); tprof[slot] += _t - tmark; tmark = _t; } } while (0)
+#define MEGA_BARRIER() do { ok = grid_barrier(p, c); MEGA_MARK(8); } while (0)
 
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
     GemmPhase qkv_g{&p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H};
     prefetch_phase(c, qkv_g);
     norm_phase(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
-    if (!(ok = grid_barrier(p, c))) break;
+    MEGA_MARK(0);
+    MEGA_BARRIER(); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
       qkv_g.map = &L.wqkv;
       gemm_phase(p, c, qkv_g);
+      MEGA_MARK(1);
       GemmPhase o_g{&L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, o_g);
-      if (!(ok = grid_barrier(p, c))) break;
-      for (int bh = blockIdx.x; bh < p.B * p.heads; bh += gridDim.x) attention_item(p, l, bh, pos, smem_f);
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_BARRIER(); if (!ok) break;
+      {
+        const int pair = warp >> 1, half = warp & 1, npairs = MEGA_THREADS / 64;
+        float* psm = smem_f + (size_t)pair * (p.Lmax + 16 + 64 + 2 * 66);
+        for (int bh = blockIdx.x + (int)gridDim.x * pair; bh < p.B * p.heads; bh += (int)gridDim.x * npairs)
+          attention_pair(p, l, bh, pos, psm, half, pair);
+      }
+      MEGA_MARK(2);
+      MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, o_g);
+      MEGA_MARK(3);
       GemmPhase gu_g{&L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
       prefetch_phase(c, gu_g);
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_BARRIER(); if (!ok) break;
       norm_phase(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_MARK(0);
+      MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, gu_g);
+      MEGA_MARK(4);
       GemmPhase d_g{&L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, d_g);
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, d_g);
+      MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
       GemmPhase nx_g{last ? p.lm_head : &p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, 1, p.xn, H,
                      last ? EPI_LOGITS : EPI_STORE_BF16, last ? (void*)p.logits : (void*)p.qkv,
                      last ? p.ldl : (long long)(3 * H)};
       prefetch_phase(c, nx_g);
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_BARRIER(); if (!ok) break;
       norm_phase(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
-      if (!(ok = grid_barrier(p, c))) break;
+      MEGA_MARK(0);
+      MEGA_BARRIER(); if (!ok) break;
       if (last) {
         gemm_phase(p, c, nx_g);                                       // lm_head
-        if (!(ok = grid_barrier(p, c))) break;
+        MEGA_MARK(6);
+        MEGA_BARRIER(); if (!ok) break;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) sample_row(p, b, pos, smem_u);
-        if (!(ok = grid_barrier(p, c))) break;
+        MEGA_MARK(7);
+        MEGA_BARRIER(); if (!ok) break;
       }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && ok) *p.dpos = pos0 + p.steps;
+  if (profiling) for (int i = 0; i < 9; ++i) p.prof[i] += tprof[i];
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 32); }
@@ -542,7 +628,7 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
   const int a_rows = p.B <= 64 ? 64 : 128;
   IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
             "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
-  IVG_CHECK((size_t)(p.Lmax + 8 + 64 + 16) * 4 <= MEGA_A_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
+  IVG_CHECK((size_t)(p.Lmax + 16 + 64 + 2 * 66) * 4 * (MEGA_THREADS / 64) <= MEGA_A_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
   static bool attr_set = false;

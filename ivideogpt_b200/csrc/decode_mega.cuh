@@ -4,7 +4,7 @@
 
 namespace ivg {
 
-constexpr int MEGA_THREADS = 256;
+constexpr int MEGA_THREADS = 512;
 constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
@@ -46,6 +46,7 @@ struct MegaParams {
   int* error;               // zero-initialised; 1 = barrier timeout
   const MegaLayer* lw;      // device array [layers]
   const CUtensorMap* lm_head;   // device pointer (box {64, 16})
+  long long* prof;              // optional [16] cycle counters filled by CTA 0 (phase breakdown), may be null
 };
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);

@@ -15,10 +15,35 @@ namespace ivg {
 // ---------------------------------------------------------------------------------------------
 constexpr int GN_SLAB_ROWS = 64;  // pixels per partial-sum CTA
 
+// 16-byte vector of T -> 8 floats (bf16) or 4 floats (fp32)
+template <typename T> struct GnVec { static constexpr int N = 16 / sizeof(T); };
+template <typename T>
+__device__ __forceinline__ void gn_load(const T* p, float (&f)[16 / sizeof(T)]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  if constexpr (sizeof(T) == 2) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+  } else {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void gn_store(T* p, const float (&f)[16 / sizeof(T)]) {
+  uint4 u;
+  if constexpr (sizeof(T) == 2) {
+    u = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  } else {
+    u = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 template <typename T>
 __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int rows, int C, int G,
                                   int slabs) {
-  // grid: (slabs, N).  part layout [N][slabs][G][2]
+  // grid: (slabs, N), 256 threads = (C/VN channel vectors) x (row lanes).  part layout [N][slabs][G][2]
+  constexpr int VN = GnVec<T>::N;
   extern __shared__ float gn_sm[];  // [G][2] accumulators
   const int n = blockIdx.y, slab = blockIdx.x;
   const int cpg = C / G;
@@ -27,20 +52,29 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
   const int r0 = slab * GN_SLAB_ROWS;
   const int r1 = min(rows, r0 + GN_SLAB_ROWS);
   const T* base = x + ((size_t)n * rows) * C;
-  // each thread owns a fixed channel pair position -> walks rows
-  const int vecC = C / 2;
-  for (int cv = threadIdx.x; cv < vecC; cv += blockDim.x) {
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-    const int c = cv * 2;
-    for (int r = r0; r < r1; ++r) {
-      float a = to_f32(base[(size_t)r * C + c]);
-      float b = to_f32(base[(size_t)r * C + c + 1]);
-      s0 += a; q0 = fmaf(a, a, q0);
-      s1 += b; q1 = fmaf(b, b, q1);
+  const int cvecs = C / VN;
+  const int rlanes = blockDim.x / cvecs;          // >= 1 (C/VN <= 256)
+  const int cv = threadIdx.x % cvecs, rl = threadIdx.x / cvecs;
+  if (rl < rlanes) {
+    float s[VN], q[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int r = r0 + rl; r < r1; r += rlanes) {
+      float f[VN];
+      gn_load<T>(base + (size_t)r * C + cv * VN, f);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
-    const int g0 = c / cpg, g1 = (c + 1) / cpg;
-    atomicAdd(&gn_sm[2 * g0], s0); atomicAdd(&gn_sm[2 * g0 + 1], q0);
-    atomicAdd(&gn_sm[2 * g1], s1); atomicAdd(&gn_sm[2 * g1 + 1], q1);
+    // fold the VN channels into their groups before touching shared memory
+    int g_prev = (cv * VN) / cpg;
+    float ss = 0.f, qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      const int g = (cv * VN + i) / cpg;
+      if (g != g_prev) { atomicAdd(&gn_sm[2 * g_prev], ss); atomicAdd(&gn_sm[2 * g_prev + 1], qq); ss = 0.f; qq = 0.f; g_prev = g; }
+      ss += s[i]; qq += q[i];
+    }
+    atomicAdd(&gn_sm[2 * g_prev], ss); atomicAdd(&gn_sm[2 * g_prev + 1], qq);
   }
   __syncthreads();
   float* dst = part + ((size_t)n * slabs + slab) * G * 2;
@@ -64,32 +98,36 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
   stats[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// y = (x - mean) * rstd * gamma + beta ; optional SiLU ; optional + pos[(row % pos_rows)][C]
+// y = (x - mean) * rstd * gamma + beta ; optional SiLU ; optional + pos[(row % pos_rows)][C].  16 bytes per thread.
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ pos, long long total_rows, int rows_per_sample, int C, int G,
                                 int silu, int pos_rows) {
+  constexpr int VN = GnVec<T>::N;
   const int cpg = C / G;
-  const int vecC = C / 2;
+  const int vecC = C / VN;
   const long long total = total_rows * vecC;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / vecC;
-    const int c = (int)(i - row * vecC) * 2;
+    const int c = (int)(i - row * vecC) * VN;
     const int n = (int)(row / rows_per_sample);
-    float v0 = to_f32(x[row * C + c]), v1 = to_f32(x[row * C + c + 1]);
-    const float* st0 = stats + ((size_t)n * G + c / cpg) * 2;
-    const float* st1 = stats + ((size_t)n * G + (c + 1) / cpg) * 2;
-    v0 = (v0 - st0[0]) * st0[1] * gamma[c] + beta[c];
-    v1 = (v1 - st1[0]) * st1[1] * gamma[c + 1] + beta[c + 1];
-    if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
-    if (pos) {
-      const long long pr = row % pos_rows;
-      v0 += pos[pr * C + c]; v1 += pos[pr * C + c + 1];
+    float f[VN];
+    gn_load<T>(x + row * C + c, f);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const float* st = stats + ((size_t)n * G + (c + k) / cpg) * 2;
+      float v = (f[k] - __ldg(st)) * __ldg(st + 1) * __ldg(gamma + c + k) + __ldg(beta + c + k);
+      if (silu) v = silu_f(v);
+      f[k] = v;
     }
-    y[row * C + c] = from_f32<T>(v0);
-    y[row * C + c + 1] = from_f32<T>(v1);
+    if (pos) {
+      const float* pr = pos + (row % pos_rows) * C + c;
+#pragma unroll
+      for (int k = 0; k < VN; ++k) f[k] += __ldg(pr + k);
+    }
+    gn_store<T>(y + row * C + c, f);
   }
 }
 
@@ -98,7 +136,7 @@ int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows,
                       cudaStream_t st) {
   const int slabs = cdiv(rows, GN_SLAB_ROWS);
   dim3 grid(slabs, N);
-  gn_partial_kernel<T><<<grid, 128, 2 * G * sizeof(float), st>>>(x, part_ws, rows, C, G, slabs);
+  gn_partial_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>(x, part_ws, rows, C, G, slabs);
   gn_finalize_kernel<<<N, 64, 0, st>>>(part_ws, stats, slabs, G, (double)rows * (C / G), eps);
   count_launch(2);
   IVG_LAUNCH_CHECK();
@@ -107,7 +145,8 @@ int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows,
 
 int gn_stats_launch(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G, float eps,
                     cudaStream_t st) {
-  IVG_CHECK(C % G == 0 && C % 2 == 0 && G <= 64, "groupnorm: bad C=%d G=%d", C, G);
+  IVG_CHECK(C % G == 0 && C % 8 == 0 && C / (dtype == DT_BF16 ? 8 : 4) <= 256 && G <= 64, "groupnorm: bad C=%d G=%d", C, G);
+  IVG_CHECK(((uintptr_t)x & 15) == 0, "groupnorm: x must be 16-byte aligned");
   if (N == 0) return 0;
   if (dtype == DT_BF16) return gn_stats_launch_t((const __nv_bfloat16*)x, part_ws, stats, N, rows, C, G, eps, st);
   return gn_stats_launch_t((const float*)x, part_ws, stats, N, rows, C, G, eps, st);
@@ -117,7 +156,7 @@ int gn_apply_launch(int dtype, const void* x, void* y, const float* stats, const
                     const float* pos, long long total_rows, int rows_per_sample, int C, int G, int silu, int pos_rows,
                     cudaStream_t st) {
   if (total_rows == 0) return 0;
-  long long work = total_rows * (C / 2);
+  long long work = total_rows * (C / (dtype == DT_BF16 ? 8 : 4));
   int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
   if (dtype == DT_BF16)
     gn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats, gamma,
@@ -252,12 +291,107 @@ __global__ void conv_out3_kernel(const T* __restrict__ x, const float* __restric
   }
 }
 
+// Tiled variant for C <= 128: a CTA owns an 8 x 16 output tile; the (8+2) x (16+2) halo is normalised + activated
+// ONCE into shared memory (fp32, [pixel][C]) instead of once per tap, then each warp produces output pixels with lanes
+// splitting the channels.  The first version re-read and re-normalised every input pixel 9 times from L1/L2.
+constexpr int CO3_TH = 8, CO3_TW = 16;
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_out3_tiled_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ w /*[3][9][C]*/,
+                       const float* __restrict__ b, float* __restrict__ y, int N, int H, int W, int C, int G, int fpc,
+                       int clipT, int foff) {
+  constexpr int VN = GnVec<T>::N;
+  extern __shared__ float co_sm[];
+  float* act = co_sm;                                   // [(TH+2)*(TW+2)][C]
+  float* ws = act + (CO3_TH + 2) * (CO3_TW + 2) * C;   // [27][C]
+  const int tiles_x = W / CO3_TW, tiles_y = H / CO3_TH;
+  const int tile = blockIdx.x;
+  const int n = tile / (tiles_x * tiles_y);
+  const int t2 = tile - n * tiles_x * tiles_y;
+  const int y0 = (t2 / tiles_x) * CO3_TH, x0 = (t2 % tiles_x) * CO3_TW;
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i] = w[i];
+  const int cvecs = C / VN;
+  const int halo = (CO3_TH + 2) * (CO3_TW + 2);
+  for (int i = threadIdx.x; i < halo * cvecs; i += blockDim.x) {
+    const int cv = i % cvecs, hp = i / cvecs;
+    const int hy = hp / (CO3_TW + 2), hx = hp % (CO3_TW + 2);
+    const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+    float f[VN];
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      gn_load<T>(x + (((size_t)n * H + yy) * W + xx) * C + cv * VN, f);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        const int c = cv * VN + k;
+        const float* st = stats + ((size_t)n * G + c / cpg) * 2;
+        f[k] = silu_f((f[k] - __ldg(st)) * __ldg(st + 1) * __ldg(gamma + c) + __ldg(beta + c));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VN; ++k) f[k] = 0.f;      // zero padding applies to the ACTIVATED tensor
+    }
+#pragma unroll
+    for (int k = 0; k < VN; ++k) act[(size_t)hp * C + cv * VN + k] = f[k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t plane = (size_t)H * W;
+  const size_t nf = (size_t)(n / fpc) * clipT + foff + (n % fpc);
+  for (int px = warp; px < CO3_TH * CO3_TW; px += 8) {
+    const int py = px / CO3_TW, pxx = px % CO3_TW;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(act + (size_t)((py + t / 3) * (CO3_TW + 2) + pxx + t % 3) * C + c);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (0 * 9 + t) * C + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (1 * 9 + t) * C + c);
+        const float4 w2 = *reinterpret_cast<const float4*>(ws + (2 * 9 + t) * C + c);
+        a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
+        a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
+        a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) {
+      float* dst = y + nf * 3 * plane + (size_t)(y0 + py) * W + x0 + pxx;
+      dst[0] = a0 + __ldg(b); dst[plane] = a1 + __ldg(b + 1); dst[2 * plane] = a2 + __ldg(b + 2);
+    }
+  }
+}
+
 int conv_out3_launch(int dtype, const void* x, const float* stats, const float* gamma, const float* beta,
                      const float* w, const float* b, float* y, int N, int H, int W, int C, int G, int fpc, int clipT,
                      int foff, cudaStream_t st) {
   IVG_CHECK(fpc > 0, "conv_out3: frames-per-clip must be positive");
   IVG_CHECK(C % 2 == 0 && C % G == 0, "conv_out3: bad C");
   if (N == 0) return 0;
+  if (C <= 128 && C % 4 == 0 && C % (dtype == DT_BF16 ? 8 : 4) == 0 && H % CO3_TH == 0 && W % CO3_TW == 0) {
+    const size_t tsm = (size_t)((CO3_TH + 2) * (CO3_TW + 2) * C + 27 * C) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      IVG_CUDA(cudaFuncSetAttribute(conv_out3_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      IVG_CUDA(cudaFuncSetAttribute(conv_out3_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_set = true;
+    }
+    const long long tiles = (long long)N * (H / CO3_TH) * (W / CO3_TW);
+    IVG_CHECK(tiles < 0x7fffffffLL && tsm <= 110 * 1024, "conv_out3: tile count / shared memory out of range");
+    if (dtype == DT_BF16)
+      conv_out3_tiled_kernel<__nv_bfloat16><<<(int)tiles, 256, tsm, st>>>((const __nv_bfloat16*)x, stats, gamma, beta, w, b,
+                                                                         y, N, H, W, C, G, fpc, clipT, foff);
+    else
+      conv_out3_tiled_kernel<float><<<(int)tiles, 256, tsm, st>>>((const float*)x, stats, gamma, beta, w, b, y, N, H, W, C, G,
+                                                                 fpc, clipT, foff);
+    count_launch();
+    IVG_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (size_t)29 * C * sizeof(float);
   long long pixels = (long long)N * H * W;
   int blocks = (int)((pixels + 7) / 8 < 148 * 8 ? (pixels + 7) / 8 : 148 * 8);

@@ -300,6 +300,10 @@ class LlamaEngine:
         d.dseed = dseed.data_ptr()
         d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
         d.layers_dev = dev_tab.data_ptr(); d.lm_head_map_dev = dev_tab.data_ptr() + w.layers_n * nbytes
+        if getattr(self, "mega_profile", False):
+            self.mega_prof = self.buf("mega_prof", (16,), torch.int64)
+            self.mega_prof.zero_()
+            d.prof = self.mega_prof.data_ptr()
         _lib.check(_lib.load().ivgpt_decode_mega(C.byref(d), torch.cuda.current_stream().cuda_stream), "decode_mega")
         return sync
 

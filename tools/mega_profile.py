@@ -1,0 +1,34 @@
+"""Phase breakdown of the persistent decode megakernel (cycle counters of CTA 0) + wall time vs the CUDA-graph path."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bench import build_b200_models
+
+dev = torch.device("cuda:0")
+B = int(os.environ.get("B", "64"))
+tok, llm, _, _ = build_b200_models("cfg64", dev, torch.bfloat16)
+eng = llm.b200_engine()
+ids = torch.randint(0, 16384, (B, 514), device=dev)
+new = 237
+res = {}
+for name, kw in (("graph", dict(use_mega=False)), ("mega", dict(use_mega=True))):
+    for _ in range(2):
+        eng.generate(ids, None, new, True, 100, 1.0, 1, **kw)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, **kw); b.record(); torch.cuda.synchronize()
+    res[name + "_generate_ms"] = a.elapsed_time(b)
+# prefill only
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); eng.generate(ids, None, 1, True, 100, 1.0, 1); b.record(); torch.cuda.synchronize()
+res["prefill_plus_first_token_ms"] = a.elapsed_time(b)
+eng.mega_profile = True
+eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
+torch.cuda.synchronize()
+cyc = eng.mega_prof.cpu().tolist()[:9]
+names = ["norm", "qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "sample", "barriers"]
+mhz = 1965.0
+res["mega_phase_ms_cta0"] = {n: c / (mhz * 1e3) for n, c in zip(names, cyc)}
+res["mega_phase_us_per_step"] = {n: c / (mhz) / (new - 1) for n, c in zip(names, cyc)}
+res["decode_steps"] = new - 1
+print(json.dumps(res))
