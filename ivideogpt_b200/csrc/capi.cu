@@ -384,9 +384,9 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   ivg::MegaParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.hidden = d->hidden; p.inter = d->inter; p.heads = d->heads; p.layers = d->layers; p.vocab = d->vocab;
-  p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps; p.o_splits = d->o_splits; p.d_splits = d->d_splits;
+  p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps;
   p.x = (float*)d->x; p.xn = (__nv_bfloat16*)d->xn; p.qkv = (__nv_bfloat16*)d->qkv; p.ao = (__nv_bfloat16*)d->ao;
-  p.act = (__nv_bfloat16*)d->act; p.part = (float*)d->part; p.logits = (float*)d->logits; p.ldl = d->ldl;
+  p.act = (__nv_bfloat16*)d->act; p.ssp = (float*)d->ssp; p.logits = (float*)d->logits; p.ldl = d->ldl;
   p.kcache = (__nv_bfloat16*)d->kcache; p.vcache = (__nv_bfloat16*)d->vcache;
   p.embed = d->embed; p.norm_f = d->norm_f; p.cos_tab = d->cos_tab; p.sin_tab = d->sin_tab;
   p.tokens = d->tokens; p.tok_stride = d->tok_stride; p.dpos = d->dpos;
