@@ -157,16 +157,16 @@ int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_c
                             int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
                             float scale, void* stream);
 /* ---- persistent decode megakernel (bf16): `steps` consecutive decode steps of HF generate in ONE cooperative launch
- * (embed -> layers x {qkv, RoPE+append+attention, o(+residual), gate/up+SwiGLU, down(+residual)} -> lm_head -> sample
- * -> append; RMSNorm is folded into the GEMM epilogues).
+ * (embed -> layers x {qkv, RoPE+append+attention, o, norm, gate/up+SwiGLU, down, norm} -> lm_head -> sample -> append).
  * Weight tensor maps live in a device array of ivgpt_mega_layer_bytes()-sized records filled on the host with
  * ivgpt_mega_fill_layer() (weights are the packed operands of the multi-kernel path: wqkv [3h,h], wo [h,h],
  * wgu [2*inter,h] gate/up interleaved, wd [h,inter]) and copied to the device by the caller; lm_head_map_dev is a
  * 128-byte CUtensorMap record filled with ivgpt_mega_fill_map().  barrier/error must be zero before each launch. */
 typedef struct ivgpt_mega_desc {
   int B, hidden, inter, heads, layers, vocab, Lmax, steps;
+  int o_splits, d_splits; /* split-K of o-proj / down-proj; part holds max(o,d) x B x hidden fp32 */
   float eps;
-  void *x, *xn, *qkv, *ao, *act, *ssp /* [hidden/16][B] fp32 */, *logits;
+  void *x, *xn, *qkv, *ao, *act, *part, *logits;
   long long ldl;
   void *kcache, *vcache;
   const float *embed, *norm_f, *cos_tab, *sin_tab;

@@ -53,9 +53,10 @@ class MegaDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
         ("vocab", C.c_int), ("Lmax", C.c_int), ("steps", C.c_int),
+        ("o_splits", C.c_int), ("d_splits", C.c_int),
         ("eps", C.c_float),
         ("x", C.c_void_p), ("xn", C.c_void_p), ("qkv", C.c_void_p), ("ao", C.c_void_p), ("act", C.c_void_p),
-        ("ssp", C.c_void_p), ("logits", C.c_void_p),
+        ("part", C.c_void_p), ("logits", C.c_void_p),
         ("ldl", C.c_longlong),
         ("kcache", C.c_void_p), ("vcache", C.c_void_p),
         ("embed", C.c_void_p), ("norm_f", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),

@@ -149,6 +149,10 @@ static int pick_bn(int N, long long tiles_m_times_batch) {
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   const int sms = num_sms();
+  // 256-wide tiles cut operand traffic per FLOP by 25 % (A 16 KB + B 32 KB per 128x256x64 MACs = 96 B/clk/SM instead
+  // of 128): the 128x128 kernel was measured L2->SM bound (tensor pipe 31-47 %, profiles/r01), so take them whenever
+  // they divide N and still leave >= 2 tiles per SM.
+  if (N % 256 == 0 && tiles_m_times_batch * (N / 256) >= 2LL * sms) return 256;
   const int cands[3] = {128, 64, 32};
   for (int i = 0; i < 3; ++i)
     if (tiles_m_times_batch * ((N + cands[i] - 1) / cands[i]) >= sms) return cands[i];
@@ -384,9 +388,9 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   ivg::MegaParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.hidden = d->hidden; p.inter = d->inter; p.heads = d->heads; p.layers = d->layers; p.vocab = d->vocab;
-  p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps;
+  p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps; p.o_splits = d->o_splits; p.d_splits = d->d_splits;
   p.x = (float*)d->x; p.xn = (__nv_bfloat16*)d->xn; p.qkv = (__nv_bfloat16*)d->qkv; p.ao = (__nv_bfloat16*)d->ao;
-  p.act = (__nv_bfloat16*)d->act; p.ssp = (float*)d->ssp; p.logits = (float*)d->logits; p.ldl = d->ldl;
+  p.act = (__nv_bfloat16*)d->act; p.part = (float*)d->part; p.logits = (float*)d->logits; p.ldl = d->ldl;
   p.kcache = (__nv_bfloat16*)d->kcache; p.vcache = (__nv_bfloat16*)d->vcache;
   p.embed = d->embed; p.norm_f = d->norm_f; p.cos_tab = d->cos_tab; p.sin_tab = d->sin_tab;
   p.tokens = d->tokens; p.tok_stride = d->tok_stride; p.dpos = d->dpos;

@@ -113,37 +113,29 @@ __device__ __forceinline__ void load_a(const MegaParams& p, MegaCtx& c, const __
   __syncthreads();
 }
 
-enum { EPI_STORE_BF16 = 0, EPI_RESID_NORM = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
+enum { EPI_STORE_BF16 = 0, EPI_PARTIAL_F32 = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
 
-// RMSNorm is folded into the GEMMs around it (v4): y = W . (w_n * x * r) with r = rsqrt(mean(x^2) + eps) a per-row
-// scalar, so the consumer GEMM multiplies its accumulator rows by r, and the producer GEMM (o-proj / down-proj, which
-// owns the final residual x in its epilogue) writes  x (fp32),  xt = bf16(x * w_n)  and one partial sum of squares per
-// 16-column tile; consumers add the tiles' partials in a fixed order.  This removes both add+norm phases and their
-// device-wide barriers from every layer (7 -> 5 barriers per layer) and needs no split-K partial buffers.
 struct GemmPhase {
   const CUtensorMap* map;   // weights [N, K]
-  int N, K, kchunks;        // work items = ceil(N/16); an item accumulates kchunks K-slabs of K/kchunks in TMEM
+  int N, K, ksplits;        // work items = ceil(N/16) * ksplits, item K = K / ksplits
   const __nv_bfloat16* A;
   long long lda;
   int epi;
   void* out;                // bf16 / fp32 destination
   long long ldo;
-  int rowscale;             // multiply accumulator rows by the RMSNorm factor derived from ssp
-  int nss;                  // number of sum-of-squares partials per row valid in p.ssp
-  const float* norm_w;      // EPI_RESID_NORM: weight of the NEXT RMSNorm
 };
 
-__device__ __forceinline__ int phase_items(const GemmPhase& g) { return (g.N + MEGA_BN - 1) / MEGA_BN; }
+__device__ __forceinline__ int phase_items(const GemmPhase& g) { return ((g.N + MEGA_BN - 1) / MEGA_BN) * g.ksplits; }
 
-// issue this CTA's slabs of phase g up to unit index `upto` (exclusive), in order; unit = item * kchunks + chunk
-__device__ __forceinline__ void issue_units(MegaCtx& c, const GemmPhase& g, int upto) {
+// issue this CTA's slabs of phase g up to item index `upto` (exclusive), in order
+__device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int upto) {
   const int items = phase_items(g);
-  const int Kc = g.K / g.kchunks;
+  const int ntiles = items / g.ksplits;
+  const int Kc = g.K / g.ksplits;
   while (c.phase_issued < upto) {
-    const int it = c.phase_issued / g.kchunks, ch = c.phase_issued - it * g.kchunks;
-    const int w = blockIdx.x + it * gridDim.x;
+    const int w = blockIdx.x + c.phase_issued * gridDim.x;
     if (w >= items) break;
-    issue_slab(c, g.map, w * MEGA_BN, ch * Kc, Kc);
+    issue_slab(c, g.map, (w % ntiles) * MEGA_BN, (w / ntiles) * Kc, Kc);
     ++c.phase_issued;
   }
 }
@@ -152,88 +144,64 @@ __device__ __forceinline__ void issue_units(MegaCtx& c, const GemmPhase& g, int 
 __device__ __forceinline__ void prefetch_phase(MegaCtx& c, const GemmPhase& g) {
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
-  issue_units(c, g, 1);
+  issue_items(c, g, 1);
 }
 
 __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
   const int items = phase_items(g);
-  const int Kc = g.K / g.kchunks;
+  const int ntiles = items / g.ksplits;
+  const int Kc = g.K / g.ksplits;
   const int nkb = Kc / 64;
   const int a_rows = p.B <= 64 ? 64 : 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t IDESC = umma_idesc(1, 128, MEGA_BN);
+  int loaded_split = -1;
   int it = 0;
-  bool a_loaded = false;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-    for (int ch = 0; ch < g.kchunks; ++ch) {
-      if (g.kchunks > 1 || !a_loaded) {     // (re)load the activation slab for this K range
-        load_a(p, c, g.A, g.lda, ch * Kc, Kc, a_rows);
-        a_loaded = true;
-      }
-      if (threadIdx.x == 0) {
-        issue_units(c, g, it * g.kchunks + ch + 2);   // this unit (if not prefetched) and the next one
-        const int buf = (int)(c.consumed & 1u);
-        const uint32_t par = (c.consumed >> 1) & 1u;
-        ++c.consumed;
-        mbar_wait(c.sm.bfull + buf, par);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b[buf]);
-        for (int j = 0; j < nkb; ++j) {
-          const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
-          const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * MEGA_BN * 128));
+    const int tile = w % ntiles, split = w / ntiles;
+    if (split != loaded_split) {          // (re)load the activation slab for this K range
+      load_a(p, c, g.A, g.lda, split * Kc, Kc, a_rows);
+      loaded_split = split;
+    }
+    if (threadIdx.x == 0) {
+      issue_items(c, g, it + 2);          // this item (if not prefetched) and the next one (other buffer)
+      const int buf = (int)(c.consumed & 1u);
+      const uint32_t par = (c.consumed >> 1) & 1u;
+      ++c.consumed;
+      mbar_wait(c.sm.bfull + buf, par);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b[buf]);
+      for (int j = 0; j < nkb; ++j) {
+        const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
+        const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * MEGA_BN * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss<false>(c.tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
-                           (ch | j | k) ? 1u : 0u);
-        }
-        umma_commit(c.sm.mma_done);
+        for (int k = 0; k < 4; ++k)
+          umma_ss<false>(c.tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (j | k) ? 1u : 0u);
       }
-      if (ch + 1 < g.kchunks) {             // A slab and weight buffer are reused by the next chunk: MMAs must retire
-        mbar_wait(c.sm.mma_done, c.mphase);
-        c.mphase ^= 1;
-        __syncthreads();
-      }
+      umma_commit(c.sm.mma_done);
     }
     // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3 ----
     if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      float rs = 1.0f;
-      if (g.rowscale && row < p.B) {        // RMSNorm factor of this row from the producers' partial sums (fixed order)
-        float ss = 0.f;
-        for (int t = 0; t < g.nss; ++t) ss += p.ssp[(size_t)t * p.B + row];
-        rs = rsqrtf(ss / (float)p.hidden + p.eps);
-      }
       mbar_wait(c.sm.mma_done, c.mphase);
       tc_fence_after();
       uint32_t r[16];
       tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16), r);
       tmem_ld_wait();
       if (row < p.B) {
-        const int n0 = w * MEGA_BN;
+        const int n0 = tile * MEGA_BN;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * rs;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         if (g.epi == EPI_STORE_BF16) {
           uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + n0);
           op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        } else if (g.epi == EPI_RESID_NORM) {
-          float4* xp = reinterpret_cast<float4*>(p.x + (size_t)row * p.hidden + n0);
-          float ss = 0.f;
+        } else if (g.epi == EPI_PARTIAL_F32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ((size_t)split * p.B + row) * g.ldo + n0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 xv = xp[i];
-            xv.x += v[4 * i]; xv.y += v[4 * i + 1]; xv.z += v[4 * i + 2]; xv.w += v[4 * i + 3];
-            xp[i] = xv;
-            ss = fmaf(xv.x, xv.x, ss); ss = fmaf(xv.y, xv.y, ss); ss = fmaf(xv.z, xv.z, ss); ss = fmaf(xv.w, xv.w, ss);
-            const float4 gw = __ldg(reinterpret_cast<const float4*>(g.norm_w + n0) + i);
-            v[4 * i] = xv.x * gw.x; v[4 * i + 1] = xv.y * gw.y; v[4 * i + 2] = xv.z * gw.z; v[4 * i + 3] = xv.w * gw.w;
-          }
-          p.ssp[(size_t)w * p.B + row] = ss;
-          uint4* op = reinterpret_cast<uint4*>(p.xn + (size_t)row * p.hidden + n0);
-          op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else if (g.epi == EPI_SWIGLU) {
           uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + (n0 >> 1));
           float o[8];
@@ -248,40 +216,55 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
       }
       tc_fence_before();
     }
-    c.mphase ^= 1;          // every thread tracks the parity
-    __syncthreads();        // MMA retired (epilogue observed mma_done): TMEM accumulator, A slab, weight buffer reusable
+    c.mphase ^= 1;          // every thread tracks the parity (only warps 4..7 wait on it)
+    __syncthreads();        // MMA retired (epilogue observed mma_done): TMEM accumulator, A slab and this weight
+                            // buffer may be reused
   }
 }
 
-// ---- step start: x = E[token];  xt = bf16(x * w_n1[layer 0]);  ssp[0][m] = sum(x^2)  (one row per CTA) ----
-__device__ void embed_phase(const MegaParams& p, const float* w, int tok_col) {
+// ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
+// One row per CTA, one float4 per thread (hidden <= 1024): every load of the row is in flight at once.
+__device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col) {
   __shared__ float s_ss[MEGA_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.hidden;
   const int i = threadIdx.x * 4;
   for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
-    long long id = p.tokens[(size_t)m * p.tok_stride + tok_col];
-    id = id < 0 ? 0 : (id >= p.vocab ? p.vocab - 1 : id);
+    float* xr = p.x + (size_t)m * H;
+    const float* src = xr;
+    if (tok_row0) {
+      long long id = tok_row0[(size_t)m * p.tok_stride + tok_col];
+      id = id < 0 ? 0 : (id >= p.vocab ? p.vocab - 1 : id);
+      src = p.embed + (size_t)id * H;
+    }
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     float ss = 0.f;
     if (i < H) {
-      v = __ldg(reinterpret_cast<const float4*>(p.embed + (size_t)id * H + i));
-      *reinterpret_cast<float4*>(p.x + (size_t)m * H + i) = v;
+      v = *reinterpret_cast<const float4*>(src + i);
+      float4 q[MEGA_MAX_SPLITS];
+#pragma unroll
+      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+        if (s < nparts) q[s] = *reinterpret_cast<const float4*>(p.part + ((size_t)s * p.B + m) * H + i);
+#pragma unroll
+      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+        if (s < nparts) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }   // fixed order: reproducible
+      *reinterpret_cast<float4*>(xr + i) = v;
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
-      uint2 o;
-      o.x = pack_bf16x2(g.x * v.x, g.y * v.y);
-      o.y = pack_bf16x2(g.z * v.z, g.w * v.w);
-      *reinterpret_cast<uint2*>(p.xn + (size_t)m * H + i) = o;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
     if (lane == 0) s_ss[warp] = ss;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int k = 0; k < MEGA_THREADS / 32; ++k) tot += s_ss[k];
-      p.ssp[m] = tot;
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MEGA_THREADS / 32; ++k) tot += s_ss[k];
+    const float r = rsqrtf(tot / (float)H + p.eps);
+    if (i < H) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
+      uint2 o;
+      o.x = pack_bf16x2(g.x * (v.x * r), g.y * (v.y * r));
+      o.y = pack_bf16x2(g.z * (v.z * r), g.w * (v.w * r));
+      *reinterpret_cast<uint2*>(p.xn + (size_t)m * H + i) = o;
     }
     __syncthreads();
   }
@@ -389,188 +372,6 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
       for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
       if (lane == r) p.ao[(size_t)b * Hd + hh * 64 + d0 + r] = __float2bfloat16_rn(a * inv);
     }
-  }
-  __syncwarp();
-}
-
-// ---- v5: warp-per-item attention with a cp.async ring -------------------------------------------------------------
-// Every earlier variant (CTA per item, warp per item with 16 register-staged loads, warp pairs, L2-only loads) measured
-// the same ~53 us per layer = 2.3 TB/s: a warp ran ~22 dependent load->compute batches of ~2.4 us each.  Registers
-// cannot hold more than one batch, so the ring lives in shared memory: each lane copies 16-byte pieces with
-// cp.async.cg into its own slice of a 4-slot ring and reads back only its own pieces (a per-lane FIFO: no cross-lane
-// hazards, no barriers), keeping 3 batches (9 KB per warp, ~54 KB per SM) in flight while it computes on the fourth.
-constexpr int ATA_SLOTS = 4;
-constexpr int ATA_KROWS = 24;                 // K rows per slot (6 passes x 4 rows)  -> 3 KB
-constexpr int ATA_VPCS = 6;                   // V^T 16-byte pieces per lane per slot   -> 3 KB
-constexpr int ATA_SLOT_BYTES = ATA_KROWS * 128;
-constexpr int ATA_WARP_FLOATS = (ATA_SLOTS * ATA_SLOT_BYTES) / 4;   // ring, followed by sc[Lmax + 8] and q[64]
-
-__device__ void attention_warp_async(const MegaParams& p, int layer, int bh, int pos, float* wsm) {
-  const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
-  const int Lcur = pos + 1;
-  uint8_t* ring = reinterpret_cast<uint8_t*>(wsm);
-  float* sc = wsm + ATA_WARP_FLOATS;            // [Lmax + 8]
-  float* qs = sc + Lmax + 8;                    // [64]
-  const int b = bh / heads, hh = bh - b * heads;
-  const int lane = threadIdx.x & 31;
-  __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
-  __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
-  {
-    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
-    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
-    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
-    qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
-    qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
-    kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
-    kslab[(size_t)pos * 64 + lane + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
-    vslab[(size_t)lane * Lmax + pos] = v0;
-    vslab[(size_t)(lane + 32) * Lmax + pos] = v1;
-  }
-  __syncwarp();       // this warp's K/V stores are ordered before its cp.async reads of the same addresses
-  const int sub = lane & 7, rslot = lane >> 3;
-  float qreg[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qreg[i] = qs[sub * 8 + i];
-
-  // ---------------- scores ----------------
-  const int nkb = (Lcur + ATA_KROWS - 1) / ATA_KROWS;
-  auto issue_k = [&](int bi) {
-    if (bi < nkb) {
-      uint8_t* slot = ring + (bi % ATA_SLOTS) * ATA_SLOT_BYTES;
-#pragma unroll
-      for (int u = 0; u < ATA_KROWS / 4; ++u) {
-        const int l = bi * ATA_KROWS + u * 4 + rslot;
-        if (l < Lcur) cp_async16(slot + (u * 4 + rslot) * 128 + sub * 16, kslab + (size_t)l * 64 + sub * 8);
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int i = 0; i < ATA_SLOTS - 1; ++i) issue_k(i);
-  float mx = -INFINITY;
-  for (int bi = 0; bi < nkb; ++bi) {
-    cp_async_wait<ATA_SLOTS - 2>();
-    const uint8_t* slot = ring + (bi % ATA_SLOTS) * ATA_SLOT_BYTES;
-#pragma unroll
-    for (int u = 0; u < ATA_KROWS / 4; ++u) {
-      const int l = bi * ATA_KROWS + u * 4 + rslot;
-      float part = 0.f;
-      if (l < Lcur) {
-        const uint4 kv = *reinterpret_cast<const uint4*>(slot + (u * 4 + rslot) * 128 + sub * 16);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h2[i]);
-          part = fmaf(qreg[2 * i], f.x, part);
-          part = fmaf(qreg[2 * i + 1], f.y, part);
-        }
-      }
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (l < Lcur) {
-        mx = fmaxf(mx, part);
-        if (sub == 0) sc[l] = part;
-      }
-    }
-    issue_k(bi + ATA_SLOTS - 1);            // refills the slot this lane finished reading one iteration ago
-  }
-  cp_async_wait<0>();
-
-  // ---------------- V^T pipeline set-up (independent of the scores: start it before the softmax) ----------------
-  // piece index q (per lane) -> (group g of 16 output dims, row r in group, chunk c of 256 positions)
-  const int nchunks = (Lcur + 255) / 256;
-  const int ppg = 16 * nchunks;                                   // pieces per lane per group
-  const int npieces = 4 * ppg;
-  const int nvb = (npieces + ATA_VPCS - 1) / ATA_VPCS;
-  auto issue_v = [&](int bi) {
-    if (bi < nvb) {
-      uint8_t* slot = ring + (bi % ATA_SLOTS) * ATA_SLOT_BYTES + lane * (ATA_VPCS * 16);
-#pragma unroll
-      for (int u = 0; u < ATA_VPCS; ++u) {
-        const int q = bi * ATA_VPCS + u;
-        if (q < npieces) {
-          const int g = q / ppg, rem = q - g * ppg;
-          const int r = rem / nchunks, cch = rem - r * nchunks;
-          const int l = cch * 256 + lane * 8;
-          if (l < Lcur) cp_async16(slot + u * 16, vslab + (size_t)(g * 16 + r) * Lmax + l);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int i = 0; i < ATA_SLOTS - 1; ++i) issue_v(i);
-
-  // ---------------- softmax ----------------
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  __syncwarp();
-  float sum = 0.f;
-  for (int l = lane; l < Lcur + 8; l += 32) {
-    const float e = l < Lcur ? __expf(sc[l] - mx) : 0.f;
-    sc[l] = e;
-    sum += e;
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float inv = 1.0f / sum;
-  __syncwarp();
-
-  // ---------------- P . V ----------------
-  float acc[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-  int cur_g = 0;
-  for (int bi = 0; bi < nvb; ++bi) {
-    cp_async_wait<ATA_SLOTS - 2>();
-    const uint8_t* slot = ring + (bi % ATA_SLOTS) * ATA_SLOT_BYTES + lane * (ATA_VPCS * 16);
-#pragma unroll
-    for (int u = 0; u < ATA_VPCS; ++u) {
-      const int q = bi * ATA_VPCS + u;
-      if (q < npieces) {
-        const int g = q / ppg, rem = q - g * ppg;
-        const int r = rem / nchunks, cch = rem - r * nchunks;
-        if (g != cur_g) {                     // group finished: reduce its 16 accumulators across lanes and store
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) {
-            float a = acc[rr];
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-            if (lane == rr) p.ao[(size_t)b * Hd + hh * 64 + cur_g * 16 + rr] = __float2bfloat16_rn(a * inv);
-            acc[rr] = 0.f;
-          }
-          cur_g = g;
-        }
-        const int l = cch * 256 + lane * 8;
-        if (l < Lcur) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(slot + u * 16);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
-          const int nvalid = Lcur - l;         // cache beyond Lcur is uninitialised: select, never multiply
-          float a = 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h2[i]);
-            a += (2 * i < nvalid) ? sc[l + 2 * i] * f.x : 0.f;
-            a += (2 * i + 1 < nvalid) ? sc[l + 2 * i + 1] * f.y : 0.f;
-          }
-          // acc[r] += a with a compile-time-indexable register array
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) acc[rr] += (rr == r) ? a : 0.f;
-        }
-      }
-    }
-    issue_v(bi + ATA_SLOTS - 1);
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int rr = 0; rr < 16; ++rr) {
-    float a = acc[rr];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if (lane == rr) p.ao[(size_t)b * Hd + hh * 64 + cur_g * 16 + rr] = __float2bfloat16_rn(a * inv);
   }
   __syncwarp();
 }
@@ -866,28 +667,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 #define MEGA_MARK(slot) do { if (profiling) { const long long _t = clock64(); tprof[slot] += _t - tmark; tmark = _t; } } while (0)
 #define MEGA_BARRIER() do { ok = grid_barrier(p, c); MEGA_MARK(8); } while (0)
 
-  const int NT = H / MEGA_BN;                       // tiles (= sum-of-squares partials) of a hidden-wide GEMM
-  const int dchunks = (p.inter + MEGA_MAXK - 1) / MEGA_MAXK;
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
-    GemmPhase qkv_g{&p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H, 1, 1, nullptr};
+    GemmPhase qkv_g{&p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H};
     prefetch_phase(c, qkv_g);
-    embed_phase(p, p.lw[0].n1, pos);
+    norm_phase(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
     MEGA_BARRIER(); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
-      const bool last = (l == p.layers - 1);
       qkv_g.map = &L.wqkv;
-      qkv_g.nss = (l == 0) ? 1 : NT;
       gemm_phase(p, c, qkv_g);
       MEGA_MARK(1);
-      GemmPhase o_g{&L.wo, H, H, 1, p.ao, H, EPI_RESID_NORM, nullptr, 0, 0, 0, L.n2};
+      GemmPhase o_g{&L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, o_g);
       MEGA_BARRIER(); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
         for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
-          attention_warp_async(p, l, bh, pos, smem_f + (size_t)warp * (ATA_WARP_FLOATS + p.Lmax + 8 + 64));
+          attention_warp(p, l, bh, pos, smem_f + (size_t)warp * (p.Lmax + 8 + 64));
       } else {
         const int pair = warp >> 1, half = warp & 1, npairs = MEGA_THREADS / 64;
         float* psm = smem_f + (size_t)pair * (p.Lmax + 16 + 64 + 2 * 66);
@@ -896,26 +693,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       MEGA_MARK(2);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase(p, c, o_g);                                             // x += attn.Wo^T ; xt, ssp for norm2
+      gemm_phase(p, c, o_g);
       MEGA_MARK(3);
-      GemmPhase gu_g{&L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter, 1, NT, nullptr};
+      GemmPhase gu_g{&L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
       prefetch_phase(c, gu_g);
+      MEGA_BARRIER(); if (!ok) break;
+      norm_phase(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
+      MEGA_MARK(0);
       MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, gu_g);
       MEGA_MARK(4);
-      GemmPhase d_g{&L.wd, H, p.inter, dchunks, p.act, p.inter, EPI_RESID_NORM, nullptr, 0, 0, 0,
-                    last ? p.norm_f : p.lw[l + 1].n1};
+      GemmPhase d_g{&L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, d_g);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase(p, c, d_g);                                             // x += act.Wd^T ; xt, ssp for the next norm
+      gemm_phase(p, c, d_g);
       MEGA_MARK(5);
+      const bool last = (l == p.layers - 1);
       GemmPhase nx_g{last ? p.lm_head : &p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, 1, p.xn, H,
                      last ? EPI_LOGITS : EPI_STORE_BF16, last ? (void*)p.logits : (void*)p.qkv,
-                     last ? p.ldl : (long long)(3 * H), 1, NT, nullptr};
+                     last ? p.ldl : (long long)(3 * H)};
       prefetch_phase(c, nx_g);
       MEGA_BARRIER(); if (!ok) break;
+      norm_phase(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
+      MEGA_MARK(0);
+      MEGA_BARRIER(); if (!ok) break;
       if (last) {
-        gemm_phase(p, c, nx_g);                                          // lm_head
+        gemm_phase(p, c, nx_g);                                       // lm_head
         MEGA_MARK(6);
         MEGA_BARRIER(); if (!ok) break;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) sample_row(p, b, pos, smem_u);
@@ -934,17 +737,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
   IVG_CHECK(p.B >= 1 && p.B <= 128, "decode_mega: batch %d not in [1,128]", p.B);
   IVG_CHECK(p.hidden % 64 == 0 && p.hidden <= MEGA_MAXK, "decode_mega: hidden %d unsupported", p.hidden);
-  IVG_CHECK(p.inter % 64 == 0 && p.inter % ((p.inter + MEGA_MAXK - 1) / MEGA_MAXK) == 0 &&
-                (p.inter / ((p.inter + MEGA_MAXK - 1) / MEGA_MAXK)) % 64 == 0,
-            "decode_mega: intermediate size %d is not a whole number of 64-aligned K chunks <= %d", p.inter, MEGA_MAXK);
-  IVG_CHECK(p.hidden % MEGA_BN == 0, "decode_mega: hidden %% 16 != 0");
+  IVG_CHECK(p.o_splits >= 1 && p.o_splits <= MEGA_MAX_SPLITS && p.hidden % (64 * p.o_splits) == 0,
+            "decode_mega: bad o_splits %d for hidden %d", p.o_splits, p.hidden);
+  IVG_CHECK(p.d_splits >= 1 && p.d_splits <= MEGA_MAX_SPLITS && p.inter % (64 * p.d_splits) == 0 &&
+                p.inter / p.d_splits <= MEGA_MAXK,
+            "decode_mega: bad d_splits %d for intermediate size %d", p.d_splits, p.inter);
   IVG_CHECK(p.hidden == p.heads * 64, "decode_mega: head_dim must be 64");
   const int a_rows = p.B <= 64 ? 64 : 128;
-  IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES &&
-                (long long)a_rows * (p.inter / ((p.inter + MEGA_MAXK - 1) / MEGA_MAXK)) * 2 <= MEGA_A_BYTES,
+  IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
             "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
   IVG_CHECK((size_t)(p.Lmax + 16 + 64 + 2 * 66) * 4 * (MEGA_THREADS / 64) <= MEGA_A_BYTES &&
-                (size_t)(ATA_WARP_FLOATS + p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_A_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
+                (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_A_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
   static bool attr_set = false;

@@ -4,7 +4,7 @@
 
 namespace ivg {
 
-constexpr int MEGA_THREADS = 256;   // 256: one warp per attention item; 512: warp pairs (measured slower, kept for reference)
+constexpr int MEGA_THREADS = 256;   // 256: one warp per attention item (fastest measured); 512: warp pairs
 constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
@@ -20,13 +20,14 @@ struct MegaLayer {
 
 struct MegaParams {
   int B, hidden, inter, heads, layers, vocab, Lmax, steps;
+  int o_splits, d_splits;   // split-K factors of the o-proj (K = hidden) and down-proj (K = inter) phases
   float eps;
   float* x;                 // [B, hidden] fp32 residual stream
-  __nv_bfloat16* xn;        // [B, hidden]  xt = bf16(x * w_norm) -- the UNNORMALISED, weighted A operand
+  __nv_bfloat16* xn;        // [B, hidden]
   __nv_bfloat16* qkv;       // [B, 3*hidden]
   __nv_bfloat16* ao;        // [B, hidden]
   __nv_bfloat16* act;       // [B, inter]
-  float* ssp;               // [hidden/16][B] per-tile partial sums of squares of the residual stream (RMSNorm)
+  float* part;              // [max(o_splits, d_splits)][B][hidden]
   float* logits;            // [B, ldl]
   long long ldl;
   __nv_bfloat16* kcache;    // [layers][B][heads][Lmax][64]

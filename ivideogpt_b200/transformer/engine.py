@@ -223,14 +223,24 @@ class LlamaEngine:
     # ---- persistent decode megakernel (bf16, B <= 64 with these widths) --------------------------------------
     def mega_supported(self, B: int, Lmax: int) -> bool:
         w = self.w
-        if self.dtype != torch.bfloat16 or B < 1 or B > 128:
+        if self.dtype != torch.bfloat16 or B < 1:
             return False
         a_rows = 64 if B <= 64 else 128
-        chunks = (w.inter + 1023) // 1024
-        if w.inter % chunks or (w.inter // chunks) % 64 or w.hidden % 64 or w.hidden > 1024:
+        if B > 128:
             return False
-        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // chunks) * 2 <= 128 * 1024
-                and (w.vocab + 256) * 4 <= 128 * 1024 and (3072 + Lmax + 72) * 4 * 8 <= 128 * 1024)
+        o_s, d_s = self._mega_splits()
+        if o_s is None:
+            return False
+        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024
+                and (w.vocab + 256) * 4 <= 128 * 1024 and (Lmax + 88) * 4 <= 128 * 1024)
+
+    def _mega_splits(self):
+        w = self.w
+        o_s = next((s for s in (3, 2, 4, 1) if w.hidden % (64 * s) == 0), None)
+        d_s = next((s for s in range(1, 9) if w.inter % (64 * s) == 0 and w.inter // s <= 1024), None)
+        if o_s is None or d_s is None:
+            return None, None
+        return o_s, d_s
 
     def _mega_tables(self):
         """Device-resident array of per-layer weight tensor maps (+ the lm_head map), built once per engine."""
@@ -263,19 +273,21 @@ class LlamaEngine:
         w = self.w
         h = w.hidden
         dev_tab, nbytes = self._mega_tables()
+        o_s, d_s = self._mega_splits()
         kc, vc = self.kv_cache(B, Lmax)
         logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
         sync = self.buf("mega_sync", (2,), torch.int32)
         sync.zero_()
         d = _lib.MegaDesc()
         d.B, d.hidden, d.inter, d.heads, d.layers, d.vocab, d.Lmax, d.steps = B, h, w.inter, w.heads, w.layers_n, w.vocab, Lmax, steps
+        d.o_splits, d.d_splits = o_s, d_s
         d.eps = w.eps
         d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
         d.xn = self.buf("xnd", (B, h), self.dtype).data_ptr()
         d.qkv = self.buf("qkvd", (B, 3 * h), self.dtype).data_ptr()
         d.ao = self.buf("aod", (B, h), self.dtype).data_ptr()
         d.act = self.buf("actd", (B, w.inter), self.dtype).data_ptr()
-        d.ssp = self.buf("mega_ssp", (h // 16, B), torch.float32).data_ptr()
+        d.part = self.buf("mega_part", (max(o_s, d_s), B, h), torch.float32).data_ptr()
         d.logits = logits.data_ptr(); d.ldl = logits.stride(0)
         d.kcache = kc.data_ptr(); d.vcache = vc.data_ptr()
         d.embed = w.embed.data_ptr(); d.norm_f = w.norm.data_ptr(); d.cos_tab = w.cos.data_ptr(); d.sin_tab = w.sin.data_ptr()
