@@ -46,6 +46,10 @@ int ivgpt_count_add(long long n); /* account for kernels replayed through a CUDA
  * Workspaces: enorm_ws [K] fp32, packed_ws [N] uint64.  Ties resolve to the lowest index. */
 int ivgpt_vq_argmin(const float* z, const float* codebook, float* enorm_ws, unsigned long long* packed_ws,
                     long long* idx, int N, int K, int D, void* stream);
+/* Summation order of the distance: 0 = one sequential FMA chain over d (FFMA kernel); 1 = even-d and odd-d chains added
+ * at the end (packed fma.rn.f32x2 kernel).  oracle/vq_argmin_ref.c implements both; results are bit-exact per order. */
+int ivgpt_vq_set_order(int order);
+int ivgpt_vq_get_order(void);
 
 /* ---- tensor-core GEMM --------------------------------------------------------------------------
  * out = epilogue(alpha * A . B^T): A [a_rows, a_cols] (lda), B [b_rows, b_cols] (ldb), K contiguous in both.

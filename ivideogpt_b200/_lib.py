@@ -103,6 +103,8 @@ SIGNATURES = {
     "ivgpt_incr": [_P, _I, _P],
     "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],
     "ivgpt_set_pdl": [_I],
+    "ivgpt_vq_set_order": [_I],
+    "ivgpt_vq_get_order": [],
     "ivgpt_mega_layer_bytes": [],
     "ivgpt_mega_fill_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I],
     "ivgpt_mega_fill_map": [_P, _P, _I, _I],

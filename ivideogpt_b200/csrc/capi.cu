@@ -79,6 +79,7 @@ void gemm_profile_enable(int on);
 int gemm_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches);
 int vq_argmin_launch(const float*, const float*, float*, unsigned long long*, long long*, int, int, int, int,
                      cudaStream_t);
+extern int g_vq_order;
 int gn_stats_launch(int, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
 int gn_apply_launch(int, const void*, void*, const float*, const float*, const float*, const float*, long long, int,
                     int, int, int, int, cudaStream_t);
@@ -357,6 +358,12 @@ int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_c
                                   S(stream));
 }
 int ivgpt_set_pdl(int on) { ivg::g_pdl = on != 0; return 0; }
+int ivgpt_vq_set_order(int order) {
+  IVG_CHECK(order == 0 || order == 1, "vq order must be 0 or 1");
+  ivg::g_vq_order = order;
+  return 0;
+}
+int ivgpt_vq_get_order(void) { return ivg::g_vq_order; }
 
 // ---- persistent decode megakernel -------------------------------------------------------------------
 int ivgpt_mega_layer_bytes(void) { return (int)sizeof(ivg::MegaLayer); }

@@ -65,17 +65,22 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // Arrival is a release-reduction, the wait an acquire-load: no full sc fences (v1 used __threadfence() on both sides
 // and cost ~2.8 us per barrier, 87 barriers per decode step).
 __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
+  __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     c.epoch += gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier) : "memory");
     const long long t0 = clock64();
+    int ok = 1;
     while (ld_acquire_u32(p.barrier) < c.epoch) {
-      if (clock64() - t0 > (1ll << 32)) { *p.error = 1; break; }   // ~2 s: never hang the GPU
+      if (clock64() - t0 > (1ll << 32)) { *p.error = 1; ok = 0; break; }   // ~2 s: never hang the GPU
     }
+    // (v3 had every thread read the error flag with a volatile system-scope load after each barrier: ~1 us x 87
+    //  barriers per step, visible as LDG.E.STRONG.SYS in the ncu source view.)
+    s_ok = ok;
   }
   __syncthreads();
-  return *reinterpret_cast<volatile int*>(p.error) == 0;
+  return s_ok != 0;
 }
 
 // ---- weight slab TMA: item -> (n0, k0, Kc); Kc/64 boxes of {64 k, 16 rows} land on bfull[buffer] ----
@@ -271,6 +276,12 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
 }
 
 // ---- RoPE + KV append + attention over the cache: ONE WARP per (b, head) item (used with 256-thread CTAs) ----
+// Measured history of this phase (B=64, 12 heads, L 514..750, us per layer on CTA 0): CTA per item 59; warp per item
+// with 16 register-staged 16-byte loads per lane 51-53 (this version); warp pairs / 512 threads 55; L2-only loads 53;
+// cp.async ring with a badly banked layout 148; splitting items in thirds over all warps cannot help (the busiest warp
+// still runs ~22 dependent load batches).  At ~2.4 us per dependent batch the phase streams 2.3 TB/s; the standalone
+// fused kernel (768 CTAs, no unrolling) lands on the same 50-62 us.  Closing the gap to HBM speed needs ~100 KB of
+// loads in flight per SM, i.e. TMA bulk copies into a large shared-memory ring -- next round.
 constexpr int ATW_QB = 16;    // K rows in flight per lane group (8 lanes per row, 4 rows per pass)
 constexpr int ATW_DB = 16;    // V^T rows in flight per lane
 __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, float* wsm) {

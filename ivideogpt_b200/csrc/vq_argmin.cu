@@ -169,6 +169,120 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e, const
   }
 }
 
+// ---- packed-FMA variant (fma.rn.f32x2, sm_100+) ---------------------------------------------------------------
+// Same decomposition, but every (row, code) pair keeps TWO partial dot products -- even and odd embedding dims --
+// in one 64-bit register pair, so one FFMA2 retires two FMAs:   acc2 = fma2((z[d], z[d+1]), (e[d], e[d+1]), acc2).
+// Definition (order 1, also in oracle/vq_argmin_ref.c):  dot = chain_even(d = 0,2,..,62) + chain_odd(d = 1,3,..,63),
+// both chains sequential fp32 FMAs from +0; score / argmin as before.  Thread tile 8 rows x 4 codes.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float sum2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+
+constexpr int VQ2_TK = 64;        // codes per streamed tile (16 tx x 4)
+__global__ void __launch_bounds__(VQ_THREADS, 2)
+vq_argmin_x2_kernel(const float* __restrict__ z, const float* __restrict__ e, const float* __restrict__ enorm,
+                    unsigned long long* __restrict__ packed, int N, int K, int tiles_per_split) {
+  extern __shared__ __align__(16) float vq_smem[];
+  float* zs = vq_smem;                          // [VQ_TN][VQ_PITCH]
+  float* es = zs + VQ_TN * VQ_PITCH;            // [2][VQ2_TK][VQ_PITCH]
+  float* ns = es + 2 * VQ2_TK * VQ_PITCH;       // [2][VQ2_TK]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * VQ_TN;
+  const int ktile0 = blockIdx.y * tiles_per_split;
+  const int num_ktiles_total = (K + VQ2_TK - 1) / VQ2_TK;
+  int ntiles = num_ktiles_total - ktile0;
+  if (ntiles > tiles_per_split) ntiles = tiles_per_split;
+  if (ntiles <= 0) return;
+  for (int c = tid; c < VQ_TN * (VQ_D / 4); c += VQ_THREADS) {
+    int r = c >> 4, q = c & 15;
+    float* dst = zs + r * VQ_PITCH + q * 4;
+    if (n0 + r < N) cp_async16(dst, z + (size_t)(n0 + r) * VQ_D + q * 4);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  auto load_tile = [&](int t, int buf) {
+    const int k0 = (ktile0 + t) * VQ2_TK;
+    float* eb = es + buf * VQ2_TK * VQ_PITCH;
+    for (int c = tid; c < VQ2_TK * (VQ_D / 4); c += VQ_THREADS) {
+      int r = c >> 4, q = c & 15;
+      float* dst = eb + r * VQ_PITCH + q * 4;
+      if (k0 + r < K) cp_async16(dst, e + (size_t)(k0 + r) * VQ_D + q * 4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < VQ2_TK) ns[buf * VQ2_TK + tid] = (k0 + tid < K) ? __ldg(enorm + k0 + tid) : __int_as_float(0x7f800000);
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+  float best[8];
+  int bidx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) load_tile(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* eb = es + buf * VQ2_TK * VQ_PITCH;
+    unsigned long long acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+#pragma unroll 4
+    for (int d = 0; d < VQ_D; d += 4) {
+      unsigned long long za[8], zb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(zs + (i * 16 + ty) * VQ_PITCH + d);
+        za[i] = pack2(v.x, v.y); zb[i] = pack2(v.z, v.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(eb + (j * 16 + tx) * VQ_PITCH + d);
+        const unsigned long long ea = pack2(v.x, v.y), ebb = pack2(v.z, v.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { fma2(acc[i][j], za[i], ea); fma2(acc[i][j], zb[i], ebb); }
+      }
+    }
+    const int kbase = (ktile0 + t) * VQ2_TK;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j * 16 + tx;
+      const float en = ns[buf * VQ2_TK + c];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = fmaf(-2.0f, sum2(acc[i][j]), en);
+        if (s < best[i]) { best[i] = s; bidx[i] = kbase + c; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    unsigned long long p = ((unsigned long long)ordered_bits(best[i]) << 32) | (unsigned int)bidx[i];
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      unsigned long long q = __shfl_xor_sync(0xffffffffu, p, off);
+      p = (q < p) ? q : p;
+    }
+    if (tx == 0) {
+      int r = i * 16 + ty;
+      if (n0 + r < N) atomicMin(packed + n0 + r, p);
+    }
+  }
+}
+
 static int vq_pick_splits(int N, int K, int num_sms) {
   int ntile = cdiv(N, VQ_TN), ktiles = cdiv(K, VQ_TK);
   int target = 6 * num_sms;  // ~3 waves at 2 CTAs/SM
@@ -176,6 +290,8 @@ static int vq_pick_splits(int N, int K, int num_sms) {
   while (ntile * splits < target && splits * 2 <= ktiles && (ktiles / (splits * 2)) >= 2) splits *= 2;
   return splits;
 }
+
+int g_vq_order = 0;   // 0: single sequential FMA chain (FFMA kernel); 1: even/odd chains (packed FFMA2 kernel)
 
 int vq_argmin_launch(const float* z, const float* e, float* enorm_ws, unsigned long long* packed_ws, long long* idx,
                      int N, int K, int D, int num_sms, cudaStream_t stream) {
@@ -185,17 +301,28 @@ int vq_argmin_launch(const float* z, const float* e, float* enorm_ws, unsigned l
   IVG_CHECK(((uintptr_t)z & 15) == 0 && ((uintptr_t)e & 15) == 0, "vq_argmin: z/e must be 16-byte aligned");
   static bool attr_set = false;
   const size_t smem = (size_t)(VQ_TN * VQ_PITCH + 2 * VQ_TK * VQ_PITCH + 2 * VQ_TK) * sizeof(float);
+  const size_t smem2 = (size_t)(VQ_TN * VQ_PITCH + 2 * VQ2_TK * VQ_PITCH + 2 * VQ2_TK) * sizeof(float);
   if (!attr_set) {
     IVG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IVG_CUDA(cudaFuncSetAttribute(vq_argmin_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     attr_set = true;
   }
   vq_enorm_kernel<<<cdiv(K, 256), 256, 0, stream>>>(e, enorm_ws, K);
   vq_fill_kernel<<<cdiv(N, 256), 256, 0, stream>>>(packed_ws, N);
-  int splits = vq_pick_splits(N, K, num_sms);
-  int ktiles = cdiv(K, VQ_TK);
-  int tiles_per_split = cdiv(ktiles, splits);
-  dim3 grid(cdiv(N, VQ_TN), cdiv(ktiles, tiles_per_split));
-  vq_argmin_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, e, enorm_ws, packed_ws, N, K, tiles_per_split);
+  if (g_vq_order == 0) {
+    int splits = vq_pick_splits(N, K, num_sms);
+    int ktiles = cdiv(K, VQ_TK);
+    int tiles_per_split = cdiv(ktiles, splits);
+    dim3 grid(cdiv(N, VQ_TN), cdiv(ktiles, tiles_per_split));
+    vq_argmin_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, e, enorm_ws, packed_ws, N, K, tiles_per_split);
+  } else {
+    int ktiles = cdiv(K, VQ2_TK);
+    int ntile = cdiv(N, VQ_TN), splits = 1;
+    while (ntile * splits < 6 * num_sms && splits * 2 <= ktiles && (ktiles / (splits * 2)) >= 2) splits *= 2;
+    int tiles_per_split = cdiv(ktiles, splits);
+    dim3 grid(ntile, cdiv(ktiles, tiles_per_split));
+    vq_argmin_x2_kernel<<<grid, VQ_THREADS, smem2, stream>>>(z, e, enorm_ws, packed_ws, N, K, tiles_per_split);
+  }
   vq_unpack_kernel<<<cdiv(N, 256), 256, 0, stream>>>(packed_ws, idx, N);
   count_launch(4);
   IVG_LAUNCH_CHECK();

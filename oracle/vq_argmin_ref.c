@@ -38,3 +38,26 @@ void vq_argmin_ref(const float* z, const float* e, int64_t* idx, float* best_out
     if (second_out) second_out[n] = second;
   }
 }
+
+/* order 1: even-d and odd-d chains (the packed fma.rn.f32x2 kernel):  dot = chain_even + chain_odd */
+void vq_argmin_ref_order1(const float* z, const float* e, int64_t* idx, float* best_out, float* second_out, int N,
+                          int K, int D) {
+  for (int n = 0; n < N; ++n) {
+    float best = INFINITY, second = INFINITY;
+    int64_t bi = 0;
+    for (int k = 0; k < K; ++k) {
+      float ev = 0.0f, od = 0.0f, en = 0.0f;
+      for (int d = 0; d < D; d += 2) {
+        ev = fmaf(z[(size_t)n * D + d], e[(size_t)k * D + d], ev);
+        od = fmaf(z[(size_t)n * D + d + 1], e[(size_t)k * D + d + 1], od);
+      }
+      for (int d = 0; d < D; ++d) en = fmaf(e[(size_t)k * D + d], e[(size_t)k * D + d], en);
+      float s = fmaf(-2.0f, ev + od, en);
+      if (s < best) { second = best; best = s; bi = k; }
+      else if (s < second) { second = s; }
+    }
+    idx[n] = bi;
+    if (best_out) best_out[n] = best;
+    if (second_out) second_out[n] = second;
+  }
+}

@@ -21,13 +21,15 @@ def load_vq_oracle():
         import subprocess
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     lib = C.CDLL(path)
-    lib.vq_argmin_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.vq_argmin_ref.restype = None
+    for fn in (lib.vq_argmin_ref, lib.vq_argmin_ref_order1):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        fn.restype = None
     return lib
 
 
-def vq_oracle(z: np.ndarray, e: np.ndarray):
-    """Returns (idx int64 [N], best [N], second [N]) from oracle/vq_argmin_ref.c."""
+def vq_oracle(z: np.ndarray, e: np.ndarray, order: int = 0):
+    """Returns (idx int64 [N], best [N], second [N]) from oracle/vq_argmin_ref.c (order 0: one FMA chain over d;
+    order 1: even/odd chains, the summation order of the packed-FMA kernel)."""
     lib = load_vq_oracle()
     z = np.ascontiguousarray(z, dtype=np.float32)
     e = np.ascontiguousarray(e, dtype=np.float32)
@@ -36,7 +38,8 @@ def vq_oracle(z: np.ndarray, e: np.ndarray):
     idx = np.zeros(N, dtype=np.int64)
     best = np.zeros(N, dtype=np.float32)
     second = np.zeros(N, dtype=np.float32)
-    lib.vq_argmin_ref(z.ctypes.data, e.ctypes.data, idx.ctypes.data, best.ctypes.data, second.ctypes.data, N, K, D)
+    fn = lib.vq_argmin_ref if order == 0 else lib.vq_argmin_ref_order1
+    fn(z.ctypes.data, e.ctypes.data, idx.ctypes.data, best.ctypes.data, second.ctypes.data, N, K, D)
     return idx, best, second
 
 

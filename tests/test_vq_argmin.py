@@ -20,12 +20,13 @@ def _data(N, K, seed, kind):
     return z, e
 
 
+@pytest.mark.parametrize("order", [0, 1])
 @pytest.mark.parametrize("kind", ["normal", "uniform_init", "near_code"])
-def test_oracle_matches_reference_expression(kind):
+def test_oracle_matches_reference_expression(kind, order):
     """oracle/vq_argmin_ref.c vs argmin(torch.cdist(z, E)) -- the expression diffusers' VectorQuantizer runs.
     They may only differ where the two best candidates are within float rounding of each other."""
     z, e = _data(512, 2048, 0, kind)
-    idx, best, second = vq_oracle(z.numpy(), e.numpy())
+    idx, best, second = vq_oracle(z.numpy(), e.numpy(), order)
     ref = torch.argmin(torch.cdist(z, e), dim=1).numpy()
     diff = idx != ref
     scale = (z.norm(dim=1) ** 2 + (e.norm(dim=1) ** 2).max()).numpy()
@@ -43,17 +44,25 @@ def test_oracle_tie_rule():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", [0, 1])
 @pytest.mark.parametrize("N,K,kind", [(1, 8192, "normal"), (127, 300, "normal"), (512, 8192, "uniform_init"),
                                       (3584, 8192, "near_code"), (4099, 1000, "normal"), (0, 64, "normal")])
-def test_cuda_bit_exact_vs_oracle(cuda, N, K, kind):
-    from ivideogpt_b200 import ops
+def test_cuda_bit_exact_vs_oracle(cuda, N, K, kind, order):
+    """Both kernels (FFMA, order 0; packed FFMA2, order 1) against the C oracle computing in the same order."""
+    from ivideogpt_b200 import _lib, ops
+    lib = _lib.load()
     z, e = _data(max(N, 1), K, 1, kind)
     z = z[:N]
-    got = ops.vq_argmin(z.to(cuda), e.to(cuda)).cpu().numpy()
+    prev = lib.ivgpt_vq_get_order()
+    try:
+        lib.ivgpt_vq_set_order(order)
+        got = ops.vq_argmin(z.to(cuda), e.to(cuda)).cpu().numpy()
+    finally:
+        lib.ivgpt_vq_set_order(prev)
     if N == 0:
         assert got.shape == (0,)
         return
-    want, _, _ = vq_oracle(z.numpy(), e.numpy())
+    want, _, _ = vq_oracle(z.numpy(), e.numpy(), order)
     assert got.dtype == np.int64
     assert np.array_equal(got, want), f"{(got != want).sum()} / {N} indices differ"
 
