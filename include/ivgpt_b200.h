@@ -188,6 +188,25 @@ int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, co
                           const float* n1, const float* n2, int hidden, int inter);
 int ivgpt_mega_fill_map(void* host_map, const void* w, int rows, int cols);
 int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream);
+/* ---- training pieces: backward of LlamaForCausalLM.forward(labels) (train_gpt.py:792-798) and the AdamW update
+ * (train_gpt.py:648-658,803).  All contractions of the backward pass are ivgpt_gemm calls on transposed operands. */
+int ivgpt_transpose(int dtype, const void* in, void* out, int batch, int rows, int cols, long long ld_in,
+                    long long ld_out, long long bs_in, long long bs_out, void* stream);
+int ivgpt_swiglu(int dtype, int backward, const void* gu /* [M,2I] gate/up interleaved */, const void* dact, void* out,
+                 long long n /* M*I */, void* stream);
+int ivgpt_rmsnorm_bwd(int dtype, const float* x, const float* w, const void* dy, float* dres /* += */, float* dw_part,
+                      float* dw, long long M, int hidden, float eps, void* stream);
+int ivgpt_softmax_bwd(int dtype, const void* P, const float* dP, void* dS, long long rows, int Lq, int Lk, long long ld,
+                      int causal, float scale, void* stream);
+int ivgpt_rope_bwd(int dtype, const float* dq, const float* dk, const float* dv, void* dqkv, int B, int L, int heads,
+                   const float* cos_tab, const float* sin_tab, void* stream);
+int ivgpt_ce_bwd(int dtype, const float* logits, long long ld, int B, int L, int V, const long long* labels,
+                 const float* count, float gscale, void* dlogits, long long ldd, void* stream);
+int ivgpt_embed_bwd(const long long* ids, const float* dx, float* dE, long long M, int hidden, long long vocab,
+                    void* stream);
+int ivgpt_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int step, float gscale, void* stream);
+int ivgpt_add_to_f32(int dtype, float* y, const void* x, long long n, void* stream);
 /* Programmatic dependent launch for the kernels of the decode step (prologue overlap inside CUDA graphs). */
 int ivgpt_set_pdl(int on);
 

@@ -103,6 +103,15 @@ SIGNATURES = {
     "ivgpt_incr": [_P, _I, _P],
     "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],
     "ivgpt_set_pdl": [_I],
+    "ivgpt_transpose": [_I, _P, _P, _I, _I, _I, _L, _L, _L, _L, _P],
+    "ivgpt_swiglu": [_I, _I, _P, _P, _P, _L, _P],
+    "ivgpt_rmsnorm_bwd": [_I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "ivgpt_softmax_bwd": [_I, _P, _P, _P, _L, _I, _I, _L, _I, _F, _P],
+    "ivgpt_rope_bwd": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "ivgpt_ce_bwd": [_I, _P, _L, _I, _I, _I, _P, _P, _F, _P, _L, _P],
+    "ivgpt_embed_bwd": [_P, _P, _P, _L, _I, _L, _P],
+    "ivgpt_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "ivgpt_add_to_f32": [_I, _P, _P, _L, _P],
     "ivgpt_vq_set_order": [_I],
     "ivgpt_vq_get_order": [],
     "ivgpt_mega_layer_bytes": [],

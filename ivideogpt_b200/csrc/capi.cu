@@ -108,6 +108,19 @@ int topk_sample_launch(const float*, long long, int, int, int, float, unsigned l
                        long long*, long long, const int*, const unsigned long long*, cudaStream_t);
 int ce_loss_launch(const float*, long long, int, int, int, const long long*, float*, float*, float*, cudaStream_t);
 int incr_launch(int*, int, cudaStream_t);
+int transpose_launch(int, const void*, void*, int, int, int, long long, long long, long long, long long, cudaStream_t);
+int swiglu_launch(int, int, const void*, const void*, void*, long long, cudaStream_t);
+int rmsnorm_bwd_launch(int, const float*, const float*, const void*, float*, float*, float*, long long, int, float,
+                       cudaStream_t);
+int softmax_bwd_launch(int, const void*, const float*, void*, long long, int, int, long long, int, float, cudaStream_t);
+int rope_bwd_launch(int, const float*, const float*, const float*, void*, int, int, int, const float*, const float*,
+                    cudaStream_t);
+int ce_bwd_launch(int, const float*, long long, int, int, int, const long long*, const float*, float, void*, long long,
+                  cudaStream_t);
+int embed_bwd_launch(const long long*, const float*, float*, long long, int, long long, cudaStream_t);
+int adamw_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float,
+                 cudaStream_t);
+int add_to_f32_launch(int, float*, const void*, long long, cudaStream_t);
 int decode_attn_fused_launch(int, const void*, void*, void*, void*, int, int, int, int, const int*, const float*,
                              const float*, float, cudaStream_t);
 
@@ -358,6 +371,42 @@ int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_c
                                   S(stream));
 }
 int ivgpt_set_pdl(int on) { ivg::g_pdl = on != 0; return 0; }
+
+// ---- training (backward) pieces ------------------------------------------------------------------------
+int ivgpt_transpose(int dtype, const void* in, void* out, int batch, int rows, int cols, long long ld_in,
+                    long long ld_out, long long bs_in, long long bs_out, void* stream) {
+  return transpose_launch(dtype, in, out, batch, rows, cols, ld_in, ld_out, bs_in, bs_out, S(stream));
+}
+int ivgpt_swiglu(int dtype, int backward, const void* gu, const void* dact, void* out, long long n, void* stream) {
+  return swiglu_launch(dtype, backward, gu, dact, out, n, S(stream));
+}
+int ivgpt_rmsnorm_bwd(int dtype, const float* x, const float* w, const void* dy, float* dres, float* dw_part, float* dw,
+                      long long M, int hidden, float eps, void* stream) {
+  return rmsnorm_bwd_launch(dtype, x, w, dy, dres, dw_part, dw, M, hidden, eps, S(stream));
+}
+int ivgpt_softmax_bwd(int dtype, const void* P, const float* dP, void* dS, long long rows, int Lq, int Lk, long long ld,
+                      int causal, float scale, void* stream) {
+  return softmax_bwd_launch(dtype, P, dP, dS, rows, Lq, Lk, ld, causal, scale, S(stream));
+}
+int ivgpt_rope_bwd(int dtype, const float* dq, const float* dk, const float* dv, void* dqkv, int B, int L, int heads,
+                   const float* cos_tab, const float* sin_tab, void* stream) {
+  return rope_bwd_launch(dtype, dq, dk, dv, dqkv, B, L, heads, cos_tab, sin_tab, S(stream));
+}
+int ivgpt_ce_bwd(int dtype, const float* logits, long long ld, int B, int L, int V, const long long* labels,
+                 const float* count, float gscale, void* dlogits, long long ldd, void* stream) {
+  return ce_bwd_launch(dtype, logits, ld, B, L, V, labels, count, gscale, dlogits, ldd, S(stream));
+}
+int ivgpt_embed_bwd(const long long* ids, const float* dx, float* dE, long long M, int hidden, long long vocab,
+                    void* stream) {
+  return embed_bwd_launch(ids, dx, dE, M, hidden, vocab, S(stream));
+}
+int ivgpt_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int step, float gscale, void* stream) {
+  return adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale, S(stream));
+}
+int ivgpt_add_to_f32(int dtype, float* y, const void* x, long long n, void* stream) {
+  return add_to_f32_launch(dtype, y, x, n, S(stream));
+}
 int ivgpt_vq_set_order(int order) {
   IVG_CHECK(order == 0 || order == 1, "vq order must be 0 or 1");
   ivg::g_vq_order = order;

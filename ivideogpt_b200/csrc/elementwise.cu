@@ -42,13 +42,14 @@ __device__ __forceinline__ void gn_store(T* p, const float (&f)[16 / sizeof(T)])
 template <typename T>
 __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int rows, int C, int G,
                                   int slabs) {
-  // grid: (slabs, N), 256 threads = (C/VN channel vectors) x (row lanes).  part layout [N][slabs][G][2]
+  // grid: (slabs, N), 256 threads = (C/VN channel vectors) x (row lanes).  part layout [N][slabs][G][2].
+  // Bit-reproducible: per-thread channel sums go to shared memory and every group is reduced by ONE thread in a fixed
+  // order (the atomics of the first vectorised version made the statistics differ in the last ulp from run to run, and
+  // ~40 TF32 layers amplified that to 4e-3 in pixel space -- caught by the batch-independence test).
   constexpr int VN = GnVec<T>::N;
-  extern __shared__ float gn_sm[];  // [G][2] accumulators
+  extern __shared__ float gn_sm[];  // [rlanes][C][2]
   const int n = blockIdx.y, slab = blockIdx.x;
   const int cpg = C / G;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gn_sm[i] = 0.f;
-  __syncthreads();
   const int r0 = slab * GN_SLAB_ROWS;
   const int r1 = min(rows, r0 + GN_SLAB_ROWS);
   const T* base = x + ((size_t)n * rows) * C;
@@ -65,37 +66,46 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
 #pragma unroll
       for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
-    // fold the VN channels into their groups before touching shared memory
-    int g_prev = (cv * VN) / cpg;
-    float ss = 0.f, qq = 0.f;
+    float* dst = gn_sm + ((size_t)rl * C + cv * VN) * 2;
 #pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      const int g = (cv * VN + i) / cpg;
-      if (g != g_prev) { atomicAdd(&gn_sm[2 * g_prev], ss); atomicAdd(&gn_sm[2 * g_prev + 1], qq); ss = 0.f; qq = 0.f; g_prev = g; }
-      ss += s[i]; qq += q[i];
-    }
-    atomicAdd(&gn_sm[2 * g_prev], ss); atomicAdd(&gn_sm[2 * g_prev + 1], qq);
+    for (int i = 0; i < VN; ++i) { dst[2 * i] = s[i]; dst[2 * i + 1] = q[i]; }
   }
   __syncthreads();
-  float* dst = part + ((size_t)n * slabs + slab) * G * 2;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) dst[i] = gn_sm[i];
+  if ((int)threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float ss = 0.f, qq = 0.f;
+    for (int l = 0; l < rlanes; ++l)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        ss += gn_sm[((size_t)l * C + c) * 2];
+        qq += gn_sm[((size_t)l * C + c) * 2 + 1];
+      }
+    float* o = part + (((size_t)n * slabs + slab) * G + g) * 2;
+    o[0] = ss; o[1] = qq;
+  }
 }
 
 __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int slabs, int G,
                                    double count, float eps) {
-  // grid: N, block: G threads (G <= 64).  stats layout [N][G][2] = (mean, rstd)
-  const int n = blockIdx.x, g = threadIdx.x;
+  // grid: N, block: 32 x G threads -- a warp per group strides the slabs, fixed-order shuffle tree, fp64 combine.
+  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < slabs; ++i) {
+  for (int i = lane; i < slabs; i += 32) {
     const float* p = part + ((size_t)n * slabs + i) * G * 2 + 2 * g;
     s += (double)p[0]; q += (double)p[1];
   }
-  double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[((size_t)n * G + g) * 2] = (float)mean;
-  stats[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if (lane == 0) {
+    double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)n * G + g) * 2] = (float)mean;
+    stats[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 // y = (x - mean) * rstd * gamma + beta ; optional SiLU ; optional + pos[(row % pos_rows)][C].  16 bytes per thread.
@@ -136,8 +146,9 @@ int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows,
                       cudaStream_t st) {
   const int slabs = cdiv(rows, GN_SLAB_ROWS);
   dim3 grid(slabs, N);
-  gn_partial_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>(x, part_ws, rows, C, G, slabs);
-  gn_finalize_kernel<<<N, 64, 0, st>>>(part_ws, stats, slabs, G, (double)rows * (C / G), eps);
+  const size_t smem = (size_t)(256 / (C / GnVec<T>::N)) * C * 2 * sizeof(float);
+  gn_partial_kernel<T><<<grid, 256, smem, st>>>(x, part_ws, rows, C, G, slabs);
+  gn_finalize_kernel<<<N, 32 * G, 0, st>>>(part_ws, stats, slabs, G, (double)rows * (C / G), eps);
   count_launch(2);
   IVG_LAUNCH_CHECK();
   return 0;
@@ -145,7 +156,7 @@ int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows,
 
 int gn_stats_launch(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G, float eps,
                     cudaStream_t st) {
-  IVG_CHECK(C % G == 0 && C % 8 == 0 && C / (dtype == DT_BF16 ? 8 : 4) <= 256 && G <= 64, "groupnorm: bad C=%d G=%d", C, G);
+  IVG_CHECK(C % G == 0 && C % 8 == 0 && C / (dtype == DT_BF16 ? 8 : 4) <= 256 && G <= 32, "groupnorm: bad C=%d G=%d", C, G);
   IVG_CHECK(((uintptr_t)x & 15) == 0, "groupnorm: x must be 16-byte aligned");
   if (N == 0) return 0;
   if (dtype == DT_BF16) return gn_stats_launch_t((const __nv_bfloat16*)x, part_ws, stats, N, rows, C, G, eps, st);

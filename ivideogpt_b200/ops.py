@@ -317,7 +317,8 @@ def topk_sample(logits, ld, rows, V, k, temperature, seed, step, out, out_stride
 
 
 def ce_loss(logits, ld, B, L, V, labels):
-    """Shifted cross-entropy over logits [B,L,ld] fp32 / labels [B,L] int64; returns (mean loss 0-d, per-row)."""
+    """Shifted cross-entropy over logits [B,L,ld] fp32 / labels [B,L] int64; returns (mean loss 0-d, per-row losses,
+    count [1] = number of labelled positions, on the device)."""
     _cuda(logits, labels)
     assert labels.dtype == torch.int64 and labels.is_contiguous()
     rows = B * (L - 1)
@@ -326,8 +327,100 @@ def ce_loss(logits, ld, B, L, V, labels):
     out = torch.empty(2, dtype=torch.float32, device=logits.device)
     _lib.check(_lib.load().ivgpt_ce_loss(logits.data_ptr(), ld, B, L, V, labels.data_ptr(), loss_rows.data_ptr(),
                                          valid.data_ptr(), out.data_ptr(), _stream()), "ce_loss")
-    return out[0], loss_rows[:rows]
+    return out[0], loss_rows[:rows], out[1:2]
 
 
 def incr(p, by=1):
     _lib.check(_lib.load().ivgpt_incr(p.data_ptr(), by, _stream()), "incr")
+
+
+# ------------------------------------------------------------------------------------------------
+# training (backward) pieces
+# ------------------------------------------------------------------------------------------------
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad_to: int = 8) -> torch.Tensor:
+    """Batched 2-D transpose of the last two dims: x [..., R, C] (last dim contiguous) -> [..., C, Rp] with
+    Rp = R rounded up to `pad_to` (TMA row pitches must be multiples of 16 bytes); returns the [..., C, :R] view."""
+    _cuda(x, out)
+    assert x.stride(-1) == 1
+    R, Cc = x.shape[-2], x.shape[-1]
+    batch = x.numel() // (R * Cc) if x.dim() > 2 else 1
+    if x.dim() > 2:
+        lead = x.shape[:-2]
+        assert x.is_contiguous() or x.dim() == 3, "batched transpose needs a contiguous (or 3-D strided) input"
+        bs_in = x.stride(-3) if x.dim() >= 3 else R * x.stride(-2)
+        if x.dim() > 3:
+            assert x.is_contiguous()
+    else:
+        lead, bs_in = (), 0
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    if out is None:
+        out = torch.zeros(*lead, Cc, Rp, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().ivgpt_transpose(_dt(x), x.data_ptr(), out.data_ptr(), batch, R, Cc, x.stride(-2), Rp, bs_in,
+                                           Cc * Rp, _stream()), "transpose")
+    return out[..., :R]
+
+
+def swiglu(gu: torch.Tensor, dact: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """forward: act [M,I] from interleaved gu [M,2I]; backward (dact given): d_gu [M,2I]."""
+    _cuda(gu, dact)
+    assert gu.is_contiguous()
+    M, I2 = gu.shape
+    if dact is None:
+        out = torch.empty(M, I2 // 2, dtype=gu.dtype, device=gu.device)
+        _lib.check(_lib.load().ivgpt_swiglu(_dt(gu), 0, gu.data_ptr(), None, out.data_ptr(), M * (I2 // 2), _stream()), "swiglu")
+    else:
+        assert dact.is_contiguous() and dact.dtype == gu.dtype
+        out = torch.empty_like(gu)
+        _lib.check(_lib.load().ivgpt_swiglu(_dt(gu), 1, gu.data_ptr(), dact.data_ptr(), out.data_ptr(), M * (I2 // 2), _stream()), "swiglu_bwd")
+    return out
+
+
+def rmsnorm_bwd(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, dres: torch.Tensor, eps: float) -> torch.Tensor:
+    """dres (fp32, in place) += d/dx of rmsnorm; returns dw (fp32 [H])."""
+    _cuda(x, w, dy, dres)
+    M, H = x.shape
+    assert x.dtype == torch.float32 and dres.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    part = torch.empty((M + 7) // 8, H, dtype=torch.float32, device=x.device)
+    dw = torch.empty(H, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_rmsnorm_bwd(_dt(dy), x.data_ptr(), w.data_ptr(), dy.data_ptr(), dres.data_ptr(),
+                                             part.data_ptr(), dw.data_ptr(), M, H, eps, _stream()), "rmsnorm_bwd")
+    return dw
+
+
+def softmax_bwd(P, dP, dS, rows, Lq, Lk, ld, causal, scale):
+    _lib.check(_lib.load().ivgpt_softmax_bwd(_dt(P), P.data_ptr(), dP.data_ptr(), dS.data_ptr(), rows, Lq, Lk, ld,
+                                             int(causal), scale, _stream()), "softmax_bwd")
+
+
+def rope_bwd(dq, dk, dv, dqkv, B, L, heads, cos_tab, sin_tab):
+    _lib.check(_lib.load().ivgpt_rope_bwd(_dt(dqkv), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dqkv.data_ptr(), B, L,
+                                          heads, cos_tab.data_ptr(), sin_tab.data_ptr(), _stream()), "rope_bwd")
+
+
+def ce_bwd(logits, ld, B, L, V, labels, count, gscale, dlogits):
+    _lib.check(_lib.load().ivgpt_ce_bwd(_dt(dlogits), logits.data_ptr(), ld, B, L, V, labels.data_ptr(), count.data_ptr(),
+                                        gscale, dlogits.data_ptr(), dlogits.stride(-2), _stream()), "ce_bwd")
+
+
+def embed_bwd(ids, dx, dE):
+    _lib.check(_lib.load().ivgpt_embed_bwd(ids.data_ptr(), dx.data_ptr(), dE.data_ptr(), ids.numel(), dE.shape[1],
+                                           dE.shape[0], _stream()), "embed_bwd")
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0):
+    _cuda(p, g, m, v)
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (p, g, m, v))
+    _lib.check(_lib.load().ivgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                       eps, weight_decay, step, gscale, _stream()), "adamw")
+
+
+def add_to_f32(y, x):
+    _lib.check(_lib.load().ivgpt_add_to_f32(_dt(x), y.data_ptr(), x.data_ptr(), x.numel(), _stream()), "add_to_f32")
+
+
+def transpose_raw(src: torch.Tensor, src_off: int, dst: torch.Tensor, batch: int, R: int, Cc: int, ld_in: int,
+                  ld_out: int, bs_in: int, bs_out: int):
+    """dst[b][c][r] = src[src_off + b*bs_in + r*ld_in + c]  (element offsets); dst row pitch ld_out, batch pitch bs_out."""
+    es = src.element_size()
+    _lib.check(_lib.load().ivgpt_transpose(_dt(src), src.data_ptr() + src_off * es, dst.data_ptr(), batch, R, Cc, ld_in,
+                                           ld_out, bs_in, bs_out, _stream()), "transpose")

@@ -82,11 +82,19 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
             expect = torch.arange(L, device=src.device).expand(B, L)
             if position_ids.shape != expect.shape or not bool((position_ids == expect).all()):
                 raise NotImplementedError("only default position_ids (0..L-1) are supported")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and labels is not None \
-                and self.training:
-            raise NotImplementedError(
-                "B200LlamaForCausalLM: the training backward pass (train_gpt.py:798) is not built yet; call under "
-                "torch.no_grad() / model.eval() for loss evaluation.")
+        if torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters()):
+            # training step (train_gpt.py:792-798): forward + backward on the B200 kernels; the returned loss carries a
+            # grad_fn whose backward hands the already-computed parameter gradients to autograd (DDP hooks included).
+            if input_ids is None:
+                raise NotImplementedError("training from inputs_embeds (action-conditioned fine-tuning) is not built yet")
+            if float(getattr(self.config, "attention_dropout", 0.0) or 0.0) > 0.0 and self.training:
+                import warnings
+                warnings.warn("B200LlamaForCausalLM: attention_dropout > 0 is ignored (dropout 0 is what loss parity "
+                              "is defined on; see DESIGN.md)", stacklevel=2)
+            names, params = zip(*self.named_parameters())
+            loss = _TrainLossFn.apply(self, input_ids, labels, names, *params)
+            return CausalLMOutputWithPast(loss=loss, logits=None, past_key_values=None, hidden_states=None,
+                                          attentions=None)
         eng = self.b200_engine()
         with torch.no_grad():
             Lmax = (L + 7) // 8 * 8
@@ -96,7 +104,7 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
             V = self.config.vocab_size
             loss = None
             if labels is not None:
-                loss, _ = ops.ce_loss(logits_pad, logits_pad.stride(1), B, L, V, labels.contiguous())
+                loss, _, _ = ops.ce_loss(logits_pad, logits_pad.stride(1), B, L, V, labels.contiguous())
             logits = logits_pad[:, :, :V]
             hs = None
             if want_h:
@@ -147,6 +155,28 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
 
     def gradient_checkpointing_enable(self, *a, **k):  # accepted and ignored (train_gpt.py:598-600)
         return None
+
+
+class _TrainLossFn(torch.autograd.Function):
+    """loss = Llama(input_ids, labels); gradients of every parameter are produced by LlamaTrainEngine in the forward
+    call (activations never outlive it) and released to autograd in backward."""
+
+    @staticmethod
+    def forward(ctx, model, input_ids, labels, names, *params):
+        from .train_engine import LlamaTrainEngine
+        eng = model.b200_engine()
+        train = LlamaTrainEngine(eng.w)
+        loss, grads = train.forward_backward(input_ids, labels)
+        ctx.grads = [grads[n] for n in names]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        out = []
+        for g in ctx.grads:
+            out.append(g.mul_(gout) if g.is_contiguous() else g * gout)
+        ctx.grads = None
+        return (None, None, None, None) + tuple(out)
 
 
 def register():

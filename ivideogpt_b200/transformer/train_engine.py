@@ -1,0 +1,188 @@
+"""Forward + backward of the Llama-style transformer on the B200 kernels (training step of reference
+train_gpt.py:766-804: `outputs = model(input_ids, labels)` -> `accelerator.backward(loss)`).
+
+Every contraction -- forward projections, dgrad, wgrad, the four attention-backward products -- is a launch of the
+tcgen05 GEMM (gemm_tc.cu); both operands of that kernel are K-major, so wgrad / attention-backward operands are first
+re-laid out by the batched transpose kernel.  Activations needed by the backward pass are kept per layer (B = 16 clips
+of 751 tokens: ~0.6 GB per layer).  Attention dropout is not implemented (dropout 0 == what loss parity is defined on,
+SURVEY.md section 7); a configured attention_dropout > 0 is ignored with a warning.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+from .._lib import BF16, F32
+from .engine import LlamaWeights
+
+
+def _r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class LlamaTrainEngine:
+    def __init__(self, weights: LlamaWeights):
+        self.w = weights
+        self.dt = weights.dtype
+        self.code = BF16 if self.dt == torch.bfloat16 else F32
+        w = weights
+        # transposed weight copies for dgrad (dX = dY . W  needs W^T as the K-major B operand)
+        self.wT = []
+        for lw in w.layers:
+            self.wT.append({k: self._t2(lw[k]) for k in ("wqkv", "wo", "wgu", "wd")})
+        self.lmT = self._t2(w.lm_head)
+
+    # ---- small helpers ------------------------------------------------------------------------------------
+    def _t2(self, x: torch.Tensor) -> torch.Tensor:
+        """[R, C] -> [C, R] (row pitch padded to 8), returned as the [C, :R] view."""
+        R, Cc = x.shape
+        out = torch.zeros(Cc, _r8(R), dtype=x.dtype, device=x.device)
+        ops.transpose_raw(x, 0, out, 1, R, Cc, x.stride(0), out.stride(0), 0, 0)
+        return out[:, :R]
+
+    def _cast(self, x32: torch.Tensor) -> torch.Tensor:
+        return ops.convert(x32, self.dt)
+
+    def _wgrad(self, dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+        """dW [N, K] = dY[M, N]^T . X[M, K]   (fp32 output)"""
+        return ops.gemm(self._t2(dY), self._t2(X), out_dtype=torch.float32)
+
+    # ---- forward + backward --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0):
+        """Returns (loss 0-d fp32 tensor, grads dict keyed by HF parameter name -> fp32 tensor)."""
+        w, dt, code = self.w, self.dt, self.code
+        B, L = ids.shape
+        M, h, H, I, V = B * L, w.hidden, w.heads, w.inter, w.vocab
+        Lp = _r8(L)
+        dev = ids.device
+        ids = ids.contiguous()
+        labels = labels.contiguous()
+        x = torch.empty(M, h, dtype=torch.float32, device=dev)
+        ops.embed(ids, ids.stride(0), L, None, w.embed, x, M)
+        saved: List[Dict[str, torch.Tensor]] = []
+        kc = torch.zeros(B, H, Lp, 64, dtype=dt, device=dev)
+        vc = torch.zeros(B, H, 64, Lp, dtype=dt, device=dev)
+        for li, lw in enumerate(w.layers):
+            s: Dict[str, torch.Tensor] = {"xin": x.clone()}
+            xn1 = torch.empty(M, h, dtype=dt, device=dev)
+            ops.rmsnorm(x, lw["n1"], xn1, M, w.eps)
+            qkv = ops.gemm(xn1, lw["wqkv"])
+            q = torch.empty(B, H, L, 64, dtype=dt, device=dev)
+            k = torch.zeros(B, H, Lp, 64, dtype=dt, device=dev)
+            vt = torch.zeros(B, H, 64, Lp, dtype=dt, device=dev)
+            ops.rope_kv(qkv, q, k, vt, B, L, H, Lp, 0, None, w.cos, w.sin)
+            sc = torch.empty(B * H, L, Lp, dtype=torch.float32, device=dev)
+            ops.gemm_raw(ops.gemm_desc(
+                dtype=code, a=q.data_ptr(), lda=64, a_bstride=L * 64, a_rows=L, a_cols=64, a_batches=B * H,
+                b=k.data_ptr(), ldb=64, b_bstride=Lp * 64, b_rows=L, b_cols=64, b_batches=B * H,
+                M=L, N=L, K=64, batch=B * H, heads=1, a_bsel=2, b_bsel=2, o_bsel=2, causal_skip=1,
+                out=sc.data_ptr(), ldo=Lp, out_bstride=L * Lp, out_dtype=F32, alpha=0.125))
+            P = torch.empty(B * H, L, Lp, dtype=dt, device=dev)
+            ops.softmax(sc, P, B * H * L, L, L, Lp, Lp, True, 0)
+            ao = torch.empty(M, h, dtype=dt, device=dev)
+            ops.gemm_raw(ops.gemm_desc(
+                dtype=code, a=P.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
+                b=vt.data_ptr(), ldb=Lp, b_bstride=64 * Lp, b_rows=64, b_cols=L, b_batches=B * H,
+                M=L, N=64, K=L, batch=B * H, heads=H, a_bsel=2, b_bsel=2, o_bsel=1, o_nhead=64,
+                out=ao.data_ptr(), ldo=h, out_bstride=L * h, out_dtype=code))
+            ops.gemm(ao, lw["wo"], residual=x, out=x)
+            s["xmid"] = x.clone()
+            xn2 = torch.empty(M, h, dtype=dt, device=dev)
+            ops.rmsnorm(x, lw["n2"], xn2, M, w.eps)
+            gu = ops.gemm(xn2, lw["wgu"])
+            act = ops.swiglu(gu)
+            ops.gemm(act, lw["wd"], residual=x, out=x)
+            s.update(xn1=xn1, qkv=qkv, q=q, k=k, P=P, ao=ao, xn2=xn2, gu=gu, act=act)
+            saved.append(s)
+        xnf = torch.empty(M, h, dtype=dt, device=dev)
+        ops.rmsnorm(x, w.norm, xnf, M, w.eps)
+        Vp = _r8(V)
+        logits = torch.empty(B, L, Vp, dtype=torch.float32, device=dev)
+        ops.gemm(xnf, w.lm_head, out=logits.view(M, Vp)[:, :V])
+        loss, _, count = ops.ce_loss(logits, Vp, B, L, V, labels)
+
+        # ---------------- backward ----------------
+        grads: Dict[str, torch.Tensor] = {}
+        dlogits = torch.empty(B, L, Vp, dtype=dt, device=dev)
+        ops.ce_bwd(logits, Vp, B, L, V, labels, count, float(grad_scale), dlogits)
+        dl2 = dlogits.view(M, Vp)[:, :V]
+        grads["lm_head.weight"] = self._wgrad(dl2, xnf)
+        d_xnf = ops.gemm(dl2, self.lmT)
+        del logits, dlogits
+        dx = torch.zeros(M, h, dtype=torch.float32, device=dev)
+        grads["model.norm.weight"] = ops.rmsnorm_bwd(x, w.norm, d_xnf, dx, w.eps)
+        for li in reversed(range(w.layers_n)):
+            lw, wt, s = w.layers[li], self.wT[li], saved[li]
+            pre = f"model.layers.{li}."
+            # ---- MLP ----
+            dxT = self._cast(dx)
+            d_act = ops.gemm(dxT, wt["wd"])
+            grads[pre + "mlp.down_proj.weight"] = self._wgrad(dxT, s["act"])
+            d_gu = ops.swiglu(s["gu"], d_act)
+            d_xn2 = ops.gemm(d_gu, wt["wgu"])
+            g_gu = self._wgrad(d_gu, s["xn2"])
+            grads[pre + "mlp.gate_proj.weight"] = g_gu[0::2]
+            grads[pre + "mlp.up_proj.weight"] = g_gu[1::2]
+            grads[pre + "post_attention_layernorm.weight"] = ops.rmsnorm_bwd(s["xmid"], lw["n2"], d_xn2, dx, w.eps)
+            # ---- attention ----
+            dxT = self._cast(dx)
+            d_ao = ops.gemm(dxT, wt["wo"])
+            grads[pre + "self_attn.o_proj.weight"] = self._wgrad(dxT, s["ao"])
+            qkv, P = s["qkv"], s["P"]
+            dP = torch.empty(B * H, L, Lp, dtype=torch.float32, device=dev)
+            ops.gemm_raw(ops.gemm_desc(      # dP[b,h] = dO_h . V_h^T      (V_h read in place from the fused qkv buffer)
+                dtype=code, a=d_ao.data_ptr(), lda=h, a_bstride=L * h, a_rows=L, a_cols=h, a_batches=B,
+                b=qkv.data_ptr(), ldb=3 * h, b_bstride=L * 3 * h, b_rows=L, b_cols=3 * h, b_batches=B,
+                M=L, N=L, K=64, batch=B * H, heads=H, a_bsel=1, a_bdiv=1, b_bsel=1, b_bdiv=1, o_bsel=2,
+                a_khead=64, b_kbase=2 * h, b_khead=64, causal_skip=1,
+                out=dP.data_ptr(), ldo=Lp, out_bstride=L * Lp, out_dtype=F32))
+            dS = torch.empty(B * H, L, Lp, dtype=dt, device=dev)
+            ops.softmax_bwd(P, dP, dS, B * H * L, L, L, Lp, True, 0.125)
+            del dP
+            Pt = torch.zeros(B * H, L, Lp, dtype=dt, device=dev)
+            ops.transpose_raw(P, 0, Pt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
+            d_aoT = torch.zeros(B, h, Lp, dtype=dt, device=dev)
+            ops.transpose_raw(d_ao, 0, d_aoT, B, L, h, h, Lp, L * h, h * Lp)
+            dV = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
+            ops.gemm_raw(ops.gemm_desc(      # dV[b,h] = P^T . dO_h
+                dtype=code, a=Pt.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
+                b=d_aoT.data_ptr(), ldb=Lp, b_bstride=h * Lp, b_rows=h, b_cols=L, b_batches=B,
+                M=L, N=64, K=L, batch=B * H, heads=H, a_bsel=2, b_bsel=1, b_bdiv=1, o_bsel=2, b_nhead=64,
+                out=dV.data_ptr(), ldo=64, out_bstride=L * 64, out_dtype=F32))
+            del Pt
+            kT = torch.zeros(B * H, 64, Lp, dtype=dt, device=dev)
+            ops.transpose_raw(s["k"], 0, kT, B * H, L, 64, 64, Lp, Lp * 64, 64 * Lp)
+            dQ = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
+            ops.gemm_raw(ops.gemm_desc(      # dQ'[b,h] = dS . K'
+                dtype=code, a=dS.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
+                b=kT.data_ptr(), ldb=Lp, b_bstride=64 * Lp, b_rows=64, b_cols=L, b_batches=B * H,
+                M=L, N=64, K=L, batch=B * H, heads=1, a_bsel=2, b_bsel=2, o_bsel=2,
+                out=dQ.data_ptr(), ldo=64, out_bstride=L * 64, out_dtype=F32))
+            dSt = torch.zeros(B * H, L, Lp, dtype=dt, device=dev)
+            ops.transpose_raw(dS, 0, dSt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
+            qT = torch.zeros(B * H, 64, Lp, dtype=dt, device=dev)
+            ops.transpose_raw(s["q"], 0, qT, B * H, L, 64, 64, Lp, L * 64, 64 * Lp)
+            dK = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
+            ops.gemm_raw(ops.gemm_desc(      # dK'[b,h] = dS^T . Q'
+                dtype=code, a=dSt.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
+                b=qT.data_ptr(), ldb=Lp, b_bstride=64 * Lp, b_rows=64, b_cols=L, b_batches=B * H,
+                M=L, N=64, K=L, batch=B * H, heads=1, a_bsel=2, b_bsel=2, o_bsel=2,
+                out=dK.data_ptr(), ldo=64, out_bstride=L * 64, out_dtype=F32))
+            del dS, dSt
+            d_qkv = torch.empty(M, 3 * h, dtype=dt, device=dev)
+            ops.rope_bwd(dQ, dK, dV, d_qkv, B, L, H, w.cos, w.sin)
+            d_xn1 = ops.gemm(d_qkv, wt["wqkv"])
+            g_qkv = self._wgrad(d_qkv, s["xn1"])
+            grads[pre + "self_attn.q_proj.weight"] = g_qkv[0:h]
+            grads[pre + "self_attn.k_proj.weight"] = g_qkv[h:2 * h]
+            grads[pre + "self_attn.v_proj.weight"] = g_qkv[2 * h:3 * h]
+            grads[pre + "input_layernorm.weight"] = ops.rmsnorm_bwd(s["xin"], lw["n1"], d_xn1, dx, w.eps)
+            saved[li] = None
+        dE = torch.zeros(V, h, dtype=torch.float32, device=dev)
+        ops.embed_bwd(ids, dx, dE)
+        grads["model.embed_tokens.weight"] = dE
+        return loss, grads

@@ -137,3 +137,34 @@ def test_decode_megakernel_matches_multikernel_path(cuda):
         lg = mine(input_ids=s1[:, :-1]).logits[:, -1]
     topk = lg.topk(6, dim=-1).indices
     assert all(int(s1[i, -1]) in topk[i].tolist() for i in range(5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol_loss,min_cos", [(torch.float32, 1e-3, 0.9995), (torch.bfloat16, 5e-3, 0.99)])
+def test_training_forward_backward_vs_hf_autograd(cuda, dtype, tol_loss, min_cos):
+    """Row a8 backward: loss and every parameter gradient of model(input_ids, labels) against HF autograd (fp32, CPU)."""
+    from oracle.llama_ref import TINY_LLAMA
+    ref, mine = _pair(TINY_LLAMA, cuda, dtype, scale=2.0)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 1026, (3, 75), generator=g)
+    labels = ids.clone()
+    labels[:, :40] = -100
+    ref.train()
+    for p in ref.parameters():
+        p.grad = None
+    out = ref(input_ids=ids, labels=labels)
+    out.loss.backward()
+    mine.train()
+    got = mine(input_ids=ids.to(cuda), labels=labels.to(cuda))
+    assert got.loss.requires_grad
+    got.loss.backward()
+    assert abs(float(got.loss) - float(out.loss)) / float(out.loss) < tol_loss
+    worst = 1.0
+    for (n, p), (n2, q) in zip(ref.named_parameters(), mine.named_parameters()):
+        assert n == n2 and q.grad is not None, n
+        a, b = q.grad.detach().float().cpu().flatten().double(), p.grad.flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        worst = min(worst, cos)
+        assert cos > min_cos, f"{n}: cos {cos}"
+        assert abs(float(a.norm() / b.norm()) - 1.0) < 0.05, f"{n}: norm ratio {float(a.norm() / b.norm())}"
+    assert worst > min_cos
