@@ -34,6 +34,10 @@ WORKLOADS = {
     "cfg256": ("ctx_vae256", "llama_138m", 256, 16),
     "cfg64-medium": ("ctx_vae64", "llama_436m", 64, 32),
     "tiny": (None, None, 64, 2),
+    # train_gpt.py step (BASELINE config 5): frozen tokenizer -> tokens/labels -> Llama fwd+bwd (bf16 compute, fp32
+    # master weights) -> gradient all-reduce over ranks -> fused AdamW.  per-device batch 16 (oxe-64-act-free.sh:26)
+    "train64": ("ctx_vae64", "llama_138m", 64, 16),
+    "train-tiny": (None, None, 64, 2),
 }
 
 
@@ -340,9 +344,101 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """One training step of reference train_gpt.py:766-804 per bench step; metric = clips/s."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ivideogpt_b200 import _lib, ops
+    base = "tiny" if args.workload == "train-tiny" else "cfg64"
+    _, _, res, default_b = WORKLOADS[args.workload]
+    B = args.batch or default_b
+    ctx, seg = args.context_length, args.segment_length
+    tok, llm, _, _ = build_b200_models(base, dev, torch.bfloat16)
+    tok.set_compute_dtype(torch.float32)          # train_gpt.py runs the frozen tokenizer in fp32 (TF32 convs)
+    llm.train()
+    params = [p for p in llm.parameters()]
+    m_state = [torch.zeros_like(p) for p in params]
+    v_state = [torch.zeros_like(p) for p in params]
+    clips = synthetic_clips(B, seg, res, seed=rank).to(dev)
+    step_no = [0]
+
+    def train_step():
+        with torch.no_grad():
+            tokens, labels = tok.tokenize(clips, ctx)                     # train_gpt.py:776-779
+        loss = llm(input_ids=tokens, labels=labels).loss                  # :792
+        loss.backward()                                                   # :798
+        if world > 1:                                                     # DDP's gradient all-reduce (sum; mean via gscale)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        step_no[0] += 1
+        for p, m, v in zip(params, m_state, v_state):                     # :803 AdamW (lr 1e-4, wd 0.01 on matrices)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            ops.adamw(p.data, g, m, v, 1e-4, 0.9, 0.999, 1e-8, 0.01 if p.dim() >= 2 else 0.0, step_no[0], 1.0 / world)
+            p.grad = None
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        train_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    barrier()
+    n0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    losses = [train_step() for _ in range(args.steps)]
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.finish() if sampler else None
+    if rank == 0:
+        ms_step = float(t.item()) / args.steps
+        tokens_per_clip = ctx * 257 + 17 * (seg - ctx) - 1
+        flops_clip = 6.0 * 125.8e6 * tokens_per_clip + 31e9            # BASELINE.md: ~567 + 31 GFLOP per clip (fwd+bwd)
+        peak_tf, _, src = measured_peaks()
+        ach = world * B * flops_clip / (ms_step * 1e-3) / 1e12 / world
+        print(json.dumps({
+            "metric": "train_clips_per_sec", "value": world * B / (ms_step / 1e3), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: train_gpt.py step, {B} clips/GPU of {res}x{res}x{seg}, frozen fp32 "
+                                   f"tokenizer -> Llama fwd+bwd bf16 -> all-reduce -> AdamW", "per_gpu_batch": B,
+                       "parallelism": f"dp{world}", "attention_dropout": 0.0},
+            "loss_first_last": [float(losses[0]), float(losses[-1])], "gpu_launches": _lib.launch_count() - n0,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "training step (all tcgen05 GEMMs)", "achieved": ach, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": f"bf16_tflops_sustained ({src})",
+                         "traffic": None, "note": "model-FLOPs utilisation of the transformer fwd+bwd only"},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload.startswith("train"):
+        run_train(a)
     else:
         run_b200(a)
