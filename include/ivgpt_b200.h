@@ -94,17 +94,28 @@ typedef struct ivgpt_conv_desc {
   const void* residual; int res_dtype;
   int act;
   void* out; int out_dtype;
+  /* optional fused GroupNorm statistics of the output (the nn.GroupNorm that consumes it): partial (sum, sum of
+   * squares) per (frame, slab, group) written to gn_part [N][gn_slabs][gn_groups][2]; gn_slabs from ivgpt_conv3x3_plan,
+   * finish with ivgpt_groupnorm_finalize.  NULL = off. */
+  float* gn_part; int gn_groups;
 } ivgpt_conv_desc;
 int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream);
+/* tile width the launcher would pick for this problem (set d->bn to it to pin the choice) and the number of
+ * GroupNorm partial slabs per frame it implies. */
+int ivgpt_conv3x3_plan(const ivgpt_conv_desc* d, int* bn, int* gn_slabs);
+/* stats [samples][G][2] = (mean, rstd) from partial sums part [samples][slabs][G][2]; count = elements per group. */
+int ivgpt_groupnorm_finalize(const float* part, float* stats, int samples, int slabs, int G, double count, float eps,
+                             void* stream);
 
 /* ---- GroupNorm (nn.GroupNorm in ResnetBlock2D / conv_norm_out / CrossAttentionBlock) --------------
  * x [N, rows, C]; stats [N, G, 2] = (mean, rstd); part_ws [N * ceil(rows/64) * G * 2] fp32. */
 int ivgpt_groupnorm_stats(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G,
                           float eps, void* stream);
-/* y = (x-mean)*rstd*gamma+beta, optional SiLU, optional + pos[row % pos_rows][C] (conditional_vae.py:44-47). */
+/* y = (x-mean)*rstd*gamma+beta, optional SiLU, optional + pos[row % pos_rows][C] (conditional_vae.py:44-47).
+ * coef_ws: fp32 workspace [2 * samples * C] for the per-(sample, channel) scale / shift. */
 int ivgpt_groupnorm_apply(int dtype, const void* x, void* y, const float* stats, const float* gamma,
-                          const float* beta, const float* pos, long long total_rows, int rows_per_sample, int C,
-                          int G, int silu, int pos_rows, void* stream);
+                          const float* beta, const float* pos, float* coef_ws, long long total_rows,
+                          int rows_per_sample, int C, int G, int silu, int pos_rows, void* stream);
 
 /* conv_in: 3x3 conv 3 -> Cout on NCHW fp32 pixels -> NHWC (vae.py:86,149).  w [Cout][27], b [Cout].
  * Frame n of the N processed frames is read from slot (n / frames_per_clip) * clip_frames + frame_offset +

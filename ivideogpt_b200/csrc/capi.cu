@@ -81,8 +81,9 @@ int vq_argmin_launch(const float*, const float*, float*, unsigned long long*, lo
                      cudaStream_t);
 extern int g_vq_order;
 int gn_stats_launch(int, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
-int gn_apply_launch(int, const void*, void*, const float*, const float*, const float*, const float*, long long, int,
-                    int, int, int, int, cudaStream_t);
+int gn_finalize_launch(const float*, float*, int, int, int, double, float, cudaStream_t);
+int gn_apply_launch(int, const void*, void*, const float*, const float*, const float*, const float*, float*, long long,
+                    int, int, int, int, int, cudaStream_t);
 int conv_in_launch(int, const float*, const float*, const float*, void*, int, int, int, int, int, int, int,
                    cudaStream_t);
 int conv_out3_launch(int, const void*, const float*, const float*, const float*, const float*, const float*, float*,
@@ -221,6 +222,25 @@ int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream) {
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
+int ivgpt_conv3x3_plan(const ivgpt_conv_desc* d, int* bn_out, int* gn_slabs) {
+  IVG_CHECK(d != nullptr && bn_out != nullptr && gn_slabs != nullptr, "conv3x3_plan: null argument");
+  const int Hout = d->Hin / d->stride, Wout = d->Win / d->stride;
+  const int tw = Wout < 128 ? Wout : 128;
+  IVG_CHECK(tw > 0 && 128 % tw == 0, "conv3x3_plan: output width %d unsupported", Wout);
+  const int th = 128 / tw;
+  IVG_CHECK(Hout % th == 0 && Wout % tw == 0, "conv3x3_plan: output %dx%d not tileable", Hout, Wout);
+  const long long tiles_img = (long long)(Hout / th) * (Wout / tw);
+  const int bn = d->bn ? d->bn : pick_bn(d->Cout, (long long)d->N * tiles_img);
+  *bn_out = bn;
+  *gn_slabs = (int)(tiles_img * ((d->Cout + bn - 1) / bn) * 4);
+  return 0;
+}
+
+int ivgpt_groupnorm_finalize(const float* part, float* stats, int samples, int slabs, int G, double count, float eps,
+                             void* stream) {
+  return gn_finalize_launch(part, stats, samples, slabs, G, count, eps, S(stream));
+}
+
 int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
   IVG_CHECK(d != nullptr, "conv3x3: null descriptor");
   IVG_CHECK(d->dtype == DT_F32 || d->dtype == DT_BF16, "conv3x3: bad dtype %d", d->dtype);
@@ -287,6 +307,10 @@ int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
   p.residual = d->residual; p.ldr = d->Cout; p.res_dtype = d->res_dtype;
   p.act = d->act; p.alpha = 1.0f;
   p.tiles_m = (int)tiles_m; p.tiles_n = (d->Cout + bn - 1) / bn;
+  if (d->gn_part) {
+    IVG_CHECK(d->gn_groups > 0 && d->gn_groups <= 32 && d->Cout % d->gn_groups == 0, "conv3x3: bad gn_groups %d", d->gn_groups);
+    p.gn_part = d->gn_part; p.gn_groups = d->gn_groups;
+  }
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
@@ -295,10 +319,10 @@ int ivgpt_groupnorm_stats(int dtype, const void* x, float* part_ws, float* stats
   return gn_stats_launch(dtype, x, part_ws, stats, N, rows, C, G, eps, S(stream));
 }
 int ivgpt_groupnorm_apply(int dtype, const void* x, void* y, const float* stats, const float* gamma,
-                          const float* beta, const float* pos, long long total_rows, int rows_per_sample, int C,
-                          int G, int silu, int pos_rows, void* stream) {
-  return gn_apply_launch(dtype, x, y, stats, gamma, beta, pos, total_rows, rows_per_sample, C, G, silu, pos_rows,
-                         S(stream));
+                          const float* beta, const float* pos, float* coef_ws, long long total_rows,
+                          int rows_per_sample, int C, int G, int silu, int pos_rows, void* stream) {
+  return gn_apply_launch(dtype, x, y, stats, gamma, beta, pos, coef_ws, total_rows, rows_per_sample, C, G, silu,
+                         pos_rows, S(stream));
 }
 int ivgpt_conv_in(int dtype, const float* x, const float* w, const float* b, void* y, int N, int H, int W, int Cout,
                   int frames_per_clip, int clip_frames, int frame_offset, void* stream) {

@@ -40,6 +40,9 @@ struct GemmParams {
   int act;           // 0 none, 1 SiLU, 2 SwiGLU over interleaved column pairs (out has N/2 columns)
   float alpha;
   int tiles_m, tiles_n;
+  // ---- fused GroupNorm statistics of the OUTPUT (mode 1): per (image, tile, n-tile, epilogue warp) partial sums ----
+  float* gn_part;    // [images][slabs][gn_groups][2] (sum, sum of squares), slabs = tiles_per_image * tiles_n * 4; or null
+  int gn_groups;
 };
 
 }  // namespace ivg

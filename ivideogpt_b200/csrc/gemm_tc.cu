@@ -35,7 +35,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barrier block + alignment slack
+  static constexpr int GN_OFFSET = BAR_OFFSET + 256;     // 4 warps x 32 groups x (sum, sumsq) fp32 = 1 KB
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 + 1024;  // + barrier block + GN accumulators + alignment slack
 };
 
 template <typename T, int BN>
@@ -161,6 +162,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile owned by this thread
+    float* gn_acc = reinterpret_cast<float*>(smem + SM::GN_OFFSET) + q * 64;   // this warp's [32 groups][2]
+    const bool gn_on = (p.gn_part != nullptr) && (p.mode == 1);
+    const int gn_cpg = gn_on ? p.N / p.gn_groups : 1;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int bz = tile / tiles_mn;
@@ -191,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       const int ocol0 = n0 + h * p.o_nhead;  // column in the output matrix (before SwiGLU halving)
 
+      if (gn_on) { gn_acc[lane] = 0.f; gn_acc[lane + 32] = 0.f; __syncwarp(); }
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
@@ -201,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(taddr + (uint32_t)c, r);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!gn_on) { if (!row_ok) continue; }
         if (n0 + c >= p.N) continue;
         float v[16];
 #pragma unroll
@@ -237,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           continue;
         }
-        if (p.residual) {
+        if (p.residual && row_ok) {
           const long long roff = (long long)o_b * p.res_bstride + orow * p.ldr + ocol0 + c;
           if (p.res_dtype == DT_BF16) {
             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
@@ -252,6 +257,28 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         if (p.act == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        }
+        if (gn_on) {
+          // statistics of the values being written (fp32, before rounding), reduced over the warp's 32 pixels; the
+          // control flow below depends only on column indices, so it is warp-uniform.
+          int g_prev = (n0 + c) / gn_cpg;
+          float ss = 0.f, qq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int g = (n0 + c + j) / gn_cpg;
+            if (g != g_prev) {
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, off); qq += __shfl_xor_sync(0xffffffffu, qq, off); }
+              if (lane == 0) { gn_acc[2 * g_prev] += ss; gn_acc[2 * g_prev + 1] += qq; }
+              ss = 0.f; qq = 0.f; g_prev = g;
+            }
+            const float x = (row_ok && n0 + c + j < p.N) ? v[j] : 0.f;
+            ss += x; qq = fmaf(x, x, qq);
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, off); qq += __shfl_xor_sync(0xffffffffu, qq, off); }
+          if (lane == 0 && g_prev < p.gn_groups) { gn_acc[2 * g_prev] += ss; gn_acc[2 * g_prev + 1] += qq; }
+          if (!row_ok) continue;
         }
         const long long ooff = (long long)o_b * p.out_bstride + orow * p.ldo + ocol0 + c;
         const bool full = (n0 + c + 16 <= p.N);
@@ -281,6 +308,14 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (gn_on) {
+        const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
+        const int img = tm / tiles_img, t_in = tm - img * tiles_img;
+        const int slabs = tiles_img * p.tiles_n * 4;
+        float* dst = p.gn_part + (((size_t)img * slabs) + ((size_t)t_in * p.tiles_n + tn) * 4 + q) * p.gn_groups * 2;
+        if (lane < p.gn_groups) { dst[2 * lane] = gn_acc[2 * lane]; dst[2 * lane + 1] = gn_acc[2 * lane + 1]; }
+        __syncwarp();
+      }
     }
   }
 

@@ -113,8 +113,10 @@ def gemm_raw(d: GemmDesc):
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1,
             x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-            out_dtype: Optional[torch.dtype] = None, bn: int = 0) -> torch.Tensor:
-    """3x3 conv over NHWC x [N,H,W,Cin] with packed weights [Cout, 9*Cin (+C2)]; optional fused 1x1 source x2."""
+            out_dtype: Optional[torch.dtype] = None, bn: int = 0, gn_groups: int = 0) -> torch.Tensor:
+    """3x3 conv over NHWC x [N,H,W,Cin] with packed weights [Cout, 9*Cin (+C2)]; optional fused 1x1 source x2.
+    gn_groups > 0: the epilogue also emits GroupNorm partial statistics of the output; they ride on the returned tensor
+    as `out.gn_part = (partials [N, slabs, G, 2], slabs)` for groupnorm_stats_from_parts()."""
     _cuda(x, w_packed, bias, x2, residual)
     assert x.is_contiguous() and w_packed.is_contiguous() and x.dtype == w_packed.dtype
     N, H, W, Cin = x.shape
@@ -138,7 +140,16 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
         d.residual = residual.data_ptr(); d.res_dtype = _dt(residual)
     d.act = act
     d.out = out.data_ptr(); d.out_dtype = _dt(out)
+    part = None
+    if gn_groups > 0:
+        bn_c, slabs_c = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.load().ivgpt_conv3x3_plan(C.byref(d), C.byref(bn_c), C.byref(slabs_c)), "conv3x3_plan")
+        d.bn = bn_c.value
+        part = torch.empty(N, slabs_c.value, gn_groups, 2, dtype=torch.float32, device=x.device)
+        d.gn_part = part.data_ptr(); d.gn_groups = gn_groups
     _lib.check(_lib.load().ivgpt_conv3x3(C.byref(d), _stream()), "conv3x3")
+    if part is not None:
+        out.gn_part = (part, slabs_c.value)
     return out
 
 
@@ -159,6 +170,21 @@ def groupnorm_stats(x: torch.Tensor, samples: int, groups: int, eps: float) -> t
     return stats
 
 
+def groupnorm_stats_from_parts(x: torch.Tensor, samples: int, groups: int, eps: float) -> torch.Tensor:
+    """Statistics of a conv output whose epilogue already produced partial sums (x.gn_part); `samples` may merge
+    several consecutive frames (joint kv_norm)."""
+    part, slabs = x.gn_part
+    frames = part.shape[0]
+    assert frames % samples == 0 and part.shape[2] == groups
+    per = frames // samples
+    Cc = x.shape[-1]
+    count = float(x.numel() // (samples * Cc)) * (Cc // groups)
+    stats = torch.empty(samples, groups, 2, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_groupnorm_finalize(part.data_ptr(), stats.data_ptr(), samples, slabs * per, groups,
+                                                    count, eps, _stream()), "groupnorm_finalize")
+    return stats
+
+
 def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,
                     pos: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x, stats, gamma, beta, pos)
@@ -171,8 +197,9 @@ def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, b
     if pos is not None:
         assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[1] == Cc
         pos_rows = pos.shape[0]
+    coef = torch.empty(2 * samples * Cc, dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().ivgpt_groupnorm_apply(_dt(x), x.data_ptr(), y.data_ptr(), stats.data_ptr(),
-                                                 gamma.data_ptr(), beta.data_ptr(), _ptr(pos), total_rows,
+                                                 gamma.data_ptr(), beta.data_ptr(), _ptr(pos), coef.data_ptr(), total_rows,
                                                  total_rows // samples, Cc, groups, int(silu), pos_rows, _stream()),
                "groupnorm_apply")
     return y

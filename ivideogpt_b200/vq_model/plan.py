@@ -108,20 +108,23 @@ class TokenizerPlan:
     # ---- building blocks --------------------------------------------------------------------------
     def _gn(self, x, norm, silu: bool, samples: Optional[int] = None, pos=None):
         n = x.shape[0] if samples is None else samples
-        stats = ops.groupnorm_stats(x, n, norm.num_groups, norm.eps)
+        if getattr(x, "gn_part", None) is not None and x.gn_part[0].shape[2] == norm.num_groups:
+            stats = ops.groupnorm_stats_from_parts(x, n, norm.num_groups, norm.eps)   # fused in the producing conv
+        else:
+            stats = ops.groupnorm_stats(x, n, norm.num_groups, norm.eps)
         return ops.groupnorm_apply(x, stats, self.pw.f32(norm.weight), self.pw.f32(norm.bias), silu,
                                    None if pos is None else self.pw.f32(pos))
 
     def resnet(self, x, r: ResnetParams):
         y = self._gn(x, r.norm1, True)
         w1, b1 = self.pw.conv3(r.conv1, self.dtype)
-        h = ops.conv3x3(y, w1, b1)
+        h = ops.conv3x3(y, w1, b1, gn_groups=r.norm2.num_groups)
         y2 = self._gn(h, r.norm2, True)
         if r.conv_shortcut is not None:
             w2, b2 = self.pw.conv3(r.conv2, self.dtype, shortcut=r.conv_shortcut)
-            return ops.conv3x3(y2, w2, b2, x2=x)
+            return ops.conv3x3(y2, w2, b2, x2=x, gn_groups=self.groups)
         w2, b2 = self.pw.conv3(r.conv2, self.dtype)
-        return ops.conv3x3(y2, w2, b2, residual=x)
+        return ops.conv3x3(y2, w2, b2, residual=x, gn_groups=self.groups)
 
     def attention(self, q_tok, kv_tok, wq, bq, wk, bk, wv, bv, heads: int, frames_per_clip: int):
         """q_tok [F, Lq, C], kv_tok [B, Lkv, C] (F = B*frames_per_clip) -> O [F*Lq, C] (before out-proj)."""
@@ -206,7 +209,7 @@ class TokenizerPlan:
                 x = self.resnet(x, r)
             if stage.downsamplers is not None:
                 wd, bd = self.pw.conv3(stage.downsamplers[0].conv, self.dtype)
-                x = ops.conv3x3(x, wd, bd, stride=2)
+                x = ops.conv3x3(x, wd, bd, stride=2, gn_groups=self.groups)
             if ctx_feats is not None and x.shape[2] <= enc.max_att_resolution:
                 x = self.cross_attention(x, ctx_feats[i + 1], enc.cross_att_blocks[k], B)
                 k += 1
@@ -224,7 +227,7 @@ class TokenizerPlan:
         """latent [F,16,16,latent] NHWC -> frames written into out_clips [B,T,3,H,W]."""
         B = out_clips.shape[0]
         wi, bi = self.pw.conv3(dec.conv_in, self.dtype)
-        x = ops.conv3x3(latent, wi, bi)
+        x = ops.conv3x3(latent, wi, bi, gn_groups=self.groups)
         feats = [x]
         x = self.mid(x, dec.mid_block)
         feats.append(x)
@@ -236,11 +239,14 @@ class TokenizerPlan:
             if stage.upsamplers is not None:
                 x = ops.upsample2x(x)
                 wu, bu = self.pw.conv3(stage.upsamplers[0].conv, self.dtype)
-                x = ops.conv3x3(x, wu, bu)
+                x = ops.conv3x3(x, wu, bu, gn_groups=self.groups)
             if ctx_feats is not None and x.shape[2] <= dec.max_att_resolution:
                 x = self.cross_attention(x, ctx_feats[i + 2], dec.cross_att_blocks[i + 1], B)
             feats.append(x)
-        stats = ops.groupnorm_stats(x, x.shape[0], dec.conv_norm_out.num_groups, dec.conv_norm_out.eps)
+        if getattr(x, "gn_part", None) is not None:
+            stats = ops.groupnorm_stats_from_parts(x, x.shape[0], dec.conv_norm_out.num_groups, dec.conv_norm_out.eps)
+        else:
+            stats = ops.groupnorm_stats(x, x.shape[0], dec.conv_norm_out.num_groups, dec.conv_norm_out.eps)
         w3, b3 = self.pw.conv_out3(dec.conv_out)
         ops.conv_out3(x, stats, self.pw.f32(dec.conv_norm_out.weight), self.pw.f32(dec.conv_norm_out.bias), w3, b3,
                       out_clips, frame_offset, frames_per_clip)

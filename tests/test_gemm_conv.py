@@ -155,3 +155,21 @@ def test_conv3x3_fused_shortcut_and_residual(cuda, dtype):
     out = ops.conv3x3(y.permute(0, 2, 3, 1).contiguous().to(cuda), _pack_conv(w2, dtype).to(cuda), b2.to(cuda),
                       residual=r.permute(0, 2, 3, 1).contiguous().to(cuda), out_dtype=torch.float32)
     assert rel_err(out.permute(0, 3, 1, 2), want) < TOL_EXACT_INPUTS
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,H,Cin,Cout,joint", [(4, 16, 64, 768, 2), (2, 32, 128, 128, 1), (3, 64, 128, 256, 1)])
+def test_conv3x3_fused_groupnorm_statistics(cuda, dtype, N, H, Cin, Cout, joint):
+    """Partial sums emitted by the conv epilogue give the same (mean, rstd) as the stand-alone statistics kernels run
+    on the conv output (fp32 output here, so both see identical values)."""
+    from ivideogpt_b200 import ops
+    x = _mk((N, H, H, Cin), dtype, 41).to(cuda)
+    w = _mk((Cout, 9 * Cin), dtype, 42, 0.05).to(cuda)
+    b = torch.randn(Cout, device=cuda)
+    out = ops.conv3x3(x, w, b, out_dtype=torch.float32, gn_groups=32)
+    assert hasattr(out, "gn_part")
+    samples = N // joint
+    got = ops.groupnorm_stats_from_parts(out, samples, 32, 1e-6)
+    want = ops.groupnorm_stats(out, samples, 32, 1e-6)
+    assert rel_err(got[..., 0], want[..., 0]) < 1e-4 or float((got[..., 0] - want[..., 0]).abs().max()) < 1e-5
+    assert rel_err(got[..., 1], want[..., 1]) < 1e-4
