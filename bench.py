@@ -424,7 +424,7 @@ def run_train(args):
             "config": {"workload": f"{args.workload}: train_gpt.py step, {B} clips/GPU of {res}x{res}x{seg}, frozen fp32 "
                                    f"tokenizer -> Llama fwd+bwd bf16 -> all-reduce -> AdamW", "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "attention_dropout": 0.0},
-            "loss_first_last": [float(losses[0]), float(losses[-1])], "gpu_launches": _lib.launch_count() - n0,
+            "loss_first_last": [float(losses[0].detach()), float(losses[-1].detach())], "gpu_launches": _lib.launch_count() - n0,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "training step (all tcgen05 GEMMs)", "achieved": ach, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": f"bf16_tflops_sustained ({src})",
