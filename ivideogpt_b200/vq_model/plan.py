@@ -17,6 +17,7 @@ Layout decisions (B200-first, not a translation):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -104,6 +105,11 @@ class TokenizerPlan:
         self.groups = groups
         self.dtype = compute_dtype
         self.pw = PackedWeights()
+        # GroupNorm statistics can be emitted by the producing conv's epilogue (ops.conv3x3(gn_groups=...)).  Measured
+        # round 1: the per-chunk warp-shuffle reduction in that epilogue slowed the conv kernel from 963 to 583 TFLOP/s,
+        # more than the separate statistics pass costs -- kept available (and unit-tested) but switched off until the
+        # epilogue reduction is restructured (per-warp shared-memory transpose once per tile).
+        self.fused_stats = groups if os.environ.get("IVGPT_FUSED_GN_STATS", "0") == "1" else 0
 
     # ---- building blocks --------------------------------------------------------------------------
     def _gn(self, x, norm, silu: bool, samples: Optional[int] = None, pos=None):
@@ -118,13 +124,13 @@ class TokenizerPlan:
     def resnet(self, x, r: ResnetParams):
         y = self._gn(x, r.norm1, True)
         w1, b1 = self.pw.conv3(r.conv1, self.dtype)
-        h = ops.conv3x3(y, w1, b1, gn_groups=r.norm2.num_groups)
+        h = ops.conv3x3(y, w1, b1, gn_groups=self.fused_stats)
         y2 = self._gn(h, r.norm2, True)
         if r.conv_shortcut is not None:
             w2, b2 = self.pw.conv3(r.conv2, self.dtype, shortcut=r.conv_shortcut)
-            return ops.conv3x3(y2, w2, b2, x2=x, gn_groups=self.groups)
+            return ops.conv3x3(y2, w2, b2, x2=x, gn_groups=self.fused_stats)
         w2, b2 = self.pw.conv3(r.conv2, self.dtype)
-        return ops.conv3x3(y2, w2, b2, residual=x, gn_groups=self.groups)
+        return ops.conv3x3(y2, w2, b2, residual=x, gn_groups=self.fused_stats)
 
     def attention(self, q_tok, kv_tok, wq, bq, wk, bk, wv, bv, heads: int, frames_per_clip: int):
         """q_tok [F, Lq, C], kv_tok [B, Lkv, C] (F = B*frames_per_clip) -> O [F*Lq, C] (before out-proj)."""
@@ -209,7 +215,7 @@ class TokenizerPlan:
                 x = self.resnet(x, r)
             if stage.downsamplers is not None:
                 wd, bd = self.pw.conv3(stage.downsamplers[0].conv, self.dtype)
-                x = ops.conv3x3(x, wd, bd, stride=2, gn_groups=self.groups)
+                x = ops.conv3x3(x, wd, bd, stride=2, gn_groups=self.fused_stats)
             if ctx_feats is not None and x.shape[2] <= enc.max_att_resolution:
                 x = self.cross_attention(x, ctx_feats[i + 1], enc.cross_att_blocks[k], B)
                 k += 1
@@ -227,7 +233,7 @@ class TokenizerPlan:
         """latent [F,16,16,latent] NHWC -> frames written into out_clips [B,T,3,H,W]."""
         B = out_clips.shape[0]
         wi, bi = self.pw.conv3(dec.conv_in, self.dtype)
-        x = ops.conv3x3(latent, wi, bi, gn_groups=self.groups)
+        x = ops.conv3x3(latent, wi, bi, gn_groups=self.fused_stats)
         feats = [x]
         x = self.mid(x, dec.mid_block)
         feats.append(x)
@@ -239,7 +245,7 @@ class TokenizerPlan:
             if stage.upsamplers is not None:
                 x = ops.upsample2x(x)
                 wu, bu = self.pw.conv3(stage.upsamplers[0].conv, self.dtype)
-                x = ops.conv3x3(x, wu, bu, gn_groups=self.groups)
+                x = ops.conv3x3(x, wu, bu, gn_groups=self.fused_stats)
             if ctx_feats is not None and x.shape[2] <= dec.max_att_resolution:
                 x = self.cross_attention(x, ctx_feats[i + 2], dec.cross_att_blocks[i + 1], B)
             feats.append(x)
