@@ -148,8 +148,11 @@ int ivgpt_embed(const long long* ids, long long ids_stride, int L, const int* dp
 int ivgpt_add_rows(float* x, const float* e, long long n, void* stream);
 int ivgpt_rmsnorm(int dtype, const float* x, const float* w, void* y, long long M, int hidden, float eps,
                   void* stream);
-int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, int B, int Lq, int heads,
-                  int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, void* stream);
+/* v_rows (optional, may be NULL): second copy of V laid out [B][heads][Lmax][64] like K -- what ivgpt_decode_mega's
+ * attention phase streams; v_cache_t [B][heads][64][Lmax] is the K-major operand of the prefill P.V product. */
+int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, void* v_rows, int B, int Lq,
+                  int heads, int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab,
+                  void* stream);
 int ivgpt_softmax(int dtype, const float* S, void* P, long long rows, int Lq, int Lk, long long lds, long long ldp,
                   int causal, int causal_off, void* stream);
 int ivgpt_decode_attn(int dtype, const void* q, const void* k_cache, const void* v_cache_t, void* out, int B,
@@ -193,6 +196,10 @@ typedef struct ivgpt_mega_desc {
   const void* layers_dev; const void* lm_head_map_dev;
   long long* prof; /* optional device [16]: SM-cycle totals of CTA 0 per phase kind (norm, qkv, attention, o, gate/up,
                       down, lm_head, sample, barriers); NULL to disable */
+  void* vrows;     /* bf16 [layers][B][heads][Lmax][64]: V cache in K's layout (filled by ivgpt_rope_kv), used and
+                      appended to when attn_mode == 0 */
+  int attn_mode;   /* attention phase: 0 = K/V streamed by 1-D bulk copies (TMA) into a shared-memory ring,
+                      1 = register-staged loads */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,

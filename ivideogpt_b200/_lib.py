@@ -68,6 +68,8 @@ class MegaDesc(C.Structure):
         ("barrier", C.c_void_p), ("error", C.c_void_p),
         ("layers_dev", C.c_void_p), ("lm_head_map_dev", C.c_void_p),
         ("prof", C.c_void_p),
+        ("vrows", C.c_void_p),
+        ("attn_mode", C.c_int),
     ]
 
 
@@ -97,7 +99,7 @@ SIGNATURES = {
     "ivgpt_embed": [_P, _L, _I, _P, _P, _P, _L, _I, _L, _P],
     "ivgpt_add_rows": [_P, _P, _L, _P],
     "ivgpt_rmsnorm": [_I, _P, _P, _P, _L, _I, _F, _P],
-    "ivgpt_rope_kv": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ivgpt_rope_kv": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ivgpt_softmax": [_I, _P, _P, _L, _I, _I, _L, _L, _I, _I, _P],
     "ivgpt_decode_attn": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _P],
     "ivgpt_argmax": [_P, _L, _I, _I, _P, _L, _P, _P],

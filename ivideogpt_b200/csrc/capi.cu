@@ -99,7 +99,7 @@ int embed_launch(const long long*, long long, int, const int*, const float*, flo
                  cudaStream_t);
 int add_rows_launch(float*, const float*, long long, cudaStream_t);
 int rmsnorm_launch(int, const float*, const float*, void*, long long, int, float, cudaStream_t);
-int rope_kv_launch(int, const void*, void*, void*, void*, int, int, int, int, int, const int*, const float*,
+int rope_kv_launch(int, const void*, void*, void*, void*, void*, int, int, int, int, int, const int*, const float*,
                    const float*, cudaStream_t);
 int softmax_launch(int, const float*, void*, long long, int, int, long long, long long, int, int, cudaStream_t);
 int decode_attn_launch(int, const void*, const void*, const void*, void*, int, int, int, int, const int*, float,
@@ -361,10 +361,11 @@ int ivgpt_rmsnorm(int dtype, const float* x, const float* w, void* y, long long 
                   void* stream) {
   return rmsnorm_launch(dtype, x, w, y, M, hidden, eps, S(stream));
 }
-int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, int B, int Lq, int heads,
-                  int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, void* stream) {
-  return rope_kv_launch(dtype, qkv, q_out, k_cache, v_cache_t, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab,
-                        S(stream));
+int ivgpt_rope_kv(int dtype, const void* qkv, void* q_out, void* k_cache, void* v_cache_t, void* v_rows, int B, int Lq,
+                  int heads, int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab,
+                  void* stream) {
+  return rope_kv_launch(dtype, qkv, q_out, k_cache, v_cache_t, v_rows, B, Lq, heads, Lmax, pos0, dpos, cos_tab,
+                        sin_tab, S(stream));
 }
 int ivgpt_softmax(int dtype, const float* Sm, void* P, long long rows, int Lq, int Lk, long long lds, long long ldp,
                   int causal, int causal_off, void* stream) {
@@ -471,7 +472,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.Lmax = d->Lmax; p.steps = d->steps; p.eps = d->eps; p.o_splits = d->o_splits; p.d_splits = d->d_splits;
   p.x = (float*)d->x; p.xn = (__nv_bfloat16*)d->xn; p.qkv = (__nv_bfloat16*)d->qkv; p.ao = (__nv_bfloat16*)d->ao;
   p.act = (__nv_bfloat16*)d->act; p.part = (float*)d->part; p.logits = (float*)d->logits; p.ldl = d->ldl;
-  p.kcache = (__nv_bfloat16*)d->kcache; p.vcache = (__nv_bfloat16*)d->vcache;
+  p.kcache = (__nv_bfloat16*)d->kcache; p.vcache = (__nv_bfloat16*)d->vcache; p.vrows = (__nv_bfloat16*)d->vrows;
   p.embed = d->embed; p.norm_f = d->norm_f; p.cos_tab = d->cos_tab; p.sin_tab = d->sin_tab;
   p.tokens = d->tokens; p.tok_stride = d->tok_stride; p.dpos = d->dpos;
   p.do_sample = d->do_sample; p.topk = d->topk; p.inv_temp = d->inv_temp; p.dseed = d->dseed;
@@ -479,6 +480,8 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.lw = reinterpret_cast<const ivg::MegaLayer*>(d->layers_dev);
   p.lm_head = reinterpret_cast<const CUtensorMap*>(d->lm_head_map_dev);
   p.prof = d->prof;
+  p.attn_mode = d->attn_mode;
+  IVG_CHECK(p.attn_mode != 0 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
   if (p.steps <= 0) return 0;
   return ivg::decode_mega_launch(p, num_sms(), S(stream));
 }

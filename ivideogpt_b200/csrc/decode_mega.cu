@@ -33,6 +33,8 @@ struct MegaSmem {
   uint64_t* bfull;       // [2]
   uint64_t* mma_done;    // [1]
   uint32_t* tmem_holder;
+  uint64_t* ring_bar;    // [8 warps][8 slots] attention ring: slot filled
+  float* sc;             // attention scratch, MEGA_SC_BYTES
 };
 
 struct MegaCtx {
@@ -387,6 +389,176 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
   __syncwarp();
 }
 
+// 1-D bulk copy (TMA engine, no tensor map) global -> shared, completing on an mbarrier.  dst/src 16-byte aligned,
+// bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+// ring-slot wait that can never hang the GPU: after ~1 s the error flag is raised (the host raises) and bit 31 of
+// `par` makes every later wait of this warp fall through.
+__device__ __forceinline__ void ring_wait(const MegaParams& p, uint64_t* bar, uint32_t& par, int slot) {
+  if (!(par >> 31)) {
+    const uint32_t phase = (par >> slot) & 1u;
+    if (!mbar_try_wait(bar, phase)) {
+      const long long t0 = clock64();
+      while (!mbar_try_wait(bar, phase)) {
+        if (clock64() - t0 > (1ll << 31)) { *p.error = 2; par |= 0x80000000u; break; }
+      }
+    }
+    if (__any_sync(0xffffffffu, (par >> 31) != 0u)) par |= 0x80000000u;
+  }
+  par ^= 1u << slot;
+}
+
+// ---- RoPE + KV append + attention over the cache: one warp per (b, head) item, K/V streamed through a ring ----
+// The register-staged version above stalls once per batch of loads (~22 dependent batches of ~2.4 us per item).  Here
+// lane 0 keeps `nslot` 4 KB bulk copies in flight per warp (the CTA's 128 KB activation region is split between the
+// warps that own an item this round: 5-6 of 8 at B=64 x 12 heads on 148 SMs, i.e. 20-24 KB per warp and ~120 KB per
+// SM in flight), the copy engine writes shared memory directly and the warp consumes slot after slot.  Both K and V
+// are read from [Lmax][64] slabs (V from the row-major second cache `vrows`), 32 positions = 4 KB per unit:
+//   units 0 .. nK-1 : K rows -> scores (8 lanes per row, butterfly over the 8 lanes; same arithmetic as above)
+//   units nK .. 2nK-1 : V rows -> lane (sub, rslot) accumulates dims [8 sub, 8 sub + 8) over positions = rslot mod 4;
+//                       no cross-lane traffic until one 2-step reduction at the end of the item.
+// V units do not depend on the softmax, so they are already in flight while the scores are being computed.
+// (First ring version streamed V^T rows, one bulk copy per row and a 5-step butterfly per row: 61 us/layer, slower
+// than the register version -- the phase is bound by dependent instruction chains at 5-6 warps per SM, not by bytes
+// in flight alone.)
+__device__ void attention_ring(const MegaParams& p, int layer, int bh, int pos, float* wsm, uint8_t* ring, int nslot,
+                               uint64_t* bars, uint32_t& par) {
+  const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
+  const int n = pos + 1;
+  float* sc = wsm;                    // [Lmax + 8]
+  float* qs = wsm + Lmax + 8;         // [64]
+  const int b = bh / heads, hh = bh - b * heads;
+  const int lane = threadIdx.x & 31;
+  __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
+  __nv_bfloat16* vslab = p.vrows + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
+  {
+    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
+    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
+    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
+    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
+    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
+    qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
+    qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
+    kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
+    kslab[(size_t)pos * 64 + lane + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
+    vslab[(size_t)pos * 64 + lane] = v0;
+    vslab[(size_t)pos * 64 + lane + 32] = v1;
+  }
+  // the appended rows are read back below by the copy engine (async proxy): every lane orders its own generic-proxy
+  // stores before it, then the warp converges and lane 0 starts issuing
+  fence_proxy_async_all();
+  __syncwarp();
+
+  const int nK = (n + 31) >> 5;
+  const int units = 2 * nK;
+  auto issue = [&](int u, int slot) {                         // lane 0 only
+    const int c = u < nK ? u : u - nK;
+    const int r0 = c << 5;
+    const uint32_t bytes = (uint32_t)(n - r0 < 32 ? n - r0 : 32) * 128u;
+    mbar_expect_tx(bars + slot, bytes);
+    bulk_g2s(ring + (size_t)slot * MEGA_RING_SLOT, (u < nK ? kslab : vslab) + (size_t)r0 * 64, bytes, bars + slot);
+  };
+  if (lane == 0) {
+    const int pre = units < nslot ? units : nslot;
+    for (int u = 0; u < pre; ++u) issue(u, u);
+  }
+  const int sub = lane & 7, rslot = lane >> 3;
+  float qreg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qreg[i] = qs[sub * 8 + i];
+  float mx = -INFINITY;
+  int slot = 0;
+  for (int u = 0; u < nK; ++u) {
+    ring_wait(p, bars + slot, par, slot);
+    const uint8_t* src = ring + (size_t)slot * MEGA_RING_SLOT + rslot * 128 + sub * 16;
+    uint4 kv[8];
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) kv[ps] = *reinterpret_cast<const uint4*>(src + ps * 512);
+    __syncwarp();                                             // every lane has read the slot: refill it
+    if (lane == 0 && u + nslot < units) issue(u + nslot, slot);
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      const int l = (u << 5) + ps * 4 + rslot;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[ps]);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h2[i]);
+        part = fmaf(qreg[2 * i], f.x, part);
+        part = fmaf(qreg[2 * i + 1], f.y, part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (l < n) {
+        mx = fmaxf(mx, part);
+        if (sub == 0) sc[l] = part;
+      }
+    }
+    slot = slot + 1 == nslot ? 0 : slot + 1;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  __syncwarp();
+  float sum = 0.f;
+  for (int l = lane; l < (nK << 5); l += 32) {                // zero-fills the tail of the last 32-row unit
+    const float e = l < n ? __expf(sc[l] - mx) : 0.f;
+    sc[l] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.0f / sum;
+  __syncwarp();
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int u = nK; u < units; ++u) {
+    ring_wait(p, bars + slot, par, slot);
+    const uint8_t* src = ring + (size_t)slot * MEGA_RING_SLOT + rslot * 128 + sub * 16;
+    const int l0 = ((u - nK) << 5) + rslot;
+    uint4 vv[8];
+    float pl[8];
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      vv[ps] = *reinterpret_cast<const uint4*>(src + ps * 512);
+      pl[ps] = sc[l0 + ps * 4];
+    }
+    __syncwarp();
+    if (lane == 0 && u + nslot < units) issue(u + nslot, slot);
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      if (l0 + ps * 4 < n) {                                  // rows past n in the last unit hold stale bytes
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[ps]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          acc[2 * i] = fmaf(pl[ps], f.x, acc[2 * i]);
+          acc[2 * i + 1] = fmaf(pl[ps], f.y, acc[2 * i + 1]);
+        }
+      }
+    }
+    slot = slot + 1 == nslot ? 0 : slot + 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (rslot == 0) {
+    uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                         pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+    *reinterpret_cast<uint4*>(p.ao + (size_t)b * Hd + hh * 64 + sub * 8) = o;
+  }
+  __syncwarp();
+}
+
 // ---- RoPE + KV append + attention over the cache: a PAIR of warps per (b, head) item ----
 // v1 gave each item a whole CTA: with one CTA per SM an item's loads form a latency chain (~10 us/item, 2.5 TB/s).
 // v2 used one warp per item (6 of 8 warps busy).  v3: 16 warps per CTA, each item split along the sequence between two
@@ -653,10 +825,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   c.sm.bfull = reinterpret_cast<uint64_t*>(c.sm.b[1] + MEGA_B_BYTES);
   c.sm.mma_done = c.sm.bfull + 2;
   c.sm.tmem_holder = reinterpret_cast<uint32_t*>(c.sm.mma_done + 1);
+  c.sm.ring_bar = c.sm.bfull + 16;                                   // 64 barriers, 128 B past the GEMM ones
+  c.sm.sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c.sm.bfull) + MEGA_BAR_BYTES);
+  uint32_t ring_par = 0;                                             // expected parity per ring slot of this warp
   c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.mphase = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(c.sm.bfull, 1); mbar_init(c.sm.bfull + 1, 1); mbar_init(c.sm.mma_done, 1);
+    for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(c.sm.tmem_holder, 32); tmem_relinquish(); }
@@ -694,8 +870,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       prefetch_phase(c, o_g);
       MEGA_BARRIER(); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
-        for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
-          attention_warp(p, l, bh, pos, smem_f + (size_t)warp * (p.Lmax + 8 + 64));
+        if (p.attn_mode == 0) {
+          // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
+          fence_proxy_async();
+          const int total = p.B * p.heads;
+          for (int base = blockIdx.x; base < total; base += (int)gridDim.x * 8) {
+            int active = (total - base + (int)gridDim.x - 1) / (int)gridDim.x;     // warps of this CTA with an item
+            active = active > 8 ? 8 : active;
+            int nslot = (MEGA_A_BYTES / MEGA_RING_SLOT) / active;
+            nslot = nslot > 8 ? 8 : nslot;
+            if (warp < active)
+              attention_ring(p, l, base + (int)gridDim.x * warp, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
+                             c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par);
+            __syncthreads();                 // the next round partitions the ring differently
+          }
+        } else {
+          for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
+            attention_warp(p, l, bh, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64));
+        }
       } else {
         const int pair = warp >> 1, half = warp & 1, npairs = MEGA_THREADS / 64;
         float* psm = smem_f + (size_t)pair * (p.Lmax + 16 + 64 + 2 * 66);
@@ -758,7 +950,7 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
   IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
             "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
   IVG_CHECK((size_t)(p.Lmax + 16 + 64 + 2 * 66) * 4 * (MEGA_THREADS / 64) <= MEGA_A_BYTES &&
-                (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_A_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
+                (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
   static bool attr_set = false;

@@ -9,7 +9,10 @@ constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
 constexpr int MEGA_B_BYTES = MEGA_BN * MEGA_MAXK * 2;   // 32 KB per slab
-constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MEGA_BAR_BYTES = 1024;           // mbarriers: 2 weight slabs, MMA done, TMEM holder, 8 x 8 attention-ring slots
+constexpr int MEGA_SC_BYTES = 30 * 1024;       // attention scratch: per warp scores[Lmax + 8] + q[64] fp32
+constexpr int MEGA_RING_SLOT = 4096;           // attention K/V ring slot (32 K rows, or up to 8 V^T rows)
+constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + MEGA_BAR_BYTES + MEGA_SC_BYTES;
 constexpr int MEGA_MAX_SPLITS = 8;
 
 struct MegaLayer {
@@ -32,6 +35,7 @@ struct MegaParams {
   long long ldl;
   __nv_bfloat16* kcache;    // [layers][B][heads][Lmax][64]
   __nv_bfloat16* vcache;    // [layers][B][heads][64][Lmax]
+  __nv_bfloat16* vrows;     // [layers][B][heads][Lmax][64] (attn_mode 0)
   const float* embed;       // [vocab, hidden] fp32
   const float* norm_f;      // final RMSNorm weight
   const float* cos_tab;     // [max_pos, 32]
@@ -47,6 +51,7 @@ struct MegaParams {
   const MegaLayer* lw;      // device array [layers]
   const CUtensorMap* lm_head;   // device pointer (box {64, 16})
   long long* prof;              // optional [16] cycle counters filled by CTA 0 (phase breakdown), may be null
+  int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
 };
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);

@@ -93,8 +93,8 @@ int rmsnorm_launch(int dtype, const float* x, const float* w, void* y, long long
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void rope_kv_kernel(const T* __restrict__ qkv, T* __restrict__ qout, T* __restrict__ kcache,
-                               T* __restrict__ vcache, int B, int Lq, int heads, int Lmax, int pos0,
-                               const int* __restrict__ dpos, const float* __restrict__ cos_tab,
+                               T* __restrict__ vcache, T* __restrict__ vrows, int B, int Lq, int heads, int Lmax,
+                               int pos0, const int* __restrict__ dpos, const float* __restrict__ cos_tab,
                                const float* __restrict__ sin_tab) {
   // thread = (b, l, head, i in 0..31)
   if (dpos) pos0 += *dpos;
@@ -121,22 +121,28 @@ __global__ void rope_kv_kernel(const T* __restrict__ qkv, T* __restrict__ qout, 
     T* vo = vcache + ((size_t)b * heads + hh) * 64 * Lmax + pos;
     vo[(size_t)i * Lmax] = row[2 * Hd + hh * 64 + i];
     vo[(size_t)(i + 32) * Lmax] = row[2 * Hd + hh * 64 + i + 32];
+    if (vrows) {      // second copy, [pos][64] like K: the layout the decode megakernel streams (decode_mega.cu)
+      T* vr = vrows + (((size_t)b * heads + hh) * Lmax + pos) * 64;
+      vr[i] = row[2 * Hd + hh * 64 + i];
+      vr[i + 32] = row[2 * Hd + hh * 64 + i + 32];
+    }
   }
 }
 
-int rope_kv_launch(int dtype, const void* qkv, void* qout, void* kcache, void* vcache, int B, int Lq, int heads,
-                   int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, cudaStream_t st) {
+int rope_kv_launch(int dtype, const void* qkv, void* qout, void* kcache, void* vcache, void* vrows, int B, int Lq,
+                   int heads, int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, cudaStream_t st) {
   IVG_CHECK(pos0 + Lq <= Lmax, "rope_kv: pos0+Lq=%d exceeds cache length %d", pos0 + Lq, Lmax);
   if (B == 0 || Lq == 0) return 0;
   long long work = (long long)B * Lq * heads * 32;
   int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
   if (dtype == DT_BF16)
     rope_kv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)qout,
-                                                          (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, B, Lq, heads,
-                                                          Lmax, pos0, dpos, cos_tab, sin_tab);
+                                                          (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache,
+                                                          (__nv_bfloat16*)vrows, B, Lq, heads, Lmax, pos0, dpos,
+                                                          cos_tab, sin_tab);
   else
-    rope_kv_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, (float*)qout, (float*)kcache, (float*)vcache, B,
-                                                  Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab);
+    rope_kv_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, (float*)qout, (float*)kcache, (float*)vcache,
+                                                  (float*)vrows, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab);
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;

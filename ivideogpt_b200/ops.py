@@ -305,9 +305,9 @@ def rmsnorm(x, w, y, M, eps):
                                          _stream()), "rmsnorm")
 
 
-def rope_kv(qkv, q_out, k_cache, v_cache_t, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab):
+def rope_kv(qkv, q_out, k_cache, v_cache_t, B, Lq, heads, Lmax, pos0, dpos, cos_tab, sin_tab, v_rows=None):
     _lib.check(_lib.load().ivgpt_rope_kv(_dt(qkv), qkv.data_ptr(), q_out.data_ptr(), k_cache.data_ptr(),
-                                         v_cache_t.data_ptr(), B, Lq, heads, Lmax, pos0, _ptr(dpos),
+                                         v_cache_t.data_ptr(), _ptr(v_rows), B, Lq, heads, Lmax, pos0, _ptr(dpos),
                                          cos_tab.data_ptr(), sin_tab.data_ptr(), _stream()), "rope_kv")
 
 

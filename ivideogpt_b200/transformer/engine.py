@@ -20,6 +20,8 @@ from __future__ import annotations
 import math
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 
 from .. import ops
@@ -105,6 +107,11 @@ class LlamaEngine:
         v = self.buf("vcache_t", (w.layers_n, B, w.heads, 64, Lmax), self.dtype)
         return k, v
 
+    def v_rows(self, B, Lmax):
+        """Second V cache in K's [Lmax][64] layout: written by the prefill's rope_kv, streamed by the decode megakernel."""
+        w = self.w
+        return self.buf("vcache_rows", (w.layers_n, B, w.heads, Lmax, 64), self.dtype)
+
     # ---- one transformer layer over M = B*Lq rows -----------------------------------------------------
     def _layer(self, li, x, B, Lq, kc, vc, Lmax, pos0, dpos, prefill: bool):
         w, dt, code = self.w, self.dtype, self.code
@@ -116,7 +123,8 @@ class LlamaEngine:
         qkv = self.buf("qkv", (M, 3 * h), dt)
         ops.gemm(xn, lw["wqkv"], out=qkv)
         q = self.buf("q", (B, H, Lq, 64), dt)
-        ops.rope_kv(qkv, q, kc[li], vc[li], B, Lq, H, Lmax, pos0, dpos, w.cos, w.sin)
+        vr = self.v_rows(B, Lmax)[li] if (prefill and dt == torch.bfloat16) else None
+        ops.rope_kv(qkv, q, kc[li], vc[li], B, Lq, H, Lmax, pos0, dpos, w.cos, w.sin, v_rows=vr)
         ao = self.buf("attn_out", (M, h), dt)
         if prefill:
             Lk = pos0 + Lq
@@ -232,7 +240,7 @@ class LlamaEngine:
         if o_s is None:
             return False
         return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024
-                and (w.vocab + 256) * 4 <= 128 * 1024 and (Lmax + 88) * 4 <= 128 * 1024)
+                and (w.vocab + 256) * 4 <= 128 * 1024 and (Lmax + 72) * 4 * 8 <= 30 * 1024)
 
     def _mega_splits(self):
         w = self.w
@@ -289,7 +297,7 @@ class LlamaEngine:
         d.act = self.buf("actd", (B, w.inter), self.dtype).data_ptr()
         d.part = self.buf("mega_part", (max(o_s, d_s), B, h), torch.float32).data_ptr()
         d.logits = logits.data_ptr(); d.ldl = logits.stride(0)
-        d.kcache = kc.data_ptr(); d.vcache = vc.data_ptr()
+        d.kcache = kc.data_ptr(); d.vcache = vc.data_ptr(); d.vrows = self.v_rows(B, Lmax).data_ptr()
         d.embed = w.embed.data_ptr(); d.norm_f = w.norm.data_ptr(); d.cos_tab = w.cos.data_ptr(); d.sin_tab = w.sin.data_ptr()
         d.tokens = tokens.data_ptr(); d.tok_stride = tokens.stride(0)
         d.dpos = dpos.data_ptr()
@@ -300,6 +308,7 @@ class LlamaEngine:
         d.dseed = dseed.data_ptr()
         d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
         d.layers_dev = dev_tab.data_ptr(); d.lm_head_map_dev = dev_tab.data_ptr() + w.layers_n * nbytes
+        d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
         if getattr(self, "mega_profile", False):
             self.mega_prof = self.buf("mega_prof", (16,), torch.int64)
             self.mega_prof.zero_()
@@ -348,8 +357,10 @@ class LlamaEngine:
                                  f"{self.w.hidden}/{self.w.inter}")
             sync = self._decode_mega(B, Lmax, tokens, dpos, sample_cfg, dseed, steps)
             out = tokens.clone()
-            if int(sync[1].item()) != 0:
-                raise RuntimeError("decode megakernel: device-wide barrier timed out (a CTA was not co-resident?)")
+            err = int(sync[1].item())
+            if err != 0:
+                raise RuntimeError("decode megakernel: device-wide barrier timed out (a CTA was not co-resident?)" if err == 1
+                                   else "decode megakernel: an attention ring slot never filled (bulk copy fault)")
             return out
         if not use_graph:
             ops.set_pdl(use_pdl)

@@ -140,6 +140,29 @@ def test_decode_megakernel_matches_multikernel_path(cuda):
 
 
 @pytest.mark.gpu
+def test_decode_megakernel_attention_ring_vs_register_path(cuda):
+    """The attention phase of the megakernel has two implementations (K/V streamed by bulk copies into a shared-memory
+    ring, and register-staged loads); both do the same arithmetic per position, so a greedy rollout over a long
+    cache (several ring refills, partial last K chunk, V^T rows of non-multiple-of-8 length) must agree."""
+    from oracle.llama_ref import TINY_LLAMA
+    cfg = dict(TINY_LLAMA, hidden_size=192, intermediate_size=768, num_attention_heads=3, num_key_value_heads=3,
+               max_position_embeddings=1024)
+    ref, mine = _pair(cfg, cuda, torch.bfloat16, scale=3.0)
+    ids = torch.randint(0, 1026, (64, 301), generator=torch.Generator().manual_seed(11)).to(cuda)
+    eng = mine.b200_engine()
+    outs = []
+    for mode in (1, 0):
+        eng.mega_attn_mode = mode
+        outs.append(eng.generate(ids, None, 45, False, 0, 1.0, 0, use_mega=True))
+    eng.mega_attn_mode = 0
+    g = eng.generate(ids, None, 45, False, 0, 1.0, 0, use_mega=False)
+    regs, ring = outs
+    assert torch.equal(ring[:, :302], g[:, :302])
+    assert (ring == regs).float().mean().item() > 0.98, (ring != regs).nonzero()[:5]
+    assert (ring == g).float().mean().item() > 0.9
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol_loss,min_cos", [(torch.float32, 1e-3, 0.9995), (torch.bfloat16, 5e-3, 0.99)])
 def test_training_forward_backward_vs_hf_autograd(cuda, dtype, tol_loss, min_cos):
     """Row a8 backward: loss and every parameter gradient of model(input_ids, labels) against HF autograd (fp32, CPU)."""

@@ -11,7 +11,9 @@ eng = llm.b200_engine()
 ids = torch.randint(0, 16384, (B, 514), device=dev)
 new = 237
 res = {}
-for name, kw in (("graph", dict(use_mega=False)), ("mega", dict(use_mega=True))):
+for name, kw, mode in (("graph", dict(use_mega=False), 0), ("mega_regs", dict(use_mega=True), 1),
+                       ("mega", dict(use_mega=True), 0)):
+    eng.mega_attn_mode = mode
     for _ in range(2):
         eng.generate(ids, None, new, True, 100, 1.0, 1, **kw)
     torch.cuda.synchronize()
@@ -23,12 +25,13 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record(); eng.generate(ids, None, 1, True, 100, 1.0, 1); b.record(); torch.cuda.synchronize()
 res["prefill_plus_first_token_ms"] = a.elapsed_time(b)
 eng.mega_profile = True
-eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
-torch.cuda.synchronize()
-cyc = eng.mega_prof.cpu().tolist()[:9]
 names = ["norm", "qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "sample", "barriers"]
 mhz = 1965.0
-res["mega_phase_ms_cta0"] = {n: c / (mhz * 1e3) for n, c in zip(names, cyc)}
-res["mega_phase_us_per_step"] = {n: c / (mhz) / (new - 1) for n, c in zip(names, cyc)}
+for mode, tag in ((1, "_regs"), (0, "")):
+    eng.mega_attn_mode = mode
+    eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
+    torch.cuda.synchronize()
+    cyc = eng.mega_prof.cpu().tolist()[:9]
+    res["mega_phase_us_per_step" + tag] = {n: c / (mhz) / (new - 1) for n, c in zip(names, cyc)}
 res["decode_steps"] = new - 1
 print(json.dumps(res))
