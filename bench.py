@@ -285,6 +285,18 @@ def run_b200(args):
         time.sleep(0.3)
     total_ms, per_step, launches = timed(step_resident, args.steps, profile=True)
     clocks = sampler.finish() if sampler else None
+    # where the step goes (one extra, untimed-for-the-headline pass with events between the three API calls)
+    sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sev[0].record()
+    _prompt = tok.tokenize_context(clips_dev)
+    sev[1].record()
+    _out = llm.generate(_prompt, **gen_kw)
+    sev[2].record()
+    tok.detokenize(_out, ctx)
+    sev[3].record()
+    torch.cuda.synchronize()
+    stages = {"tokenize_context_ms": sev[0].elapsed_time(sev[1]), "generate_ms": sev[1].elapsed_time(sev[2]),
+              "detokenize_ms": sev[2].elapsed_time(sev[3])}
     # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), measured in the timed region above
     prof = {}
     for bucket, name in ((1, "conv"), (0, "gemm")):
@@ -327,7 +339,7 @@ def run_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (U[0,1) pixels, seeded random weights in the reference state-dict layout)",
         "config": workload_config(args, B, res),
-        "per_step_ms": per_step, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "per_step_ms": per_step, "stages_ms": stages, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "e2e": {"value": frames_per_step / (e2e_ms / e2e_steps / 1e3), "unit": "frames/s",
                 "h2d_bytes_per_step": px_bytes, "d2h_bytes_per_step": px_bytes, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "CompressiveVQModel.tokenize(all frames) -> B200LlamaForCausalLM.generate -> detokenize -> .cpu()"},

@@ -739,8 +739,18 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ float s_hi[MEGA_THREADS];
   __shared__ int s_win, s_lastmass;
-#pragma unroll 8
-  for (int c = tid; c < V; c += MEGA_THREADS) keys[c] = mega_fkey(row[c] * p.inv_temp);
+  {   // 16-byte loads, all of a thread's requests in flight before the first use (rows are 16-byte aligned: ldl % 4 == 0)
+    const int V4 = V >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    uint4* keys4 = reinterpret_cast<uint4*>(keys);
+#pragma unroll 4
+    for (int c = tid; c < V4; c += MEGA_THREADS) {
+      const float4 v = row4[c];
+      keys4[c] = make_uint4(mega_fkey(v.x * p.inv_temp), mega_fkey(v.y * p.inv_temp), mega_fkey(v.z * p.inv_temp),
+                            mega_fkey(v.w * p.inv_temp));
+    }
+    for (int c = (V4 << 2) + tid; c < V; c += MEGA_THREADS) keys[c] = mega_fkey(row[c] * p.inv_temp);
+  }
   if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)(p.topk < V ? p.topk : V); s_win = 0x7fffffff; s_lastmass = 0; }
   __syncthreads();
   for (int pass = 0; pass < 4; ++pass) {
@@ -749,9 +759,15 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
     __syncthreads();
     const uint32_t prefix = s_prefix;
     const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int c = tid; c < V; c += MEGA_THREADS) {
-      const uint32_t kk = keys[c];
-      if ((kk & mask) == prefix) atomicAdd(&hist[(kk >> shift) & 255], 1u);
+    // logits share a few exponents, so the leading digits fall into a handful of bins: aggregate equal bins inside
+    // the warp (match.any) and let one lane add the count -- plain per-key shared-memory atomics serialised to ~30 us
+    for (int c0 = 0; c0 < V; c0 += MEGA_THREADS) {
+      const int c = c0 + tid;
+      const uint32_t kk = c < V ? keys[c] : 0u;
+      const bool in = c < V && (kk & mask) == prefix;
+      const uint32_t bin = in ? ((kk >> shift) & 255u) : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
     }
     __syncthreads();
     if (tid == 0) {
