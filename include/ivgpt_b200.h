@@ -176,10 +176,11 @@ int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_c
                             float scale, void* stream);
 /* ---- persistent decode megakernel (bf16): `steps` consecutive decode steps of HF generate in ONE cooperative launch
  * (embed -> layers x {qkv, RoPE+append+attention, o, norm, gate/up+SwiGLU, down, norm} -> lm_head -> sample -> append).
- * Weight tensor maps live in a device array of ivgpt_mega_layer_bytes()-sized records filled on the host with
- * ivgpt_mega_fill_layer() (weights are the packed operands of the multi-kernel path: wqkv [3h,h], wo [h,h],
- * wgu [2*inter,h] gate/up interleaved, wd [h,inter]) and copied to the device by the caller; lm_head_map_dev is a
- * 128-byte CUtensorMap record filled with ivgpt_mega_fill_map().  barrier/error must be zero before each launch. */
+ * Weights are streamed as whole 16-row K-slabs by 1-D bulk copies, so every matrix (wqkv [3h,h], wo [h,h], wgu
+ * [2*inter,h] gate/up interleaved, wd [h,inter], lm_head [vocab,h]; bf16 row-major) is first re-laid once with
+ * ivgpt_mega_pack_weight() into a buffer of ivgpt_mega_packed_elems(rows, cols) bf16.  The per-layer pointers live in
+ * a device array of ivgpt_mega_layer_bytes()-sized records filled on the host with ivgpt_mega_fill_layer() and copied
+ * to the device by the caller.  barrier/error must be zero before each launch. */
 typedef struct ivgpt_mega_desc {
   int B, hidden, inter, heads, layers, vocab, Lmax, steps;
   int o_splits, d_splits; /* split-K of o-proj / down-proj; part holds max(o,d) x B x hidden fp32 */
@@ -193,7 +194,7 @@ typedef struct ivgpt_mega_desc {
   int do_sample, topk; float inv_temp;
   const unsigned long long* dseed;
   unsigned int* barrier; int* error;
-  const void* layers_dev; const void* lm_head_map_dev;
+  const void* layers_dev; const void* lm_head_packed;
   long long* prof; /* optional device [16]: SM-cycle totals of CTA 0 per phase kind (norm, qkv, attention, o, gate/up,
                       down, lm_head, sample, barriers); NULL to disable */
   void* vrows;     /* bf16 [layers][B][heads][Lmax][64]: V cache in K's layout (filled by ivgpt_rope_kv), used and
@@ -202,9 +203,10 @@ typedef struct ivgpt_mega_desc {
                       1 = register-staged loads */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
-int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,
-                          const float* n1, const float* n2, int hidden, int inter);
-int ivgpt_mega_fill_map(void* host_map, const void* w, int rows, int cols);
+long long ivgpt_mega_packed_elems(int rows, int cols);
+int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);
+int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv_packed, const void* wo_packed, const void* wgu_packed,
+                          const void* wd_packed, const float* n1, const float* n2);
 int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream);
 /* ---- training pieces: backward of LlamaForCausalLM.forward(labels) (train_gpt.py:792-798) and the AdamW update
  * (train_gpt.py:648-658,803).  All contractions of the backward pass are ivgpt_gemm calls on transposed operands. */

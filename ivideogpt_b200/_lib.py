@@ -66,7 +66,7 @@ class MegaDesc(C.Structure):
         ("do_sample", C.c_int), ("topk", C.c_int), ("inv_temp", C.c_float),
         ("dseed", C.c_void_p),
         ("barrier", C.c_void_p), ("error", C.c_void_p),
-        ("layers_dev", C.c_void_p), ("lm_head_map_dev", C.c_void_p),
+        ("layers_dev", C.c_void_p), ("lm_head_packed", C.c_void_p),
         ("prof", C.c_void_p),
         ("vrows", C.c_void_p),
         ("attn_mode", C.c_int),
@@ -120,11 +120,13 @@ SIGNATURES = {
     "ivgpt_vq_set_order": [_I],
     "ivgpt_vq_get_order": [],
     "ivgpt_mega_layer_bytes": [],
-    "ivgpt_mega_fill_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I],
-    "ivgpt_mega_fill_map": [_P, _P, _I, _I],
+    "ivgpt_mega_fill_layer": [_P, _P, _P, _P, _P, _P, _P],
+    "ivgpt_mega_packed_elems": [_I, _I],
+    "ivgpt_mega_pack_weight": [_P, _P, _I, _I, _P],
     "ivgpt_decode_mega": [C.POINTER(MegaDesc), _P],
 }
-_RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong}
+_RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong,
+             "ivgpt_mega_packed_elems": C.c_longlong}
 
 _lib = None
 

@@ -442,24 +442,19 @@ int ivgpt_vq_get_order(void) { return ivg::g_vq_order; }
 // ---- persistent decode megakernel -------------------------------------------------------------------
 int ivgpt_mega_layer_bytes(void) { return (int)sizeof(ivg::MegaLayer); }
 
-static int mega_weight_map(CUtensorMap* m, const void* w, int rows, int cols) {
-  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
-  uint64_t str[1] = {(uint64_t)cols * 2};
-  uint32_t box[2] = {64, (uint32_t)ivg::MEGA_BN};
-  return make_tensor_map(m, DT_BF16, w, 2, dims, str, box, 1);
+long long ivgpt_mega_packed_elems(int rows, int cols) {
+  return (long long)((rows + ivg::MEGA_BN - 1) / ivg::MEGA_BN) * ivg::MEGA_BN * cols;
 }
 
-int ivgpt_mega_fill_map(void* host_map, const void* w, int rows, int cols) {
-  return mega_weight_map(reinterpret_cast<CUtensorMap*>(host_map), w, rows, cols);
+int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream) {
+  return ivg::mega_pack_weight_launch(w, out, rows, cols, S(stream));
 }
 
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,
-                          const float* n1, const float* n2, int hidden, int inter) {
+                          const float* n1, const float* n2) {
   ivg::MegaLayer* L = reinterpret_cast<ivg::MegaLayer*>(host_layer);
-  if (mega_weight_map(&L->wqkv, wqkv, 3 * hidden, hidden)) return 1;
-  if (mega_weight_map(&L->wo, wo, hidden, hidden)) return 1;
-  if (mega_weight_map(&L->wgu, wgu, 2 * inter, hidden)) return 1;
-  if (mega_weight_map(&L->wd, wd, hidden, inter)) return 1;
+  L->wqkv = (const __nv_bfloat16*)wqkv; L->wo = (const __nv_bfloat16*)wo;
+  L->wgu = (const __nv_bfloat16*)wgu; L->wd = (const __nv_bfloat16*)wd;
   L->n1 = n1; L->n2 = n2;
   return 0;
 }
@@ -478,7 +473,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.do_sample = d->do_sample; p.topk = d->topk; p.inv_temp = d->inv_temp; p.dseed = d->dseed;
   p.barrier = d->barrier; p.error = d->error;
   p.lw = reinterpret_cast<const ivg::MegaLayer*>(d->layers_dev);
-  p.lm_head = reinterpret_cast<const CUtensorMap*>(d->lm_head_map_dev);
+  p.lm_head = reinterpret_cast<const __nv_bfloat16*>(d->lm_head_packed);
   p.prof = d->prof;
   p.attn_mode = d->attn_mode;
   IVG_CHECK(p.attn_mode != 0 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");

@@ -11,8 +11,11 @@
 //            down GEMM (split-K) | add+norm } x layers | lm_head GEMM | sample+append
 // GEMM phases (tcgen05, M = 128-row UMMA with the first B rows valid, N = 16 per work item so every SM streams its
 // own slice of the weight matrix):
-//   * B operand (weights) : TMA, SWIZZLE_128B, whole K-slab of the item in one burst; the slab of the NEXT phase is
-//     issued before the device-wide barrier, so the weight fetch overlaps the barrier + the neighbour phase.
+//   * B operand (weights) : pre-packed once (ivgpt_mega_pack_weight) into the exact 128B-swizzled shared-memory image
+//     of every 16-row work item, so an item's whole K-slab is ONE contiguous 1-D bulk copy (8-32 KB); up to four slabs
+//     are in flight per CTA and the first slabs of the NEXT phase are issued before the device-wide barrier, so the
+//     weight stream overlaps the barrier + the neighbour phase.  (Until v6 the slab was 12 tensor-map boxes of 16 x
+//     128 B with one slab of look-ahead: ~3.4 us per item, 1.4 TB/s on the lm_head phase.)
 //   * A operand (activations, <= 128 x 1024 bf16): written by the previous phase with ordinary stores, so it is
 //     loaded with ordinary loads and laid out in shared memory by hand in the 128B-swizzled K-major format
 //     (16-byte chunk c of row r lands at chunk c ^ (r & 7)); rows >= B of the UMMA tile alias whatever follows in
@@ -29,8 +32,11 @@ namespace ivg {
 
 struct MegaSmem {
   uint8_t* a;            // A region (1024-aligned)
-  uint8_t* b[2];         // weight slabs
-  uint64_t* bfull;       // [2]
+  uint8_t* b0;           // weight slab buffers: nbuf x slab_bytes, directly above the activation slab
+  uint32_t slab_bytes;   // 16 rows x max K per item x 2 B
+  uint32_t nbuf;         // 2..4
+  uint32_t a_bytes;      // activation slab / attention ring / sampler scratch region size
+  uint64_t* bfull;       // [4]
   uint64_t* mma_done;    // [1]
   uint32_t* tmem_holder;
   uint64_t* ring_bar;    // [8 warps][8 slots] attention ring: slot filled
@@ -42,7 +48,7 @@ struct MegaCtx {
   uint32_t tmem_base;
   uint32_t epoch;          // barrier target (thread 0)
   // Weight-slab queue (thread 0 only).  This CTA's slab loads form one deterministic sequence over the whole kernel;
-  // load #i always goes to buffer i & 1 and is consumed with parity (i >> 1) & 1.  At most two are in flight.
+  // load #i always goes to buffer i % nbuf and is consumed with parity (i / nbuf) & 1.  At most nbuf are in flight.
   uint32_t issued, consumed;
   int phase_issued;        // items of the CURRENT/coming phase whose slab has been issued already
   uint32_t mphase;         // parity of mma_done (all threads)
@@ -85,14 +91,24 @@ __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
   return s_ok != 0;
 }
 
-// ---- weight slab TMA: item -> (n0, k0, Kc); Kc/64 boxes of {64 k, 16 rows} land on bfull[buffer] ----
-__device__ __forceinline__ void issue_slab(MegaCtx& c, const CUtensorMap* map, int n0, int k0, int Kc) {
-  const int buf = (int)(c.issued & 1u);
+// 1-D bulk copy (TMA engine, no tensor map) global -> shared, completing on an mbarrier.  dst/src 16-byte aligned,
+// bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// ---- weight slab: item (tile, split) of a packed matrix -> one contiguous copy of Kc * 32 bytes ----
+// packed layout (ivgpt_mega_pack_weight): [tile = n / 16][k-block = k / 64][row = n % 16][chunk ^ (row & 7)][8 bf16]
+__device__ __forceinline__ void issue_slab(MegaCtx& c, const __nv_bfloat16* packed, int K, int tile, int k0, int Kc) {
+  const uint32_t buf = c.issued % c.sm.nbuf;
   ++c.issued;
-  const int nkb = Kc / 64;
-  mbar_expect_tx(c.sm.bfull + buf, (uint32_t)(nkb * MEGA_BN * 128));
-  for (int j = 0; j < nkb; ++j)
-    tma_load_2d(c.sm.b[buf] + j * (MEGA_BN * 128), map, c.sm.bfull + buf, k0 + j * 64, n0);
+  const uint32_t bytes = (uint32_t)Kc * (MEGA_BN * 2);
+  mbar_expect_tx(c.sm.bfull + buf, bytes);
+  bulk_g2s(c.sm.b0 + (size_t)buf * c.sm.slab_bytes, packed + ((size_t)tile * K + k0) * MEGA_BN, bytes, c.sm.bfull + buf);
 }
 
 // ---- A operand: rows [0, B) x k [k0, k0+Kc) of a row-major bf16 matrix -> swizzled 64-row K-major tiles ----
@@ -123,7 +139,7 @@ __device__ __forceinline__ void load_a(const MegaParams& p, MegaCtx& c, const __
 enum { EPI_STORE_BF16 = 0, EPI_PARTIAL_F32 = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
 
 struct GemmPhase {
-  const CUtensorMap* map;   // weights [N, K]
+  const __nv_bfloat16* w;   // packed weights of [N, K]
   int N, K, ksplits;        // work items = ceil(N/16) * ksplits, item K = K / ksplits
   const __nv_bfloat16* A;
   long long lda;
@@ -142,7 +158,7 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
   while (c.phase_issued < upto) {
     const int w = blockIdx.x + c.phase_issued * gridDim.x;
     if (w >= items) break;
-    issue_slab(c, g.map, (w % ntiles) * MEGA_BN, (w / ntiles) * Kc, Kc);
+    issue_slab(c, g.w, g.K, w % ntiles, (w / ntiles) * Kc, Kc);
     ++c.phase_issued;
   }
 }
@@ -151,7 +167,7 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
 __device__ __forceinline__ void prefetch_phase(MegaCtx& c, const GemmPhase& g) {
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
-  issue_items(c, g, 1);
+  issue_items(c, g, (int)c.sm.nbuf);      // every buffer is free here: the previous GEMM phase has retired
 }
 
 __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
@@ -171,13 +187,13 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
       loaded_split = split;
     }
     if (threadIdx.x == 0) {
-      issue_items(c, g, it + 2);          // this item (if not prefetched) and the next one (other buffer)
-      const int buf = (int)(c.consumed & 1u);
-      const uint32_t par = (c.consumed >> 1) & 1u;
+      issue_items(c, g, it + (int)c.sm.nbuf);   // this item (if not prefetched) and the following nbuf - 1
+      const uint32_t buf = c.consumed % c.sm.nbuf;
+      const uint32_t par = (c.consumed / c.sm.nbuf) & 1u;
       ++c.consumed;
       mbar_wait(c.sm.bfull + buf, par);
       tc_fence_after();
-      const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b[buf]);
+      const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
       for (int j = 0; j < nkb; ++j) {
         const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
         const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * MEGA_BN * 128));
@@ -389,15 +405,6 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
   __syncwarp();
 }
 
-// 1-D bulk copy (TMA engine, no tensor map) global -> shared, completing on an mbarrier.  dst/src 16-byte aligned,
-// bytes a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 // ring-slot wait that can never hang the GPU: after ~1 s the error flag is raised (the host raises) and bit 31 of
 // `par` makes every later wait of this warp fall through.
 __device__ __forceinline__ void ring_wait(const MegaParams& p, uint64_t* bar, uint32_t& par, int slot) {
@@ -836,10 +843,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   MegaCtx c;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mega_raw) + 1023) & ~(uintptr_t)1023);
   c.sm.a = base;
-  c.sm.b[0] = base + MEGA_A_BYTES;
-  c.sm.b[1] = c.sm.b[0] + MEGA_B_BYTES;
-  c.sm.bfull = reinterpret_cast<uint64_t*>(c.sm.b[1] + MEGA_B_BYTES);
-  c.sm.mma_done = c.sm.bfull + 2;
+  {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
+    const int a_rows = p.B <= 64 ? 64 : 128;
+    const int kmax = p.hidden > p.inter / p.d_splits ? p.hidden : p.inter / p.d_splits;
+    c.sm.a_bytes = (uint32_t)(a_rows * kmax * 2);
+    if (c.sm.a_bytes < 64u * 1024u) c.sm.a_bytes = 64u * 1024u;      // attention ring / sampler scratch floor
+    c.sm.slab_bytes = (uint32_t)(MEGA_BN * kmax * 2);
+    const uint32_t nb = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - c.sm.a_bytes) / c.sm.slab_bytes;
+    c.sm.nbuf = nb > 4u ? 4u : nb;
+    c.sm.b0 = base + c.sm.a_bytes;
+  }
+  c.sm.bfull = reinterpret_cast<uint64_t*>(base + MEGA_A_BYTES + 2 * MEGA_B_BYTES);
+  c.sm.mma_done = c.sm.bfull + 4;
   c.sm.tmem_holder = reinterpret_cast<uint32_t*>(c.sm.mma_done + 1);
   c.sm.ring_bar = c.sm.bfull + 16;                                   // 64 barriers, 128 B past the GEMM ones
   c.sm.sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c.sm.bfull) + MEGA_BAR_BYTES);
@@ -847,7 +862,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.mphase = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    mbar_init(c.sm.bfull, 1); mbar_init(c.sm.bfull + 1, 1); mbar_init(c.sm.mma_done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(c.sm.bfull + i, 1);
+    mbar_init(c.sm.mma_done, 1);
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
@@ -872,17 +888,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
-    GemmPhase qkv_g{&p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H};
+    GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H};
     prefetch_phase(c, qkv_g);
     norm_phase(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
     MEGA_BARRIER(); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
-      qkv_g.map = &L.wqkv;
+      qkv_g.w = L.wqkv;
       gemm_phase(p, c, qkv_g);
       MEGA_MARK(1);
-      GemmPhase o_g{&L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
+      GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, o_g);
       MEGA_BARRIER(); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
@@ -893,7 +909,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           for (int base = blockIdx.x; base < total; base += (int)gridDim.x * 8) {
             int active = (total - base + (int)gridDim.x - 1) / (int)gridDim.x;     // warps of this CTA with an item
             active = active > 8 ? 8 : active;
-            int nslot = (MEGA_A_BYTES / MEGA_RING_SLOT) / active;
+            int nslot = (int)(c.sm.a_bytes / MEGA_RING_SLOT) / active;   // weight slabs of the o-proj sit above a_bytes
             nslot = nslot > 8 ? 8 : nslot;
             if (warp < active)
               attention_ring(p, l, base + (int)gridDim.x * warp, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
@@ -914,7 +930,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, o_g);
       MEGA_MARK(3);
-      GemmPhase gu_g{&L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
+      GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
       prefetch_phase(c, gu_g);
       MEGA_BARRIER(); if (!ok) break;
       norm_phase(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
@@ -922,13 +938,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, gu_g);
       MEGA_MARK(4);
-      GemmPhase d_g{&L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
+      GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, d_g);
       MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, d_g);
       MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
-      GemmPhase nx_g{last ? p.lm_head : &p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, 1, p.xn, H,
+      GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, 1, p.xn, H,
                      last ? EPI_LOGITS : EPI_STORE_BF16, last ? (void*)p.logits : (void*)p.qkv,
                      last ? p.ldl : (long long)(3 * H)};
       prefetch_phase(c, nx_g);
@@ -951,6 +967,37 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 32); }
+}
+
+// ---- one-off weight packing: [rows, cols] bf16 row-major -> per 16-row work item the 128B-swizzled K-major image ----
+// out[tile][k-block][row][chunk' = chunk ^ (row & 7)][8]; rows padded with zeros to a multiple of 16.
+__global__ void mega_pack_weight_kernel(const uint4* __restrict__ w, uint4* __restrict__ out, int rows, int cols,
+                                        long long chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i & 7);
+    const int r = (int)((i >> 3) & 15);
+    const long long jt = i >> 7;
+    const int nkb = cols >> 6;
+    const int j = (int)(jt % nkb);
+    const long long tile = jt / nkb;
+    const long long n = tile * 16 + r;
+    const int ch = cp ^ (r & 7);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < rows) v = w[(n * cols + j * 64 + ch * 8) >> 3];
+    out[i] = v;
+  }
+}
+
+int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, cudaStream_t st) {
+  IVG_CHECK(cols % 64 == 0 && rows >= 1, "mega_pack_weight: cols %d must be a multiple of 64", cols);
+  const long long tiles = (rows + MEGA_BN - 1) / MEGA_BN;
+  const long long chunks = tiles * (cols / 64) * 16 * 8;
+  const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
+  mega_pack_weight_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(w), reinterpret_cast<uint4*>(out), rows,
+                                                  cols, chunks);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
 }
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {

@@ -16,7 +16,7 @@ constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + MEG
 constexpr int MEGA_MAX_SPLITS = 8;
 
 struct MegaLayer {
-  CUtensorMap wqkv, wo, wgu, wd;   // B operands, box {64 k, 16 rows}, SWIZZLE_128B
+  const __nv_bfloat16 *wqkv, *wo, *wgu, *wd;   // B operands packed by mega_pack_weight (16-row swizzled slab images)
   const float* n1;
   const float* n2;
 };
@@ -49,11 +49,12 @@ struct MegaParams {
   unsigned int* barrier;    // zero-initialised
   int* error;               // zero-initialised; 1 = barrier timeout
   const MegaLayer* lw;      // device array [layers]
-  const CUtensorMap* lm_head;   // device pointer (box {64, 16})
+  const __nv_bfloat16* lm_head; // packed like the layer weights, rows padded to a multiple of 16
   long long* prof;              // optional [16] cycle counters filled by CTA 0 (phase breakdown), may be null
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
 };
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);
+int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, cudaStream_t st);
 
 }  // namespace ivg

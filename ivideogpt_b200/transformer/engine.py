@@ -251,28 +251,37 @@ class LlamaEngine:
         return o_s, d_s
 
     def _mega_tables(self):
-        """Device-resident array of per-layer weight tensor maps (+ the lm_head map), built once per engine."""
+        """Packed weight copies (16-row swizzled slab images, see ivgpt_mega_pack_weight) and the device-resident array
+        of per-layer pointer records, built once per engine."""
         if getattr(self, "_mega_dev", None) is not None:
             return self._mega_dev
         import ctypes as C
         from .. import _lib
         lib = _lib.load()
         w = self.w
+        dev = w.embed.device
+        keep = []
+
+        def pack(t):
+            rows, cols = t.shape
+            assert t.dtype == torch.bfloat16 and t.is_contiguous()
+            out = torch.empty(int(lib.ivgpt_mega_packed_elems(rows, cols)), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.ivgpt_mega_pack_weight(t.data_ptr(), out.data_ptr(), rows, cols, ops._stream()),
+                       "mega_pack_weight")
+            keep.append(out)
+            return out.data_ptr()
+
         nbytes = lib.ivgpt_mega_layer_bytes()
-        host = (C.c_uint8 * (nbytes * w.layers_n + 128 + 64))()
-        base = C.addressof(host)
-        base_al = (base + 63) // 64 * 64
+        host = (C.c_uint8 * (nbytes * w.layers_n + 64))()
+        base_al = (C.addressof(host) + 63) // 64 * 64
         for i, lw in enumerate(w.layers):
-            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, lw["wqkv"].data_ptr(), lw["wo"].data_ptr(),
-                                                 lw["wgu"].data_ptr(), lw["wd"].data_ptr(), lw["n1"].data_ptr(),
-                                                 lw["n2"].data_ptr(), w.hidden, w.inter), "mega_fill_layer")
-        _lib.check(lib.ivgpt_mega_fill_map(base_al + w.layers_n * nbytes, w.lm_head.data_ptr(), w.vocab, w.hidden),
-                   "mega_fill_map")
-        total = nbytes * w.layers_n + 128
-        raw = bytes((C.c_uint8 * total).from_address(base_al))
-        dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.w.embed.device)
-        assert dev.data_ptr() % 64 == 0
-        self._mega_dev = (dev, nbytes)
+            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"]),
+                                                 pack(lw["wd"]), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
+                       "mega_fill_layer")
+        lm_head = pack(w.lm_head)
+        raw = bytes((C.c_uint8 * (nbytes * w.layers_n)).from_address(base_al))
+        tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._mega_dev = (tab, lm_head, keep)
         return self._mega_dev
 
     def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps):
@@ -280,7 +289,7 @@ class LlamaEngine:
         from .. import _lib
         w = self.w
         h = w.hidden
-        dev_tab, nbytes = self._mega_tables()
+        dev_tab, lm_head_packed, _ = self._mega_tables()
         o_s, d_s = self._mega_splits()
         kc, vc = self.kv_cache(B, Lmax)
         logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
@@ -307,7 +316,7 @@ class LlamaEngine:
             d.do_sample, d.topk, d.inv_temp = 1, sample_cfg[0], 1.0 / sample_cfg[1]
         d.dseed = dseed.data_ptr()
         d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
-        d.layers_dev = dev_tab.data_ptr(); d.lm_head_map_dev = dev_tab.data_ptr() + w.layers_n * nbytes
+        d.layers_dev = dev_tab.data_ptr(); d.lm_head_packed = lm_head_packed
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
         if getattr(self, "mega_profile", False):
             self.mega_prof = self.buf("mega_prof", (16,), torch.int64)
