@@ -199,6 +199,8 @@ typedef struct ivgpt_mega_desc {
                       down, lm_head, sample, barriers); NULL to disable */
   void* vrows;     /* bf16 [layers][B][heads][Lmax][64]: V cache in K's layout (filled by ivgpt_rope_kv), used and
                       appended to when attn_mode == 0 */
+  void* attn_part; /* fp32 [SMs][4][72] scratch and */
+  void* attn_cnt;  /* uint32 [SMs] zeroed counters for attention items cut along the sequence (attn_mode 0) */
   int attn_mode;   /* attention phase: 0 = K/V streamed by 1-D bulk copies (TMA) into a shared-memory ring,
                       1 = register-staged loads */
 } ivgpt_mega_desc;

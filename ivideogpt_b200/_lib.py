@@ -69,6 +69,7 @@ class MegaDesc(C.Structure):
         ("layers_dev", C.c_void_p), ("lm_head_packed", C.c_void_p),
         ("prof", C.c_void_p),
         ("vrows", C.c_void_p),
+        ("attn_part", C.c_void_p), ("attn_cnt", C.c_void_p),
         ("attn_mode", C.c_int),
     ]
 

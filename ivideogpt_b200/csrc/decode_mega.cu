@@ -423,65 +423,83 @@ __device__ __forceinline__ void ring_wait(const MegaParams& p, uint64_t* bar, ui
 
 // ---- RoPE + KV append + attention over the cache: one warp per (b, head) item, K/V streamed through a ring ----
 // The register-staged version above stalls once per batch of loads (~22 dependent batches of ~2.4 us per item).  Here
-// lane 0 keeps `nslot` 4 KB bulk copies in flight per warp (the CTA's 128 KB activation region is split between the
-// warps that own an item this round: 5-6 of 8 at B=64 x 12 heads on 148 SMs, i.e. 20-24 KB per warp and ~120 KB per
-// SM in flight), the copy engine writes shared memory directly and the warp consumes slot after slot.  Both K and V
+// lane 0 keeps `nslot` 4 KB bulk copies in flight per warp (the activation region is split between the warps that own
+// work this phase), the copy engine writes shared memory directly and the warp consumes slot after slot.  Both K and V
 // are read from [Lmax][64] slabs (V from the row-major second cache `vrows`), 32 positions = 4 KB per unit:
-//   units 0 .. nK-1 : K rows -> scores (8 lanes per row, butterfly over the 8 lanes; same arithmetic as above)
-//   units nK .. 2nK-1 : V rows -> lane (sub, rslot) accumulates dims [8 sub, 8 sub + 8) over positions = rslot mod 4;
-//                       no cross-lane traffic until one 2-step reduction at the end of the item.
-// V units do not depend on the softmax, so they are already in flight while the scores are being computed.
-// (First ring version streamed V^T rows, one bulk copy per row and a 5-step butterfly per row: 61 us/layer, slower
-// than the register version -- the phase is bound by dependent instruction chains at 5-6 warps per SM, not by bytes
-// in flight alone.)
-__device__ void attention_ring(const MegaParams& p, int layer, int bh, int pos, float* wsm, uint8_t* ring, int nslot,
-                               uint64_t* bars, uint32_t& par) {
+//   K units : rows -> scores (8 lanes per row, butterfly over the 8 lanes; same arithmetic as above)
+//   V units : lane (sub, rslot) accumulates dims [8 sub, 8 sub + 8) over positions = rslot mod 4; no cross-lane
+//             traffic until one 2-step reduction at the end.
+// V units do not depend on the softmax, so they are already in flight while the scores are being computed.  The row
+// of the token being decoded never goes through the ring: its score and value come from registers, so the first
+// copies (old rows only) are issued before the RoPE arithmetic.
+// A call handles K/V units [u0, u1) of the item and, when `tail` is set, the new row (and the K/V append); it returns
+// the flash-decoding partial (max, sum, unnormalised accumulator) -- whole items use [0, nK) with tail, the items
+// left over after an even deal (768 items on 148 SMs leave 28) are cut into MEGA_ATT_SPLIT parts on otherwise idle warps.
+// (History: V^T rows + a butterfly per row 61 us/layer; this layout 34.7; 5.5 TB/s is what the ring sustains in
+// isolation, tools/probes/ring_probe.cu.)
+constexpr int MEGA_ATT_SPLIT = 4;
+
+__device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos, int u0, int u1, bool tail, float* wsm,
+                                 uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par, float& m_out, float& l_out,
+                                 float (&acc)[8]) {
   const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
-  const int n = pos + 1;
-  float* sc = wsm;                    // [Lmax + 8]
-  float* qs = wsm + Lmax + 8;         // [64]
+  float* sc = wsm;                    // [Lmax + 8] (indexed from row 32 * u0)
+  float* qs = wsm + Lmax + 8;         // [64] q, later the new row's v
   const int b = bh / heads, hh = bh - b * heads;
   const int lane = threadIdx.x & 31;
   __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
   __nv_bfloat16* vslab = p.vrows + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
-  {
-    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
-    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
-    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
-    qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
-    qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
-    kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
-    kslab[(size_t)pos * 64 + lane + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
-    vslab[(size_t)pos * 64 + lane] = v0;
-    vslab[(size_t)pos * 64 + lane + 32] = v1;
-  }
-  // the appended rows are read back below by the copy engine (async proxy): every lane orders its own generic-proxy
-  // stores before it, then the warp converges and lane 0 starts issuing
-  fence_proxy_async_all();
-  __syncwarp();
-
-  const int nK = (n + 31) >> 5;
-  const int units = 2 * nK;
-  auto issue = [&](int u, int slot) {                         // lane 0 only
-    const int c = u < nK ? u : u - nK;
+  const int nU = u1 - u0;
+  const int units = 2 * nU;
+  const int row0 = u0 << 5;
+  // optional fine-grained timing of the phase (CTA 0, warp 0, lane 0): prof[9..13] = prologue, K loop, softmax, V loop, tail
+  const bool tprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tm = tprof ? clock64() : 0;
+#define ATT_MARK(slot_) do { if (tprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - tm; tm = clock64(); } } while (0)
+  auto issue = [&](int u, int slot) {                         // lane 0 only; rows < pos were written in earlier steps
+    const int c = u0 + (u < nU ? u : u - nU);
     const int r0 = c << 5;
-    const uint32_t bytes = (uint32_t)(n - r0 < 32 ? n - r0 : 32) * 128u;
+    const uint32_t bytes = (uint32_t)(pos - r0 < 32 ? pos - r0 : 32) * 128u;
     mbar_expect_tx(bars + slot, bytes);
-    bulk_g2s(ring + (size_t)slot * MEGA_RING_SLOT, (u < nK ? kslab : vslab) + (size_t)r0 * 64, bytes, bars + slot);
+    bulk_g2s(ring + (size_t)slot * MEGA_RING_SLOT, (u < nU ? kslab : vslab) + (size_t)r0 * 64, bytes, bars + slot);
   };
   if (lane == 0) {
     const int pre = units < nslot ? units : nslot;
     for (int u = 0; u < pre; ++u) issue(u, u);
   }
+  float s_new = -INFINITY;
+  float v0f = 0.f, v1f = 0.f;
+  __nv_bfloat16 ka, kb, v0, v1;       // the new K/V row (this lane's two dims); appended to the caches at the very end
+  {
+    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
+    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
+    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
+    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
+    v0 = row[2 * Hd + hh * 64 + lane]; v1 = row[2 * Hd + hh * 64 + lane + 32];
+    const float qa = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
+    const float qb = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
+    qs[lane] = qa;
+    qs[lane + 32] = qb;
+    ka = __float2bfloat16_rn(k0 * cs - k1 * sn); kb = __float2bfloat16_rn(k1 * cs + k0 * sn);
+    if (tail) {
+      v0f = __bfloat162float(v0); v1f = __bfloat162float(v1);
+      float sn_ = fmaf(qa, __bfloat162float(ka), qb * __bfloat162float(kb));
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) sn_ += __shfl_xor_sync(0xffffffffu, sn_, off);
+      s_new = sn_;
+    }
+  }
+  __syncwarp();
   const int sub = lane & 7, rslot = lane >> 3;
   float qreg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) qreg[i] = qs[sub * 8 + i];
-  float mx = -INFINITY;
+  __syncwarp();
+  if (tail) { qs[lane] = v0f; qs[lane + 32] = v1f; }          // q is in registers now: the slot carries the new v row
+  float mx = s_new;
   int slot = 0;
-  for (int u = 0; u < nK; ++u) {
+  ATT_MARK(9);
+  for (int u = 0; u < nU; ++u) {
     ring_wait(p, bars + slot, par, slot);
     const uint8_t* src = ring + (size_t)slot * MEGA_RING_SLOT + rslot * 128 + sub * 16;
     uint4 kv[8];
@@ -489,47 +507,68 @@ __device__ void attention_ring(const MegaParams& p, int layer, int bh, int pos, 
     for (int ps = 0; ps < 8; ++ps) kv[ps] = *reinterpret_cast<const uint4*>(src + ps * 512);
     __syncwarp();                                             // every lane has read the slot: refill it
     if (lane == 0 && u + nslot < units) issue(u + nslot, slot);
+    float part[8];
 #pragma unroll
     for (int ps = 0; ps < 8; ++ps) {
-      const int l = (u << 5) + ps * 4 + rslot;
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[ps]);
-      float part = 0.f;
+      float a = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __bfloat1622float2(h2[i]);
-        part = fmaf(qreg[2 * i], f.x, part);
-        part = fmaf(qreg[2 * i + 1], f.y, part);
+        a = fmaf(qreg[2 * i], f.x, a);
+        a = fmaf(qreg[2 * i + 1], f.y, a);
       }
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (l < n) {
-        mx = fmaxf(mx, part);
-        if (sub == 0) sc[l] = part;
-      }
+      part[ps] = a;
+    }
+    // 8 rows x 8 lanes -> transposed butterfly (7 shuffles instead of 24): afterwards lane `sub` holds the full dot
+    // product of pass ps == sub.  Same pairing order (4, 2, 1) as the plain butterfly, so the sums are bit-identical.
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = (sub & 4) ? part[i] : part[i + 4];
+      const float keep = (sub & 4) ? part[i + 4] : part[i];
+      part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = (sub & 2) ? part[i] : part[i + 2];
+      const float keep = (sub & 2) ? part[i + 2] : part[i];
+      part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+      const float send = (sub & 1) ? part[0] : part[1];
+      const float keep = (sub & 1) ? part[1] : part[0];
+      part[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const int ll = (u << 5) + sub * 4 + rslot;                // row index relative to row0
+    if (row0 + ll < pos) {
+      mx = fmaxf(mx, part[0]);
+      sc[ll] = part[0];
     }
     slot = slot + 1 == nslot ? 0 : slot + 1;
   }
+  ATT_MARK(10);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   __syncwarp();
   float sum = 0.f;
-  for (int l = lane; l < (nK << 5); l += 32) {                // zero-fills the tail of the last 32-row unit
-    const float e = l < n ? __expf(sc[l] - mx) : 0.f;
-    sc[l] = e;
+#pragma unroll 4
+  for (int ll = lane; ll < (nU << 5); ll += 32) {             // zero-fills the tail of the last 32-row unit
+    const float e = (row0 + ll < pos) ? __expf(sc[ll] - mx) : 0.f;
+    sc[ll] = e;
     sum += e;
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float inv = 1.0f / sum;
+  const float e_new = tail ? __expf(s_new - mx) : 0.f;
+  sum += e_new;
   __syncwarp();
-  float acc[8];
+  ATT_MARK(11);
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int u = nK; u < units; ++u) {
+  for (int u = 0; u < nU; ++u) {
     ring_wait(p, bars + slot, par, slot);
     const uint8_t* src = ring + (size_t)slot * MEGA_RING_SLOT + rslot * 128 + sub * 16;
-    const int l0 = ((u - nK) << 5) + rslot;
+    const int l0 = (u << 5) + rslot;
     uint4 vv[8];
     float pl[8];
 #pragma unroll
@@ -538,10 +577,10 @@ __device__ void attention_ring(const MegaParams& p, int layer, int bh, int pos, 
       pl[ps] = sc[l0 + ps * 4];
     }
     __syncwarp();
-    if (lane == 0 && u + nslot < units) issue(u + nslot, slot);
+    if (lane == 0 && nU + u + nslot < units) issue(nU + u + nslot, slot);
 #pragma unroll
     for (int ps = 0; ps < 8; ++ps) {
-      if (l0 + ps * 4 < n) {                                  // rows past n in the last unit hold stale bytes
+      if (row0 + l0 + ps * 4 < pos) {                         // rows past the end of the last unit hold stale bytes
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[ps]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -553,17 +592,83 @@ __device__ void attention_ring(const MegaParams& p, int layer, int bh, int pos, 
     }
     slot = slot + 1 == nslot ? 0 : slot + 1;
   }
+  ATT_MARK(12);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
   }
-  if (rslot == 0) {
-    uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                         pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
-    *reinterpret_cast<uint4*>(p.ao + (size_t)b * Hd + hh * 64 + sub * 8) = o;
+  if (tail) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(e_new, qs[sub * 8 + i], acc[i]);
+  }
+  m_out = mx;
+  l_out = sum;
+  if (tail) {                         // append the new row; later steps read it through the copy engine (async proxy)
+    kslab[(size_t)pos * 64 + lane] = ka;
+    kslab[(size_t)pos * 64 + lane + 32] = kb;
+    vslab[(size_t)pos * 64 + lane] = v0;
+    vslab[(size_t)pos * 64 + lane + 32] = v1;
+    fence_proxy_async_all();
   }
   __syncwarp();
+  ATT_MARK(13);
+#undef ATT_MARK
+}
+
+__device__ __forceinline__ void attention_store(const MegaParams& p, int bh, const float (&acc)[8], float inv) {
+  const int b = bh / p.heads, hh = bh - b * p.heads;
+  const int lane = threadIdx.x & 31;
+  if ((lane >> 3) == 0) {
+    const uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                               pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+    *reinterpret_cast<uint4*>(p.ao + (size_t)b * p.hidden + hh * 64 + (lane & 7) * 8) = o;
+  }
+}
+
+// one left-over item cut along the sequence: every part publishes (max, sum, acc[64]); the part that arrives last
+// (monotonic counter, MEGA_ATT_SPLIT arrivals per item, layer and step) merges them and writes the output row.
+__device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, float* wsm,
+                               uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
+  const int lane = threadIdx.x & 31;
+  const int nK = (pos + 31) >> 5;
+  const int u0 = (nK * q) / MEGA_ATT_SPLIT, u1 = (nK * (q + 1)) / MEGA_ATT_SPLIT;
+  float m, l, acc[8];
+  attention_stream(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, wsm, ring, nslot, bars, par, m, l, acc);
+  float* rec = p.attn_part + ((size_t)extra * MEGA_ATT_SPLIT + q) * 72;
+  if ((lane >> 3) == 0) {
+    float4* dst = reinterpret_cast<float4*>(rec + 8 + (lane & 7) * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (lane == 0) { rec[0] = m; rec[1] = l; }
+  }
+  __threadfence();                    // every writer releases its part of the record, then lane 0 counts the arrival
+  __syncwarp();
+  unsigned int old = 0;
+  if (lane == 0) {
+    old = atomicAdd(p.attn_cnt + extra, 1u);
+    __threadfence();
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if ((old + 1u) % MEGA_ATT_SPLIT != 0u) return;
+  // last arriver: merge (records are read past L1 -- the same addresses were read one layer ago)
+  const float* base = p.attn_part + (size_t)extra * MEGA_ATT_SPLIT * 72;
+  float mm[MEGA_ATT_SPLIT], M = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MEGA_ATT_SPLIT; ++k) { mm[k] = __ldcg(base + k * 72); M = fmaxf(M, mm[k]); }
+  float L = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < MEGA_ATT_SPLIT; ++k) {
+    const float w = __expf(mm[k] - M);
+    L = fmaf(__ldcg(base + k * 72 + 1), w, L);
+    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(base + k * 72 + 8 + (lane & 7) * 8));
+    const float4 a1 = __ldcg(reinterpret_cast<const float4*>(base + k * 72 + 8 + (lane & 7) * 8) + 1);
+    o[0] = fmaf(a0.x, w, o[0]); o[1] = fmaf(a0.y, w, o[1]); o[2] = fmaf(a0.z, w, o[2]); o[3] = fmaf(a0.w, w, o[3]);
+    o[4] = fmaf(a1.x, w, o[4]); o[5] = fmaf(a1.y, w, o[5]); o[6] = fmaf(a1.z, w, o[6]); o[7] = fmaf(a1.w, w, o[7]);
+  }
+  attention_store(p, bh, o, 1.0f / L);
 }
 
 // ---- RoPE + KV append + attention over the cache: a PAIR of warps per (b, head) item ----
@@ -905,16 +1010,45 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         if (p.attn_mode == 0) {
           // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
           fence_proxy_async();
-          const int total = p.B * p.heads;
-          for (int base = blockIdx.x; base < total; base += (int)gridDim.x * 8) {
-            int active = (total - base + (int)gridDim.x - 1) / (int)gridDim.x;     // warps of this CTA with an item
-            active = active > 8 ? 8 : active;
-            int nslot = (int)(c.sm.a_bytes / MEGA_RING_SLOT) / active;   // weight slabs of the o-proj sit above a_bytes
+          const int total = p.B * p.heads, G = (int)gridDim.x;
+          const int full = total / G, extras = total - full * G;
+          const int free_w = 8 - full;
+          if (full <= 8 && (extras == 0 || (free_w > 0 && extras * MEGA_ATT_SPLIT <= free_w * G))) {
+            // even deal: `full` whole items per CTA, the left-over items cut in MEGA_ATT_SPLIT parts on idle warps
+            const int nparts = extras * MEGA_ATT_SPLIT;
+            const int my_parts = nparts > (int)blockIdx.x ? (nparts - (int)blockIdx.x + G - 1) / G : 0;
+            const int active = full + my_parts;
+            int nslot = active > 0 ? (int)(c.sm.a_bytes / MEGA_RING_SLOT) / active : 1;   // o-proj slabs sit above a_bytes
             nslot = nslot > 8 ? 8 : nslot;
-            if (warp < active)
-              attention_ring(p, l, base + (int)gridDim.x * warp, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
-                             c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par);
-            __syncthreads();                 // the next round partitions the ring differently
+            float* wsm = c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64);
+            uint8_t* ring = c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT;
+            if (warp < full) {
+              const int bh = (int)blockIdx.x + G * warp;
+              float m, lsum, acc[8];
+              attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, wsm, ring, nslot, c.sm.ring_bar + warp * 8, ring_par,
+                               m, lsum, acc);
+              attention_store(p, bh, acc, 1.0f / lsum);
+            } else if (warp < active) {
+              const int pi = (int)blockIdx.x + G * (warp - full);
+              attention_part(p, l, full * G + pi / MEGA_ATT_SPLIT, pos, pi / MEGA_ATT_SPLIT, pi % MEGA_ATT_SPLIT, wsm, ring,
+                             nslot, c.sm.ring_bar + warp * 8, ring_par);
+            }
+          } else {
+            for (int base = blockIdx.x; base < total; base += G * 8) {
+              int active = (total - base + G - 1) / G;            // warps of this CTA with an item this round
+              active = active > 8 ? 8 : active;
+              int nslot = (int)(c.sm.a_bytes / MEGA_RING_SLOT) / active;
+              nslot = nslot > 8 ? 8 : nslot;
+              if (warp < active) {
+                const int bh = base + G * warp;
+                float m, lsum, acc[8];
+                attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
+                                 c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par, m,
+                                 lsum, acc);
+                attention_store(p, bh, acc, 1.0f / lsum);
+              }
+              __syncthreads();                 // the next round partitions the ring differently
+            }
           }
         } else {
           for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
@@ -963,7 +1097,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && ok) *p.dpos = pos0 + p.steps;
-  if (profiling) for (int i = 0; i < 9; ++i) p.prof[i] += tprof[i];
+  if (profiling) for (int i = 0; i < 9; ++i) p.prof[i] += tprof[i];   // slots 9..13: attention_stream's own marks
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 32); }

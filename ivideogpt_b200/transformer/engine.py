@@ -293,7 +293,7 @@ class LlamaEngine:
         o_s, d_s = self._mega_splits()
         kc, vc = self.kv_cache(B, Lmax)
         logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
-        sync = self.buf("mega_sync", (2,), torch.int32)
+        sync = self.buf("mega_sync", (1024,), torch.int32)     # [0] barrier, [1] error, [64..] attention part counters
         sync.zero_()
         d = _lib.MegaDesc()
         d.B, d.hidden, d.inter, d.heads, d.layers, d.vocab, d.Lmax, d.steps = B, h, w.inter, w.heads, w.layers_n, w.vocab, Lmax, steps
@@ -317,6 +317,8 @@ class LlamaEngine:
         d.dseed = dseed.data_ptr()
         d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
         d.layers_dev = dev_tab.data_ptr(); d.lm_head_packed = lm_head_packed
+        d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
+        d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
         if getattr(self, "mega_profile", False):
             self.mega_prof = self.buf("mega_prof", (16,), torch.int64)

@@ -31,7 +31,11 @@ for mode, tag in ((1, "_regs"), (0, "")):
     eng.mega_attn_mode = mode
     eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
     torch.cuda.synchronize()
-    cyc = eng.mega_prof.cpu().tolist()[:9]
+    allc = eng.mega_prof.cpu().tolist()
+    cyc = allc[:9]
     res["mega_phase_us_per_step" + tag] = {n: c / (mhz) / (new - 1) for n, c in zip(names, cyc)}
+    if mode == 0:
+        res["attention_warp0_us_per_step"] = {n: c / mhz / (new - 1) for n, c in
+                                              zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])}
 res["decode_steps"] = new - 1
 print(json.dumps(res))
