@@ -477,8 +477,8 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.prof = d->prof;
   p.attn_mode = d->attn_mode;
   p.attn_part = (float*)d->attn_part; p.attn_cnt = (unsigned int*)d->attn_cnt;
-  IVG_CHECK(p.attn_mode != 0 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
-  IVG_CHECK(p.attn_mode != 0 || (p.attn_part != nullptr && p.attn_cnt != nullptr),
+  IVG_CHECK(p.attn_mode == 1 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
+  IVG_CHECK(p.attn_mode == 1 || (p.attn_part != nullptr && p.attn_cnt != nullptr),
             "decode_mega: attn_mode 0 needs attn_part [SMs*4*72 floats] and attn_cnt [SMs uints, zeroed]");
   if (p.steps <= 0) return 0;
   return ivg::decode_mega_launch(p, num_sms(), S(stream));

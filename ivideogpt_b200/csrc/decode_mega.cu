@@ -439,9 +439,64 @@ __device__ __forceinline__ void ring_wait(const MegaParams& p, uint64_t* bar, ui
 // isolation, tools/probes/ring_probe.cu.)
 constexpr int MEGA_ATT_SPLIT = 4;
 
-__device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos, int u0, int u1, bool tail, float* wsm,
-                                 uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par, float& m_out, float& l_out,
-                                 float (&acc)[8]) {
+// unit u of the item's [u0, u0 + nU) K units followed by the same V units -> ring slot (lane 0 only; rows < pos were
+// written in earlier steps)
+__device__ __forceinline__ void att_issue(const MegaParams& p, int layer, int bh, int pos, int u0, int nU, int u, int slot,
+                                          uint8_t* ring, uint64_t* bars) {
+  const size_t slab = ((size_t)layer * p.B * p.heads + bh) * p.Lmax * 64;
+  const int c = u0 + (u < nU ? u : u - nU);
+  const int r0 = c << 5;
+  const uint32_t bytes = (uint32_t)(pos - r0 < 32 ? pos - r0 : 32) * 128u;
+  mbar_expect_tx(bars + slot, bytes);
+  bulk_g2s(ring + (size_t)slot * MEGA_RING_SLOT, (u < nU ? p.kcache : p.vrows) + slab + (size_t)r0 * 64, bytes, bars + slot);
+}
+
+// what a warp does in the attention phase of this step
+struct AttWork {
+  int kind;            // 0 nothing, 1 whole item, 2 part of a left-over item
+  int bh, u0, u1, extra, q, nslot;
+  bool tail;
+};
+
+// even deal: `full` whole items per CTA, the left-over items cut in MEGA_ATT_SPLIT parts on otherwise idle warps
+__device__ __forceinline__ bool att_even_deal(const MegaParams& p) {
+  const int total = p.B * p.heads, G = (int)gridDim.x;
+  const int full = total / G, extras = total - full * G, free_w = 8 - full;
+  return full <= 8 && (extras == 0 || (free_w > 0 && extras * MEGA_ATT_SPLIT <= free_w * G));
+}
+__device__ __forceinline__ AttWork att_assign(const MegaParams& p, uint32_t a_bytes, int warp, int pos) {
+  const int total = p.B * p.heads, G = (int)gridDim.x;
+  const int full = total / G, extras = total - full * G;
+  const int nparts = extras * MEGA_ATT_SPLIT;
+  const int my_parts = nparts > (int)blockIdx.x ? (nparts - (int)blockIdx.x + G - 1) / G : 0;
+  const int active = full + my_parts;
+  AttWork w;
+  w.kind = 0;
+  w.nslot = active > 0 ? (int)(a_bytes / MEGA_RING_SLOT) / active : 1;     // o-proj slabs sit above a_bytes
+  w.nslot = w.nslot > 8 ? 8 : w.nslot;
+  const int nK = (pos + 31) >> 5;
+  if (warp < full) {
+    w.kind = 1; w.bh = (int)blockIdx.x + G * warp; w.u0 = 0; w.u1 = nK; w.tail = true; w.extra = 0; w.q = 0;
+  } else if (warp < active) {
+    const int pi = (int)blockIdx.x + G * (warp - full);
+    w.kind = 2; w.extra = pi / MEGA_ATT_SPLIT; w.q = pi % MEGA_ATT_SPLIT; w.bh = full * G + w.extra;
+    w.u0 = (nK * w.q) / MEGA_ATT_SPLIT; w.u1 = (nK * (w.q + 1)) / MEGA_ATT_SPLIT; w.tail = w.q == MEGA_ATT_SPLIT - 1;
+  }
+  return w;
+}
+// first ring fill: old K/V rows do not depend on this step's qkv projection, so it is issued BEFORE the device-wide
+// barrier that precedes the attention phase and lands while the CTA waits there
+__device__ __forceinline__ void attention_prefetch(const MegaParams& p, int layer, int pos, const AttWork& w, uint8_t* ring,
+                                                   uint64_t* bars) {
+  if (w.kind == 0 || (threadIdx.x & 31) != 0) return;
+  const int nU = w.u1 - w.u0, units = 2 * nU;
+  const int pre = units < w.nslot ? units : w.nslot;
+  for (int u = 0; u < pre; ++u) att_issue(p, layer, w.bh, pos, w.u0, nU, u, u, ring, bars);
+}
+
+__device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos, int u0, int u1, bool tail, bool issued,
+                                 float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par, float& m_out,
+                                 float& l_out, float (&acc)[8]) {
   const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
   float* sc = wsm;                    // [Lmax + 8] (indexed from row 32 * u0)
   float* qs = wsm + Lmax + 8;         // [64] q, later the new row's v
@@ -456,14 +511,8 @@ __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos
   const bool tprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long tm = tprof ? clock64() : 0;
 #define ATT_MARK(slot_) do { if (tprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - tm; tm = clock64(); } } while (0)
-  auto issue = [&](int u, int slot) {                         // lane 0 only; rows < pos were written in earlier steps
-    const int c = u0 + (u < nU ? u : u - nU);
-    const int r0 = c << 5;
-    const uint32_t bytes = (uint32_t)(pos - r0 < 32 ? pos - r0 : 32) * 128u;
-    mbar_expect_tx(bars + slot, bytes);
-    bulk_g2s(ring + (size_t)slot * MEGA_RING_SLOT, (u < nU ? kslab : vslab) + (size_t)r0 * 64, bytes, bars + slot);
-  };
-  if (lane == 0) {
+  auto issue = [&](int u, int slot) { att_issue(p, layer, bh, pos, u0, nU, u, slot, ring, bars); };
+  if (lane == 0 && !issued) {
     const int pre = units < nslot ? units : nslot;
     for (int u = 0; u < pre; ++u) issue(u, u);
   }
@@ -628,13 +677,11 @@ __device__ __forceinline__ void attention_store(const MegaParams& p, int bh, con
 
 // one left-over item cut along the sequence: every part publishes (max, sum, acc[64]); the part that arrives last
 // (monotonic counter, MEGA_ATT_SPLIT arrivals per item, layer and step) merges them and writes the output row.
-__device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, float* wsm,
-                               uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
+__device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, int u0, int u1, bool issued,
+                               float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
   const int lane = threadIdx.x & 31;
-  const int nK = (pos + 31) >> 5;
-  const int u0 = (nK * q) / MEGA_ATT_SPLIT, u1 = (nK * (q + 1)) / MEGA_ATT_SPLIT;
   float m, l, acc[8];
-  attention_stream(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, wsm, ring, nslot, bars, par, m, l, acc);
+  attention_stream(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
   float* rec = p.attn_part + ((size_t)extra * MEGA_ATT_SPLIT + q) * 72;
   if ((lane >> 3) == 0) {
     float4* dst = reinterpret_cast<float4*>(rec + 8 + (lane & 7) * 8);
@@ -847,10 +894,14 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
     return;
   }
   uint32_t* keys = smem_u;
-  uint32_t* hist = smem_u + V;
-  __shared__ uint32_t s_prefix, s_remaining;
+  uint32_t* hist = smem_u + V;        // 256 bins (radix fallback) / candidate list (MEGA_SAMPLE_CAP entries)
+  constexpr int CAP = 192;
+  __shared__ uint32_t s_prefix, s_remaining, s_bound, s_nc;
+  __shared__ __align__(16) uint32_t s_tmax[MEGA_THREADS];
   __shared__ float s_hi[MEGA_THREADS];
   __shared__ int s_win, s_lastmass;
+  const uint32_t want = (uint32_t)(p.topk < V ? p.topk : V);
+  uint32_t tmax = 0u;
   {   // 16-byte loads, all of a thread's requests in flight before the first use (rows are 16-byte aligned: ldl % 4 == 0)
     const int V4 = V >> 2;
     const float4* row4 = reinterpret_cast<const float4*>(row);
@@ -858,42 +909,87 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
 #pragma unroll 4
     for (int c = tid; c < V4; c += MEGA_THREADS) {
       const float4 v = row4[c];
-      keys4[c] = make_uint4(mega_fkey(v.x * p.inv_temp), mega_fkey(v.y * p.inv_temp), mega_fkey(v.z * p.inv_temp),
-                            mega_fkey(v.w * p.inv_temp));
+      const uint4 k4 = make_uint4(mega_fkey(v.x * p.inv_temp), mega_fkey(v.y * p.inv_temp), mega_fkey(v.z * p.inv_temp),
+                                  mega_fkey(v.w * p.inv_temp));
+      keys4[c] = k4;
+      tmax = max(max(tmax, k4.x), max(k4.y, max(k4.z, k4.w)));
     }
-    for (int c = (V4 << 2) + tid; c < V; c += MEGA_THREADS) keys[c] = mega_fkey(row[c] * p.inv_temp);
+    for (int c = (V4 << 2) + tid; c < V; c += MEGA_THREADS) { const uint32_t k = mega_fkey(row[c] * p.inv_temp); keys[c] = k; tmax = max(tmax, k); }
   }
-  if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)(p.topk < V ? p.topk : V); s_win = 0x7fffffff; s_lastmass = 0; }
+  s_tmax[tid] = tmax;
+  if (tid == 0) { s_prefix = 0; s_remaining = want; s_win = 0x7fffffff; s_lastmass = 0; s_bound = 0u; s_nc = 0u; }
   __syncthreads();
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    for (int i = tid; i < 256; i += MEGA_THREADS) hist[i] = 0;
+  // ---- k-th largest key.  Fast path: a lower bound from the per-thread maxima (the want-th largest of them has at
+  // least `want` keys at or above it), the ~130 keys above the bound are compacted and ranked exhaustively.  The radix
+  // select below remains for top_k > 256 and for degenerate rows (many equal logits). ----
+  bool fast = want <= (uint32_t)MEGA_THREADS;
+  if (fast) {
+    uint32_t ge = 0;
+    const uint4* tm4 = reinterpret_cast<const uint4*>(s_tmax);
+#pragma unroll 8
+    for (int j = 0; j < MEGA_THREADS / 4; ++j) {
+      const uint4 t = tm4[j];
+      ge += (t.x >= tmax) + (t.y >= tmax) + (t.z >= tmax) + (t.w >= tmax);
+    }
+    uint32_t cand_b = ge >= want ? tmax : 0u;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cand_b = max(cand_b, __shfl_xor_sync(0xffffffffu, cand_b, off));
+    if (lane == 0 && cand_b) atomicMax(&s_bound, cand_b);
     __syncthreads();
-    const uint32_t prefix = s_prefix;
-    const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    // logits share a few exponents, so the leading digits fall into a handful of bins: aggregate equal bins inside
-    // the warp (match.any) and let one lane add the count -- plain per-key shared-memory atomics serialised to ~30 us
-    for (int c0 = 0; c0 < V; c0 += MEGA_THREADS) {
-      const int c = c0 + tid;
-      const uint32_t kk = c < V ? keys[c] : 0u;
-      const bool in = c < V && (kk & mask) == prefix;
-      const uint32_t bin = in ? ((kk >> shift) & 255u) : 256u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-      if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+    const uint32_t bound = s_bound;
+    for (int c = tid; c < V; c += MEGA_THREADS) {
+      const uint32_t kk = keys[c];
+      if (kk >= bound) { const uint32_t i = atomicAdd(&s_nc, 1u); if (i < (uint32_t)CAP) hist[i] = kk; }
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t rem = s_remaining;
-      int bb = 255;
-      for (; bb > 0; --bb) { if (hist[bb] >= rem) break; rem -= hist[bb]; }
-      s_prefix = prefix | ((uint32_t)bb << shift);
-      s_remaining = rem;
+    const uint32_t nc = s_nc;
+    fast = nc <= (uint32_t)CAP;
+    if (fast) {
+      uint32_t best = 0u;
+      for (uint32_t c = tid; c < nc; c += MEGA_THREADS) {
+        const uint32_t mine = hist[c];
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < nc; ++j) cnt += hist[j] >= mine;
+        if (cnt >= want) best = max(best, mine);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+      if (lane == 0 && best) atomicMax(&s_prefix, best);
     }
     __syncthreads();
+  }
+  if (!fast) {
+    if (tid == 0) s_prefix = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < 256; i += MEGA_THREADS) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      // logits share a few exponents, so the leading digits fall into a handful of bins: aggregate equal bins inside
+      // the warp (match.any) and let one lane add the count
+      for (int c0 = 0; c0 < V; c0 += MEGA_THREADS) {
+        const int c = c0 + tid;
+        const uint32_t kk = c < V ? keys[c] : 0u;
+        const bool in = c < V && (kk & mask) == prefix;
+        const uint32_t bin = in ? ((kk >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t rem = s_remaining;
+        int bb = 255;
+        for (; bb > 0; --bb) { if (hist[bb] >= rem) break; rem -= hist[bb]; }
+        s_prefix = prefix | ((uint32_t)bb << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+    }
   }
   const uint32_t kth = s_prefix;
-  uint32_t mk = 0;
-  for (int c = tid; c < V; c += MEGA_THREADS) mk = max(mk, keys[c]);
+  uint32_t mk = tmax;                 // this thread's keys were all loaded by itself above
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) mk = max(mk, __shfl_xor_sync(0xffffffffu, mk, off));
   if (lane == 0) s_redi[warp] = (int)mk;
@@ -1005,33 +1101,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase(c, o_g);
+      const bool ring_prefetch = MEGA_THREADS == 256 && p.attn_mode == 0 && att_even_deal(p);
+      if (ring_prefetch) {
+        // the activation slab is dead (this CTA's MMAs have retired): start filling the attention ring with old K/V rows.
+        // The region was last written through the generic proxy (cp.async), the copies below are async-proxy writes.
+        fence_proxy_async();
+        const AttWork w = att_assign(p, c.sm.a_bytes, warp, pos);
+        attention_prefetch(p, l, pos, w, c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT, c.sm.ring_bar + warp * 8);
+      }
       MEGA_BARRIER(); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
-        if (p.attn_mode == 0) {
+        if (p.attn_mode != 1) {
           // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
           fence_proxy_async();
           const int total = p.B * p.heads, G = (int)gridDim.x;
-          const int full = total / G, extras = total - full * G;
-          const int free_w = 8 - full;
-          if (full <= 8 && (extras == 0 || (free_w > 0 && extras * MEGA_ATT_SPLIT <= free_w * G))) {
-            // even deal: `full` whole items per CTA, the left-over items cut in MEGA_ATT_SPLIT parts on idle warps
-            const int nparts = extras * MEGA_ATT_SPLIT;
-            const int my_parts = nparts > (int)blockIdx.x ? (nparts - (int)blockIdx.x + G - 1) / G : 0;
-            const int active = full + my_parts;
-            int nslot = active > 0 ? (int)(c.sm.a_bytes / MEGA_RING_SLOT) / active : 1;   // o-proj slabs sit above a_bytes
-            nslot = nslot > 8 ? 8 : nslot;
+          if (att_even_deal(p)) {
+            const AttWork w = att_assign(p, c.sm.a_bytes, warp, pos);     // same assignment the prefetch used
             float* wsm = c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64);
-            uint8_t* ring = c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT;
-            if (warp < full) {
-              const int bh = (int)blockIdx.x + G * warp;
+            uint8_t* ring = c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT;
+            if (w.kind == 1) {
               float m, lsum, acc[8];
-              attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, wsm, ring, nslot, c.sm.ring_bar + warp * 8, ring_par,
-                               m, lsum, acc);
-              attention_store(p, bh, acc, 1.0f / lsum);
-            } else if (warp < active) {
-              const int pi = (int)blockIdx.x + G * (warp - full);
-              attention_part(p, l, full * G + pi / MEGA_ATT_SPLIT, pos, pi / MEGA_ATT_SPLIT, pi % MEGA_ATT_SPLIT, wsm, ring,
-                             nslot, c.sm.ring_bar + warp * 8, ring_par);
+              attention_stream(p, l, w.bh, pos, w.u0, w.u1, true, ring_prefetch, wsm, ring, w.nslot, c.sm.ring_bar + warp * 8,
+                               ring_par, m, lsum, acc);
+              attention_store(p, w.bh, acc, 1.0f / lsum);
+            } else if (w.kind == 2) {
+              attention_part(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
+                             c.sm.ring_bar + warp * 8, ring_par);
             }
           } else {
             for (int base = blockIdx.x; base < total; base += G * 8) {
@@ -1042,7 +1137,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               if (warp < active) {
                 const int bh = base + G * warp;
                 float m, lsum, acc[8];
-                attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
+                attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, false, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
                                  c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par, m,
                                  lsum, acc);
                 attention_store(p, bh, acc, 1.0f / lsum);

@@ -12,7 +12,8 @@ ids = torch.randint(0, 16384, (B, 514), device=dev)
 new = 237
 res = {}
 for name, kw, mode in (("graph", dict(use_mega=False), 0), ("mega_regs", dict(use_mega=True), 1),
-                       ("mega", dict(use_mega=True), 0)):
+                       ("mega_noprefetch", dict(use_mega=True), 2), ("mega", dict(use_mega=True), 0),
+                       ("mega_noprefetch2", dict(use_mega=True), 2), ("mega2", dict(use_mega=True), 0)):
     eng.mega_attn_mode = mode
     for _ in range(2):
         eng.generate(ids, None, new, True, 100, 1.0, 1, **kw)
@@ -27,7 +28,7 @@ res["prefill_plus_first_token_ms"] = a.elapsed_time(b)
 eng.mega_profile = True
 names = ["norm", "qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "sample", "barriers"]
 mhz = 1965.0
-for mode, tag in ((1, "_regs"), (0, "")):
+for mode, tag in ((2, "_noprefetch"), (0, "")):
     eng.mega_attn_mode = mode
     eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
     torch.cuda.synchronize()
