@@ -297,9 +297,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     stages = {"tokenize_context_ms": sev[0].elapsed_time(sev[1]), "generate_ms": sev[1].elapsed_time(sev[2]),
               "detokenize_ms": sev[2].elapsed_time(sev[3])}
-    # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), measured in the timed region above
+    # per-launch CUDA-event times of the three kernel families, measured in the timed region above
     prof = {}
-    for bucket, name in ((1, "conv"), (0, "gemm")):
+    for bucket, name in ((1, "conv"), (0, "gemm"), (2, "mega")):
         ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
         lib.ivgpt_profile_collect(bucket, C.byref(ms), C.byref(fl), C.byref(n))
         prof[name] = (ms.value, fl.value, n.value)
@@ -318,21 +318,7 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = frames_per_step / (ms_per_step / 1e3)
     peak_tf, peak_gbs, peak_src = measured_peaks()
-    conv_ms, conv_fl, conv_n = prof["conv"]
-    gemm_ms, gemm_fl, gemm_n = prof["gemm"]
-    dom = "conv" if conv_ms >= gemm_ms else "gemm"
-    dms, dfl, dn = prof[dom]
-    achieved = dfl / (dms * 1e-3) / 1e12 if dms > 0 else 0.0
-    dense_peak = peak_tf if args.dtype == "bf16" else peak_tf / 2.0    # tf32 runs at half the bf16 rate
-    roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{args.dtype}> ({'implicit-GEMM 3x3 conv' if dom == 'conv' else 'plain/batched GEMM'})",
-                "achieved": achieved, "peak": dense_peak, "unit": "TFLOP/s", "frac": achieved / dense_peak,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})" + ("" if args.dtype == "bf16" else " / 2 for tf32"),
-                "launches_per_step": dn / args.steps, "kernel_ms_per_step": dms / args.steps,
-                "share_of_step": dms / total_ms, "traffic": None,
-                "other": {"gemm" if dom == "conv" else "conv": {
-                    "ms_per_step": (gemm_ms if dom == "conv" else conv_ms) / args.steps,
-                    "tflops": ((gemm_fl / (gemm_ms * 1e-3) / 1e12) if dom == "conv" and gemm_ms > 0 else
-                               (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else 0.0)}}}
+    roofline = build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src)
     px_bytes = clips_host.numel() * 4
     out = {
         "metric": "predicted_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -354,6 +340,56 @@ def run_b200(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mega_traffic():
+    """`traffic` of the dominant kernel from the committed `ncu --set full` capture (bytes per launch), or None."""
+    path = os.path.join(ROOT, "profiles", "r01", "ncu_decode_mega_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return None
+
+
+def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src):
+    """Roofline of the DOMINANT kernel (largest summed device time in the timed region).
+
+    decode_mega_kernel is HBM-bound: algorithmic bytes per launch = per decode step the bf16 block
+    + lm_head weights once, plus the K and V rows of every earlier position of every clip and layer:
+        steps * 2 * (block + lm_head params)  +  sum_{pos} B * pos * layers * 2 * hidden * 2 bytes.
+    gemm_tc_kernel is tensor-pipe bound: algorithmic FLOPs 2*M*N*K per launch (causal tiles excluded)."""
+    fam = {}
+    conv_ms, conv_fl, conv_n = prof["conv"]
+    gemm_ms, gemm_fl, gemm_n = prof["gemm"]
+    mega_ms, mega_steps, mega_n = prof["mega"]
+    dense_peak = peak_tf if args.dtype == "bf16" else peak_tf / 2.0    # tf32 runs at half the bf16 rate
+    tsrc = f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})" + ("" if args.dtype == "bf16" else " / 2 for tf32")
+    for name, ms, fl, n, label in (("conv", conv_ms, conv_fl, conv_n, "implicit-GEMM 3x3 conv"),
+                                   ("gemm", gemm_ms, gemm_fl, gemm_n, "plain/batched GEMM")):
+        ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        fam[name] = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{args.dtype}> ({label})", "achieved": ach,
+                     "peak": dense_peak, "unit": "TFLOP/s", "frac": ach / dense_peak, "peak_source": tsrc,
+                     "launches_per_step": n / args.steps, "kernel_ms_per_step": ms / args.steps,
+                     "share_of_step": ms / total_ms, "traffic": None}
+    if mega_n > 0 and mega_ms > 0:
+        w = llm.b200_engine().w
+        wbytes = 2.0 * (w.layers_n * (4 * w.hidden * w.hidden + 3 * w.hidden * w.inter) + w.vocab * w.hidden)
+        L0 = ctx * 257                                   # prompt length; decode step i feeds position L0 + i
+        steps = max_new - 1
+        kv = sum(B * (L0 + i) * w.layers_n * 2 * w.hidden * 2.0 for i in range(steps))
+        per_launch = steps * wbytes + kv
+        ach = per_launch * mega_n / (mega_ms * 1e-3) / 1e9
+        fam["mega"] = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent decode rollout, one launch per step of the bench)",
+                       "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                       "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                       "launches_per_step": mega_n / args.steps, "kernel_ms_per_step": mega_ms / args.steps,
+                       "share_of_step": mega_ms / total_ms, "algorithmic_bytes_per_launch": per_launch,
+                       "decode_steps_per_launch": steps, "traffic": mega_traffic()}
+    dom = max(fam, key=lambda k: fam[k]["kernel_ms_per_step"])
+    roofline = dict(fam[dom])
+    roofline["other"] = {k: {kk: v[kk] for kk in ("bound", "achieved", "unit", "frac", "kernel_ms_per_step", "share_of_step")}
+                         for k, v in fam.items() if k != dom}
+    return roofline
 
 
 def run_train(args):

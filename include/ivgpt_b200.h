@@ -32,9 +32,10 @@ extern "C" {
 const char* ivgpt_last_error(void);
 unsigned long long ivgpt_launch_count(void); /* kernels launched by this library since load */
 int ivgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* Measurement hooks (bench.py): when enabled, every tensor-core GEMM (bucket 0) / conv (bucket 1) launch issued
- * outside stream capture is bracketed by CUDA events on its own stream; collect() synchronises them and returns the
- * summed device time, the summed algorithmic FLOPs (2*M*N*K, causal tiles excluded) and the launch count. */
+/* Measurement hooks (bench.py): when enabled, every tensor-core GEMM (bucket 0) / conv (bucket 1) / decode-megakernel
+ * (bucket 2) launch issued outside stream capture is bracketed by CUDA events on its own stream; collect() synchronises
+ * them and returns the summed device time, the summed work (buckets 0/1: algorithmic FLOPs 2*M*N*K, causal tiles
+ * excluded; bucket 2: decode steps -- bench.py turns steps into weight + KV bytes) and the launch count. */
 int ivgpt_profile_enable(int on);
 int ivgpt_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches);
 int ivgpt_count_add(long long n); /* account for kernels replayed through a CUDA graph */
@@ -195,7 +196,7 @@ typedef struct ivgpt_mega_desc {
   const unsigned long long* dseed;
   unsigned int* barrier; int* error;
   const void* layers_dev; const void* lm_head_packed;
-  long long* prof; /* optional device [16]: SM-cycle totals of CTA 0 per phase kind (norm, qkv, attention, o, gate/up,
+  long long* prof; /* optional device [24]: SM-cycle totals of CTA 0 per phase kind (norm, qkv, attention, o, gate/up,
                       down, lm_head, sample, barriers); NULL to disable */
   void* vrows;     /* bf16 [layers][B][heads][Lmax][64]: V cache in K's layout (filled by ivgpt_rope_kv), used and
                       appended to when attn_mode == 0 */

@@ -77,6 +77,8 @@ static int num_sms() {
 int gemm_tc_dispatch(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream);
 void gemm_profile_enable(int on);
 int gemm_profile_collect(int bucket, double* ms_total, double* flops_total, long long* launches);
+int profile_begin(int bucket, double work, cudaStream_t stream);
+void profile_end(int idx, cudaStream_t stream);
 int vq_argmin_launch(const float*, const float*, float*, unsigned long long*, long long*, int, int, int, int,
                      cudaStream_t);
 extern int g_vq_order;
@@ -481,7 +483,10 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   IVG_CHECK(p.attn_mode == 1 || (p.attn_part != nullptr && p.attn_cnt != nullptr),
             "decode_mega: attn_mode 0 needs attn_part [SMs*4*72 floats] and attn_cnt [SMs uints, zeroed]");
   if (p.steps <= 0) return 0;
-  return ivg::decode_mega_launch(p, num_sms(), S(stream));
+  const int rec = ivg::profile_begin(2, (double)p.steps, S(stream));      // bench.py roofline leg: work = decode steps
+  const int rc = ivg::decode_mega_launch(p, num_sms(), S(stream));
+  ivg::profile_end(rec, S(stream));
+  return rc;
 }
 
 }  // extern "C"

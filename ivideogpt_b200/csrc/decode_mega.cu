@@ -182,10 +182,16 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
   int it = 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
     const int tile = w % ntiles, split = w / ntiles;
+    // optional fine-grained timing (CTA 0, thread 0): prof[14..17] = activation slab load, weight slab wait, MMA issue,
+    // commit -> end of epilogue
+    const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long gt = gprof ? clock64() : 0;
+#define GEMM_MARK(slot_) do { if (gprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - gt; gt = t_; } } while (0)
     if (split != loaded_split) {          // (re)load the activation slab for this K range
       load_a(p, c, g.A, g.lda, split * Kc, Kc, a_rows);
       loaded_split = split;
     }
+    GEMM_MARK(14);
     if (threadIdx.x == 0) {
       issue_items(c, g, it + (int)c.sm.nbuf);   // this item (if not prefetched) and the following nbuf - 1
       const uint32_t buf = c.consumed % c.sm.nbuf;
@@ -193,6 +199,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
       ++c.consumed;
       mbar_wait(c.sm.bfull + buf, par);
       tc_fence_after();
+      GEMM_MARK(15);
       const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
       for (int j = 0; j < nkb; ++j) {
         const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
@@ -202,6 +209,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
           umma_ss<false>(c.tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (j | k) ? 1u : 0u);
       }
       umma_commit(c.sm.mma_done);
+      GEMM_MARK(16);
     }
     // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3 ----
     if (warp >= 4 && warp < 8) {
@@ -242,6 +250,8 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
     c.mphase ^= 1;          // every thread tracks the parity (only warps 4..7 wait on it)
     __syncthreads();        // MMA retired (epilogue observed mma_done): TMEM accumulator, A slab and this weight
                             // buffer may be reused
+    GEMM_MARK(17);
+#undef GEMM_MARK
   }
 }
 

@@ -50,7 +50,7 @@ struct MegaParams {
   int* error;               // zero-initialised; 1 = barrier timeout
   const MegaLayer* lw;      // device array [layers]
   const __nv_bfloat16* lm_head; // packed like the layer weights, rows padded to a multiple of 16
-  long long* prof;              // optional [16] cycle counters filled by CTA 0 (phase breakdown), may be null
+  long long* prof;              // optional [24] cycle counters filled by CTA 0 (phase breakdown; 9..13 attention, 14..17 GEMM item), may be null
   float* attn_part;             // [SMs][4][72] flash-decoding partials of the items cut along the sequence (attn_mode 0)
   unsigned int* attn_cnt;       // [SMs] zero-initialised arrival counters of those items
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)

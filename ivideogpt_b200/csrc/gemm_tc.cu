@@ -368,6 +368,25 @@ int gemm_profile_collect(int bucket, double* ms_total, double* flops_total, long
   return 0;
 }
 
+// generic bracket for launchers in other translation units (bucket 2 = decode megakernel): returns a record index or -1
+int profile_begin(int bucket, double work, cudaStream_t stream) {
+  if (!g_prof_on) return -1;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return -1;
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r.e0 = g_prof_pool.back().first; r.e1 = g_prof_pool.back().second; g_prof_pool.pop_back(); }
+  else { if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1; }
+  r.flops = work;
+  r.bucket = bucket;
+  cudaEventRecord(r.e0, stream);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void profile_end(int idx, cudaStream_t stream) {
+  if (idx >= 0 && idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, stream);
+}
+
 static int dispatch_inner(int dtype, int bn, const GemmMaps& maps, const GemmParams& p, int num_sms,
                           cudaStream_t stream) {
   if (dtype == DT_BF16) {

@@ -321,7 +321,7 @@ class LlamaEngine:
         d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
         if getattr(self, "mega_profile", False):
-            self.mega_prof = self.buf("mega_prof", (16,), torch.int64)
+            self.mega_prof = self.buf("mega_prof", (24,), torch.int64)
             self.mega_prof.zero_()
             d.prof = self.mega_prof.data_ptr()
         _lib.check(_lib.load().ivgpt_decode_mega(C.byref(d), torch.cuda.current_stream().cuda_stream), "decode_mega")

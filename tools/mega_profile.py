@@ -11,9 +11,11 @@ eng = llm.b200_engine()
 ids = torch.randint(0, 16384, (B, 514), device=dev)
 new = 237
 res = {}
-for name, kw, mode in (("graph", dict(use_mega=False), 0), ("mega_regs", dict(use_mega=True), 1),
-                       ("mega_noprefetch", dict(use_mega=True), 2), ("mega", dict(use_mega=True), 0),
-                       ("mega_noprefetch2", dict(use_mega=True), 2), ("mega2", dict(use_mega=True), 0)):
+VARIANTS = (("graph", dict(use_mega=False), 0), ("mega_regs", dict(use_mega=True), 1),
+            ("mega_noprefetch", dict(use_mega=True), 2), ("mega", dict(use_mega=True), 0))
+if os.environ.get("MEGA_ONLY", "0") == "1":
+    VARIANTS = (("mega", dict(use_mega=True), 0),)
+for name, kw, mode in VARIANTS:
     eng.mega_attn_mode = mode
     for _ in range(2):
         eng.generate(ids, None, new, True, 100, 1.0, 1, **kw)
@@ -38,5 +40,7 @@ for mode, tag in ((2, "_noprefetch"), (0, "")):
     if mode == 0:
         res["attention_warp0_us_per_step"] = {n: c / mhz / (new - 1) for n, c in
                                               zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])}
+        res["gemm_item_us_per_step"] = {n: c / mhz / (new - 1) for n, c in
+                                        zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}
 res["decode_steps"] = new - 1
 print(json.dumps(res))
