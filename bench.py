@@ -384,7 +384,12 @@ def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs
                        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
                        "launches_per_step": mega_n / args.steps, "kernel_ms_per_step": mega_ms / args.steps,
                        "share_of_step": mega_ms / total_ms, "algorithmic_bytes_per_launch": per_launch,
-                       "decode_steps_per_launch": steps, "traffic": mega_traffic()}
+                       "decode_steps_per_launch": steps, "traffic": None}
+        cap = mega_traffic()
+        if cap:   # ncu --set full DRAM bytes of a shorter launch of the same kernel, scaled by its measured ratio to that launch's algorithmic bytes
+            fam["mega"]["traffic"] = cap["ratio_to_algorithmic"] * per_launch
+            fam["mega"]["traffic_source"] = (f"profiles/r01/ncu_decode_mega_traffic.json: {cap['dram_bytes'] / 1e9:.2f} GB DRAM over a "
+                                             f"{cap['decode_steps']}-step launch = {cap['ratio_to_algorithmic']:.3f} x algorithmic, scaled to {steps} steps")
     dom = max(fam, key=lambda k: fam[k]["kernel_ms_per_step"])
     roofline = dict(fam[dom])
     roofline["other"] = {k: {kk: v[kk] for kk in ("bound", "achieved", "unit", "frac", "kernel_ms_per_step", "share_of_step")}

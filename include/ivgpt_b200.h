@@ -169,6 +169,14 @@ int ivgpt_topk_sample(const float* logits, long long ld, int rows, int V, int k,
 int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const long long* labels, float* loss_rows,
                   float* valid_ws, float* loss_out, void* stream);
 int ivgpt_incr(int* p, int by, void* stream);
+/* Forced separator slots of the action-conditioned rollout (ivideogpt/transformer/action_model.py:78-114): every
+ * `period`-th position from slot0 holds `token` instead of a sampled one (:109-110) and the embedding fed there gets
+ * slot_emb[b, i, :] = action_linear(a_i) added (:80-81).  Position is read from device memory (*dpos = position being
+ * fed).  x [B, hidden] fp32, slot_emb [B, nslots, hidden] fp32, tokens [B, tok_stride] int64. */
+int ivgpt_slot_embed_add(float* x, const float* slot_emb, const int* dpos, int B, int hidden, int slot0, int period,
+                         int nslots, void* stream);
+int ivgpt_slot_force(long long* tokens, long long tok_stride, const int* dpos, int B, int slot0, int period,
+                     long long token, void* stream);
 /* One decode step of attention for the newest token (HF generate's per-token forward with a KV cache): RoPE on q/k,
  * append k / v to the caches at position pos (= *dpos when dpos != NULL), attention over positions [0, pos].
  * qkv [B, 3*hidden], k_cache [B,heads,Lmax,64], v_cache_t [B,heads,64,Lmax], out [B, hidden]. */
@@ -204,6 +212,13 @@ typedef struct ivgpt_mega_desc {
   void* attn_cnt;  /* uint32 [SMs] zeroed counters for attention items cut along the sequence (attn_mode 0) */
   int attn_mode;   /* attention phase: 0 = K/V streamed by 1-D bulk copies (TMA) into a shared-memory ring,
                       1 = register-staged loads */
+  /* forced separator slots (action-conditioned rollout, action_model.py:78-114); slot_period == 0 disables.
+   * Position q >= slot0 with (q - slot0) % slot_period == 0 is slot i = (q - slot0) / slot_period: its token is
+   * slot_token (never sampled) and slot_emb[b, i, :] (fp32 [B, nslots, hidden], may be NULL) is added to its embedding. */
+  int slot0, slot_period, nslots;
+  long long slot_token;
+  const float* slot_emb;
+  int mma_m64;     /* GEMM phases: 1 = M=64 tcgen05.mma when B <= 64 (reads only the real activation rows), 0 = M=128 */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);

@@ -71,6 +71,10 @@ class MegaDesc(C.Structure):
         ("vrows", C.c_void_p),
         ("attn_part", C.c_void_p), ("attn_cnt", C.c_void_p),
         ("attn_mode", C.c_int),
+        ("slot0", C.c_int), ("slot_period", C.c_int), ("nslots", C.c_int),
+        ("slot_token", C.c_longlong),
+        ("slot_emb", C.c_void_p),
+        ("mma_m64", C.c_int),
     ]
 
 
@@ -107,6 +111,8 @@ SIGNATURES = {
     "ivgpt_topk_sample": [_P, _L, _I, _I, _I, _F, _U, _U, _P, _L, _P, _P, _P],
     "ivgpt_ce_loss": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P],
     "ivgpt_incr": [_P, _I, _P],
+    "ivgpt_slot_embed_add": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ivgpt_slot_force": [_P, _L, _P, _I, _I, _I, _L, _P],
     "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],
     "ivgpt_set_pdl": [_I],
     "ivgpt_transpose": [_I, _P, _P, _I, _I, _I, _L, _L, _L, _L, _P],

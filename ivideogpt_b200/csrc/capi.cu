@@ -111,6 +111,8 @@ int topk_sample_launch(const float*, long long, int, int, int, float, unsigned l
                        long long*, long long, const int*, const unsigned long long*, cudaStream_t);
 int ce_loss_launch(const float*, long long, int, int, int, const long long*, float*, float*, float*, cudaStream_t);
 int incr_launch(int*, int, cudaStream_t);
+int slot_embed_add_launch(float*, const float*, const int*, int, int, int, int, int, cudaStream_t);
+int slot_force_launch(long long*, long long, const int*, int, int, int, long long, cudaStream_t);
 int transpose_launch(int, const void*, void*, int, int, int, long long, long long, long long, long long, cudaStream_t);
 int swiglu_launch(int, int, const void*, const void*, void*, long long, cudaStream_t);
 int rmsnorm_bwd_launch(int, const float*, const float*, const void*, float*, float*, float*, long long, int, float,
@@ -391,6 +393,14 @@ int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const 
   return ce_loss_launch(logits, ld, B, L, V, labels, loss_rows, valid_ws, loss_out, S(stream));
 }
 int ivgpt_incr(int* p, int by, void* stream) { return incr_launch(p, by, S(stream)); }
+int ivgpt_slot_embed_add(float* x, const float* slot_emb, const int* dpos, int B, int hidden, int slot0, int period,
+                         int nslots, void* stream) {
+  return slot_embed_add_launch(x, slot_emb, dpos, B, hidden, slot0, period, nslots, S(stream));
+}
+int ivgpt_slot_force(long long* tokens, long long tok_stride, const int* dpos, int B, int slot0, int period,
+                     long long token, void* stream) {
+  return slot_force_launch(tokens, tok_stride, dpos, B, slot0, period, token, S(stream));
+}
 int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_cache_t, void* out, int B, int heads,
                             int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
                             float scale, void* stream) {
@@ -479,6 +489,10 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.prof = d->prof;
   p.attn_mode = d->attn_mode;
   p.attn_part = (float*)d->attn_part; p.attn_cnt = (unsigned int*)d->attn_cnt;
+  p.slot_emb = d->slot_emb; p.slot0 = d->slot0; p.slot_period = d->slot_period; p.nslots = d->nslots;
+  p.slot_token = d->slot_token;
+  p.mma_m64 = d->mma_m64;
+  IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");
   IVG_CHECK(p.attn_mode == 1 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
   IVG_CHECK(p.attn_mode == 1 || (p.attn_part != nullptr && p.attn_cnt != nullptr),
             "decode_mega: attn_mode 0 needs attn_part [SMs*4*72 floats] and attn_cnt [SMs uints, zeroed]");

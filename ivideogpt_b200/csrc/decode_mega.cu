@@ -177,7 +177,11 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
   const int nkb = Kc / 64;
   const int a_rows = p.B <= 64 ? 64 : 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t IDESC = umma_idesc(1, 128, MEGA_BN);
+  // B <= 64 with mma_m64: M = 64 UMMA -- the instruction fetches only the 64 real activation rows from shared memory
+  // (the M = 128 form reads 128 x 32 B per MMA and was measured operand-fetch bound at ~80 cycles per N = 16 MMA,
+  // profiles/r01/mega_phase_breakdown_v9.json).  TMEM rows of an M = 64 accumulator: row r -> lane 32*(r/16) + r%16.
+  const bool m64 = p.mma_m64 != 0 && a_rows == 64;
+  const uint32_t IDESC = m64 ? umma_idesc(1, 64, MEGA_BN) : umma_idesc(1, 128, MEGA_BN);
   int loaded_split = -1;
   int it = 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
@@ -214,7 +218,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
     // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3 ----
     if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
-      const int row = q * 32 + lane;
+      const int row = m64 ? (lane < 16 ? q * 16 + lane : p.B) : q * 32 + lane;
       mbar_wait(c.sm.mma_done, c.mphase);
       tc_fence_after();
       uint32_t r[16];
@@ -274,6 +278,12 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
     float ss = 0.f;
     if (i < H) {
       v = *reinterpret_cast<const float4*>(src + i);
+      if (tok_row0 && p.slot_emb && p.slot_period > 0 && tok_col >= p.slot0 && (tok_col - p.slot0) % p.slot_period == 0 &&
+          (tok_col - p.slot0) / p.slot_period < p.nslots) {       // forced slot: + action_linear(a_i), action_model.py:80-81
+        const float4 e = *reinterpret_cast<const float4*>(
+            p.slot_emb + ((size_t)m * p.nslots + (tok_col - p.slot0) / p.slot_period) * H + i);
+        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      }
       float4 q[MEGA_MAX_SPLITS];
 #pragma unroll
       for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
@@ -884,6 +894,10 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   constexpr int NW = MEGA_THREADS / 32;
   __shared__ float s_redf[NW];
   __shared__ int s_redi[NW];
+  if (p.slot_period > 0 && pos + 1 >= p.slot0 && (pos + 1 - p.slot0) % p.slot_period == 0) {
+    if (tid == 0) *out = p.slot_token;       // forced separator, never sampled (action_model.py:109-110); CTA-uniform
+    return;
+  }
   if (!p.do_sample) {
     float bv = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 8

@@ -681,4 +681,56 @@ int incr_launch(int* p, int by, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forced "slot" positions of an action-conditioned rollout (reference ivideogpt/transformer/action_model.py:78-114):
+// every `period`-th position from `slot0` holds the separator token, never a sampled one, and the embedding fed at
+// slot i gets action_linear(a_i) added (:80-81).  Both kernels read the position from device memory (graph-safe).
+//   slot_embed_add : x[b, :] += slot_emb[b, i, :]   if the position being fed, *dpos, is slot i
+//   slot_force     : tokens[b, *dpos + 1] = token   if position *dpos + 1 is a slot
+// ---------------------------------------------------------------------------------------------
+__global__ void slot_embed_add_kernel(float* __restrict__ x, const float* __restrict__ slot_emb, const int* __restrict__ dpos,
+                                      int B, int Hd, int slot0, int period, int nslots) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pos = *dpos;
+  if (pos < slot0 || (pos - slot0) % period != 0) return;
+  const int i = (pos - slot0) / period;
+  if (i >= nslots) return;
+  const int hv = Hd / 4;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < B * hv; t += gridDim.x * blockDim.x) {
+    const int b = t / hv, c = t - b * hv;
+    float4 v = reinterpret_cast<float4*>(x)[t];
+    const float4 e = __ldg(reinterpret_cast<const float4*>(slot_emb + ((size_t)b * nslots + i) * Hd) + c);
+    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    reinterpret_cast<float4*>(x)[t] = v;
+  }
+}
+int slot_embed_add_launch(float* x, const float* slot_emb, const int* dpos, int B, int Hd, int slot0, int period,
+                          int nslots, cudaStream_t st) {
+  IVG_CHECK(Hd % 4 == 0 && period >= 1 && nslots >= 1 && dpos != nullptr, "slot_embed_add: bad arguments");
+  const int work = B * (Hd / 4);
+  IVG_CUDA(launch_k(slot_embed_add_kernel, dim3((work + 255) / 256), dim3(256), 0, st, x, slot_emb, dpos, B, Hd, slot0,
+                    period, nslots));
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void slot_force_kernel(long long* __restrict__ tokens, long long stride, const int* __restrict__ dpos, int B,
+                                  int slot0, int period, long long token) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int nxt = *dpos + 1;
+  if (nxt < slot0 || (nxt - slot0) % period != 0) return;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) tokens[(size_t)b * stride + nxt] = token;
+}
+int slot_force_launch(long long* tokens, long long stride, const int* dpos, int B, int slot0, int period, long long token,
+                      cudaStream_t st) {
+  IVG_CHECK(period >= 1 && dpos != nullptr, "slot_force: bad arguments");
+  IVG_CUDA(launch_k(slot_force_kernel, dim3((B + 127) / 128), dim3(128), 0, st, tokens, stride, dpos, B, slot0, period, token));
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ivg

@@ -361,6 +361,19 @@ def incr(p, by=1):
     _lib.check(_lib.load().ivgpt_incr(p.data_ptr(), by, _stream()), "incr")
 
 
+def slot_embed_add(x, slot_emb, dpos, B, hidden, slot0, period):
+    """x[b] += slot_emb[b, i] when the position being fed (*dpos) is forced slot i (action_model.py:80-81)."""
+    assert slot_emb.dtype == torch.float32 and slot_emb.is_contiguous() and slot_emb.shape[0] == B
+    _lib.check(_lib.load().ivgpt_slot_embed_add(x.data_ptr(), slot_emb.data_ptr(), dpos.data_ptr(), B, hidden, slot0, period,
+                                                slot_emb.shape[1], _stream()), "slot_embed_add")
+
+
+def slot_force(tokens, dpos, B, slot0, period, token):
+    """tokens[b, *dpos + 1] = token when that position is a forced slot (action_model.py:109-110)."""
+    _lib.check(_lib.load().ivgpt_slot_force(tokens.data_ptr(), tokens.stride(0), dpos.data_ptr(), B, slot0, period,
+                                            int(token), _stream()), "slot_force")
+
+
 # ------------------------------------------------------------------------------------------------
 # training (backward) pieces
 # ------------------------------------------------------------------------------------------------

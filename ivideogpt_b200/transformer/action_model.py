@@ -6,10 +6,15 @@ Token layout (context c, segment s, 16 tokens per future frame):
 The embedding of action a_{i+c-1} is added to the input embedding at the i-th sdf slot
 (prelude_tokens_num + 17*i), reference :80-81 (generate) and :171-177 (forward).
 
-Status: `generate` / `generate_without_action` / `forward` (loss evaluation) run on the sm_100a kernels.  Each
-future frame re-prefills its history exactly as the reference does (:78-114); a persistent-cache variant is the
-first "next" row of SURVEY.md section 8(f).  The tiny action/reward linears (action_dim -> hidden, hidden -> 1)
-are evaluated with torch.nn.functional.linear on the device: they are not on the frames/s hot path.
+Status: `generate` / `generate_without_action` / `forward` (loss evaluation) run on the sm_100a kernels.
+The reference re-prefills the whole history for every future frame (:78-114, O(frames x history)); here the rollout keeps
+ONE KV cache: one prefill of the prompt, then a single decode run (the persistent
+megakernel in bf16, the CUDA-graph step in TF32) in which the separator slots are forced to `token_for_sdf` and receive
+their action embedding inside the kernel (`slot_cfg` of LlamaEngine.generate).  Same token sequence as the reference's
+loop under greedy decoding (tests/test_action_model.py, against vectors produced by the reference file itself);
+`persistent_cache = False` selects the reference-shaped per-frame re-prefill loop.  The tiny action/reward linears
+(action_dim -> hidden, hidden -> 1) are evaluated with torch.nn.functional.linear on the device: they are not on the
+frames/s hot path.
 """
 from __future__ import annotations
 
@@ -43,6 +48,22 @@ class HeadModelWithAction(nn.Module):
             self.reward_linear = nn.Linear(hidden, 1)
         if action_recon:
             self.action_recon_linear = nn.Linear(hidden, action_dim)
+        self.persistent_cache = True          # one KV cache per rollout instead of the reference's per-frame re-prefill
+
+    def _persistent_layout(self, T, per_frame, with_action):
+        """(slot0, period) of the forced separator positions when the rollout can keep one cache, else None.
+        The reference appends a separator after every `per_frame` generated tokens (:109-110): positions
+        T + per_frame + j*(per_frame + 1).  With actions these must coincide with the action slots P + i*(n + 1)."""
+        if not self.persistent_cache or not hasattr(self.llm, "b200_engine"):
+            return None
+        first = T + per_frame
+        if not with_action:
+            return first, per_frame + 1
+        period = self.tokens_num_per_dyna + 1
+        if per_frame != self.tokens_num_per_dyna or first < self.prelude_tokens_num or \
+                (first - self.prelude_tokens_num) % period != 0 or T <= self.prelude_tokens_num:
+            return None
+        return self.prelude_tokens_num, period
 
     # ------------------------------------------------------------------------------------------------------
     def get_input_embeddings(self, input_ids):
@@ -72,6 +93,22 @@ class HeadModelWithAction(nn.Module):
                                          self.action_linear.bias.float())
         embeds = self.get_input_embeddings(inputs_token)
         tokens = inputs_token.to(torch.int64)
+        layout = self._persistent_layout(T, per_frame, True)
+        if layout is not None:
+            slot0, period = layout
+            n_prompt_slots = (T - 1 - slot0) // period + 1            # slots already inside the prompt (normally 1)
+            for i in range(n_prompt_slots):
+                embeds[:, slot0 + i * period, :] += act[:, i + self.context - 1, :]
+            nslots = n_prompt_slots + self._frames()
+            slot_emb = torch.zeros(B, nslots, act.shape[-1], dtype=torch.float32, device=act.device)
+            avail = min(nslots, act.shape[1] - (self.context - 1))
+            slot_emb[:, :avail] = act[:, self.context - 1: self.context - 1 + avail]
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if do_sample else 0
+            out = self.llm.b200_engine().generate(None, embeds, int(max_new_tokens), bool(do_sample), int(top_k or 0),
+                                                  float(temperature), seed,
+                                                  slot_cfg=(slot0, period, self.token_for_sdf, slot_emb))
+            out[:, :T] = tokens
+            return out
         sdf = torch.full((B, 1), self.token_for_sdf, dtype=torch.int64, device=tokens.device)
         for i in range(self._frames()):
             slot = self.prelude_tokens_num + i * (self.tokens_num_per_dyna + 1)
@@ -90,6 +127,12 @@ class HeadModelWithAction(nn.Module):
         per_frame = ((max_new_tokens + 1) // self._frames()) - 1
         B, T = inputs_token.shape
         tokens = inputs_token.to(torch.int64)
+        layout = self._persistent_layout(T, per_frame, False)
+        if layout is not None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if do_sample else 0
+            return self.llm.b200_engine().generate(tokens.contiguous(), None, int(max_new_tokens), bool(do_sample),
+                                                   int(top_k or 0), float(temperature), seed,
+                                                   slot_cfg=(layout[0], layout[1], self.token_for_sdf, None))
         sdf = torch.full((B, 1), self.token_for_sdf, dtype=torch.int64, device=tokens.device)
         for _ in range(self._frames()):
             new = self.llm.generate(inputs_embeds=self.get_input_embeddings(tokens), do_sample=do_sample,

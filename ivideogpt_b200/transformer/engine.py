@@ -186,11 +186,13 @@ class LlamaEngine:
         return logits, None
 
     # ---- one decode step, position read from device memory ----------------------------------------------------
-    def _decode_step(self, B, Lmax, tokens, dpos, sample_cfg, dseed=None):
+    def _decode_step(self, B, Lmax, tokens, dpos, sample_cfg, dseed=None, slot=None):
         w = self.w
         h = w.hidden
         x = self.buf("xd", (B, h), torch.float32)
         ops.embed(tokens, tokens.stride(0), 1, dpos, w.embed, x, B)
+        if slot is not None and slot[3] is not None:
+            ops.slot_embed_add(x, slot[3], dpos, B, h, slot[0], slot[1])
         kc, vc = self.kv_cache(B, Lmax)
         for li in range(w.layers_n):
             self._layer_decode(li, x, B, kc, vc, Lmax, dpos)
@@ -200,6 +202,8 @@ class LlamaEngine:
         logits = self.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)
         ops.gemm(xn, w.lm_head, out=logits[:, :V])
         self._sample(logits, B, tokens, dpos, sample_cfg, 0, dseed)
+        if slot is not None:
+            ops.slot_force(tokens, dpos, B, slot[0], slot[1], slot[2])
         ops.incr(dpos, 1)
 
     def _layer_decode(self, li, x, B, kc, vc, Lmax, dpos):
@@ -284,7 +288,7 @@ class LlamaEngine:
         self._mega_dev = (tab, lm_head, keep)
         return self._mega_dev
 
-    def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps):
+    def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps, slot=None):
         import ctypes as C
         from .. import _lib
         w = self.w
@@ -320,6 +324,11 @@ class LlamaEngine:
         d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
         d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
+        d.mma_m64 = int(getattr(self, "mega_m64", int(os.environ.get("IVGPT_MEGA_M64", "1"))))
+        if slot is not None:
+            d.slot0, d.slot_period, d.slot_token = int(slot[0]), int(slot[1]), int(slot[2])
+            d.nslots = int(slot[3].shape[1]) if slot[3] is not None else 1
+            d.slot_emb = slot[3].data_ptr() if slot[3] is not None else None
         if getattr(self, "mega_profile", False):
             self.mega_prof = self.buf("mega_prof", (24,), torch.int64)
             self.mega_prof.zero_()
@@ -331,11 +340,16 @@ class LlamaEngine:
     @torch.no_grad()
     def generate(self, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], max_new_tokens: int,
                  do_sample: bool, top_k: int, temperature: float, seed: int, use_graph: bool = True,
-                 use_pdl: bool = True, use_mega: Optional[bool] = None) -> torch.Tensor:
+                 use_pdl: bool = True, use_mega: Optional[bool] = None, slot_cfg=None) -> torch.Tensor:
         """Returns the token buffer [B, L + max_new_tokens] (prompt slots hold ids, or zeros for embeds).
 
         The decode step is captured ONCE per (batch, length, sampling mode) into a CUDA graph: position and RNG seed
-        live in device memory, the token buffer is a persistent engine buffer, so later calls only replay."""
+        live in device memory, the token buffer is a persistent engine buffer, so later calls only replay.
+
+        slot_cfg = (slot0, period, token, slot_emb | None): forced separator slots of the action-conditioned rollout
+        (action_model.py:78-114) -- every position q >= L with (q - slot0) % period == 0 holds `token` instead of a
+        sampled one and slot_emb[b, (q - slot0) // period] (fp32 [B, nslots, hidden]) is added to its embedding, so the
+        whole rollout keeps ONE KV cache instead of re-prefilling the history for every frame."""
         src = ids if ids is not None else embeds
         B, L = src.shape[0], src.shape[1]
         dev = src.device
@@ -354,8 +368,19 @@ class LlamaEngine:
         dseed = self.buf("dseed", (1,), torch.int64)
         dseed.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
         dpos = self.buf("dpos", (1,), torch.int32)
+        slot = None
+        if slot_cfg is not None:
+            s0, period, stok, semb = slot_cfg
+            if semb is not None:
+                assert semb.dim() == 3 and semb.shape[0] == B and semb.shape[2] == self.w.hidden
+                persistent = self.buf("slot_emb", tuple(semb.shape), torch.float32)   # stable address for graph replay
+                persistent.copy_(semb)
+                semb = persistent
+            slot = (int(s0), int(period), int(stok), semb)
         logits, _ = self.prefill(B, L, Lmax, ids.contiguous() if ids is not None else None, embeds, False)
         self._sample(logits, B, tokens, None, sample_cfg, L, dseed)       # first new token -> tokens[:, L]
+        if slot is not None and L >= slot[0] and (L - slot[0]) % slot[1] == 0:
+            tokens[:, L] = slot[2]
         steps = max_new_tokens - 1
         if steps == 0:
             return tokens.clone()
@@ -366,7 +391,7 @@ class LlamaEngine:
             if not self.mega_supported(B, Lmax):
                 raise ValueError(f"decode megakernel does not support B={B}, dtype={self.dtype}, widths "
                                  f"{self.w.hidden}/{self.w.inter}")
-            sync = self._decode_mega(B, Lmax, tokens, dpos, sample_cfg, dseed, steps)
+            sync = self._decode_mega(B, Lmax, tokens, dpos, sample_cfg, dseed, steps, slot)
             out = tokens.clone()
             err = int(sync[1].item())
             if err != 0:
@@ -377,12 +402,13 @@ class LlamaEngine:
             ops.set_pdl(use_pdl)
             try:
                 for _ in range(steps):
-                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed, slot)
             finally:
                 ops.set_pdl(False)
             return tokens.clone()
         from .. import _lib
-        key = ("decode", B, Lmax, total, sample_cfg, use_pdl)
+        key = ("decode", B, Lmax, total, sample_cfg, use_pdl,
+               None if slot is None else (slot[0], slot[1], slot[2], None if slot[3] is None else tuple(slot[3].shape)))
         entry = self._graphs.get(key)
         done = 0
         if entry is None:
@@ -391,13 +417,13 @@ class LlamaEngine:
             ops.set_pdl(use_pdl)
             try:
                 with torch.cuda.stream(side):
-                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)   # warm-up run (is decode step 1)
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed, slot)   # warm-up run (is decode step 1)
                 torch.cuda.current_stream(dev).wait_stream(side)
                 done = 1
                 g = torch.cuda.CUDAGraph()
                 n0 = _lib.launch_count()
                 with torch.cuda.graph(g):
-                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed)
+                    self._decode_step(B, Lmax, tokens, dpos, sample_cfg, dseed, slot)
                 per_step = _lib.launch_count() - n0
                 _lib.load().ivgpt_count_add(-per_step)        # capture records kernels without running them
             finally:
