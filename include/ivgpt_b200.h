@@ -218,6 +218,10 @@ typedef struct ivgpt_mega_desc {
   int slot0, slot_period, nslots;
   long long slot_token;
   const float* slot_emb;
+  int a_bulk;      /* 1 = xn / ao / act are kept in global memory as the 128B-swizzled K-major shared-memory image of the
+                      GEMM A operand ([k/64][row < a_rows][chunk ^ (row & 7)][8], a_rows = 64 if B <= 64 else 128), so a
+                      phase loads its activation slab with ONE bulk copy; the three buffers must then hold a_rows rows.
+                      0 = row-major [B, K] loaded with cp.async */
   int mma_m64;     /* GEMM phases: 1 = M=64 tcgen05.mma when B <= 64 (reads only the real activation rows), 0 = M=128 */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);

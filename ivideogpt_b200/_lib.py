@@ -74,6 +74,7 @@ class MegaDesc(C.Structure):
         ("slot0", C.c_int), ("slot_period", C.c_int), ("nslots", C.c_int),
         ("slot_token", C.c_longlong),
         ("slot_emb", C.c_void_p),
+        ("a_bulk", C.c_int),
         ("mma_m64", C.c_int),
     ]
 

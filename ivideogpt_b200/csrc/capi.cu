@@ -492,6 +492,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.slot_emb = d->slot_emb; p.slot0 = d->slot0; p.slot_period = d->slot_period; p.nslots = d->nslots;
   p.slot_token = d->slot_token;
   p.mma_m64 = d->mma_m64;
+  p.a_bulk = d->a_bulk;
   IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");
   IVG_CHECK(p.attn_mode == 1 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
   IVG_CHECK(p.attn_mode == 1 || (p.attn_part != nullptr && p.attn_cnt != nullptr),

@@ -38,6 +38,7 @@ struct MegaSmem {
   uint32_t a_bytes;      // activation slab / attention ring / sampler scratch region size
   uint64_t* bfull;       // [4]
   uint64_t* mma_done;    // [1]
+  uint64_t* abar;        // [1] activation slab landed (a_bulk)
   uint32_t* tmem_holder;
   uint64_t* ring_bar;    // [8 warps][8 slots] attention ring: slot filled
   float* sc;             // attention scratch, MEGA_SC_BYTES
@@ -52,6 +53,7 @@ struct MegaCtx {
   uint32_t issued, consumed;
   int phase_issued;        // items of the CURRENT/coming phase whose slab has been issued already
   uint32_t mphase;         // parity of mma_done (all threads)
+  uint32_t aphase;         // parity of abar (thread 0)
 };
 
 // 16-byte global load cached in L2 only.  With ~200 KB of the SM's 228 KB configured as shared memory the L1 data
@@ -69,11 +71,25 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// ---- activation images (a_bulk) ----
+// With a_bulk the GEMM A operands produced inside the kernel (xn, ao, act) live in global memory ALREADY in the
+// 128B-swizzled K-major shared-memory image the tensor core reads: [k-block = k/64][row][chunk ^ (row & 7)][8 bf16],
+// a_rows (64 or 128) rows per k-block.  A K range of a phase is then one contiguous run of k-blocks: the whole
+// activation slab is ONE 1-D bulk copy by the copy engine instead of 24 cp.async per thread + wait + __syncthreads.
+__device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long long ld) {
+  if (!p.a_bulk) return (size_t)m * (size_t)ld + (size_t)k;
+  const int a_rows = p.B <= 64 ? 64 : 128;
+  return (size_t)(k >> 6) * (size_t)(a_rows * 64) + (size_t)m * 64 + (size_t)((((k >> 3) & 7) ^ (m & 7)) << 3) + (size_t)(k & 7);
+}
+
 // device-wide barrier; returns false when it timed out (error flag is set, every CTA leaves the kernel).
 // Arrival is a release-reduction, the wait an acquire-load: no full sc fences (v1 used __threadfence() on both sides
 // and cost ~2.8 us per barrier, 87 barriers per decode step).
 __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
   __shared__ int s_ok;
+  // a_bulk: this CTA's generic-proxy writes (activation images in global memory, scratch in the shared activation region)
+  // must be ordered before the copy-engine (async proxy) accesses that follow the barrier, here and in other CTAs
+  if (p.a_bulk) asm volatile("fence.proxy.async;\n" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
     c.epoch += gridDim.x;
@@ -100,6 +116,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// mbarrier wait that can never hang the GPU: after ~1 s the error flag is raised (the host raises) and the wait falls through
+__device__ __forceinline__ void mbar_wait_bounded(const MegaParams& p, uint64_t* bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 31)) { *p.error = code; break; }
+  }
+}
 
 // ---- weight slab: item (tile, split) of a packed matrix -> one contiguous copy of Kc * 32 bytes ----
 // packed layout (ivgpt_mega_pack_weight): [tile = n / 16][k-block = k / 64][row = n % 16][chunk ^ (row & 7)][8 bf16]
@@ -191,8 +216,19 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
     const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long gt = gprof ? clock64() : 0;
 #define GEMM_MARK(slot_) do { if (gprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - gt; gt = t_; } } while (0)
+    bool a_pending = false;
     if (split != loaded_split) {          // (re)load the activation slab for this K range
-      load_a(p, c, g.A, g.lda, split * Kc, Kc, a_rows);
+      if (p.a_bulk) {
+        if (threadIdx.x == 0) {           // one bulk copy: k-blocks [split*Kc/64, +nkb) of the swizzled image are contiguous
+          asm volatile("fence.proxy.async;\n" ::: "memory");
+          const uint32_t bytes = (uint32_t)(nkb * a_rows * 128);
+          mbar_expect_tx(c.sm.abar, bytes);
+          bulk_g2s(c.sm.a, g.A + (size_t)((split * Kc) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
+        }
+        a_pending = true;
+      } else {
+        load_a(p, c, g.A, g.lda, split * Kc, Kc, a_rows);
+      }
       loaded_split = split;
     }
     GEMM_MARK(14);
@@ -201,7 +237,8 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
       const uint32_t buf = c.consumed % c.sm.nbuf;
       const uint32_t par = (c.consumed / c.sm.nbuf) & 1u;
       ++c.consumed;
-      mbar_wait(c.sm.bfull + buf, par);
+      if (a_pending) { mbar_wait_bounded(p, c.sm.abar, c.aphase, 3); c.aphase ^= 1u; }
+      mbar_wait_bounded(p, c.sm.bfull + buf, par, 4);
       tc_fence_after();
       GEMM_MARK(15);
       const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
@@ -219,7 +256,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
     if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
       const int row = m64 ? (lane < 16 ? q * 16 + lane : p.B) : q * 32 + lane;
-      mbar_wait(c.sm.mma_done, c.mphase);
+      mbar_wait_bounded(p, c.sm.mma_done, c.mphase, 5);
       tc_fence_after();
       uint32_t r[16];
       tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16), r);
@@ -238,7 +275,7 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
 #pragma unroll
           for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else if (g.epi == EPI_SWIGLU) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + (n0 >> 1));
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + a_off(p, row, n0 >> 1, g.ldo));
           float o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = silu_f(v[2 * i]) * v[2 * i + 1];
@@ -307,7 +344,7 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
       uint2 o;
       o.x = pack_bf16x2(g.x * (v.x * r), g.y * (v.y * r));
       o.y = pack_bf16x2(g.z * (v.z * r), g.w * (v.w * r));
-      *reinterpret_cast<uint2*>(p.xn + (size_t)m * H + i) = o;
+      *reinterpret_cast<uint2*>(p.xn + a_off(p, m, i, H)) = o;
     }
     __syncthreads();
   }
@@ -419,7 +456,7 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
       float a = acc[r];
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == r) p.ao[(size_t)b * Hd + hh * 64 + d0 + r] = __float2bfloat16_rn(a * inv);
+      if (lane == r) p.ao[a_off(p, b, hh * 64 + d0 + r, Hd)] = __float2bfloat16_rn(a * inv);
     }
   }
   __syncwarp();
@@ -691,7 +728,7 @@ __device__ __forceinline__ void attention_store(const MegaParams& p, int bh, con
   if ((lane >> 3) == 0) {
     const uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
                                pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
-    *reinterpret_cast<uint4*>(p.ao + (size_t)b * p.hidden + hh * 64 + (lane & 7) * 8) = o;
+    *reinterpret_cast<uint4*>(p.ao + a_off(p, b, hh * 64 + (lane & 7) * 8, p.hidden)) = o;
   }
 }
 
@@ -867,7 +904,7 @@ __device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, 
     for (int k = 0; k < 2; ++k) {
       const int d = lane + 32 * k;
       const float o = (comb[2 + d] * e0 + comb[66 + 2 + d] * e1) * inv;
-      p.ao[(size_t)b * Hd + hh * 64 + d] = __float2bfloat16_rn(o);
+      p.ao[a_off(p, b, hh * 64 + d, Hd)] = __float2bfloat16_rn(o);
     }
   }
   pair_barrier(pair);                 // scratch reusable by the pair's next item
@@ -1081,14 +1118,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   c.sm.bfull = reinterpret_cast<uint64_t*>(base + MEGA_A_BYTES + 2 * MEGA_B_BYTES);
   c.sm.mma_done = c.sm.bfull + 4;
   c.sm.tmem_holder = reinterpret_cast<uint32_t*>(c.sm.mma_done + 1);
+  c.sm.abar = c.sm.bfull + 8;
   c.sm.ring_bar = c.sm.bfull + 16;                                   // 64 barriers, 128 B past the GEMM ones
   c.sm.sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c.sm.bfull) + MEGA_BAR_BYTES);
   uint32_t ring_par = 0;                                             // expected parity per ring slot of this warp
-  c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.mphase = 0;
+  c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.mphase = 0; c.aphase = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(c.sm.bfull + i, 1);
     mbar_init(c.sm.mma_done, 1);
+    mbar_init(c.sm.abar, 1);
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }

@@ -54,6 +54,7 @@ struct MegaParams {
   float* attn_part;             // [SMs][4][72] flash-decoding partials of the items cut along the sequence (attn_mode 0)
   unsigned int* attn_cnt;       // [SMs] zero-initialised arrival counters of those items
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
+  int a_bulk;                   // 1: xn / ao / act are swizzled shared-memory images in global memory, loaded by one bulk copy
   int mma_m64;                  // 1: M = 64 UMMA in the GEMM phases when B <= 64 (0: M = 128 with the upper rows unused)
   // forced separator slots of the action-conditioned rollout (action_model.py:78-114); slot_period == 0 disables
   int slot0, slot_period, nslots;

@@ -304,10 +304,11 @@ class LlamaEngine:
         d.o_splits, d.d_splits = o_s, d_s
         d.eps = w.eps
         d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
-        d.xn = self.buf("xnd", (B, h), self.dtype).data_ptr()
+        a_rows = 64 if B <= 64 else 128       # rows of the swizzled activation images (a_bulk)
+        d.xn = self.buf("mega_xn", (a_rows, h), self.dtype).data_ptr()
         d.qkv = self.buf("qkvd", (B, 3 * h), self.dtype).data_ptr()
-        d.ao = self.buf("aod", (B, h), self.dtype).data_ptr()
-        d.act = self.buf("actd", (B, w.inter), self.dtype).data_ptr()
+        d.ao = self.buf("mega_ao", (a_rows, h), self.dtype).data_ptr()
+        d.act = self.buf("mega_act", (a_rows, w.inter), self.dtype).data_ptr()
         d.part = self.buf("mega_part", (max(o_s, d_s), B, h), torch.float32).data_ptr()
         d.logits = logits.data_ptr(); d.ldl = logits.stride(0)
         d.kcache = kc.data_ptr(); d.vcache = vc.data_ptr(); d.vrows = self.v_rows(B, Lmax).data_ptr()
@@ -324,6 +325,7 @@ class LlamaEngine:
         d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
         d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
+        d.a_bulk = int(getattr(self, "mega_a_bulk", int(os.environ.get("IVGPT_MEGA_ABULK", "1"))))
         d.mma_m64 = int(getattr(self, "mega_m64", int(os.environ.get("IVGPT_MEGA_M64", "1"))))
         if slot is not None:
             d.slot0, d.slot_period, d.slot_token = int(slot[0]), int(slot[1]), int(slot[2])
@@ -395,8 +397,11 @@ class LlamaEngine:
             out = tokens.clone()
             err = int(sync[1].item())
             if err != 0:
-                raise RuntimeError("decode megakernel: device-wide barrier timed out (a CTA was not co-resident?)" if err == 1
-                                   else "decode megakernel: an attention ring slot never filled (bulk copy fault)")
+                raise RuntimeError({1: "decode megakernel: device-wide barrier timed out (a CTA was not co-resident?)",
+                                    2: "decode megakernel: an attention ring slot never filled (bulk copy fault)",
+                                    3: "decode megakernel: the activation slab never landed (bulk copy fault)",
+                                    4: "decode megakernel: a weight slab never landed (bulk copy fault)",
+                                    5: "decode megakernel: tensor-core completion never signalled"}.get(err, f"decode megakernel: error {err}"))
             return out
         if not use_graph:
             ops.set_pdl(use_pdl)

@@ -16,7 +16,7 @@ for W in ${QUICK_WORKLOADS}; do
   echo "== bench(quick) $W exit $? ($(( $(date +%s) - t0 )) s)" >> $S; cat gpurun_out/bench_$W.json >> $S; tail -5 gpurun_out/bench_$W.err >> $S
 done
 if [ "${RUN_MEGA_PROFILE:-1}" = "1" ]; then
-  MEGA_ONLY=${MEGA_ONLY:-1} timeout 600 python tools/mega_profile.py > gpurun_out/mega_profile.json 2> gpurun_out/mega_profile.err
+  timeout 600 python tools/mega_profile.py > gpurun_out/mega_profile.json 2> gpurun_out/mega_profile.err
   echo "== mega_profile exit $? ($(( $(date +%s) - t0 )) s)" >> $S; cat gpurun_out/mega_profile.json >> $S; tail -3 gpurun_out/mega_profile.err >> $S
 fi
 if [ "${RUN_NCU:-1}" = "1" ]; then

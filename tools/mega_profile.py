@@ -1,4 +1,5 @@
-"""Phase breakdown of the persistent decode megakernel (cycle counters of CTA 0) + wall time vs the CUDA-graph path."""
+"""Phase breakdown of the persistent decode megakernel (cycle counters of CTA 0) + wall time per operand-path variant.
+VARIANTS env: comma list of m64:bulk[:attn_mode] triples, default "0:0,1:0,0:1,1:1"."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,41 +7,48 @@ from bench import build_b200_models
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", "64"))
-tok, llm, _, _ = build_b200_models("cfg64", dev, torch.bfloat16)
+workload = os.environ.get("WORKLOAD", "cfg64")
+tok, llm, _, _ = build_b200_models(workload, dev, torch.bfloat16)
 eng = llm.b200_engine()
 ids = torch.randint(0, 16384, (B, 514), device=dev)
 new = 237
-res = {}
-VARIANTS = (("graph", dict(use_mega=False), 0), ("mega_regs", dict(use_mega=True), 1),
-            ("mega_noprefetch", dict(use_mega=True), 2), ("mega", dict(use_mega=True), 0))
-if os.environ.get("MEGA_ONLY", "0") == "1":
-    VARIANTS = (("mega", dict(use_mega=True), 0),)
-for name, kw, mode in VARIANTS:
-    eng.mega_attn_mode = mode
-    for _ in range(2):
-        eng.generate(ids, None, new, True, 100, 1.0, 1, **kw)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, **kw); b.record(); torch.cuda.synchronize()
-    res[name + "_generate_ms"] = a.elapsed_time(b)
-# prefill only
+mhz = 1965.0
+names = ["norm", "qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "sample", "barriers"]
+res = {"B": B, "workload": workload, "decode_steps": new - 1}
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+eng.generate(ids, None, 1, True, 100, 1.0, 1)
 a.record(); eng.generate(ids, None, 1, True, 100, 1.0, 1); b.record(); torch.cuda.synchronize()
 res["prefill_plus_first_token_ms"] = a.elapsed_time(b)
-eng.mega_profile = True
-names = ["norm", "qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "sample", "barriers"]
-mhz = 1965.0
-for mode, tag in ((2, "_noprefetch"), (0, "")):
-    eng.mega_attn_mode = mode
-    eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
-    torch.cuda.synchronize()
-    allc = eng.mega_prof.cpu().tolist()
-    cyc = allc[:9]
-    res["mega_phase_us_per_step" + tag] = {n: c / (mhz) / (new - 1) for n, c in zip(names, cyc)}
-    if mode == 0:
-        res["attention_warp0_us_per_step"] = {n: c / mhz / (new - 1) for n, c in
-                                              zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])}
-        res["gemm_item_us_per_step"] = {n: c / mhz / (new - 1) for n, c in
-                                        zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}
-res["decode_steps"] = new - 1
+if os.environ.get("WITH_GRAPH", "0") == "1":
+    for _ in range(2):
+        eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=False)
+    a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=False); b.record(); torch.cuda.synchronize()
+    res["graph_generate_ms"] = a.elapsed_time(b)
+for spec in os.environ.get("VARIANTS", "0:0,1:0,0:1,1:1").split(","):
+    f = [int(v) for v in spec.split(":")]
+    eng.mega_m64, eng.mega_a_bulk = f[0], f[1]
+    eng.mega_attn_mode = f[2] if len(f) > 2 else 0
+    tag = f"m64={f[0]},a_bulk={f[1]},attn={eng.mega_attn_mode}"
+    eng.mega_profile = False
+    try:
+        for _ in range(2):
+            eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
+        ts = []
+        for _ in range(3):
+            a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        eng.mega_profile = True
+        eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
+        torch.cuda.synchronize()
+        allc = eng.mega_prof.cpu().tolist()
+        res[tag] = {
+            "generate_ms": sorted(ts)[1],
+            "phase_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in zip(names, allc[:9])},
+            "attention_warp0_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
+                                            zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])},
+            "gemm_item_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
+                                      zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}}
+    except Exception as e:  # a variant that faults must not hide the others
+        res[tag] = {"error": repr(e)[:300]}
+        break
 print(json.dumps(res))
