@@ -223,12 +223,21 @@ typedef struct ivgpt_mega_desc {
                       phase loads its activation slab with ONE bulk copy; the three buffers must then hold a_rows rows.
                       0 = row-major [B, K] loaded with cp.async */
   int mma_m64;     /* GEMM phases: 1 = M=64 tcgen05.mma when B <= 64 (reads only the real activation rows), 0 = M=128 */
+  /* gemm_mode 1: weight-stationary GEMM phases -- the 64 weight rows of a work item are the MMA's M side, the batch its N
+   * side.  The five weight matrices are then packed with ivgpt_mega_pack_weight64() (wgu with swiglu_pairs = 1), a_bulk
+   * must be 1, a_rows (rows of the activation images, a multiple of 8 >= B) is the MMA's N, o_splits / d_splits may go
+   * up to 12, and the qkv projection is split-K too: qkvp holds its fp32 partials [qkv_splits][B][3*hidden] (the
+   * attention phase sums them), `qkv` is unused. */
+  int gemm_mode, qkv_splits, a_rows;
+  void* qkvp;
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv_packed, const void* wo_packed, const void* wgu_packed,
                           const void* wd_packed, const float* n1, const float* n2);
+long long ivgpt_mega_packed_elems64(int rows, int cols);
+int ivgpt_mega_pack_weight64(const void* w, void* out, int rows, int cols, int swiglu_pairs, void* stream);
 int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream);
 /* ---- training pieces: backward of LlamaForCausalLM.forward(labels) (train_gpt.py:792-798) and the AdamW update
  * (train_gpt.py:648-658,803).  All contractions of the backward pass are ivgpt_gemm calls on transposed operands. */

@@ -462,6 +462,14 @@ int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* s
   return ivg::mega_pack_weight_launch(w, out, rows, cols, S(stream));
 }
 
+long long ivgpt_mega_packed_elems64(int rows, int cols) {
+  return (long long)((rows + ivg::MEGA_WM - 1) / ivg::MEGA_WM) * ivg::MEGA_WM * cols;
+}
+
+int ivgpt_mega_pack_weight64(const void* w, void* out, int rows, int cols, int swiglu_pairs, void* stream) {
+  return ivg::mega_pack_weight64_launch(w, out, rows, cols, swiglu_pairs, S(stream));
+}
+
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, const void* wgu, const void* wd,
                           const float* n1, const float* n2) {
   ivg::MegaLayer* L = reinterpret_cast<ivg::MegaLayer*>(host_layer);
@@ -493,6 +501,8 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.slot_token = d->slot_token;
   p.mma_m64 = d->mma_m64;
   p.a_bulk = d->a_bulk;
+  p.gemm_mode = d->gemm_mode; p.qkv_splits = d->qkv_splits; p.qkvp = (float*)d->qkvp;
+  p.a_rows = d->gemm_mode == 0 ? (d->B <= 64 ? 64 : 128) : d->a_rows;
   IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");
   IVG_CHECK(p.attn_mode == 1 || p.vrows != nullptr, "decode_mega: attn_mode 0 needs the row-major V cache (vrows)");
   IVG_CHECK(p.attn_mode == 1 || (p.attn_part != nullptr && p.attn_cnt != nullptr),

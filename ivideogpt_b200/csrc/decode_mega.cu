@@ -39,6 +39,7 @@ struct MegaSmem {
   uint64_t* bfull;       // [4]
   uint64_t* mma_done;    // [1]
   uint64_t* abar;        // [1] activation slab landed (a_bulk)
+  uint64_t* bempty;      // [4] gemm_mode 1: the MMAs that read weight slab buffer i have retired
   uint32_t* tmem_holder;
   uint64_t* ring_bar;    // [8 warps][8 slots] attention ring: slot filled
   float* sc;             // attention scratch, MEGA_SC_BYTES
@@ -78,7 +79,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // activation slab is ONE 1-D bulk copy by the copy engine instead of 24 cp.async per thread + wait + __syncthreads.
 __device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long long ld) {
   if (!p.a_bulk) return (size_t)m * (size_t)ld + (size_t)k;
-  const int a_rows = p.B <= 64 ? 64 : 128;
+  const int a_rows = p.a_rows;
   return (size_t)(k >> 6) * (size_t)(a_rows * 64) + (size_t)m * 64 + (size_t)((((k >> 3) & 7) ^ (m & 7)) << 3) + (size_t)(k & 7);
 }
 
@@ -189,22 +190,23 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
 }
 
 // called before the barrier that precedes phase g: weights do not depend on anything, start fetching them now
-__device__ __forceinline__ void prefetch_phase(MegaCtx& c, const GemmPhase& g) {
+__device__ __forceinline__ void prefetch_phase0(MegaCtx& c, const GemmPhase& g) {
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
   issue_items(c, g, (int)c.sm.nbuf);      // every buffer is free here: the previous GEMM phase has retired
 }
 
-__device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
+__device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
   const int items = phase_items(g);
   const int ntiles = items / g.ksplits;
   const int Kc = g.K / g.ksplits;
   const int nkb = Kc / 64;
   const int a_rows = p.B <= 64 ? 64 : 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // B <= 64 with mma_m64: M = 64 UMMA -- the instruction fetches only the 64 real activation rows from shared memory
-  // (the M = 128 form reads 128 x 32 B per MMA and was measured operand-fetch bound at ~80 cycles per N = 16 MMA,
-  // profiles/r01/mega_phase_breakdown_v9.json).  TMEM rows of an M = 64 accumulator: row r -> lane 32*(r/16) + r%16.
+  // B <= 64 with mma_m64: M = 64 UMMA -- the instruction fetches only the 64 real activation rows from shared memory.
+  // Measured neutral (profiles/r01/mega_phase_breakdown_v10_operand_paths.json): an N = 16 MMA costs ~80 cycles of issue
+  // whatever its M, i.e. this phase is bound by the NUMBER of tcgen05.mma instructions -- which is why gemm_mode 1 below
+  // turns the product around.  TMEM rows of an M = 64 accumulator: row r -> lane 32*(r/16) + r%16.
   const bool m64 = p.mma_m64 != 0 && a_rows == 64;
   const uint32_t IDESC = m64 ? umma_idesc(1, 64, MEGA_BN) : umma_idesc(1, 128, MEGA_BN);
   int loaded_split = -1;
@@ -296,6 +298,154 @@ __device__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) 
   }
 }
 
+// =====================================================================================================================
+// gemm_mode 1: weight-stationary GEMM phases.
+// Measured on the mode-0 phases above (profiles/r01/mega_phase_breakdown_v9/v10): a tcgen05.mma with N = 16 costs ~80
+// cycles of issue on the single issuing thread whatever M is, so a step's ~3600 MMAs alone took ~165 us, and every CTA
+// re-read the whole [B, K] activation matrix from L2 for each phase.  Here the product is turned around:
+//     D[64 weight rows, a_rows batch columns] += W_tile[64, 16] . X[a_rows, 16]^T        (M = 64, N = a_rows, K = 16)
+// one instruction now covers 64 weight rows instead of 16 (~3.4x fewer instructions per step), a work item is
+// (64-row tile, K split) so a CTA loads only the K range of the activations it needs (one bulk copy of the swizzled
+// image, see a_off), and weights stream through 32 KB slabs of 64 rows x <=256 k with up to nbuf in flight.
+//   qkv    : 3h/64 tiles x qkv_splits        -> fp32 partials [split][B][3h], summed by the attention prologue
+//   o/down : h/64 tiles x o_splits/d_splits  -> fp32 partials [split][B][h], summed by the norm phase (fixed order)
+//   gate/up: 2*inter/64 tiles, whole K streamed in chunks, SwiGLU in the epilogue (weights packed so that gate_i / up_i
+//            sit 8 TMEM lanes apart in the same warp: one shuffle)
+//   lm_head: ceil(vocab/64) tiles, whole K streamed.
+// Accumulator row r (weight row) lives in TMEM lane 32*(r/16) + r%16, column b = batch row.
+// =====================================================================================================================
+__device__ __forceinline__ int w64_chunk(int Ks) {        // K per weight slab: largest multiple of 64 <= 256 dividing Ks
+  return Ks % 256 == 0 ? 256 : (Ks % 192 == 0 ? 192 : (Ks % 128 == 0 ? 128 : 64));
+}
+__device__ __forceinline__ int w64_items(const GemmPhase& g) { return ((g.N + MEGA_WM - 1) / MEGA_WM) * g.ksplits; }
+
+// issue this CTA's weight slabs of phase g up to slab index `upto` (exclusive); slab s = (item s / nch, chunk s % nch)
+__device__ __forceinline__ void w64_issue(const MegaParams& p, MegaCtx& c, const GemmPhase& g, int upto) {
+  const int items = w64_items(g);
+  const int ntiles = items / g.ksplits;
+  const int Ks = g.K / g.ksplits;
+  const int chunk = w64_chunk(Ks);
+  const int nch = Ks / chunk;
+  while (c.phase_issued < upto) {
+    const int it = c.phase_issued / nch, ch = c.phase_issued - it * nch;
+    const int w = blockIdx.x + it * gridDim.x;
+    if (w >= items) break;
+    const int tile = w % ntiles, split = w / ntiles;
+    const uint32_t buf = c.issued % c.sm.nbuf;
+    const uint32_t use = c.issued / c.sm.nbuf;
+    if (use > 0) mbar_wait_bounded(p, c.sm.bempty + buf, (use - 1) & 1u, 6);      // previous occupant's MMAs retired
+    ++c.issued;
+    const uint32_t bytes = (uint32_t)chunk * 128u;                                 // 64 rows x chunk x 2 B
+    mbar_expect_tx(c.sm.bfull + buf, bytes);
+    const size_t kb0 = (size_t)(split * Ks + ch * chunk) >> 6;
+    bulk_g2s(c.sm.b0 + (size_t)buf * c.sm.slab_bytes, g.w + ((size_t)tile * (size_t)(g.K >> 6) + kb0) * (MEGA_WM * 64), bytes,
+             c.sm.bfull + buf);
+    ++c.phase_issued;
+  }
+}
+
+__device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
+  const int items = w64_items(g);
+  const int ntiles = items / g.ksplits;
+  const int Ks = g.K / g.ksplits;
+  const int chunk = w64_chunk(Ks);
+  const int nch = Ks / chunk;
+  const int a_rows = p.a_rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t IDESC = umma_idesc(1, MEGA_WM, a_rows);
+  int loaded_split = -1;
+  int it = 0;
+  for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+    const int tile = w % ntiles, split = w / ntiles;
+    const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long gt = gprof ? clock64() : 0;
+#define GEMM_MARK(slot_) do { if (gprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - gt; gt = t_; } } while (0)
+    if (threadIdx.x == 0) {
+      bool a_pending = false;
+      if (split != loaded_split) {        // this split's K range of the activation image: contiguous k-blocks, one bulk copy
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        const uint32_t bytes = (uint32_t)((Ks >> 6) * a_rows * 128);
+        mbar_expect_tx(c.sm.abar, bytes);
+        bulk_g2s(c.sm.a, g.A + (size_t)((split * Ks) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
+        a_pending = true;
+      }
+      GEMM_MARK(14);
+      const uint32_t a0 = smem_u32(c.sm.a);
+      for (int ch = 0; ch < nch; ++ch) {
+        w64_issue(p, c, g, it * nch + ch + (int)c.sm.nbuf);     // this slab (if not prefetched) and the next nbuf - 1
+        const uint32_t buf = c.consumed % c.sm.nbuf;
+        const uint32_t par = (c.consumed / c.sm.nbuf) & 1u;
+        ++c.consumed;
+        if (a_pending) { mbar_wait_bounded(p, c.sm.abar, c.aphase, 3); c.aphase ^= 1u; a_pending = false; }
+        mbar_wait_bounded(p, c.sm.bfull + buf, par, 4);
+        tc_fence_after();
+        GEMM_MARK(15);
+        const uint32_t w0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
+        const int nkb = chunk >> 6;
+        for (int j = 0; j < nkb; ++j) {
+          const uint64_t wdesc = umma_desc_sw128_kmajor(w0 + (uint32_t)(j * MEGA_WM * 128));
+          const uint64_t xdesc = umma_desc_sw128_kmajor(a0 + (uint32_t)((ch * nkb + j) * a_rows * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss<false>(c.tmem_base, wdesc + (uint64_t)(k * 2), xdesc + (uint64_t)(k * 2), IDESC, (ch | j | k) ? 1u : 0u);
+        }
+        umma_commit(c.sm.bempty + buf);                         // slab buffer reusable once these MMAs retire
+        GEMM_MARK(16);
+      }
+      umma_commit(c.sm.mma_done);
+    }
+    loaded_split = split;
+    // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3; lanes 0..15 of a quadrant hold weight rows 16 q + lane ----
+    if (warp >= 4 && warp < 8) {
+      const int q = warp & 3;
+      const int R = q * 16 + (lane & 15);
+      const bool lane_ok = lane < 16;
+      const int n = tile * MEGA_WM + R;
+      mbar_wait_bounded(p, c.sm.mma_done, c.mphase, 5);
+      tc_fence_after();
+      for (int c0 = 0; c0 < a_rows; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (g.epi == EPI_SWIGLU) {
+          // packed row order inside each 16-row group: 8 gate rows then the 8 matching up rows (mega_pack_weight64)
+          const int i = tile * (MEGA_WM / 2) + q * 8 + (lane & 7);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float gv = __uint_as_float(r[j]);
+            const float uv = __shfl_down_sync(0xffffffffu, gv, 8);
+            const int b = c0 + j;
+            if (lane < 8 && b < p.B && i < (g.N >> 1))
+              reinterpret_cast<__nv_bfloat16*>(g.out)[a_off(p, b, i, g.ldo)] = __float2bfloat16_rn(silu_f(gv) * uv);
+          }
+        } else {
+          float* op = reinterpret_cast<float*>(g.out) + (g.epi == EPI_PARTIAL_F32 ? (size_t)split * p.B * g.ldo : (size_t)0) + n;
+          if (lane_ok && n < g.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.B) op[(size_t)(c0 + j) * g.ldo] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    c.mphase ^= 1;
+    __syncthreads();        // accumulator drained, activation slab reusable
+    GEMM_MARK(17);
+#undef GEMM_MARK
+  }
+}
+
+__device__ __forceinline__ void prefetch_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
+  if (p.gemm_mode == 0) { prefetch_phase0(c, g); return; }
+  if (threadIdx.x != 0) return;
+  c.phase_issued = 0;
+  w64_issue(p, c, g, (int)c.sm.nbuf);
+}
+__device__ __forceinline__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
+  if (p.gemm_mode == 0) gemm_phase0(p, c, g); else gemm_phase_w64(p, c, g);
+}
+
 // ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
 // One row per CTA, one float4 per thread (hidden <= 1024): every load of the row is in flight at once.
 __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col) {
@@ -350,6 +500,16 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
   }
 }
 
+// q/k/v input of the attention prologue: the bf16 row of mode 0, or the sum of the qkv projection's split-K partials
+// (fixed order) rounded to bf16 exactly like the stored row would have been
+__device__ __forceinline__ float qkv_in(const MegaParams& p, int b, int col) {
+  if (p.gemm_mode == 0) return __bfloat162float(p.qkv[(size_t)b * 3 * p.hidden + col]);
+  const size_t ld = (size_t)3 * p.hidden;
+  float s = 0.f;
+  for (int sp = 0; sp < p.qkv_splits; ++sp) s += p.qkvp[((size_t)sp * p.B + b) * ld + col];
+  return __bfloat162float(__float2bfloat16_rn(s));
+}
+
 // ---- RoPE + KV append + attention over the cache: ONE WARP per (b, head) item (used with 256-thread CTAs) ----
 // Measured history of this phase (B=64, 12 heads, L 514..750, us per layer on CTA 0): CTA per item 59; warp per item
 // with 16 register-staged 16-byte loads per lane 51-53 (this version); warp pairs / 512 threads 55; L2-only loads 53;
@@ -369,11 +529,11 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
   __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
   __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
   {
-    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
-    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
+    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
+    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
+    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
     qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
@@ -577,11 +737,11 @@ __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos
   float v0f = 0.f, v1f = 0.f;
   __nv_bfloat16 ka, kb, v0, v1;       // the new K/V row (this lane's two dims); appended to the caches at the very end
   {
-    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
-    v0 = row[2 * Hd + hh * 64 + lane]; v1 = row[2 * Hd + hh * 64 + lane + 32];
+    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
+    v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
+    v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
     const float qa = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     const float qb = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     qs[lane] = qa;
@@ -802,11 +962,11 @@ __device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, 
   __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
   __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
   if (half == 1) {   // the warp that owns position `pos` appends K/V (it is the one that reads them back) and stages q
-    const __nv_bfloat16* row = p.qkv + (size_t)b * 3 * Hd;
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = __bfloat162float(row[hh * 64 + lane]), q1 = __bfloat162float(row[hh * 64 + lane + 32]);
-    const float k0 = __bfloat162float(row[Hd + hh * 64 + lane]), k1 = __bfloat162float(row[Hd + hh * 64 + lane + 32]);
-    const __nv_bfloat16 v0 = row[2 * Hd + hh * 64 + lane], v1 = row[2 * Hd + hh * 64 + lane + 32];
+    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
+    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
+    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
     qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
@@ -1105,7 +1265,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   MegaCtx c;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mega_raw) + 1023) & ~(uintptr_t)1023);
   c.sm.a = base;
-  {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
+  if (p.gemm_mode == 0) {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
     const int a_rows = p.B <= 64 ? 64 : 128;
     const int kmax = p.hidden > p.inter / p.d_splits ? p.hidden : p.inter / p.d_splits;
     c.sm.a_bytes = (uint32_t)(a_rows * kmax * 2);
@@ -1114,11 +1274,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     const uint32_t nb = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - c.sm.a_bytes) / c.sm.slab_bytes;
     c.sm.nbuf = nb > 4u ? 4u : nb;
     c.sm.b0 = base + c.sm.a_bytes;
+  } else {                  // weight-stationary mode: activations of the widest K range (gate/up, lm_head: hidden) + 32 KB weight slabs
+    const int kd = p.inter / p.d_splits;
+    const int kmax = p.hidden > kd ? p.hidden : kd;
+    c.sm.a_bytes = (uint32_t)(p.a_rows * kmax * 2);
+    if (c.sm.a_bytes < 96u * 1024u) c.sm.a_bytes = 96u * 1024u;      // attention ring / sampler scratch floor
+    c.sm.slab_bytes = (uint32_t)(MEGA_WM * MEGA_W_CHUNK * 2);
+    const uint32_t nb = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - c.sm.a_bytes) / c.sm.slab_bytes;
+    c.sm.nbuf = nb > 4u ? 4u : nb;
+    c.sm.b0 = base + c.sm.a_bytes;
   }
   c.sm.bfull = reinterpret_cast<uint64_t*>(base + MEGA_A_BYTES + 2 * MEGA_B_BYTES);
   c.sm.mma_done = c.sm.bfull + 4;
   c.sm.tmem_holder = reinterpret_cast<uint32_t*>(c.sm.mma_done + 1);
   c.sm.abar = c.sm.bfull + 8;
+  c.sm.bempty = c.sm.bfull + 9;
   c.sm.ring_bar = c.sm.bfull + 16;                                   // 64 barriers, 128 B past the GEMM ones
   c.sm.sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c.sm.bfull) + MEGA_BAR_BYTES);
   uint32_t ring_par = 0;                                             // expected parity per ring slot of this warp
@@ -1128,10 +1298,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     for (int i = 0; i < 4; ++i) mbar_init(c.sm.bfull + i, 1);
     mbar_init(c.sm.mma_done, 1);
     mbar_init(c.sm.abar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(c.sm.bempty + i, 1);
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(c.sm.tmem_holder, 32); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(c.sm.tmem_holder, 128); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1152,8 +1323,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
-    GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, 1, p.xn, H, EPI_STORE_BF16, p.qkv, 3 * H};
-    prefetch_phase(c, qkv_g);
+    const bool ws = p.gemm_mode != 0;       // weight-stationary GEMM phases: qkv goes through split-K fp32 partials
+    GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, ws ? p.qkv_splits : 1, p.xn, H, ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16,
+                    ws ? (void*)p.qkvp : (void*)p.qkv, 3 * H};
+    prefetch_phase(p, c, qkv_g);
     norm_phase(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
     MEGA_BARRIER(); if (!ok) break;
@@ -1163,7 +1336,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       gemm_phase(p, c, qkv_g);
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
-      prefetch_phase(c, o_g);
+      prefetch_phase(p, c, o_g);
       const bool ring_prefetch = MEGA_THREADS == 256 && p.attn_mode == 0 && att_even_deal(p);
       if (ring_prefetch) {
         // the activation slab is dead (this CTA's MMAs have retired): start filling the attention ring with old K/V rows.
@@ -1223,7 +1396,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       gemm_phase(p, c, o_g);
       MEGA_MARK(3);
       GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
-      prefetch_phase(c, gu_g);
+      prefetch_phase(p, c, gu_g);
       MEGA_BARRIER(); if (!ok) break;
       norm_phase(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
       MEGA_MARK(0);
@@ -1231,15 +1404,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       gemm_phase(p, c, gu_g);
       MEGA_MARK(4);
       GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
-      prefetch_phase(c, d_g);
+      prefetch_phase(p, c, d_g);
       MEGA_BARRIER(); if (!ok) break;
       gemm_phase(p, c, d_g);
       MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
-      GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, 1, p.xn, H,
-                     last ? EPI_LOGITS : EPI_STORE_BF16, last ? (void*)p.logits : (void*)p.qkv,
-                     last ? p.ldl : (long long)(3 * H)};
-      prefetch_phase(c, nx_g);
+      GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, (ws && !last) ? p.qkv_splits : 1, p.xn, H,
+                     last ? EPI_LOGITS : (ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16),
+                     last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H)};
+      prefetch_phase(p, c, nx_g);
       MEGA_BARRIER(); if (!ok) break;
       norm_phase(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
       MEGA_MARK(0);
@@ -1258,7 +1431,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   if (profiling) for (int i = 0; i < 9; ++i) p.prof[i] += tprof[i];   // slots 9..13: attention_stream's own marks
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 32); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 128); }
 }
 
 // ---- one-off weight packing: [rows, cols] bf16 row-major -> per 16-row work item the 128B-swizzled K-major image ----
@@ -1292,18 +1465,70 @@ int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, cudaSt
   return 0;
 }
 
+// ---- weight packing for gemm_mode 1: [rows, cols] bf16 row-major -> per 64-row tile the 128B-swizzled K-major image ----
+// out[tile][k-block][R (64)][chunk ^ (R & 7)][8]; rows padded with zeros to a multiple of 64.  swiglu_pairs: the source is the
+// row-interleaved (gate_0, up_0, gate_1, up_1, ...) matrix; tile t covers outputs [32 t, 32 t + 32) and each 16-row group g
+// holds gate rows of outputs 32 t + 8 g + (0..7) followed by their up rows, so the pair sits 8 TMEM lanes apart in one warp.
+__global__ void mega_pack_weight64_kernel(const uint4* __restrict__ w, uint4* __restrict__ out, int rows, int cols,
+                                          int swiglu_pairs, long long chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i & 7);
+    const int R = (int)((i >> 3) & 63);
+    const long long jt = i >> 9;
+    const int nkb = cols >> 6;
+    const int j = (int)(jt % nkb);
+    const long long tile = jt / nkb;
+    long long n = tile * 64 + R;
+    if (swiglu_pairs) {
+      const int g = R >> 4, r = R & 15;
+      n = 2 * (tile * 32 + 8 * g + (r & 7)) + (r >> 3);
+    }
+    const int ch = cp ^ (R & 7);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < rows) v = w[(n * cols + j * 64 + ch * 8) >> 3];
+    out[i] = v;
+  }
+}
+
+int mega_pack_weight64_launch(const void* w, void* out, int rows, int cols, int swiglu_pairs, cudaStream_t st) {
+  IVG_CHECK(cols % 64 == 0 && rows >= 1, "mega_pack_weight64: cols %d must be a multiple of 64", cols);
+  IVG_CHECK(!swiglu_pairs || rows % 2 == 0, "mega_pack_weight64: gate/up interleaved matrix needs an even row count");
+  const long long tiles = (rows + MEGA_WM - 1) / MEGA_WM;
+  const long long chunks = tiles * (cols / 64) * 64 * 8;
+  const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
+  mega_pack_weight64_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(w), reinterpret_cast<uint4*>(out), rows,
+                                                    cols, swiglu_pairs, chunks);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
   IVG_CHECK(p.B >= 1 && p.B <= 128, "decode_mega: batch %d not in [1,128]", p.B);
   IVG_CHECK(p.hidden % 64 == 0 && p.hidden <= MEGA_MAXK, "decode_mega: hidden %d unsupported", p.hidden);
   IVG_CHECK(p.o_splits >= 1 && p.o_splits <= MEGA_MAX_SPLITS && p.hidden % (64 * p.o_splits) == 0,
             "decode_mega: bad o_splits %d for hidden %d", p.o_splits, p.hidden);
   IVG_CHECK(p.d_splits >= 1 && p.d_splits <= MEGA_MAX_SPLITS && p.inter % (64 * p.d_splits) == 0 &&
-                p.inter / p.d_splits <= MEGA_MAXK,
+                (p.gemm_mode != 0 || p.inter / p.d_splits <= MEGA_MAXK),
             "decode_mega: bad d_splits %d for intermediate size %d", p.d_splits, p.inter);
   IVG_CHECK(p.hidden == p.heads * 64, "decode_mega: head_dim must be 64");
-  const int a_rows = p.B <= 64 ? 64 : 128;
-  IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
-            "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
+  if (p.gemm_mode == 0) {
+    const int a_rows = p.B <= 64 ? 64 : 128;
+    IVG_CHECK(p.a_rows == a_rows, "decode_mega: a_rows must be %d in gemm_mode 0", a_rows);
+    IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
+              "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
+  } else {
+    IVG_CHECK(p.a_bulk == 1, "decode_mega: gemm_mode 1 needs the swizzled activation images (a_bulk)");
+    IVG_CHECK(p.a_rows >= p.B && p.a_rows % 8 == 0 && p.a_rows <= 128, "decode_mega: a_rows %d must be a multiple of 8 in [B, 128]",
+              p.a_rows);
+    IVG_CHECK(p.qkv_splits >= 1 && p.qkv_splits <= MEGA_MAX_SPLITS && p.hidden % (64 * p.qkv_splits) == 0 && p.qkvp != nullptr,
+              "decode_mega: bad qkv_splits %d for hidden %d", p.qkv_splits, p.hidden);
+    const int kd = p.inter / p.d_splits;
+    const long long a_bytes = (long long)p.a_rows * (p.hidden > kd ? p.hidden : kd) * 2;
+    const long long a_floor = a_bytes < 96 * 1024 ? 96 * 1024 : a_bytes;
+    IVG_CHECK(a_floor + 2 * MEGA_WM * MEGA_W_CHUNK * 2 <= MEGA_A_BYTES + 2 * MEGA_B_BYTES,
+              "decode_mega: batch %d with K %d leaves no room for two weight slabs", p.B, p.hidden);
+  }
   IVG_CHECK((size_t)(p.Lmax + 16 + 64 + 2 * 66) * 4 * (MEGA_THREADS / 64) <= MEGA_A_BYTES &&
                 (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");

@@ -13,7 +13,10 @@ constexpr int MEGA_BAR_BYTES = 1024;           // mbarriers: 2 weight slabs, MMA
 constexpr int MEGA_SC_BYTES = 30 * 1024;       // attention scratch: per warp scores[Lmax + 8] + q[64] fp32
 constexpr int MEGA_RING_SLOT = 4096;           // attention K/V ring slot (32 K rows, or up to 8 V^T rows)
 constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + MEGA_BAR_BYTES + MEGA_SC_BYTES;
-constexpr int MEGA_MAX_SPLITS = 8;
+constexpr int MEGA_MAX_SPLITS = 12;
+// weight-stationary GEMM mode (gemm_mode 1): the WEIGHTS are the M side of the MMA (64 rows per work item), the batch is N
+constexpr int MEGA_WM = 64;                 // weight rows per work item
+constexpr int MEGA_W_CHUNK = 256;           // K per weight slab: 64 rows x 256 x 2 B = 32 KB
 
 struct MegaLayer {
   const __nv_bfloat16 *wqkv, *wo, *wgu, *wd;   // B operands packed by mega_pack_weight (16-row swizzled slab images)
@@ -54,6 +57,10 @@ struct MegaParams {
   float* attn_part;             // [SMs][4][72] flash-decoding partials of the items cut along the sequence (attn_mode 0)
   unsigned int* attn_cnt;       // [SMs] zero-initialised arrival counters of those items
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
+  int gemm_mode;                // 0: activations are the MMA's M side, 16 weight rows per item; 1: weight-stationary (see decode_mega.cu)
+  int qkv_splits;               // gemm_mode 1: split-K of the qkv projection (partials in qkvp, summed by the attention prologue)
+  float* qkvp;                  // gemm_mode 1: [qkv_splits][B][3*hidden] fp32
+  int a_rows;                   // rows per k-block of the activation images / shared-memory activation slab
   int a_bulk;                   // 1: xn / ao / act are swizzled shared-memory images in global memory, loaded by one bulk copy
   int mma_m64;                  // 1: M = 64 UMMA in the GEMM phases when B <= 64 (0: M = 128 with the upper rows unused)
   // forced separator slots of the action-conditioned rollout (action_model.py:78-114); slot_period == 0 disables
@@ -64,5 +71,6 @@ struct MegaParams {
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);
 int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, cudaStream_t st);
+int mega_pack_weight64_launch(const void* w, void* out, int rows, int cols, int swiglu_pairs, cudaStream_t st);
 
 }  // namespace ivg

@@ -233,18 +233,25 @@ class LlamaEngine:
             ops.topk_sample(logits, ld, B, V, k, temp, 0, 0, tokens, tokens.stride(0), dpos, out_offset, dseed)
 
     # ---- persistent decode megakernel (bf16, B <= 64 with these widths) --------------------------------------
+    def mega_mode(self) -> int:
+        """GEMM phases of the megakernel: 1 = weight-stationary (64 weight rows per MMA, default), 0 = activation-stationary."""
+        return int(getattr(self, "mega_gemm_mode", int(os.environ.get("IVGPT_MEGA_GEMM", "1"))))
+
     def mega_supported(self, B: int, Lmax: int) -> bool:
         w = self.w
-        if self.dtype != torch.bfloat16 or B < 1:
+        if self.dtype != torch.bfloat16 or B < 1 or B > 128:
             return False
+        common = (w.vocab + 256) * 4 <= 96 * 1024 and (Lmax + 72) * 4 * 8 <= 30 * 1024
+        if self.mega_mode() == 1:
+            q_s, o_s, d_s = self._mega_splits64()
+            a_rows = (B + 7) // 8 * 8
+            a_bytes = max(a_rows * max(w.hidden, w.inter // d_s) * 2, 96 * 1024)
+            return common and w.hidden % 64 == 0 and w.inter % 64 == 0 and a_bytes + 2 * 32 * 1024 <= 192 * 1024
         a_rows = 64 if B <= 64 else 128
-        if B > 128:
-            return False
         o_s, d_s = self._mega_splits()
         if o_s is None:
             return False
-        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024
-                and (w.vocab + 256) * 4 <= 128 * 1024 and (Lmax + 72) * 4 * 8 <= 30 * 1024)
+        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024 and common)
 
     def _mega_splits(self):
         w = self.w
@@ -254,11 +261,30 @@ class LlamaEngine:
             return None, None
         return o_s, d_s
 
+    def _mega_splits64(self, sms: int = 148):
+        """Split-K factors of the weight-stationary phases: the largest s <= 12 with (rows / 64) * s <= #SMs work items
+        (one round over the SMs) and K a multiple of 64 * s."""
+        w = self.w
+
+        def pick(rows, K):
+            tiles = (rows + 63) // 64
+            best = 1
+            for s in range(1, 13):
+                if K % (64 * s) == 0 and tiles * s <= sms:
+                    best = s
+            return best
+        return pick(3 * w.hidden, w.hidden), pick(w.hidden, w.hidden), pick(w.hidden, w.inter)
+
     def _mega_tables(self):
-        """Packed weight copies (16-row swizzled slab images, see ivgpt_mega_pack_weight) and the device-resident array
-        of per-layer pointer records, built once per engine."""
-        if getattr(self, "_mega_dev", None) is not None:
-            return self._mega_dev
+        """Packed weight copies (swizzled slab images: 16 rows per work item in mode 0, ivgpt_mega_pack_weight; 64 rows in
+        the weight-stationary mode 1, ivgpt_mega_pack_weight64) and the device-resident array of per-layer pointer
+        records, built once per engine and mode."""
+        mode = self.mega_mode()
+        cache = getattr(self, "_mega_dev", None)
+        if cache is None:
+            cache = self._mega_dev = {}
+        if mode in cache:
+            return cache[mode]
         import ctypes as C
         from .. import _lib
         lib = _lib.load()
@@ -266,12 +292,17 @@ class LlamaEngine:
         dev = w.embed.device
         keep = []
 
-        def pack(t):
+        def pack(t, swiglu_pairs=0):
             rows, cols = t.shape
             assert t.dtype == torch.bfloat16 and t.is_contiguous()
-            out = torch.empty(int(lib.ivgpt_mega_packed_elems(rows, cols)), dtype=torch.bfloat16, device=dev)
-            _lib.check(lib.ivgpt_mega_pack_weight(t.data_ptr(), out.data_ptr(), rows, cols, ops._stream()),
-                       "mega_pack_weight")
+            if mode == 1:
+                out = torch.empty(int(lib.ivgpt_mega_packed_elems64(rows, cols)), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.ivgpt_mega_pack_weight64(t.data_ptr(), out.data_ptr(), rows, cols, swiglu_pairs, ops._stream()),
+                           "mega_pack_weight64")
+            else:
+                out = torch.empty(int(lib.ivgpt_mega_packed_elems(rows, cols)), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.ivgpt_mega_pack_weight(t.data_ptr(), out.data_ptr(), rows, cols, ops._stream()),
+                           "mega_pack_weight")
             keep.append(out)
             return out.data_ptr()
 
@@ -279,14 +310,14 @@ class LlamaEngine:
         host = (C.c_uint8 * (nbytes * w.layers_n + 64))()
         base_al = (C.addressof(host) + 63) // 64 * 64
         for i, lw in enumerate(w.layers):
-            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"]),
+            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"], 1),
                                                  pack(lw["wd"]), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
                        "mega_fill_layer")
         lm_head = pack(w.lm_head)
         raw = bytes((C.c_uint8 * (nbytes * w.layers_n)).from_address(base_al))
         tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        self._mega_dev = (tab, lm_head, keep)
-        return self._mega_dev
+        cache[mode] = (tab, lm_head, keep)
+        return cache[mode]
 
     def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps, slot=None):
         import ctypes as C
@@ -294,7 +325,12 @@ class LlamaEngine:
         w = self.w
         h = w.hidden
         dev_tab, lm_head_packed, _ = self._mega_tables()
-        o_s, d_s = self._mega_splits()
+        mode = self.mega_mode()
+        if mode == 1:
+            q_s, o_s, d_s = self._mega_splits64()
+        else:
+            q_s = 1
+            o_s, d_s = self._mega_splits()
         kc, vc = self.kv_cache(B, Lmax)
         logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
         sync = self.buf("mega_sync", (1024,), torch.int32)     # [0] barrier, [1] error, [64..] attention part counters
@@ -304,7 +340,11 @@ class LlamaEngine:
         d.o_splits, d.d_splits = o_s, d_s
         d.eps = w.eps
         d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
-        a_rows = 64 if B <= 64 else 128       # rows of the swizzled activation images (a_bulk)
+        # rows of the swizzled activation images: the MMA's N in the weight-stationary mode, 64 / 128 MMA rows in mode 0
+        a_rows = (B + 7) // 8 * 8 if mode == 1 else (64 if B <= 64 else 128)
+        d.gemm_mode, d.qkv_splits, d.a_rows = mode, q_s, a_rows
+        if mode == 1:
+            d.qkvp = self.buf("mega_qkvp", (q_s, B, 3 * h), torch.float32).data_ptr()
         d.xn = self.buf("mega_xn", (a_rows, h), self.dtype).data_ptr()
         d.qkv = self.buf("qkvd", (B, 3 * h), self.dtype).data_ptr()
         d.ao = self.buf("mega_ao", (a_rows, h), self.dtype).data_ptr()
@@ -325,7 +365,7 @@ class LlamaEngine:
         d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
         d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
-        d.a_bulk = int(getattr(self, "mega_a_bulk", int(os.environ.get("IVGPT_MEGA_ABULK", "1"))))
+        d.a_bulk = 1 if mode == 1 else int(getattr(self, "mega_a_bulk", int(os.environ.get("IVGPT_MEGA_ABULK", "1"))))
         d.mma_m64 = int(getattr(self, "mega_m64", int(os.environ.get("IVGPT_MEGA_M64", "1"))))
         if slot is not None:
             d.slot0, d.slot_period, d.slot_token = int(slot[0]), int(slot[1]), int(slot[2])
