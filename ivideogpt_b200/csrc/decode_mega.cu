@@ -436,18 +436,24 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
   }
 }
 
+// GM (GEMM mode) and AM (attention mode) are template parameters of the kernel: one instantiation holds exactly one GEMM
+// path and one attention path.  (With both paths behind runtime branches the 255-register kernel spilled and the hot
+// loops of the paths that were NOT taken got slower: 238 -> 286 ms per rollout, profiles/r01 v10 -> v11.)
+template <int GM>
 __device__ __forceinline__ void prefetch_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
-  if (p.gemm_mode == 0) { prefetch_phase0(c, g); return; }
+  if constexpr (GM == 0) { prefetch_phase0(c, g); return; }
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
   w64_issue(p, c, g, (int)c.sm.nbuf);
 }
+template <int GM>
 __device__ __forceinline__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
-  if (p.gemm_mode == 0) gemm_phase0(p, c, g); else gemm_phase_w64(p, c, g);
+  if constexpr (GM == 0) gemm_phase0(p, c, g); else gemm_phase_w64(p, c, g);
 }
 
 // ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
 // One row per CTA, one float4 per thread (hidden <= 1024): every load of the row is in flight at once.
+template <int MAXP>
 __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col) {
   __shared__ float s_ss[MEGA_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -471,12 +477,12 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
             p.slot_emb + ((size_t)m * p.nslots + (tok_col - p.slot0) / p.slot_period) * H + i);
         v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
       }
-      float4 q[MEGA_MAX_SPLITS];
+      float4 q[MAXP];
 #pragma unroll
-      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+      for (int s = 0; s < MAXP; ++s)
         if (s < nparts) q[s] = *reinterpret_cast<const float4*>(p.part + ((size_t)s * p.B + m) * H + i);
 #pragma unroll
-      for (int s = 0; s < MEGA_MAX_SPLITS; ++s)
+      for (int s = 0; s < MAXP; ++s)
         if (s < nparts) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }   // fixed order: reproducible
       *reinterpret_cast<float4*>(xr + i) = v;
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
@@ -502,11 +508,18 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
 
 // q/k/v input of the attention prologue: the bf16 row of mode 0, or the sum of the qkv projection's split-K partials
 // (fixed order) rounded to bf16 exactly like the stored row would have been
+constexpr int MEGA_MAX_QKV_SPLITS = 4;
+template <int GM>
 __device__ __forceinline__ float qkv_in(const MegaParams& p, int b, int col) {
-  if (p.gemm_mode == 0) return __bfloat162float(p.qkv[(size_t)b * 3 * p.hidden + col]);
+  if constexpr (GM == 0) return __bfloat162float(p.qkv[(size_t)b * 3 * p.hidden + col]);
   const size_t ld = (size_t)3 * p.hidden;
-  float s = 0.f;
-  for (int sp = 0; sp < p.qkv_splits; ++sp) s += p.qkvp[((size_t)sp * p.B + b) * ld + col];
+  float part[MEGA_MAX_QKV_SPLITS];
+#pragma unroll
+  for (int sp = 0; sp < MEGA_MAX_QKV_SPLITS; ++sp)          // every load in flight before the first add
+    part[sp] = sp < p.qkv_splits ? p.qkvp[((size_t)sp * p.B + b) * ld + col] : 0.f;
+  float s = part[0];
+#pragma unroll
+  for (int sp = 1; sp < MEGA_MAX_QKV_SPLITS; ++sp) s += part[sp];
   return __bfloat162float(__float2bfloat16_rn(s));
 }
 
@@ -519,6 +532,7 @@ __device__ __forceinline__ float qkv_in(const MegaParams& p, int b, int col) {
 // loads in flight per SM, i.e. TMA bulk copies into a large shared-memory ring -- next round.
 constexpr int ATW_QB = 16;    // K rows in flight per lane group (8 lanes per row, 4 rows per pass)
 constexpr int ATW_DB = 16;    // V^T rows in flight per lane
+template <int GM>
 __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, float* wsm) {
   const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
   const int Lcur = pos + 1;
@@ -530,10 +544,10 @@ __device__ void attention_warp(const MegaParams& p, int layer, int bh, int pos, 
   __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
   {
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
-    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
-    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
-    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
+    const float q0 = qkv_in<GM>(p, b, hh * 64 + lane), q1 = qkv_in<GM>(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in<GM>(p, b, Hd + hh * 64 + lane), k1 = qkv_in<GM>(p, b, Hd + hh * 64 + lane + 32);
+    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane));
+    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane + 32));
     qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
@@ -711,6 +725,7 @@ __device__ __forceinline__ void attention_prefetch(const MegaParams& p, int laye
   for (int u = 0; u < pre; ++u) att_issue(p, layer, w.bh, pos, w.u0, nU, u, u, ring, bars);
 }
 
+template <int GM>
 __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos, int u0, int u1, bool tail, bool issued,
                                  float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par, float& m_out,
                                  float& l_out, float (&acc)[8]) {
@@ -738,10 +753,10 @@ __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos
   __nv_bfloat16 ka, kb, v0, v1;       // the new K/V row (this lane's two dims); appended to the caches at the very end
   {
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
-    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
-    v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
-    v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
+    const float q0 = qkv_in<GM>(p, b, hh * 64 + lane), q1 = qkv_in<GM>(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in<GM>(p, b, Hd + hh * 64 + lane), k1 = qkv_in<GM>(p, b, Hd + hh * 64 + lane + 32);
+    v0 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane));
+    v1 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane + 32));
     const float qa = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     const float qb = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     qs[lane] = qa;
@@ -894,11 +909,12 @@ __device__ __forceinline__ void attention_store(const MegaParams& p, int bh, con
 
 // one left-over item cut along the sequence: every part publishes (max, sum, acc[64]); the part that arrives last
 // (monotonic counter, MEGA_ATT_SPLIT arrivals per item, layer and step) merges them and writes the output row.
+template <int GM>
 __device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, int u0, int u1, bool issued,
                                float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
   const int lane = threadIdx.x & 31;
   float m, l, acc[8];
-  attention_stream(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
+  attention_stream<GM>(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
   float* rec = p.attn_part + ((size_t)extra * MEGA_ATT_SPLIT + q) * 72;
   if ((lane >> 3) == 0) {
     float4* dst = reinterpret_cast<float4*>(rec + 8 + (lane & 7) * 8);
@@ -948,6 +964,7 @@ __device__ __forceinline__ void pair_barrier(int pair) {   // named barrier 1 + 
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
 
+template <int GM>
 __device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, float* psm, int half, int pair) {
   // psm: per-PAIR scratch: sc[Lmax + 16] | q[64] | comb[2][66]
   const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
@@ -963,10 +980,10 @@ __device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, 
   __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
   if (half == 1) {   // the warp that owns position `pos` appends K/V (it is the one that reads them back) and stages q
     const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = qkv_in(p, b, hh * 64 + lane), q1 = qkv_in(p, b, hh * 64 + lane + 32);
-    const float k0 = qkv_in(p, b, Hd + hh * 64 + lane), k1 = qkv_in(p, b, Hd + hh * 64 + lane + 32);
-    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane));
-    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in(p, b, 2 * Hd + hh * 64 + lane + 32));
+    const float q0 = qkv_in<GM>(p, b, hh * 64 + lane), q1 = qkv_in<GM>(p, b, hh * 64 + lane + 32);
+    const float k0 = qkv_in<GM>(p, b, Hd + hh * 64 + lane), k1 = qkv_in<GM>(p, b, Hd + hh * 64 + lane + 32);
+    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane));
+    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane + 32));
     qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
     qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
     kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
@@ -1260,12 +1277,14 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   __syncthreads();
 }
 
+template <int GM, int AM>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+  constexpr int MAXP = GM == 0 ? 8 : MEGA_MAX_SPLITS;
   extern __shared__ uint8_t mega_raw[];
   MegaCtx c;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mega_raw) + 1023) & ~(uintptr_t)1023);
   c.sm.a = base;
-  if (p.gemm_mode == 0) {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
+  if constexpr (GM == 0) {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
     const int a_rows = p.B <= 64 ? 64 : 128;
     const int kmax = p.hidden > p.inter / p.d_splits ? p.hidden : p.inter / p.d_splits;
     c.sm.a_bytes = (uint32_t)(a_rows * kmax * 2);
@@ -1323,21 +1342,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
-    const bool ws = p.gemm_mode != 0;       // weight-stationary GEMM phases: qkv goes through split-K fp32 partials
+    constexpr bool ws = GM != 0;            // weight-stationary GEMM phases: qkv goes through split-K fp32 partials
     GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, ws ? p.qkv_splits : 1, p.xn, H, ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16,
                     ws ? (void*)p.qkvp : (void*)p.qkv, 3 * H};
-    prefetch_phase(p, c, qkv_g);
-    norm_phase(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
+    prefetch_phase<GM>(p, c, qkv_g);
+    norm_phase<MAXP>(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
     MEGA_BARRIER(); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
       qkv_g.w = L.wqkv;
-      gemm_phase(p, c, qkv_g);
+      gemm_phase<GM>(p, c, qkv_g);
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
-      prefetch_phase(p, c, o_g);
-      const bool ring_prefetch = MEGA_THREADS == 256 && p.attn_mode == 0 && att_even_deal(p);
+      prefetch_phase<GM>(p, c, o_g);
+      const bool ring_prefetch = MEGA_THREADS == 256 && AM == 0 && p.attn_mode == 0 && att_even_deal(p);
       if (ring_prefetch) {
         // the activation slab is dead (this CTA's MMAs have retired): start filling the attention ring with old K/V rows.
         // The region was last written through the generic proxy (cp.async), the copies below are async-proxy writes.
@@ -1347,7 +1366,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       MEGA_BARRIER(); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
-        if (p.attn_mode != 1) {
+        if constexpr (AM != 1) {
           // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
           fence_proxy_async();
           const int total = p.B * p.heads, G = (int)gridDim.x;
@@ -1357,11 +1376,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             uint8_t* ring = c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT;
             if (w.kind == 1) {
               float m, lsum, acc[8];
-              attention_stream(p, l, w.bh, pos, w.u0, w.u1, true, ring_prefetch, wsm, ring, w.nslot, c.sm.ring_bar + warp * 8,
+              attention_stream<GM>(p, l, w.bh, pos, w.u0, w.u1, true, ring_prefetch, wsm, ring, w.nslot, c.sm.ring_bar + warp * 8,
                                ring_par, m, lsum, acc);
               attention_store(p, w.bh, acc, 1.0f / lsum);
             } else if (w.kind == 2) {
-              attention_part(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
+              attention_part<GM>(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
                              c.sm.ring_bar + warp * 8, ring_par);
             }
           } else {
@@ -1373,7 +1392,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               if (warp < active) {
                 const int bh = base + G * warp;
                 float m, lsum, acc[8];
-                attention_stream(p, l, bh, pos, 0, (pos + 31) >> 5, true, false, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
+                attention_stream<GM>(p, l, bh, pos, 0, (pos + 31) >> 5, true, false, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
                                  c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par, m,
                                  lsum, acc);
                 attention_store(p, bh, acc, 1.0f / lsum);
@@ -1383,42 +1402,42 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           }
         } else {
           for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
-            attention_warp(p, l, bh, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64));
+            attention_warp<GM>(p, l, bh, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64));
         }
       } else {
         const int pair = warp >> 1, half = warp & 1, npairs = MEGA_THREADS / 64;
         float* psm = smem_f + (size_t)pair * (p.Lmax + 16 + 64 + 2 * 66);
         for (int bh = blockIdx.x + (int)gridDim.x * pair; bh < p.B * p.heads; bh += (int)gridDim.x * npairs)
-          attention_pair(p, l, bh, pos, psm, half, pair);
+          attention_pair<GM>(p, l, bh, pos, psm, half, pair);
       }
       MEGA_MARK(2);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase(p, c, o_g);
+      gemm_phase<GM>(p, c, o_g);
       MEGA_MARK(3);
       GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
-      prefetch_phase(p, c, gu_g);
+      prefetch_phase<GM>(p, c, gu_g);
       MEGA_BARRIER(); if (!ok) break;
-      norm_phase(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
+      norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
       MEGA_MARK(0);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase(p, c, gu_g);
+      gemm_phase<GM>(p, c, gu_g);
       MEGA_MARK(4);
       GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
-      prefetch_phase(p, c, d_g);
+      prefetch_phase<GM>(p, c, d_g);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase(p, c, d_g);
+      gemm_phase<GM>(p, c, d_g);
       MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
       GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, (ws && !last) ? p.qkv_splits : 1, p.xn, H,
                      last ? EPI_LOGITS : (ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16),
                      last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H)};
-      prefetch_phase(p, c, nx_g);
+      prefetch_phase<GM>(p, c, nx_g);
       MEGA_BARRIER(); if (!ok) break;
-      norm_phase(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
+      norm_phase<MAXP>(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
       MEGA_MARK(0);
       MEGA_BARRIER(); if (!ok) break;
       if (last) {
-        gemm_phase(p, c, nx_g);                                       // lm_head
+        gemm_phase<GM>(p, c, nx_g);                                       // lm_head
         MEGA_MARK(6);
         MEGA_BARRIER(); if (!ok) break;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) sample_row(p, b, pos, smem_u);
@@ -1506,9 +1525,11 @@ int mega_pack_weight64_launch(const void* w, void* out, int rows, int cols, int 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
   IVG_CHECK(p.B >= 1 && p.B <= 128, "decode_mega: batch %d not in [1,128]", p.B);
   IVG_CHECK(p.hidden % 64 == 0 && p.hidden <= MEGA_MAXK, "decode_mega: hidden %d unsupported", p.hidden);
-  IVG_CHECK(p.o_splits >= 1 && p.o_splits <= MEGA_MAX_SPLITS && p.hidden % (64 * p.o_splits) == 0,
+  IVG_CHECK(p.gemm_mode == 0 || p.gemm_mode == 1, "decode_mega: gemm_mode %d", p.gemm_mode);
+  const int max_splits = p.gemm_mode == 0 ? 8 : MEGA_MAX_SPLITS;
+  IVG_CHECK(p.o_splits >= 1 && p.o_splits <= max_splits && p.hidden % (64 * p.o_splits) == 0,
             "decode_mega: bad o_splits %d for hidden %d", p.o_splits, p.hidden);
-  IVG_CHECK(p.d_splits >= 1 && p.d_splits <= MEGA_MAX_SPLITS && p.inter % (64 * p.d_splits) == 0 &&
+  IVG_CHECK(p.d_splits >= 1 && p.d_splits <= max_splits && p.inter % (64 * p.d_splits) == 0 &&
                 (p.gemm_mode != 0 || p.inter / p.d_splits <= MEGA_MAXK),
             "decode_mega: bad d_splits %d for intermediate size %d", p.d_splits, p.inter);
   IVG_CHECK(p.hidden == p.heads * 64, "decode_mega: head_dim must be 64");
@@ -1521,7 +1542,7 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
     IVG_CHECK(p.a_bulk == 1, "decode_mega: gemm_mode 1 needs the swizzled activation images (a_bulk)");
     IVG_CHECK(p.a_rows >= p.B && p.a_rows % 8 == 0 && p.a_rows <= 128, "decode_mega: a_rows %d must be a multiple of 8 in [B, 128]",
               p.a_rows);
-    IVG_CHECK(p.qkv_splits >= 1 && p.qkv_splits <= MEGA_MAX_SPLITS && p.hidden % (64 * p.qkv_splits) == 0 && p.qkvp != nullptr,
+    IVG_CHECK(p.qkv_splits >= 1 && p.qkv_splits <= MEGA_MAX_QKV_SPLITS && p.hidden % (64 * p.qkv_splits) == 0 && p.qkvp != nullptr,
               "decode_mega: bad qkv_splits %d for hidden %d", p.qkv_splits, p.hidden);
     const int kd = p.inter / p.d_splits;
     const long long a_bytes = (long long)p.a_rows * (p.hidden > kd ? p.hidden : kd) * 2;
@@ -1533,17 +1554,21 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
                 (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
-  static bool attr_set = false;
-  if (!attr_set) {
-    IVG_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM));
-    attr_set = true;
+  const void* fn = nullptr;
+  const int am = p.attn_mode == 1 ? 1 : 0;
+  if (p.gemm_mode == 0) fn = am ? (const void*)decode_mega_kernel<0, 1> : (const void*)decode_mega_kernel<0, 0>;
+  else fn = am ? (const void*)decode_mega_kernel<1, 1> : (const void*)decode_mega_kernel<1, 0>;
+  static bool attr_set[4] = {false, false, false, false};
+  const int vi = (p.gemm_mode != 0 ? 2 : 0) + am;
+  if (!attr_set[vi]) {
+    IVG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM));
+    attr_set[vi] = true;
   }
   int max_blocks = 0;
-  IVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, decode_mega_kernel, MEGA_THREADS, MEGA_SMEM));
+  IVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, fn, MEGA_THREADS, MEGA_SMEM));
   IVG_CHECK(max_blocks >= 1, "decode_mega: kernel does not fit on an SM");
   void* args[] = {const_cast<MegaParams*>(&p)};
-  IVG_CUDA(cudaLaunchCooperativeKernel((const void*)decode_mega_kernel, dim3(num_sms), dim3(MEGA_THREADS), args,
-                                       (size_t)MEGA_SMEM, st));
+  IVG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(MEGA_THREADS), args, (size_t)MEGA_SMEM, st));
   count_launch();
   return 0;
 }

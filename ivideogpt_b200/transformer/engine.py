@@ -266,14 +266,20 @@ class LlamaEngine:
         (one round over the SMs) and K a multiple of 64 * s."""
         w = self.w
 
-        def pick(rows, K):
+        def pick(rows, K, cap, override):
             tiles = (rows + 63) // 64
+            if override:
+                assert K % (64 * override) == 0 and override <= cap, (rows, K, override)
+                return int(override)
             best = 1
-            for s in range(1, 13):
+            for s in range(1, cap + 1):
                 if K % (64 * s) == 0 and tiles * s <= sms:
                     best = s
             return best
-        return pick(3 * w.hidden, w.hidden), pick(w.hidden, w.hidden), pick(w.hidden, w.inter)
+        ov = getattr(self, "mega_splits_override", None) or tuple(
+            int(v) for v in os.environ.get("IVGPT_MEGA_SPLITS", "0:0:0").split(":"))
+        return (pick(3 * w.hidden, w.hidden, 4, ov[0]), pick(w.hidden, w.hidden, 12, ov[1]),
+                pick(w.hidden, w.inter, 12, ov[2]))
 
     def _mega_tables(self):
         """Packed weight copies (swizzled slab images: 16 rows per work item in mode 0, ivgpt_mega_pack_weight; 64 rows in

@@ -113,9 +113,15 @@ def _mega_vs_graph(cuda, cfg, B, L, new, mode, seed=9, min_agree=0.6):
     eng = mine.b200_engine()
     eng.mega_gemm_mode = mode
     assert eng.mega_supported(B, (L + new + 7) // 8 * 8)
+    V = cfg["vocab_size"]
     a = eng.generate(ids, None, new, False, 0, 1.0, 0, use_mega=False)
+    la = eng.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)[:, :V].clone()       # logits of the last decode step
     m = eng.generate(ids, None, new, False, 0, 1.0, 0, use_mega=True)
+    lm = eng.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)[:, :V].clone()
     assert m.shape == a.shape and torch.equal(m[:, :L + 1], a[:, :L + 1])     # prompt + first token come from the prefill
+    same = (m == a).all(dim=1)
+    assert int(same.sum()) >= max(1, B // 4), "too few rows stayed on the same greedy path to compare logits"
+    assert rel_err(lm[same], la[same]) < 2e-2      # same token history -> last-step logits agree to bf16 noise
     for b in range(B):
         neq = (m[b] != a[b]).nonzero()
         if len(neq):
@@ -123,7 +129,7 @@ def _mega_vs_graph(cuda, cfg, B, L, new, mode, seed=9, min_agree=0.6):
             with torch.no_grad():
                 lg = ref(input_ids=a[b:b + 1, :p].cpu()).logits[0, -1]
             top2 = lg.topk(2).values
-            assert float(top2[0] - top2[1]) < 3e-2 * float(lg.abs().max()), f"row {b} diverged at {p} without a near-tie"
+            assert float(top2[0] - top2[1]) < 6e-2 * float(lg.abs().max()), f"row {b} diverged at {p} without a near-tie"
     assert (m == a).float().mean().item() > min_agree
     return ref, mine, eng, ids
 

@@ -1,5 +1,5 @@
 """Phase breakdown of the persistent decode megakernel (cycle counters of CTA 0) + wall time per operand-path variant.
-VARIANTS env: comma list of gemm_mode:m64:bulk[:attn_mode], default "0:1:1,1:1:1"."""
+VARIANTS env: comma list of gemm_mode:m64:bulk[:attn_mode[:qkv_splits:o_splits:d_splits]], default "0:1:1,1:1:1"."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -28,7 +28,9 @@ for spec in os.environ.get("VARIANTS", "0:1:1,1:1:1").split(","):
     f = [int(v) for v in spec.split(":")]
     eng.mega_gemm_mode, eng.mega_m64, eng.mega_a_bulk = f[0], f[1], f[2]
     eng.mega_attn_mode = f[3] if len(f) > 3 else 0
-    tag = f"gemm={f[0]},m64={f[1]},a_bulk={f[2]},attn={eng.mega_attn_mode}"
+    eng.mega_splits_override = tuple(f[4:7]) if len(f) >= 7 else None
+    tag = f"gemm={f[0]},m64={f[1]},a_bulk={f[2]},attn={eng.mega_attn_mode},splits={eng.mega_splits_override}"
+    PROFILE = os.environ.get("PHASES", "1") == "1"
     eng.mega_profile = False
     try:
         for _ in range(2):
@@ -37,17 +39,18 @@ for spec in os.environ.get("VARIANTS", "0:1:1,1:1:1").split(","):
         for _ in range(3):
             a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        eng.mega_profile = True
-        eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
-        torch.cuda.synchronize()
-        allc = eng.mega_prof.cpu().tolist()
-        res[tag] = {
-            "generate_ms": sorted(ts)[1],
-            "phase_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in zip(names, allc[:9])},
-            "attention_warp0_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
-                                            zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])},
-            "gemm_item_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
-                                      zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}}
+        res[tag] = {"generate_ms": sorted(ts)[1], "generate_ms_all": ts}
+        if PROFILE:
+            eng.mega_profile = True
+            eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=True)
+            torch.cuda.synchronize()
+            allc = eng.mega_prof.cpu().tolist()
+            res[tag].update({
+                "phase_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in zip(names, allc[:9])},
+                "attention_warp0_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
+                                                zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])},
+                "gemm_item_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
+                                          zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}})
     except Exception as e:  # a variant that faults must not hide the others
         res[tag] = {"error": repr(e)[:300]}
         break
