@@ -211,6 +211,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
   const uint32_t IDESC = m64 ? umma_idesc(1, 64, MEGA_BN) : umma_idesc(1, 128, MEGA_BN);
   int loaded_split = -1;
   int it = 0;
+  const long long gt_entry = (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
     const int tile = w % ntiles, split = w / ntiles;
     // optional fine-grained timing (CTA 0, thread 0): prof[14..17] = activation slab load, weight slab wait, MMA issue,
@@ -296,6 +297,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
     GEMM_MARK(17);
 #undef GEMM_MARK
   }
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[18] += clock64() - gt_entry;
 }
 
 // =====================================================================================================================
@@ -314,8 +316,8 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
 //   lm_head: ceil(vocab/64) tiles, whole K streamed.
 // Accumulator row r (weight row) lives in TMEM lane 32*(r/16) + r%16, column b = batch row.
 // =====================================================================================================================
-__device__ __forceinline__ int w64_chunk(int Ks) {        // K per weight slab: largest multiple of 64 <= 256 dividing Ks
-  return Ks % 256 == 0 ? 256 : (Ks % 192 == 0 ? 192 : (Ks % 128 == 0 ? 128 : 64));
+__device__ __forceinline__ int w64_chunk(int Ks) {        // K per weight slab: largest multiple of 64 <= MEGA_W_CHUNK dividing Ks
+  return Ks % MEGA_W_CHUNK == 0 ? MEGA_W_CHUNK : 64;
 }
 __device__ __forceinline__ int w64_items(const GemmPhase& g) { return ((g.N + MEGA_WM - 1) / MEGA_WM) * g.ksplits; }
 
@@ -355,11 +357,15 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
   const uint32_t IDESC = umma_idesc(1, MEGA_WM, a_rows);
   int loaded_split = -1;
   int it = 0;
+  // optional timing (CTA 0, thread 0), accumulated in registers and flushed once per phase: prof[14..17] = activation
+  // copy issue, slab wait, MMA issue, commit -> end of epilogue; prof[18] = whole phase, entry to exit
+  const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long gacc0 = 0, gacc1 = 0, gacc2 = 0, gacc3 = 0;
+  const long long gt_entry = gprof ? clock64() : 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
     const int tile = w % ntiles, split = w / ntiles;
-    const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long gt = gprof ? clock64() : 0;
-#define GEMM_MARK(slot_) do { if (gprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - gt; gt = t_; } } while (0)
+#define GEMM_MARK(acc_) do { if (gprof) { const long long t_ = clock64(); acc_ += t_ - gt; gt = t_; } } while (0)
     if (threadIdx.x == 0) {
       bool a_pending = false;
       if (split != loaded_split) {        // this split's K range of the activation image: contiguous k-blocks, one bulk copy
@@ -369,7 +375,7 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
         bulk_g2s(c.sm.a, g.A + (size_t)((split * Ks) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
         a_pending = true;
       }
-      GEMM_MARK(14);
+      GEMM_MARK(gacc0);
       const uint32_t a0 = smem_u32(c.sm.a);
       for (int ch = 0; ch < nch; ++ch) {
         w64_issue(p, c, g, it * nch + ch + (int)c.sm.nbuf);     // this slab (if not prefetched) and the next nbuf - 1
@@ -379,7 +385,7 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
         if (a_pending) { mbar_wait_bounded(p, c.sm.abar, c.aphase, 3); c.aphase ^= 1u; a_pending = false; }
         mbar_wait_bounded(p, c.sm.bfull + buf, par, 4);
         tc_fence_after();
-        GEMM_MARK(15);
+        GEMM_MARK(gacc1);
         const uint32_t w0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
         const int nkb = chunk >> 6;
         for (int j = 0; j < nkb; ++j) {
@@ -390,7 +396,7 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
             umma_ss<false>(c.tmem_base, wdesc + (uint64_t)(k * 2), xdesc + (uint64_t)(k * 2), IDESC, (ch | j | k) ? 1u : 0u);
         }
         umma_commit(c.sm.bempty + buf);                         // slab buffer reusable once these MMAs retire
-        GEMM_MARK(16);
+        GEMM_MARK(gacc2);
       }
       umma_commit(c.sm.mma_done);
     }
@@ -431,8 +437,12 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
     }
     c.mphase ^= 1;
     __syncthreads();        // accumulator drained, activation slab reusable
-    GEMM_MARK(17);
+    GEMM_MARK(gacc3);
 #undef GEMM_MARK
+  }
+  if (gprof) {
+    p.prof[14] += gacc0; p.prof[15] += gacc1; p.prof[16] += gacc2; p.prof[17] += gacc3;
+    p.prof[18] += clock64() - gt_entry;
   }
 }
 
@@ -1297,7 +1307,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     const int kd = p.inter / p.d_splits;
     const int kmax = p.hidden > kd ? p.hidden : kd;
     c.sm.a_bytes = (uint32_t)(p.a_rows * kmax * 2);
-    if (c.sm.a_bytes < 96u * 1024u) c.sm.a_bytes = 96u * 1024u;      // attention ring / sampler scratch floor
+    // floor: the attention ring lives here too and streams faster with more slots (96 KB gave 4 slots per warp and a
+    // 15 % slower K/V loop than the 128 KB = 5 slots of mode 0, profiles/r01 v12)
+    if (c.sm.a_bytes < 128u * 1024u) c.sm.a_bytes = 128u * 1024u;
     c.sm.slab_bytes = (uint32_t)(MEGA_WM * MEGA_W_CHUNK * 2);
     const uint32_t nb = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - c.sm.a_bytes) / c.sm.slab_bytes;
     c.sm.nbuf = nb > 4u ? 4u : nb;
@@ -1546,7 +1558,7 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
               "decode_mega: bad qkv_splits %d for hidden %d", p.qkv_splits, p.hidden);
     const int kd = p.inter / p.d_splits;
     const long long a_bytes = (long long)p.a_rows * (p.hidden > kd ? p.hidden : kd) * 2;
-    const long long a_floor = a_bytes < 96 * 1024 ? 96 * 1024 : a_bytes;
+    const long long a_floor = a_bytes < 128 * 1024 ? 128 * 1024 : a_bytes;
     IVG_CHECK(a_floor + 2 * MEGA_WM * MEGA_W_CHUNK * 2 <= MEGA_A_BYTES + 2 * MEGA_B_BYTES,
               "decode_mega: batch %d with K %d leaves no room for two weight slabs", p.B, p.hidden);
   }

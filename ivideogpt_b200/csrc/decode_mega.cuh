@@ -16,7 +16,7 @@ constexpr int MEGA_SMEM = MEGA_A_BYTES + 2 * MEGA_B_BYTES + 1024 /*align*/ + MEG
 constexpr int MEGA_MAX_SPLITS = 12;
 // weight-stationary GEMM mode (gemm_mode 1): the WEIGHTS are the M side of the MMA (64 rows per work item), the batch is N
 constexpr int MEGA_WM = 64;                 // weight rows per work item
-constexpr int MEGA_W_CHUNK = 256;           // K per weight slab: 64 rows x 256 x 2 B = 32 KB
+constexpr int MEGA_W_CHUNK = 128;           // K per weight slab: 64 rows x 128 x 2 B = 16 KB, up to 4 in flight
 
 struct MegaLayer {
   const __nv_bfloat16 *wqkv, *wo, *wgu, *wd;   // B operands packed by mega_pack_weight (16-row swizzled slab images)

@@ -245,8 +245,8 @@ class LlamaEngine:
         if self.mega_mode() == 1:
             q_s, o_s, d_s = self._mega_splits64()
             a_rows = (B + 7) // 8 * 8
-            a_bytes = max(a_rows * max(w.hidden, w.inter // d_s) * 2, 96 * 1024)
-            return common and w.hidden % 64 == 0 and w.inter % 64 == 0 and a_bytes + 2 * 32 * 1024 <= 192 * 1024
+            a_bytes = max(a_rows * max(w.hidden, w.inter // d_s) * 2, 128 * 1024)
+            return common and w.hidden % 64 == 0 and w.inter % 64 == 0 and a_bytes + 2 * 16 * 1024 <= 192 * 1024
         a_rows = 64 if B <= 64 else 128
         o_s, d_s = self._mega_splits()
         if o_s is None:

@@ -50,7 +50,7 @@ for spec in os.environ.get("VARIANTS", "0:1:1,1:1:1").split(","):
                 "attention_warp0_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
                                                 zip(["prologue", "k_loop", "softmax", "v_loop", "tail"], allc[9:14])},
                 "gemm_item_us_per_step": {n: round(c / mhz / (new - 1), 2) for n, c in
-                                          zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end"], allc[14:18])}})
+                                          zip(["load_a", "slab_wait", "mma_issue", "commit_to_epilogue_end", "gemm_phase_total"], allc[14:19])}})
     except Exception as e:  # a variant that faults must not hide the others
         res[tag] = {"error": repr(e)[:300]}
         break
