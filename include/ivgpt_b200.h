@@ -218,11 +218,11 @@ typedef struct ivgpt_mega_desc {
   int slot0, slot_period, nslots;
   long long slot_token;
   const float* slot_emb;
-  int a_bulk;      /* 1 = xn / ao / act are kept in global memory as the 128B-swizzled K-major shared-memory image of the
-                      GEMM A operand ([k/64][row < a_rows][chunk ^ (row & 7)][8], a_rows = 64 if B <= 64 else 128), so a
-                      phase loads its activation slab with ONE bulk copy; the three buffers must then hold a_rows rows.
-                      0 = row-major [B, K] loaded with cp.async */
-  int mma_m64;     /* GEMM phases: 1 = M=64 tcgen05.mma when B <= 64 (reads only the real activation rows), 0 = M=128 */
+  int a_bulk;      /* must be 1: xn / ao / act are kept in global memory as the 128B-swizzled K-major shared-memory image of
+                      the GEMM operand ([k/64][row < a_rows][chunk ^ (row & 7)][8]; a_rows = 64 if B <= 64 else 128 in
+                      gemm_mode 0), so a phase loads its activation slab with ONE bulk copy; the three buffers hold a_rows
+                      rows.  (0 was the row-major + cp.async path of earlier builds, removed.) */
+  int mma_m64;     /* ignored: gemm_mode 0 uses the M=64 tcgen05.mma whenever B <= 64 */
   /* gemm_mode 1: weight-stationary GEMM phases -- the 64 weight rows of a work item are the MMA's M side, the batch its N
    * side.  The five weight matrices are then packed with ivgpt_mega_pack_weight64() (wgu with swiglu_pairs = 1), a_bulk
    * must be 1, a_rows (rows of the activation images, a multiple of 8 >= B) is the MMA's N, o_splits / d_splits may go

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libivgpt_b200.so")
+# IVGPT_B200_LIB: another build of the same library (A/B runs of compile-time variants); default = the in-tree build
+LIB_PATH = os.environ.get("IVGPT_B200_LIB") or os.path.join(_HERE, "libivgpt_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_SWIGLU = 0, 1, 2

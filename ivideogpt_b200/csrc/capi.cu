@@ -499,8 +499,9 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.attn_part = (float*)d->attn_part; p.attn_cnt = (unsigned int*)d->attn_cnt;
   p.slot_emb = d->slot_emb; p.slot0 = d->slot0; p.slot_period = d->slot_period; p.nslots = d->nslots;
   p.slot_token = d->slot_token;
-  p.mma_m64 = d->mma_m64;
-  p.a_bulk = d->a_bulk;
+  p.mma_m64 = 1;
+  p.a_bulk = 1;
+  IVG_CHECK(d->a_bulk == 1, "decode_mega: a_bulk must be 1 (xn / ao / act are swizzled activation images)");
   p.gemm_mode = d->gemm_mode; p.qkv_splits = d->qkv_splits; p.qkvp = (float*)d->qkvp;
   p.a_rows = d->gemm_mode == 0 ? (d->B <= 64 ? 64 : 128) : d->a_rows;
   IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");

@@ -72,13 +72,12 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-// ---- activation images (a_bulk) ----
-// With a_bulk the GEMM A operands produced inside the kernel (xn, ao, act) live in global memory ALREADY in the
+// ---- activation images ----
+// The GEMM A operands produced inside the kernel (xn, ao, act) live in global memory ALREADY in the
 // 128B-swizzled K-major shared-memory image the tensor core reads: [k-block = k/64][row][chunk ^ (row & 7)][8 bf16],
 // a_rows (64 or 128) rows per k-block.  A K range of a phase is then one contiguous run of k-blocks: the whole
 // activation slab is ONE 1-D bulk copy by the copy engine instead of 24 cp.async per thread + wait + __syncthreads.
-__device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long long ld) {
-  if (!p.a_bulk) return (size_t)m * (size_t)ld + (size_t)k;
+__device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long long /*ld: row-major stride, unused*/) {
   const int a_rows = p.a_rows;
   return (size_t)(k >> 6) * (size_t)(a_rows * 64) + (size_t)m * 64 + (size_t)((((k >> 3) & 7) ^ (m & 7)) << 3) + (size_t)(k & 7);
 }
@@ -88,9 +87,9 @@ __device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long 
 // and cost ~2.8 us per barrier, 87 barriers per decode step).
 __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
   __shared__ int s_ok;
-  // a_bulk: this CTA's generic-proxy writes (activation images in global memory, scratch in the shared activation region)
-  // must be ordered before the copy-engine (async proxy) accesses that follow the barrier, here and in other CTAs
-  if (p.a_bulk) asm volatile("fence.proxy.async;\n" ::: "memory");
+  // this CTA's generic-proxy writes (activation images in global memory, scratch in the shared activation region) must be
+  // ordered before the copy-engine (async proxy) accesses that follow the barrier, here and in other CTAs
+  asm volatile("fence.proxy.async;\n" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
     c.epoch += gridDim.x;
@@ -120,6 +119,12 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // mbarrier wait that can never hang the GPU: after ~1 s the error flag is raised (the host raises) and the wait falls through
 __device__ __forceinline__ void mbar_wait_bounded(const MegaParams& p, uint64_t* bar, uint32_t parity, int code) {
+#ifndef IVG_MEGA_BOUNDED_WAITS
+  // default: plain spin.  The bounded form (debug builds, -DIVG_MEGA_BOUNDED_WAITS) costs ~1.6 ms per 236-step rollout in
+  // register pressure (same-box A/B, profiles/r01/mega_build_variants_ab.txt)
+  mbar_wait(bar, parity);
+  return;
+#endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -137,31 +142,8 @@ __device__ __forceinline__ void issue_slab(MegaCtx& c, const __nv_bfloat16* pack
   bulk_g2s(c.sm.b0 + (size_t)buf * c.sm.slab_bytes, packed + ((size_t)tile * K + k0) * MEGA_BN, bytes, c.sm.bfull + buf);
 }
 
-// ---- A operand: rows [0, B) x k [k0, k0+Kc) of a row-major bf16 matrix -> swizzled 64-row K-major tiles ----
-// tile j (k-block j) occupies a_tile_bytes = a_rows*128 bytes; a_rows = 64 when B <= 64 else 128.
-__device__ __forceinline__ void load_a(const MegaParams& p, MegaCtx& c, const __nv_bfloat16* A, long long lda, int k0,
-                                       int Kc, int a_rows) {
-  const int nkb = Kc / 64;
-  const int chunks = nkb * a_rows * 8;            // 16-byte chunks
-  // cp.async (LDGSTS): every thread fires all of its 16-byte copies back to back -- no register staging, the whole
-  // slab is in flight at once (one CTA owns the SM, so memory-level parallelism must come from within the thread;
-  // v1 issued one load at a time: L2-latency bound, v2 staged 8 in registers).  Rows >= B are left untouched: their
-  // TMEM lanes are never read.
-  for (int i = threadIdx.x; i < chunks; i += MEGA_THREADS) {
-    const int ch = i & 7;
-    const int r = (i >> 3) % a_rows;
-    const int j = (i >> 3) / a_rows;
-    if (r < p.B) {
-      uint8_t* dst = c.sm.a + (size_t)j * a_rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-      cp_async16(dst, A + (size_t)r * lda + k0 + j * 64 + ch * 8);
-    }
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core's async proxy
-  __syncthreads();
-}
-
+// (Until round-1 v10 the activation slab was row-major in global memory and laid out in shared memory by 24 cp.async per
+// thread + wait + __syncthreads: ~2 us per phase, 97 us per step; the bulk copy of a pre-swizzled image costs 24.)
 enum { EPI_STORE_BF16 = 0, EPI_PARTIAL_F32 = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
 
 struct GemmPhase {
@@ -196,6 +178,7 @@ __device__ __forceinline__ void prefetch_phase0(MegaCtx& c, const GemmPhase& g) 
   issue_items(c, g, (int)c.sm.nbuf);      // every buffer is free here: the previous GEMM phase has retired
 }
 
+template <bool PROF>
 __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
   const int items = phase_items(g);
   const int ntiles = items / g.ksplits;
@@ -207,31 +190,27 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
   // Measured neutral (profiles/r01/mega_phase_breakdown_v10_operand_paths.json): an N = 16 MMA costs ~80 cycles of issue
   // whatever its M, i.e. this phase is bound by the NUMBER of tcgen05.mma instructions -- which is why gemm_mode 1 below
   // turns the product around.  TMEM rows of an M = 64 accumulator: row r -> lane 32*(r/16) + r%16.
-  const bool m64 = p.mma_m64 != 0 && a_rows == 64;
+  const bool m64 = a_rows == 64;
   const uint32_t IDESC = m64 ? umma_idesc(1, 64, MEGA_BN) : umma_idesc(1, 128, MEGA_BN);
   int loaded_split = -1;
   int it = 0;
-  const long long gt_entry = (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+  const long long gt_entry = (PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
     const int tile = w % ntiles, split = w / ntiles;
     // optional fine-grained timing (CTA 0, thread 0): prof[14..17] = activation slab load, weight slab wait, MMA issue,
     // commit -> end of epilogue
-    const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    const bool gprof = PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long gt = gprof ? clock64() : 0;
 #define GEMM_MARK(slot_) do { if (gprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - gt; gt = t_; } } while (0)
     bool a_pending = false;
     if (split != loaded_split) {          // (re)load the activation slab for this K range
-      if (p.a_bulk) {
-        if (threadIdx.x == 0) {           // one bulk copy: k-blocks [split*Kc/64, +nkb) of the swizzled image are contiguous
-          asm volatile("fence.proxy.async;\n" ::: "memory");
-          const uint32_t bytes = (uint32_t)(nkb * a_rows * 128);
-          mbar_expect_tx(c.sm.abar, bytes);
-          bulk_g2s(c.sm.a, g.A + (size_t)((split * Kc) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
-        }
-        a_pending = true;
-      } else {
-        load_a(p, c, g.A, g.lda, split * Kc, Kc, a_rows);
+      if (threadIdx.x == 0) {             // one bulk copy: k-blocks [split*Kc/64, +nkb) of the swizzled image are contiguous
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        const uint32_t bytes = (uint32_t)(nkb * a_rows * 128);
+        mbar_expect_tx(c.sm.abar, bytes);
+        bulk_g2s(c.sm.a, g.A + (size_t)((split * Kc) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
       }
+      a_pending = true;
       loaded_split = split;
     }
     GEMM_MARK(14);
@@ -297,7 +276,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
     GEMM_MARK(17);
 #undef GEMM_MARK
   }
-  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[18] += clock64() - gt_entry;
+  if (PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[18] += clock64() - gt_entry;
 }
 
 // =====================================================================================================================
@@ -346,6 +325,7 @@ __device__ __forceinline__ void w64_issue(const MegaParams& p, MegaCtx& c, const
   }
 }
 
+template <bool PROF>
 __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
   const int items = w64_items(g);
   const int ntiles = items / g.ksplits;
@@ -359,7 +339,7 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
   int it = 0;
   // optional timing (CTA 0, thread 0), accumulated in registers and flushed once per phase: prof[14..17] = activation
   // copy issue, slab wait, MMA issue, commit -> end of epilogue; prof[18] = whole phase, entry to exit
-  const bool gprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool gprof = PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long gacc0 = 0, gacc1 = 0, gacc2 = 0, gacc3 = 0;
   const long long gt_entry = gprof ? clock64() : 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
@@ -456,9 +436,9 @@ __device__ __forceinline__ void prefetch_phase(const MegaParams& p, MegaCtx& c, 
   c.phase_issued = 0;
   w64_issue(p, c, g, (int)c.sm.nbuf);
 }
-template <int GM>
+template <int GM, bool PROF>
 __device__ __forceinline__ void gemm_phase(const MegaParams& p, MegaCtx& c, const GemmPhase& g) {
-  if constexpr (GM == 0) gemm_phase0(p, c, g); else gemm_phase_w64(p, c, g);
+  if constexpr (GM == 0) gemm_phase0<PROF>(p, c, g); else gemm_phase_w64<PROF>(p, c, g);
 }
 
 // ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
@@ -481,12 +461,14 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
     float ss = 0.f;
     if (i < H) {
       v = *reinterpret_cast<const float4*>(src + i);
+#ifndef IVG_MEGA_NO_SLOTS
       if (tok_row0 && p.slot_emb && p.slot_period > 0 && tok_col >= p.slot0 && (tok_col - p.slot0) % p.slot_period == 0 &&
           (tok_col - p.slot0) / p.slot_period < p.nslots) {       // forced slot: + action_linear(a_i), action_model.py:80-81
         const float4 e = *reinterpret_cast<const float4*>(
             p.slot_emb + ((size_t)m * p.nslots + (tok_col - p.slot0) / p.slot_period) * H + i);
         v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
       }
+#endif
       float4 q[MAXP];
 #pragma unroll
       for (int s = 0; s < MAXP; ++s)
@@ -735,7 +717,7 @@ __device__ __forceinline__ void attention_prefetch(const MegaParams& p, int laye
   for (int u = 0; u < pre; ++u) att_issue(p, layer, w.bh, pos, w.u0, nU, u, u, ring, bars);
 }
 
-template <int GM>
+template <int GM, bool PROF>
 __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos, int u0, int u1, bool tail, bool issued,
                                  float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par, float& m_out,
                                  float& l_out, float (&acc)[8]) {
@@ -750,7 +732,7 @@ __device__ void attention_stream(const MegaParams& p, int layer, int bh, int pos
   const int units = 2 * nU;
   const int row0 = u0 << 5;
   // optional fine-grained timing of the phase (CTA 0, warp 0, lane 0): prof[9..13] = prologue, K loop, softmax, V loop, tail
-  const bool tprof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool tprof = PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long tm = tprof ? clock64() : 0;
 #define ATT_MARK(slot_) do { if (tprof) { const long long t_ = clock64(); p.prof[slot_] += t_ - tm; tm = clock64(); } } while (0)
   auto issue = [&](int u, int slot) { att_issue(p, layer, bh, pos, u0, nU, u, slot, ring, bars); };
@@ -919,12 +901,12 @@ __device__ __forceinline__ void attention_store(const MegaParams& p, int bh, con
 
 // one left-over item cut along the sequence: every part publishes (max, sum, acc[64]); the part that arrives last
 // (monotonic counter, MEGA_ATT_SPLIT arrivals per item, layer and step) merges them and writes the output row.
-template <int GM>
+template <int GM, bool PROF>
 __device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, int u0, int u1, bool issued,
                                float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
   const int lane = threadIdx.x & 31;
   float m, l, acc[8];
-  attention_stream<GM>(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
+  attention_stream<GM, PROF>(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
   float* rec = p.attn_part + ((size_t)extra * MEGA_ATT_SPLIT + q) * 72;
   if ((lane >> 3) == 0) {
     float4* dst = reinterpret_cast<float4*>(rec + 8 + (lane & 7) * 8);
@@ -1118,10 +1100,12 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   constexpr int NW = MEGA_THREADS / 32;
   __shared__ float s_redf[NW];
   __shared__ int s_redi[NW];
+#ifndef IVG_MEGA_NO_SLOTS
   if (p.slot_period > 0 && pos + 1 >= p.slot0 && (pos + 1 - p.slot0) % p.slot_period == 0) {
     if (tid == 0) *out = p.slot_token;       // forced separator, never sampled (action_model.py:109-110); CTA-uniform
     return;
   }
+#endif
   if (!p.do_sample) {
     float bv = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 8
@@ -1287,7 +1271,7 @@ __device__ void sample_row(const MegaParams& p, int b, int pos, uint32_t* smem_u
   __syncthreads();
 }
 
-template <int GM, int AM>
+template <int GM, int AM, bool PROF>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaParams p) {
   constexpr int MAXP = GM == 0 ? 8 : MEGA_MAX_SPLITS;
   extern __shared__ uint8_t mega_raw[];
@@ -1333,7 +1317,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(c.sm.tmem_holder, 128); tmem_relinquish(); }
+  constexpr uint32_t TMEM_COLS = GM == 0 ? 32 : 128;     // accumulator columns: 16 (mode 0) / a_rows <= 128 (mode 1)
+  if (warp == 1) { tmem_alloc(c.sm.tmem_holder, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1347,7 +1332,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   // phase timing (CTA 0, thread 0): slots 0 norm, 1 qkv, 2 attention, 3 o-proj, 4 gate/up, 5 down, 6 lm_head,
   // 7 sample, 8 barriers
   long long tprof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const bool profiling = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool profiling = PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long tmark = clock64();
 #define MEGA_MARK(slot) do { if (profiling) { const long long _t = clock64(); tprof[slot] += _t - tmark; tmark = _t; } } while (0)
 #define MEGA_BARRIER() do { ok = grid_barrier(p, c); MEGA_MARK(8); } while (0)
@@ -1364,7 +1349,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
       qkv_g.w = L.wqkv;
-      gemm_phase<GM>(p, c, qkv_g);
+      gemm_phase<GM, PROF>(p, c, qkv_g);
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase<GM>(p, c, o_g);
@@ -1388,11 +1373,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             uint8_t* ring = c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT;
             if (w.kind == 1) {
               float m, lsum, acc[8];
-              attention_stream<GM>(p, l, w.bh, pos, w.u0, w.u1, true, ring_prefetch, wsm, ring, w.nslot, c.sm.ring_bar + warp * 8,
+              attention_stream<GM, PROF>(p, l, w.bh, pos, w.u0, w.u1, true, ring_prefetch, wsm, ring, w.nslot, c.sm.ring_bar + warp * 8,
                                ring_par, m, lsum, acc);
               attention_store(p, w.bh, acc, 1.0f / lsum);
             } else if (w.kind == 2) {
-              attention_part<GM>(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
+              attention_part<GM, PROF>(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
                              c.sm.ring_bar + warp * 8, ring_par);
             }
           } else {
@@ -1404,7 +1389,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               if (warp < active) {
                 const int bh = base + G * warp;
                 float m, lsum, acc[8];
-                attention_stream<GM>(p, l, bh, pos, 0, (pos + 31) >> 5, true, false, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
+                attention_stream<GM, PROF>(p, l, bh, pos, 0, (pos + 31) >> 5, true, false, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64),
                                  c.sm.a + (size_t)warp * nslot * MEGA_RING_SLOT, nslot, c.sm.ring_bar + warp * 8, ring_par, m,
                                  lsum, acc);
                 attention_store(p, bh, acc, 1.0f / lsum);
@@ -1424,7 +1409,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       MEGA_MARK(2);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase<GM>(p, c, o_g);
+      gemm_phase<GM, PROF>(p, c, o_g);
       MEGA_MARK(3);
       GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
       prefetch_phase<GM>(p, c, gu_g);
@@ -1432,12 +1417,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
       MEGA_MARK(0);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase<GM>(p, c, gu_g);
+      gemm_phase<GM, PROF>(p, c, gu_g);
       MEGA_MARK(4);
       GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase<GM>(p, c, d_g);
       MEGA_BARRIER(); if (!ok) break;
-      gemm_phase<GM>(p, c, d_g);
+      gemm_phase<GM, PROF>(p, c, d_g);
       MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
       GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, (ws && !last) ? p.qkv_splits : 1, p.xn, H,
@@ -1449,7 +1434,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_MARK(0);
       MEGA_BARRIER(); if (!ok) break;
       if (last) {
-        gemm_phase<GM>(p, c, nx_g);                                       // lm_head
+        gemm_phase<GM, PROF>(p, c, nx_g);                                       // lm_head
         MEGA_MARK(6);
         MEGA_BARRIER(); if (!ok) break;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) sample_row(p, b, pos, smem_u);
@@ -1462,7 +1447,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   if (profiling) for (int i = 0; i < 9; ++i) p.prof[i] += tprof[i];   // slots 9..13: attention_stream's own marks
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, 128); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(c.tmem_base, TMEM_COLS); }
 }
 
 // ---- one-off weight packing: [rows, cols] bf16 row-major -> per 16-row work item the 128B-swizzled K-major image ----
@@ -1566,12 +1551,19 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
                 (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
+  // one instantiation per (GEMM mode, attention mode, profiling): the timed kernels carry no timing code at all (cycle
+  // counters in the 250-register kernel cost 4.5 ms per rollout even when disabled at run time, same-box A/B)
   const void* fn = nullptr;
   const int am = p.attn_mode == 1 ? 1 : 0;
-  if (p.gemm_mode == 0) fn = am ? (const void*)decode_mega_kernel<0, 1> : (const void*)decode_mega_kernel<0, 0>;
-  else fn = am ? (const void*)decode_mega_kernel<1, 1> : (const void*)decode_mega_kernel<1, 0>;
-  static bool attr_set[4] = {false, false, false, false};
-  const int vi = (p.gemm_mode != 0 ? 2 : 0) + am;
+  const int pf = p.prof != nullptr ? 1 : 0;
+  const void* table[8] = {
+      (const void*)decode_mega_kernel<0, 0, false>, (const void*)decode_mega_kernel<0, 0, true>,
+      (const void*)decode_mega_kernel<0, 1, false>, (const void*)decode_mega_kernel<0, 1, true>,
+      (const void*)decode_mega_kernel<1, 0, false>, (const void*)decode_mega_kernel<1, 0, true>,
+      (const void*)decode_mega_kernel<1, 1, false>, (const void*)decode_mega_kernel<1, 1, true>};
+  const int vi = (p.gemm_mode != 0 ? 4 : 0) + am * 2 + pf;
+  fn = table[vi];
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[vi]) {
     IVG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM));
     attr_set[vi] = true;

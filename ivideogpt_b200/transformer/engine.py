@@ -234,8 +234,9 @@ class LlamaEngine:
 
     # ---- persistent decode megakernel (bf16, B <= 64 with these widths) --------------------------------------
     def mega_mode(self) -> int:
-        """GEMM phases of the megakernel: 1 = weight-stationary (64 weight rows per MMA, default), 0 = activation-stationary."""
-        return int(getattr(self, "mega_gemm_mode", int(os.environ.get("IVGPT_MEGA_GEMM", "1"))))
+        """GEMM phases of the megakernel: 0 = activation-stationary (default, fastest measured), 1 = weight-stationary (64 weight
+        rows per MMA: 2.4x fewer tcgen05.mma issues but 285 vs 230 ms per rollout, profiles/r01/mega_build_variants_ab2.txt)."""
+        return int(getattr(self, "mega_gemm_mode", int(os.environ.get("IVGPT_MEGA_GEMM", "0"))))
 
     def mega_supported(self, B: int, Lmax: int) -> bool:
         w = self.w
@@ -371,8 +372,7 @@ class LlamaEngine:
         d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
         d.attn_cnt = sync.data_ptr() + 256
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
-        d.a_bulk = 1 if mode == 1 else int(getattr(self, "mega_a_bulk", int(os.environ.get("IVGPT_MEGA_ABULK", "1"))))
-        d.mma_m64 = int(getattr(self, "mega_m64", int(os.environ.get("IVGPT_MEGA_M64", "1"))))
+        d.a_bulk, d.mma_m64 = 1, 1
         if slot is not None:
             d.slot0, d.slot_period, d.slot_token = int(slot[0]), int(slot[1]), int(slot[2])
             d.nslots = int(slot[3].shape[1]) if slot[3] is not None else 1
