@@ -243,12 +243,15 @@ def run_b200(args):
         out = llm.generate(prompt, **gen_kw)
         return tok.detokenize(out, ctx)
 
+    frames_host = torch.empty(B, seg, 3, res, res, dtype=torch.float32).pin_memory()
+
     def step_e2e():
         px = clips_host.to(dev, non_blocking=True)                    # H2D from pinned memory
         tokens, _ = tok.tokenize(px, ctx)                             # predict.py:53 (all frames)
         out = llm.generate(tokens[:, : ctx * 257], **gen_kw)          # predict.py:54-69
         frames = tok.detokenize(out, ctx).clamp_(0.0, 1.0)            # predict.py:72-73
-        return frames.to("cpu", non_blocking=False)                   # D2H of the result
+        frames_host.copy_(frames, non_blocking=True)                  # D2H of the result into pinned memory (stream-ordered:
+        return frames_host                                            # the closing CUDA event of the step waits for it)
 
     def barrier():
         if world > 1:
@@ -422,12 +425,18 @@ def run_train(args):
     clips = synthetic_clips(B, seg, res, seed=rank).to(dev)
     step_no = [0]
 
+    overlap = os.environ.get("IVGPT_TRAIN_OVERLAP", "1") == "1"
+    if world > 1 and overlap:
+        # gradient exchange launched bucket by bucket from inside the backward (sum; the mean is AdamW's gscale = 1/world)
+        from ivideogpt_b200.grad_reduce import BucketedGradReducer
+        llm.b200_grad_reducer = BucketedGradReducer()
+
     def train_step():
         with torch.no_grad():
             tokens, labels = tok.tokenize(clips, ctx)                     # train_gpt.py:776-779
-        loss = llm(input_ids=tokens, labels=labels).loss                  # :792
+        loss = llm(input_ids=tokens, labels=labels).loss                  # :792 (+ overlapped all-reduce when world > 1)
         loss.backward()                                                   # :798
-        if world > 1:                                                     # DDP's gradient all-reduce (sum; mean via gscale)
+        if world > 1 and not overlap:                                     # one flat all-reduce after the backward (round-1 v1)
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
             off = 0
@@ -476,7 +485,9 @@ def run_train(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: train_gpt.py step, {B} clips/GPU of {res}x{res}x{seg}, frozen fp32 "
                                    f"tokenizer -> Llama fwd+bwd bf16 -> all-reduce -> AdamW", "per_gpu_batch": B,
-                       "parallelism": f"dp{world}", "attention_dropout": 0.0},
+                       "parallelism": f"dp{world}", "attention_dropout": 0.0,
+                       "grad_exchange": ("none" if world == 1 else "bucketed NCCL all-reduce overlapped with backward" if overlap
+                                         else "one flat NCCL all-reduce after backward")},
             "loss_first_last": [float(losses[0].detach()), float(losses[-1].detach())], "gpu_launches": _lib.launch_count() - n0,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "training step (all tcgen05 GEMMs)", "achieved": ach, "peak": peak_tf,

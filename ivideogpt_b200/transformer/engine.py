@@ -244,6 +244,8 @@ class LlamaEngine:
             return False
         common = (w.vocab + 256) * 4 <= 96 * 1024 and (Lmax + 72) * 4 * 8 <= 30 * 1024
         if self.mega_mode() == 1:
+            if B > 64:        # the experimental weight-stationary mode is validated for B <= 64 only (a B = 100 run showed
+                return False  # 7 % logit error on some rows, tests log of round 1); larger batches take the CUDA-graph path
             q_s, o_s, d_s = self._mega_splits64()
             a_rows = (B + 7) // 8 * 8
             a_bytes = max(a_rows * max(w.hidden, w.inter // d_s) * 2, 128 * 1024)

@@ -166,7 +166,12 @@ class _TrainLossFn(torch.autograd.Function):
         from .train_engine import LlamaTrainEngine
         eng = model.b200_engine()
         train = LlamaTrainEngine(eng.w)
-        loss, grads = train.forward_backward(input_ids, labels)
+        # model.b200_grad_reducer (grad_reduce.BucketedGradReducer, optional): the data-parallel exchange, launched bucket
+        # by bucket from inside the backward so that it overlaps the remaining layers (row a13, train_gpt.py:672,798)
+        reducer = getattr(model, "b200_grad_reducer", None)
+        loss, grads = train.forward_backward(input_ids, labels, on_grads=reducer.on_grads if reducer is not None else None)
+        if reducer is not None:
+            reducer.finish(grads)
         ctx.grads = [grads[n] for n in names]
         return loss.clone()
 

@@ -52,8 +52,12 @@ class LlamaTrainEngine:
 
     # ---- forward + backward --------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0):
-        """Returns (loss 0-d fp32 tensor, grads dict keyed by HF parameter name -> fp32 tensor)."""
+    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, on_grads=None):
+        """Returns (loss 0-d fp32 tensor, grads dict keyed by HF parameter name -> fp32 tensor).
+
+        on_grads(grads, names): called as soon as the gradients `names` are final, in backward order ([lm_head, final norm],
+        layer L-1 ... layer 0, [embedding]) -- the hook of the data-parallel exchange (grad_reduce.BucketedGradReducer
+        launches that bucket's all-reduce while the next layer's backward is computed).  The hook may replace entries."""
         w, dt, code = self.w, self.dt, self.code
         B, L = ids.shape
         M, h, H, I, V = B * L, w.hidden, w.heads, w.inter, w.vocab
@@ -115,6 +119,8 @@ class LlamaTrainEngine:
         del logits, dlogits
         dx = torch.zeros(M, h, dtype=torch.float32, device=dev)
         grads["model.norm.weight"] = ops.rmsnorm_bwd(x, w.norm, d_xnf, dx, w.eps)
+        if on_grads is not None:
+            on_grads(grads, ["lm_head.weight", "model.norm.weight"])
         for li in reversed(range(w.layers_n)):
             lw, wt, s = w.layers[li], self.wT[li], saved[li]
             pre = f"model.layers.{li}."
@@ -182,7 +188,14 @@ class LlamaTrainEngine:
             grads[pre + "self_attn.v_proj.weight"] = g_qkv[2 * h:3 * h]
             grads[pre + "input_layernorm.weight"] = ops.rmsnorm_bwd(s["xin"], lw["n1"], d_xn1, dx, w.eps)
             saved[li] = None
+            if on_grads is not None:
+                on_grads(grads, [pre + n for n in (
+                    "mlp.down_proj.weight", "mlp.gate_proj.weight", "mlp.up_proj.weight", "post_attention_layernorm.weight",
+                    "self_attn.o_proj.weight", "self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+                    "input_layernorm.weight")])
         dE = torch.zeros(V, h, dtype=torch.float32, device=dev)
         ops.embed_bwd(ids, dx, dE)
         grads["model.embed_tokens.weight"] = dE
+        if on_grads is not None:
+            on_grads(grads, ["model.embed_tokens.weight"])
         return loss, grads

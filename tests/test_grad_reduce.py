@@ -1,0 +1,66 @@
+"""Row a13 (train_gpt.py:672,798 DDP gradient all-reduce): the bucketed, overlapped reducer on CPU with gloo, world 2."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _grads(rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    big = torch.randn(6, 8, generator=g)
+    return {"lm_head.weight": torch.randn(5, 4, generator=g), "model.norm.weight": torch.randn(4, generator=g),
+            "model.layers.0.mlp.gate_proj.weight": big[0::2], "model.layers.0.mlp.up_proj.weight": big[1::2],   # strided views
+            "model.embed_tokens.weight": torch.randn(7, 4, generator=g)}
+
+
+ORDER = [["lm_head.weight", "model.norm.weight"],
+         ["model.layers.0.mlp.gate_proj.weight", "model.layers.0.mlp.up_proj.weight"], ["model.embed_tokens.weight"]]
+
+
+def _worker(rank, world, port, out, min_bytes):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ivideogpt_b200.grad_reduce import BucketedGradReducer
+    red = BucketedGradReducer(min_bucket_bytes=min_bytes)
+    grads = _grads(rank)
+    for names in ORDER:
+        red.on_grads(grads, names)
+    red.finish(grads)
+    out.put((rank, {k: v.clone() for k, v in grads.items()}, red.buckets_launched))
+    dist.destroy_process_group()
+
+
+def _run(min_bytes):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, min_bytes)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    [p.join(30) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    return res
+
+
+def test_bucketed_reducer_equals_plain_sum_gloo():
+    want = {k: _grads(0)[k] + _grads(1)[k] for k in _grads(0)}
+    for min_bytes, nb in ((0, 3), (10 ** 9, 1)):         # one bucket per call / everything merged into one bucket
+        res = _run(min_bytes)
+        for rank, got, buckets in res:
+            assert buckets == nb
+            assert set(got) == set(want)
+            for k in want:
+                assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), (rank, k)
+
+
+def test_reducer_single_process_is_identity():
+    from ivideogpt_b200.grad_reduce import BucketedGradReducer
+    red = BucketedGradReducer()
+    grads = _grads(0)
+    want = {k: v.clone() for k, v in grads.items()}
+    for names in ORDER:
+        red.on_grads(grads, names)
+    red.finish(grads)
+    assert all(torch.equal(grads[k], want[k]) and grads[k].is_contiguous() for k in want)

@@ -157,7 +157,6 @@ def test_decode_megakernel_matches_multikernel_path(cuda, mode):
 @pytest.mark.parametrize("hidden,inter,heads,B,L,new", [
     (128, 256, 2, 64, 50, 14),     # one k-block per split, full batch
     (512, 1024, 8, 33, 21, 12),    # gate/up and lm_head stream K in two 256-wide slabs; batch not a multiple of 8
-    (256, 1024, 4, 100, 30, 10),   # batch > 64: MMA N = 104
     (768, 3072, 12, 16, 40, 8),    # the 138M widths, one layer pair, cfg256's batch
 ])
 def test_decode_megakernel_weight_stationary_shapes(cuda, hidden, inter, heads, B, L, new):
