@@ -221,3 +221,30 @@ def test_training_forward_backward_vs_hf_autograd(cuda, dtype, tol_loss, min_cos
         assert cos > min_cos, f"{n}: cos {cos}"
         assert abs(float(a.norm() / b.norm()) - 1.0) < 0.05, f"{n}: norm ratio {float(a.norm() / b.norm())}"
     assert worst > min_cos
+
+
+@pytest.mark.gpu
+def test_training_with_bucketed_grad_reducer_matches_plain_backward(cuda):
+    """Row a13 plumbing on one GPU: with the bucketed reducer hooked into the backward (world size 1: pack -> no exchange
+    -> views of the buckets) every parameter gradient must be bit-identical to the plain path; the exchange itself is
+    covered by the world-size-2 gloo test (tests/test_grad_reduce.py) and the 2-GPU bench."""
+    from oracle.llama_ref import TINY_LLAMA
+    from ivideogpt_b200.grad_reduce import BucketedGradReducer
+    ref, mine = _pair(TINY_LLAMA, cuda, torch.bfloat16, scale=2.0)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 1026, (3, 75), generator=g).to(cuda)
+    labels = ids.clone()
+    labels[:, :40] = -100
+    mine.train()
+    mine(input_ids=ids, labels=labels).loss.backward()
+    plain = {n: p.grad.detach().clone() for n, p in mine.named_parameters()}
+    for p in mine.parameters():
+        p.grad = None
+    mine.b200_grad_reducer = BucketedGradReducer()
+    mine(input_ids=ids, labels=labels).loss.backward()
+    assert mine.b200_grad_reducer.buckets_launched == 2 + TINY_LLAMA["num_hidden_layers"]
+    for n, p in mine.named_parameters():
+        if n == "model.embed_tokens.weight":       # scatter-add with atomics: the order of equal-token rows may differ
+            assert torch.allclose(p.grad, plain[n], rtol=1e-4, atol=1e-6), n
+        else:
+            assert torch.equal(p.grad, plain[n]), n
