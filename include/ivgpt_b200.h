@@ -143,6 +143,16 @@ int ivgpt_tokens_gather(int dtype, const long long* tokens, const float* cb_ctx,
                         void* q_dyn, int B, int t, int f, int cr, int dr, int D, long long n_vq, long long n_dyn,
                         int L, void* stream);
 
+/* ---- input pipeline -----------------------------------------------------------------------------------
+ * Replaces inference/utils.py:12-16 NPZParser.preprocess (and ivideogpt/data/simple_dataloader.py:394,510):
+ * `images / 255` followed by torchvision's resize to [out_h, out_w] (bilinear, antialias, align_corners=False).
+ * frames: device uint8 (in_dtype 2) or fp32 (0), element (t, y, x, c) at t*stride_t + y*stride_y + x*stride_x + c*stride_c
+ * (strides in elements: [T,H,W,C] episodes as stored in the .npz files, or [T,C,H,W]); out fp32 [T, C, out_h, out_w].
+ * divisor = 255 for the reference's pipeline.  Down-scaling factors up to 19. */
+int ivgpt_preprocess_resize(int in_dtype, const void* frames, long long stride_t, long long stride_y, long long stride_x,
+                            long long stride_c, int T, int H, int W, int C, float* out, int out_h, int out_w, float divisor,
+                            void* stream);
+
 /* ---- Llama pieces (transformers LlamaForCausalLM as used by predict.py:64 / train_gpt.py:792) ----- */
 int ivgpt_embed(const long long* ids, long long ids_stride, int L, const int* dpos, const float* table, float* x,
                 long long M, int hidden, long long vocab, void* stream);

@@ -115,6 +115,7 @@ SIGNATURES = {
     "ivgpt_topk_sample": [_P, _L, _I, _I, _I, _F, _U, _U, _P, _L, _P, _P, _P],
     "ivgpt_ce_loss": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P],
     "ivgpt_incr": [_P, _I, _P],
+    "ivgpt_preprocess_resize": [_I, _P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _I, _F, _P],
     "ivgpt_slot_embed_add": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ivgpt_slot_force": [_P, _L, _P, _I, _I, _I, _L, _P],
     "ivgpt_decode_attn_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P],

@@ -111,6 +111,8 @@ int topk_sample_launch(const float*, long long, int, int, int, float, unsigned l
                        long long*, long long, const int*, const unsigned long long*, cudaStream_t);
 int ce_loss_launch(const float*, long long, int, int, int, const long long*, float*, float*, float*, cudaStream_t);
 int incr_launch(int*, int, cudaStream_t);
+int resize_aa_launch(int, const void*, long long, long long, long long, long long, int, int, int, int, float*, int, int, float,
+                     cudaStream_t);
 int slot_embed_add_launch(float*, const float*, const int*, int, int, int, int, int, cudaStream_t);
 int slot_force_launch(long long*, long long, const int*, int, int, int, long long, cudaStream_t);
 int transpose_launch(int, const void*, void*, int, int, int, long long, long long, long long, long long, cudaStream_t);
@@ -393,6 +395,12 @@ int ivgpt_ce_loss(const float* logits, long long ld, int B, int L, int V, const 
   return ce_loss_launch(logits, ld, B, L, V, labels, loss_rows, valid_ws, loss_out, S(stream));
 }
 int ivgpt_incr(int* p, int by, void* stream) { return incr_launch(p, by, S(stream)); }
+int ivgpt_preprocess_resize(int in_dtype, const void* frames, long long stride_t, long long stride_y, long long stride_x,
+                            long long stride_c, int T, int H, int W, int C, float* out, int out_h, int out_w, float divisor,
+                            void* stream) {
+  return resize_aa_launch(in_dtype, frames, stride_t, stride_y, stride_x, stride_c, T, H, W, C, out, out_h, out_w, divisor,
+                          S(stream));
+}
 int ivgpt_slot_embed_add(float* x, const float* slot_emb, const int* dpos, int B, int hidden, int slot0, int period,
                          int nslots, void* stream) {
   return slot_embed_add_launch(x, slot_emb, dpos, B, hidden, slot0, period, nslots, S(stream));

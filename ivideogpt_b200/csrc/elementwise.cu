@@ -653,4 +653,81 @@ int detok_gather_launch(int dtype, const long long* tokens, const float* cb_ctx,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Input pipeline (reference inference/utils.py:12-16 NPZParser.preprocess, ivideogpt/data/simple_dataloader.py:394,510):
+//     images = images / 255 ; images = torchvision resize(images, [S, S])       (bilinear, antialias, align_corners=False)
+// One thread per output pixel, all channels; the anti-aliased triangle filter of ATen's _upsample_bilinear2d_aa is
+// evaluated in place (weights normalised per axis, horizontal pass inside the vertical one, sequential mul + add like the
+// CPU kernel, no FMA contraction).  Input: uint8 or fp32 frames with arbitrary element strides ([T,H,W,C] as stored in the
+// .npz episodes, or the [T,C,H,W] float tensor the reference's preprocess() is handed); output fp32 [T, C, OH, OW].
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_MAXTAPS = 40;      // 2 * ceil(scale) + 2 for down-scaling factors up to 19
+struct RsAxis { int lo, n; float w[RS_MAXTAPS]; };
+
+__device__ __forceinline__ void rs_axis(int in_size, int out_size, int i, RsAxis& a) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float inv = scale >= 1.0f ? __fdiv_rn(1.0f, scale) : 1.0f;
+  const float center = __fmul_rn(scale, (float)i + 0.5f);
+  int lo = (int)(__fadd_rn(__fsub_rn(center, support), 0.5f));
+  lo = lo < 0 ? 0 : lo;
+  int hi = (int)(__fadd_rn(__fadd_rn(center, support), 0.5f));
+  hi = hi > in_size ? in_size : hi;
+  int n = hi - lo;
+  n = n > RS_MAXTAPS ? RS_MAXTAPS : n;
+  float total = 0.f;
+  for (int j = 0; j < n; ++j) {
+    float x = __fmul_rn(__fadd_rn(__fsub_rn(__fadd_rn((float)j, (float)lo), center), 0.5f), inv);
+    x = fabsf(x);
+    const float w = x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f;
+    a.w[j] = w;
+    total = __fadd_rn(total, w);
+  }
+  for (int j = 0; j < n; ++j) a.w[j] = __fdiv_rn(a.w[j], total);
+  a.lo = lo; a.n = n;
+}
+
+template <typename TIN>
+__global__ void resize_aa_kernel(const TIN* __restrict__ in, long long st, long long sy, long long sx, long long sc, int T,
+                                 int H, int W, int C, float* __restrict__ out, int OH, int OW, float divisor) {
+  const long long total = (long long)T * OH * OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const int oy = (int)((idx / OW) % OH);
+    const int t = (int)(idx / ((long long)OW * OH));
+    RsAxis ax, ay;
+    rs_axis(W, OW, ox, ax);
+    rs_axis(H, OH, oy, ay);
+    for (int c = 0; c < C; ++c) {
+      const TIN* base = in + (long long)t * st + (long long)c * sc;
+      float acc = 0.f;
+      for (int j = 0; j < ay.n; ++j) {
+        const TIN* row = base + (long long)(ay.lo + j) * sy + (long long)ax.lo * sx;
+        float h = __fmul_rn(__fdiv_rn((float)row[0], divisor), ax.w[0]);
+        for (int i = 1; i < ax.n; ++i) h = __fadd_rn(h, __fmul_rn(__fdiv_rn((float)row[(long long)i * sx], divisor), ax.w[i]));
+        acc = j == 0 ? __fmul_rn(h, ay.w[0]) : __fadd_rn(acc, __fmul_rn(h, ay.w[j]));
+      }
+      out[(((long long)t * C + c) * OH + oy) * OW + ox] = acc;
+    }
+  }
+}
+
+int resize_aa_launch(int in_dtype, const void* in, long long st, long long sy, long long sx, long long sc, int T, int H, int W,
+                     int C, float* out, int OH, int OW, float divisor, cudaStream_t stream) {
+  IVG_CHECK(in_dtype == DT_F32 || in_dtype == 2, "resize_aa: input dtype %d (0 = fp32, 2 = uint8)", in_dtype);
+  IVG_CHECK(T >= 0 && H >= 1 && W >= 1 && C >= 1 && OH >= 1 && OW >= 1 && divisor != 0.f, "resize_aa: bad geometry");
+  IVG_CHECK(2 * ((H + OH - 1) / OH) + 2 <= RS_MAXTAPS && 2 * ((W + OW - 1) / OW) + 2 <= RS_MAXTAPS,
+            "resize_aa: down-scaling factor above %d is not supported", (RS_MAXTAPS - 2) / 2);
+  if (T == 0) return 0;
+  const long long total = (long long)T * OH * OW;
+  const int blocks = (int)((total + 127) / 128 < 148 * 16 ? (total + 127) / 128 : 148 * 16);
+  if (in_dtype == 2)
+    resize_aa_kernel<unsigned char><<<blocks, 128, 0, stream>>>((const unsigned char*)in, st, sy, sx, sc, T, H, W, C, out, OH, OW, divisor);
+  else
+    resize_aa_kernel<float><<<blocks, 128, 0, stream>>>((const float*)in, st, sy, sx, sc, T, H, W, C, out, OH, OW, divisor);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ivg

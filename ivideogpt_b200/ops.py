@@ -464,3 +464,26 @@ def transpose_raw(src: torch.Tensor, src_off: int, dst: torch.Tensor, batch: int
     es = src.element_size()
     _lib.check(_lib.load().ivgpt_transpose(_dt(src), src.data_ptr() + src_off * es, dst.data_ptr(), batch, R, Cc, ld_in,
                                            ld_out, bs_in, bs_out, _stream()), "transpose")
+
+
+def preprocess_resize(frames: torch.Tensor, size_hw, channels_last: bool = True, divisor: float = 255.0) -> torch.Tensor:
+    """`images / 255` + antialiased bilinear resize (inference/utils.py:12-16).  frames: CUDA uint8 or fp32, [T,H,W,C] when
+    channels_last else [T,C,H,W] (any strides); returns fp32 [T, C, out_h, out_w]."""
+    if not frames.is_cuda:
+        raise RuntimeError("preprocess_resize requires a CUDA tensor (no CPU fallback)")
+    if frames.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"preprocess_resize: uint8 or float32 frames expected, got {frames.dtype}")
+    if frames.dim() != 4:
+        raise ValueError("preprocess_resize: frames must be 4-D")
+    if channels_last:
+        T, H, W, Cc = frames.shape
+        st, sy, sx, sc = frames.stride()
+    else:
+        T, Cc, H, W = frames.shape
+        st, sc, sy, sx = frames.stride()
+    oh, ow = int(size_hw[0]), int(size_hw[1])
+    out = torch.empty(T, Cc, oh, ow, dtype=torch.float32, device=frames.device)
+    _lib.check(_lib.load().ivgpt_preprocess_resize(2 if frames.dtype == torch.uint8 else 0, frames.data_ptr(), st, sy, sx, sc,
+                                                   T, H, W, Cc, out.data_ptr(), oh, ow, float(divisor), _stream()),
+               "preprocess_resize")
+    return out
