@@ -53,6 +53,8 @@ struct MegaCtx {
   // load #i always goes to buffer i % nbuf and is consumed with parity (i / nbuf) & 1.  At most nbuf are in flight.
   uint32_t issued, consumed;
   int phase_issued;        // items of the CURRENT/coming phase whose slab has been issued already
+  int phase_consumed;      // gemm_mode 0: items of the current phase whose slab has been waited for
+  uint32_t wait_par;       // gemm_mode 0: expected parity of bfull[i] in bit i (buffers are re-numbered per phase)
   uint32_t mphase;         // parity of mma_done (all threads)
   uint32_t aphase;         // parity of abar (thread 0)
 };
@@ -85,11 +87,17 @@ __device__ __forceinline__ size_t a_off(const MegaParams& p, int m, int k, long 
 // device-wide barrier; returns false when it timed out (error flag is set, every CTA leaves the kernel).
 // Arrival is a release-reduction, the wait an acquire-load: no full sc fences (v1 used __threadfence() on both sides
 // and cost ~2.8 us per barrier, 87 barriers per decode step).
+template <bool FENCE>
 __device__ __forceinline__ bool grid_barrier(const MegaParams& p, MegaCtx& c) {
   __shared__ int s_ok;
-  // this CTA's generic-proxy writes (activation images in global memory, scratch in the shared activation region) must be
-  // ordered before the copy-engine (async proxy) accesses that follow the barrier, here and in other CTAs
+  // FENCE: this CTA's generic-proxy writes (activation images in global memory, scratch in the shared activation region)
+  // must be ordered before the copy-engine (async proxy) accesses that follow the barrier, here and in other CTAs.  Only the
+  // barriers that follow a phase producing an activation image (norm -> xn, attention -> ao, gate/up -> act) need it.
+#ifdef IVG_MEGA_FENCE_ALL
   asm volatile("fence.proxy.async;\n" ::: "memory");
+#else
+  if constexpr (FENCE) asm volatile("fence.proxy.async;\n" ::: "memory");
+#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     c.epoch += gridDim.x;
@@ -134,13 +142,12 @@ __device__ __forceinline__ void mbar_wait_bounded(const MegaParams& p, uint64_t*
 
 // ---- weight slab: item (tile, split) of a packed matrix -> one contiguous copy of Kc * 32 bytes ----
 // packed layout (ivgpt_mega_pack_weight): [tile = n / 16][k-block = k / 64][row = n % 16][chunk ^ (row & 7)][8 bf16]
-__device__ __forceinline__ void issue_slab(MegaCtx& c, const __nv_bfloat16* packed, int K, int tile, int k0, int Kc) {
-  const uint32_t buf = c.issued % c.sm.nbuf;
-  ++c.issued;
-  const uint32_t bytes = (uint32_t)Kc * (MEGA_BN * 2);
-  mbar_expect_tx(c.sm.bfull + buf, bytes);
-  bulk_g2s(c.sm.b0 + (size_t)buf * c.sm.slab_bytes, packed + ((size_t)tile * K + k0) * MEGA_BN, bytes, c.sm.bfull + buf);
-}
+// A phase has its own tile width bn (16 weight rows per item where one round over the SMs covers the matrix; wider for
+// gate/up and lm_head, whose 16-row items needed 3 and 7 rounds of 48 MMA issues each) and with it its own slab size,
+// buffer count and buffer placement: buffer i of the phase sits at slab_off + i * slab_bytes of the operand area, load #j of
+// the phase goes to buffer j % nbuf.  Phases never overlap in time, so the buffers of one phase may alias another's.
+struct GemmPhase;
+__device__ __forceinline__ void issue_slab(MegaCtx& c, const GemmPhase& g, int tile, int k0, int Kc);
 
 // (Until round-1 v10 the activation slab was row-major in global memory and laid out in shared memory by 24 cp.async per
 // thread + wait + __syncthreads: ~2 us per phase, 97 us per step; the bulk copy of a pre-swizzled image costs 24.)
@@ -148,15 +155,25 @@ enum { EPI_STORE_BF16 = 0, EPI_PARTIAL_F32 = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 }
 
 struct GemmPhase {
   const __nv_bfloat16* w;   // packed weights of [N, K]
-  int N, K, ksplits;        // work items = ceil(N/16) * ksplits, item K = K / ksplits
+  int N, K, ksplits;        // work items = ceil(N/bn) * ksplits, item K = K / ksplits
   const __nv_bfloat16* A;
   long long lda;
   int epi;
   void* out;                // bf16 / fp32 destination
   long long ldo;
+  // gemm_mode 0 slab geometry (filled by phase_geometry); gemm_mode 1 ignores it
+  int bn;                   // weight rows per work item (multiple of 16)
+  uint32_t slab_off, slab_bytes, nbuf;
 };
 
-__device__ __forceinline__ int phase_items(const GemmPhase& g) { return ((g.N + MEGA_BN - 1) / MEGA_BN) * g.ksplits; }
+__device__ __forceinline__ int phase_items(const GemmPhase& g) { return ((g.N + g.bn - 1) / g.bn) * g.ksplits; }
+
+__device__ __forceinline__ void issue_slab(MegaCtx& c, const GemmPhase& g, int tile, int k0, int Kc) {
+  const uint32_t buf = (uint32_t)c.phase_issued % g.nbuf;
+  const uint32_t bytes = (uint32_t)Kc * (uint32_t)(g.bn * 2);
+  mbar_expect_tx(c.sm.bfull + buf, bytes);
+  bulk_g2s(c.sm.a + g.slab_off + (size_t)buf * g.slab_bytes, g.w + ((size_t)tile * g.K + k0) * g.bn, bytes, c.sm.bfull + buf);
+}
 
 // issue this CTA's slabs of phase g up to item index `upto` (exclusive), in order
 __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int upto) {
@@ -166,7 +183,7 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
   while (c.phase_issued < upto) {
     const int w = blockIdx.x + c.phase_issued * gridDim.x;
     if (w >= items) break;
-    issue_slab(c, g.w, g.K, w % ntiles, (w / ntiles) * Kc, Kc);
+    issue_slab(c, g, w % ntiles, (w / ntiles) * Kc, Kc);
     ++c.phase_issued;
   }
 }
@@ -175,7 +192,8 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
 __device__ __forceinline__ void prefetch_phase0(MegaCtx& c, const GemmPhase& g) {
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
-  issue_items(c, g, (int)c.sm.nbuf);      // every buffer is free here: the previous GEMM phase has retired
+  c.phase_consumed = 0;
+  issue_items(c, g, (int)g.nbuf);         // every buffer is free here: the previous GEMM phase has retired
 }
 
 template <bool PROF>
@@ -191,7 +209,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
   // whatever its M, i.e. this phase is bound by the NUMBER of tcgen05.mma instructions -- which is why gemm_mode 1 below
   // turns the product around.  TMEM rows of an M = 64 accumulator: row r -> lane 32*(r/16) + r%16.
   const bool m64 = a_rows == 64;
-  const uint32_t IDESC = m64 ? umma_idesc(1, 64, MEGA_BN) : umma_idesc(1, 128, MEGA_BN);
+  const uint32_t IDESC = m64 ? umma_idesc(1, 64, g.bn) : umma_idesc(1, 128, g.bn);
   int loaded_split = -1;
   int it = 0;
   const long long gt_entry = (PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
@@ -205,7 +223,9 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
     bool a_pending = false;
     if (split != loaded_split) {          // (re)load the activation slab for this K range
       if (threadIdx.x == 0) {             // one bulk copy: k-blocks [split*Kc/64, +nkb) of the swizzled image are contiguous
+#ifdef IVG_MEGA_FENCE_ALL
         asm volatile("fence.proxy.async;\n" ::: "memory");
+#endif
         const uint32_t bytes = (uint32_t)(nkb * a_rows * 128);
         mbar_expect_tx(c.sm.abar, bytes);
         bulk_g2s(c.sm.a, g.A + (size_t)((split * Kc) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
@@ -215,18 +235,19 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
     }
     GEMM_MARK(14);
     if (threadIdx.x == 0) {
-      issue_items(c, g, it + (int)c.sm.nbuf);   // this item (if not prefetched) and the following nbuf - 1
-      const uint32_t buf = c.consumed % c.sm.nbuf;
-      const uint32_t par = (c.consumed / c.sm.nbuf) & 1u;
-      ++c.consumed;
+      issue_items(c, g, it + (int)g.nbuf);      // this item (if not prefetched) and the following nbuf - 1
+      const uint32_t buf = (uint32_t)c.phase_consumed % g.nbuf;
+      const uint32_t par = (c.wait_par >> buf) & 1u;
+      c.wait_par ^= 1u << buf;
+      ++c.phase_consumed;
       if (a_pending) { mbar_wait_bounded(p, c.sm.abar, c.aphase, 3); c.aphase ^= 1u; }
       mbar_wait_bounded(p, c.sm.bfull + buf, par, 4);
       tc_fence_after();
       GEMM_MARK(15);
-      const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.b0 + (size_t)buf * c.sm.slab_bytes);
+      const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.a + g.slab_off + (size_t)buf * g.slab_bytes);
       for (int j = 0; j < nkb; ++j) {
         const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
-        const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * MEGA_BN * 128));
+        const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * g.bn * 128));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss<false>(c.tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (j | k) ? 1u : 0u);
@@ -349,7 +370,9 @@ __device__ void gemm_phase_w64(const MegaParams& p, MegaCtx& c, const GemmPhase&
     if (threadIdx.x == 0) {
       bool a_pending = false;
       if (split != loaded_split) {        // this split's K range of the activation image: contiguous k-blocks, one bulk copy
+#ifdef IVG_MEGA_FENCE_ALL
         asm volatile("fence.proxy.async;\n" ::: "memory");
+#endif
         const uint32_t bytes = (uint32_t)((Ks >> 6) * a_rows * 128);
         mbar_expect_tx(c.sm.abar, bytes);
         bulk_g2s(c.sm.a, g.A + (size_t)((split * Ks) >> 6) * (size_t)(a_rows * 64), bytes, c.sm.abar);
@@ -1335,7 +1358,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const bool profiling = PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long tmark = clock64();
 #define MEGA_MARK(slot) do { if (profiling) { const long long _t = clock64(); tprof[slot] += _t - tmark; tmark = _t; } } while (0)
-#define MEGA_BARRIER() do { ok = grid_barrier(p, c); MEGA_MARK(8); } while (0)
+#define MEGA_BARRIER(F) do { ok = grid_barrier<F>(p, c); MEGA_MARK(8); } while (0)
 
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
@@ -1345,7 +1368,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     prefetch_phase<GM>(p, c, qkv_g);
     norm_phase<MAXP>(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
-    MEGA_BARRIER(); if (!ok) break;
+    MEGA_BARRIER(true); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
       const MegaLayer& L = p.lw[l];
       qkv_g.w = L.wqkv;
@@ -1361,7 +1384,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         const AttWork w = att_assign(p, c.sm.a_bytes, warp, pos);
         attention_prefetch(p, l, pos, w, c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT, c.sm.ring_bar + warp * 8);
       }
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(false); if (!ok) break;
       if constexpr (MEGA_THREADS == 256) {
         if constexpr (AM != 1) {
           // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
@@ -1408,20 +1431,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           attention_pair<GM>(p, l, bh, pos, psm, half, pair);
       }
       MEGA_MARK(2);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, o_g);
       MEGA_MARK(3);
       GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
       prefetch_phase<GM>(p, c, gu_g);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(false); if (!ok) break;
       norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
       MEGA_MARK(0);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, gu_g);
       MEGA_MARK(4);
       GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
       prefetch_phase<GM>(p, c, d_g);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, d_g);
       MEGA_MARK(5);
       const bool last = (l == p.layers - 1);
@@ -1429,17 +1452,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                      last ? EPI_LOGITS : (ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16),
                      last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H)};
       prefetch_phase<GM>(p, c, nx_g);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(false); if (!ok) break;
       norm_phase<MAXP>(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
       MEGA_MARK(0);
-      MEGA_BARRIER(); if (!ok) break;
+      MEGA_BARRIER(true); if (!ok) break;
       if (last) {
         gemm_phase<GM, PROF>(p, c, nx_g);                                       // lm_head
         MEGA_MARK(6);
-        MEGA_BARRIER(); if (!ok) break;
+        MEGA_BARRIER(false); if (!ok) break;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) sample_row(p, b, pos, smem_u);
         MEGA_MARK(7);
-        MEGA_BARRIER(); if (!ok) break;
+        MEGA_BARRIER(false); if (!ok) break;
       }
     }
   }
