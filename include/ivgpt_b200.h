@@ -240,12 +240,17 @@ typedef struct ivgpt_mega_desc {
    * attention phase sums them), `qkv` is unused. */
   int gemm_mode, qkv_splits, a_rows;
   void* qkvp;
+  int bn_wide;     /* gemm_mode 0: weight rows per work item of the gate/up and lm_head phases (multiple of 16, <= 64; 0 = 16).
+                      wgu and lm_head must be packed with the same width (ivgpt_mega_pack_weight_bn); wider items cut those
+                      phases from 3 / 7 rounds of 48 tcgen05.mma issues over the SMs to 1 / 3 */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);
 int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv_packed, const void* wo_packed, const void* wgu_packed,
                           const void* wd_packed, const float* n1, const float* n2);
+long long ivgpt_mega_packed_elems_bn(int rows, int cols, int bn);   /* bn weight rows per tile instead of 16 */
+int ivgpt_mega_pack_weight_bn(const void* w, void* out, int rows, int cols, int bn, void* stream);
 long long ivgpt_mega_packed_elems64(int rows, int cols);
 int ivgpt_mega_pack_weight64(const void* w, void* out, int rows, int cols, int swiglu_pairs, void* stream);
 int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream);

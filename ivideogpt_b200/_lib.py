@@ -79,6 +79,7 @@ class MegaDesc(C.Structure):
         ("mma_m64", C.c_int),
         ("gemm_mode", C.c_int), ("qkv_splits", C.c_int), ("a_rows", C.c_int),
         ("qkvp", C.c_void_p),
+        ("bn_wide", C.c_int),
     ]
 
 
@@ -135,12 +136,15 @@ SIGNATURES = {
     "ivgpt_mega_fill_layer": [_P, _P, _P, _P, _P, _P, _P],
     "ivgpt_mega_packed_elems": [_I, _I],
     "ivgpt_mega_pack_weight": [_P, _P, _I, _I, _P],
+    "ivgpt_mega_packed_elems_bn": [_I, _I, _I],
+    "ivgpt_mega_pack_weight_bn": [_P, _P, _I, _I, _I, _P],
     "ivgpt_mega_packed_elems64": [_I, _I],
     "ivgpt_mega_pack_weight64": [_P, _P, _I, _I, _I, _P],
     "ivgpt_decode_mega": [C.POINTER(MegaDesc), _P],
 }
 _RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong,
-             "ivgpt_mega_packed_elems": C.c_longlong, "ivgpt_mega_packed_elems64": C.c_longlong}
+             "ivgpt_mega_packed_elems": C.c_longlong, "ivgpt_mega_packed_elems64": C.c_longlong,
+             "ivgpt_mega_packed_elems_bn": C.c_longlong}
 
 _lib = None
 

@@ -467,7 +467,15 @@ long long ivgpt_mega_packed_elems(int rows, int cols) {
 }
 
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream) {
-  return ivg::mega_pack_weight_launch(w, out, rows, cols, S(stream));
+  return ivg::mega_pack_weight_launch(w, out, rows, cols, ivg::MEGA_BN, S(stream));
+}
+
+long long ivgpt_mega_packed_elems_bn(int rows, int cols, int bn) {
+  return bn > 0 ? (long long)((rows + bn - 1) / bn) * bn * cols : 0;
+}
+
+int ivgpt_mega_pack_weight_bn(const void* w, void* out, int rows, int cols, int bn, void* stream) {
+  return ivg::mega_pack_weight_launch(w, out, rows, cols, bn, S(stream));
 }
 
 long long ivgpt_mega_packed_elems64(int rows, int cols) {
@@ -510,6 +518,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.mma_m64 = 1;
   p.a_bulk = 1;
   IVG_CHECK(d->a_bulk == 1, "decode_mega: a_bulk must be 1 (xn / ao / act are swizzled activation images)");
+  p.bn_wide = d->bn_wide > 0 ? d->bn_wide : ivg::MEGA_BN;
   p.gemm_mode = d->gemm_mode; p.qkv_splits = d->qkv_splits; p.qkvp = (float*)d->qkvp;
   p.a_rows = d->gemm_mode == 0 ? (d->B <= 64 ? 64 : 128) : d->a_rows;
   IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");

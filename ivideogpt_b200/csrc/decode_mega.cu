@@ -261,32 +261,36 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       const int row = m64 ? (lane < 16 ? q * 16 + lane : p.B) : q * 32 + lane;
       mbar_wait_bounded(p, c.sm.mma_done, c.mphase, 5);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16), r);
-      tmem_ld_wait();
-      if (row < p.B) {
-        const int n0 = tile * MEGA_BN;
-        float v[16];
+      for (int c0 = 0; c0 < g.bn; c0 += 16) {          // 16 accumulator columns (weight rows) at a time
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row < p.B) {
+          const int n0 = tile * g.bn + c0;
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (g.epi == EPI_STORE_BF16) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + n0);
-          op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        } else if (g.epi == EPI_PARTIAL_F32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ((size_t)split * p.B + row) * g.ldo + n0);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (g.epi == EPI_STORE_BF16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + n0);
+            op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          } else if (g.epi == EPI_PARTIAL_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ((size_t)split * p.B + row) * g.ldo + n0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else if (g.epi == EPI_SWIGLU) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + a_off(p, row, n0 >> 1, g.ldo));
-          float o[8];
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (g.epi == EPI_SWIGLU) {
+            if (n0 < g.N) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + a_off(p, row, n0 >> 1, g.ldo));
+              float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = silu_f(v[2 * i]) * v[2 * i + 1];
-          op[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-        } else {
-          float* op = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
+              for (int i = 0; i < 8; ++i) o[i] = silu_f(v[2 * i]) * v[2 * i + 1];
+              op[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (n0 + i < g.N) op[i] = v[i];
+            for (int i = 0; i < 16; ++i) if (n0 + i < g.N) op[i] = v[i];
+          }
         }
       }
       tc_fence_before();
@@ -1330,7 +1334,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   c.sm.ring_bar = c.sm.bfull + 16;                                   // 64 barriers, 128 B past the GEMM ones
   c.sm.sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c.sm.bfull) + MEGA_BAR_BYTES);
   uint32_t ring_par = 0;                                             // expected parity per ring slot of this warp
-  c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.mphase = 0; c.aphase = 0;
+  c.epoch = 0; c.issued = 0; c.consumed = 0; c.phase_issued = 0; c.phase_consumed = 0; c.wait_par = 0; c.mphase = 0; c.aphase = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(c.sm.bfull + i, 1);
@@ -1340,7 +1344,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
-  constexpr uint32_t TMEM_COLS = GM == 0 ? 32 : 128;     // accumulator columns: 16 (mode 0) / a_rows <= 128 (mode 1)
+  constexpr uint32_t TMEM_COLS = GM == 0 ? 64 : 128;     // accumulator columns: tile width <= 64 (mode 0) / a_rows <= 128 (mode 1)
   if (warp == 1) { tmem_alloc(c.sm.tmem_holder, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -1363,8 +1367,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   for (int step = 0; step < p.steps && ok; ++step) {
     const int pos = pos0 + step;
     constexpr bool ws = GM != 0;            // weight-stationary GEMM phases: qkv goes through split-K fp32 partials
+    // gemm_mode 0 slab geometry: narrow phases (qkv, o, down: 16-row items, one round over the SMs) keep their buffers above
+    // the largest activation slab; the wide phases (gate/up, lm_head: K = hidden) put theirs right above the K = hidden slab
+    const uint32_t narrow_off = c.sm.a_bytes, narrow_bytes = c.sm.slab_bytes, narrow_nbuf = c.sm.nbuf;
+    const int a_rows0 = p.B <= 64 ? 64 : 128;
+    const uint32_t wide_off = (uint32_t)(a_rows0 * H * 2), wide_bytes = (uint32_t)(p.bn_wide * H * 2);
+    uint32_t wide_nbuf = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - wide_off) / wide_bytes;
+    wide_nbuf = wide_nbuf > 4u ? 4u : wide_nbuf;
     GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, ws ? p.qkv_splits : 1, p.xn, H, ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16,
-                    ws ? (void*)p.qkvp : (void*)p.qkv, 3 * H};
+                    ws ? (void*)p.qkvp : (void*)p.qkv, 3 * H, MEGA_BN, narrow_off, narrow_bytes, narrow_nbuf};
     prefetch_phase<GM>(p, c, qkv_g);
     norm_phase<MAXP>(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
     MEGA_MARK(0);
@@ -1374,7 +1385,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       qkv_g.w = L.wqkv;
       gemm_phase<GM, PROF>(p, c, qkv_g);
       MEGA_MARK(1);
-      GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H};
+      GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H, MEGA_BN, narrow_off, narrow_bytes, narrow_nbuf};
       prefetch_phase<GM>(p, c, o_g);
       const bool ring_prefetch = MEGA_THREADS == 256 && AM == 0 && p.attn_mode == 0 && att_even_deal(p);
       if (ring_prefetch) {
@@ -1434,7 +1445,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, o_g);
       MEGA_MARK(3);
-      GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter};
+      GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter, p.bn_wide, wide_off, wide_bytes, wide_nbuf};
       prefetch_phase<GM>(p, c, gu_g);
       MEGA_BARRIER(false); if (!ok) break;
       norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
@@ -1442,7 +1453,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, gu_g);
       MEGA_MARK(4);
-      GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H};
+      GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H, MEGA_BN, narrow_off, narrow_bytes,
+                    narrow_nbuf};
       prefetch_phase<GM>(p, c, d_g);
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, d_g);
@@ -1450,7 +1462,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const bool last = (l == p.layers - 1);
       GemmPhase nx_g{last ? p.lm_head : p.lw[l + 1].wqkv, last ? p.vocab : 3 * H, H, (ws && !last) ? p.qkv_splits : 1, p.xn, H,
                      last ? EPI_LOGITS : (ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16),
-                     last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H)};
+                     last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H),
+                     last ? p.bn_wide : MEGA_BN, last ? wide_off : narrow_off, last ? wide_bytes : narrow_bytes,
+                     last ? wide_nbuf : narrow_nbuf};
       prefetch_phase<GM>(p, c, nx_g);
       MEGA_BARRIER(false); if (!ok) break;
       norm_phase<MAXP>(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
@@ -1474,17 +1488,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 }
 
 // ---- one-off weight packing: [rows, cols] bf16 row-major -> per 16-row work item the 128B-swizzled K-major image ----
-// out[tile][k-block][row][chunk' = chunk ^ (row & 7)][8]; rows padded with zeros to a multiple of 16.
-__global__ void mega_pack_weight_kernel(const uint4* __restrict__ w, uint4* __restrict__ out, int rows, int cols,
+// out[tile][k-block][row < bn][chunk' = chunk ^ (row & 7)][8]; rows padded with zeros to a multiple of bn (the phase's tile width).
+__global__ void mega_pack_weight_kernel(const uint4* __restrict__ w, uint4* __restrict__ out, int rows, int cols, int bn,
                                         long long chunks) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
     const int cp = (int)(i & 7);
-    const int r = (int)((i >> 3) & 15);
-    const long long jt = i >> 7;
+    const int r = (int)((i >> 3) % bn);
+    const long long jt = (i >> 3) / bn;
     const int nkb = cols >> 6;
     const int j = (int)(jt % nkb);
     const long long tile = jt / nkb;
-    const long long n = tile * 16 + r;
+    const long long n = tile * bn + r;
     const int ch = cp ^ (r & 7);
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (n < rows) v = w[(n * cols + j * 64 + ch * 8) >> 3];
@@ -1492,13 +1506,14 @@ __global__ void mega_pack_weight_kernel(const uint4* __restrict__ w, uint4* __re
   }
 }
 
-int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, cudaStream_t st) {
+int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, int bn, cudaStream_t st) {
   IVG_CHECK(cols % 64 == 0 && rows >= 1, "mega_pack_weight: cols %d must be a multiple of 64", cols);
-  const long long tiles = (rows + MEGA_BN - 1) / MEGA_BN;
-  const long long chunks = tiles * (cols / 64) * 16 * 8;
+  IVG_CHECK(bn >= 16 && bn <= 256 && bn % 16 == 0, "mega_pack_weight: tile width %d must be a multiple of 16 in [16, 256]", bn);
+  const long long tiles = (rows + bn - 1) / bn;
+  const long long chunks = tiles * (cols / 64) * bn * 8;
   const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
   mega_pack_weight_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(w), reinterpret_cast<uint4*>(out), rows,
-                                                  cols, chunks);
+                                                  cols, bn, chunks);
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
@@ -1558,6 +1573,10 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
     IVG_CHECK(p.a_rows == a_rows, "decode_mega: a_rows must be %d in gemm_mode 0", a_rows);
     IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
               "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
+    IVG_CHECK(p.bn_wide >= 16 && p.bn_wide <= 64 && p.bn_wide % 16 == 0 &&
+                  (long long)(a_rows + p.bn_wide) * p.hidden * 2 <= MEGA_A_BYTES + 2 * MEGA_B_BYTES,
+              "decode_mega: wide tile width %d (gate/up, lm_head) must be a multiple of 16 in [16, 64] whose slab fits next to the "
+              "activation slab", p.bn_wide);
   } else {
     IVG_CHECK(p.a_bulk == 1, "decode_mega: gemm_mode 1 needs the swizzled activation images (a_bulk)");
     IVG_CHECK(p.a_rows >= p.B && p.a_rows % 8 == 0 && p.a_rows <= 128, "decode_mega: a_rows %d must be a multiple of 8 in [B, 128]",

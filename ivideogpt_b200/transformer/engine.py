@@ -284,7 +284,20 @@ class LlamaEngine:
         return (pick(3 * w.hidden, w.hidden, 4, ov[0]), pick(w.hidden, w.hidden, 12, ov[1]),
                 pick(w.hidden, w.inter, 12, ov[2]))
 
-    def _mega_tables(self):
+    def _mega_bn_wide(self, B: int, sms: int = 148) -> int:
+        """gemm_mode 0: weight rows per work item of the gate/up and lm_head phases -- the smallest multiple of 16 that covers
+        gate/up in one round over the SMs, capped by what fits in shared memory next to the K = hidden activation slab."""
+        ov = int(getattr(self, "mega_bn_wide", int(os.environ.get("IVGPT_MEGA_BNWIDE", "0"))))
+        w = self.w
+        a_rows = 64 if B <= 64 else 128
+        fit = min(64, (192 * 1024 - a_rows * w.hidden * 2) // (w.hidden * 2) // 16 * 16)
+        if ov:
+            assert ov % 16 == 0 and 16 <= ov <= fit, f"mega_bn_wide {ov} does not fit (max {fit})"
+            return ov
+        want = next((bn for bn in (16, 32, 48, 64) if -(-2 * w.inter // bn) <= sms), 64)
+        return max(16, min(fit, want))
+
+    def _mega_tables(self, bn_wide: int = 16):
         """Packed weight copies (swizzled slab images: 16 rows per work item in mode 0, ivgpt_mega_pack_weight; 64 rows in
         the weight-stationary mode 1, ivgpt_mega_pack_weight64) and the device-resident array of per-layer pointer
         records, built once per engine and mode."""
@@ -292,8 +305,9 @@ class LlamaEngine:
         cache = getattr(self, "_mega_dev", None)
         if cache is None:
             cache = self._mega_dev = {}
-        if mode in cache:
-            return cache[mode]
+        key = (mode, bn_wide if mode == 0 else 0)
+        if key in cache:
+            return cache[key]
         import ctypes as C
         from .. import _lib
         lib = _lib.load()
@@ -301,10 +315,14 @@ class LlamaEngine:
         dev = w.embed.device
         keep = []
 
-        def pack(t, swiglu_pairs=0):
+        def pack(t, swiglu_pairs=0, bn=16):
             rows, cols = t.shape
             assert t.dtype == torch.bfloat16 and t.is_contiguous()
-            if mode == 1:
+            if mode == 0 and bn != 16:
+                out = torch.empty(int(lib.ivgpt_mega_packed_elems_bn(rows, cols, bn)), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.ivgpt_mega_pack_weight_bn(t.data_ptr(), out.data_ptr(), rows, cols, bn, ops._stream()),
+                           "mega_pack_weight_bn")
+            elif mode == 1:
                 out = torch.empty(int(lib.ivgpt_mega_packed_elems64(rows, cols)), dtype=torch.bfloat16, device=dev)
                 _lib.check(lib.ivgpt_mega_pack_weight64(t.data_ptr(), out.data_ptr(), rows, cols, swiglu_pairs, ops._stream()),
                            "mega_pack_weight64")
@@ -319,22 +337,23 @@ class LlamaEngine:
         host = (C.c_uint8 * (nbytes * w.layers_n + 64))()
         base_al = (C.addressof(host) + 63) // 64 * 64
         for i, lw in enumerate(w.layers):
-            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"], 1),
+            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"], 1, bn_wide),
                                                  pack(lw["wd"]), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
                        "mega_fill_layer")
-        lm_head = pack(w.lm_head)
+        lm_head = pack(w.lm_head, 0, bn_wide)
         raw = bytes((C.c_uint8 * (nbytes * w.layers_n)).from_address(base_al))
         tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        cache[mode] = (tab, lm_head, keep)
-        return cache[mode]
+        cache[key] = (tab, lm_head, keep)
+        return cache[key]
 
     def _decode_mega(self, B, Lmax, tokens, dpos, sample_cfg, dseed, steps, slot=None):
         import ctypes as C
         from .. import _lib
         w = self.w
         h = w.hidden
-        dev_tab, lm_head_packed, _ = self._mega_tables()
         mode = self.mega_mode()
+        bn_wide = self._mega_bn_wide(B) if mode == 0 else 16
+        dev_tab, lm_head_packed, _ = self._mega_tables(bn_wide)
         if mode == 1:
             q_s, o_s, d_s = self._mega_splits64()
         else:
@@ -351,7 +370,7 @@ class LlamaEngine:
         d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
         # rows of the swizzled activation images: the MMA's N in the weight-stationary mode, 64 / 128 MMA rows in mode 0
         a_rows = (B + 7) // 8 * 8 if mode == 1 else (64 if B <= 64 else 128)
-        d.gemm_mode, d.qkv_splits, d.a_rows = mode, q_s, a_rows
+        d.gemm_mode, d.qkv_splits, d.a_rows, d.bn_wide = mode, q_s, a_rows, bn_wide
         if mode == 1:
             d.qkvp = self.buf("mega_qkvp", (q_s, B, 3 * h), torch.float32).data_ptr()
         d.xn = self.buf("mega_xn", (a_rows, h), self.dtype).data_ptr()

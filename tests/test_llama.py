@@ -154,6 +154,28 @@ def test_decode_megakernel_matches_multikernel_path(cuda, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bn_wide,hidden,inter,B", [(48, 192, 768, 5), (32, 128, 256, 64), (64, 192, 768, 33), (48, 768, 3072, 16)])
+def test_decode_megakernel_wide_tiles(cuda, bn_wide, hidden, inter, B):
+    """gemm_mode 0 with wide work items (bn_wide weight rows instead of 16) in the gate/up and lm_head phases: own slab
+    geometry, several 16-column accumulator blocks per item, partial last tiles (vocab 1026 and 2*inter not multiples of 48)."""
+    from oracle.llama_ref import TINY_LLAMA
+    cfg = dict(TINY_LLAMA, hidden_size=hidden, intermediate_size=inter, num_attention_heads=hidden // 64,
+               num_key_value_heads=hidden // 64)
+    ref, mine = _pair(cfg, cuda, torch.bfloat16, scale=3.0)
+    ids = torch.randint(0, 1026, (B, 30), generator=torch.Generator().manual_seed(3)).to(cuda)
+    eng = mine.b200_engine()
+    eng.mega_gemm_mode = 0
+    outs = []
+    for bn in (16, bn_wide):
+        eng.mega_bn_wide = bn
+        outs.append((eng.generate(ids, None, 14, False, 0, 1.0, 0, use_mega=True),
+                     eng.generate(ids, None, 14, True, 20, 1.0, 5, use_mega=True)))
+    # same products, same per-element summation order: identical rollouts, greedy and seeded sampling
+    assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] != outs[1][0]).nonzero()[:5]
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("hidden,inter,heads,B,L,new", [
     (128, 256, 2, 64, 50, 14),     # one k-block per split, full batch
     (512, 1024, 8, 33, 21, 12),    # gate/up and lm_head stream K in two 256-wide slabs; batch not a multiple of 8

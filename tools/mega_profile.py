@@ -1,5 +1,6 @@
 """Phase breakdown of the persistent decode megakernel (cycle counters of CTA 0) + wall time per operand-path variant.
-VARIANTS env: comma list of gemm_mode:m64:bulk[:attn_mode[:qkv_splits:o_splits:d_splits]], default "0:1:1,1:1:1"."""
+VARIANTS env: comma list of gemm_mode:bn_wide:unused[:attn_mode[:qkv_splits:o_splits:d_splits]] (bn_wide 0/1 = automatic),
+default "0:0:1"."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,12 +25,13 @@ if os.environ.get("WITH_GRAPH", "0") == "1":
         eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=False)
     a.record(); eng.generate(ids, None, new, True, 100, 1.0, 1, use_mega=False); b.record(); torch.cuda.synchronize()
     res["graph_generate_ms"] = a.elapsed_time(b)
-for spec in os.environ.get("VARIANTS", "0:1:1,1:1:1").split(","):
+for spec in os.environ.get("VARIANTS", "0:0:1").split(","):
     f = [int(v) for v in spec.split(":")]
-    eng.mega_gemm_mode, eng.mega_m64, eng.mega_a_bulk = f[0], f[1], f[2]
+    eng.mega_gemm_mode = f[0]
+    eng.mega_bn_wide = f[1] if f[1] >= 16 else 0
     eng.mega_attn_mode = f[3] if len(f) > 3 else 0
     eng.mega_splits_override = tuple(f[4:7]) if len(f) >= 7 else None
-    tag = f"gemm={f[0]},m64={f[1]},a_bulk={f[2]},attn={eng.mega_attn_mode},splits={eng.mega_splits_override}"
+    tag = f"gemm={f[0]},bn_wide={eng.mega_bn_wide or 'auto'},attn={eng.mega_attn_mode},splits={eng.mega_splits_override}"
     PROFILE = os.environ.get("PHASES", "1") == "1"
     eng.mega_profile = False
     try:
