@@ -245,12 +245,15 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       tc_fence_after();
       GEMM_MARK(15);
       const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.a + g.slab_off + (size_t)buf * g.slab_bytes);
+      // MEGA_NACC independent accumulators, k-step t -> accumulator t % MEGA_NACC (64 TMEM columns apart), summed in a fixed
+      // order by the epilogue: consecutive MMAs no longer form one dependent chain on a single accumulator
       for (int j = 0; j < nkb; ++j) {
         const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
         const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * g.bn * 128));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss<false>(c.tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (j | k) ? 1u : 0u);
+          umma_ss<false>(c.tmem_base + (uint32_t)(((j * 4 + k) % MEGA_NACC) * 64), adesc + (uint64_t)(k * 2),
+                         bdesc + (uint64_t)(k * 2), IDESC, (j * 4 + k) >= MEGA_NACC ? 1u : 0u);
       }
       umma_commit(c.sm.mma_done);
       GEMM_MARK(16);
@@ -265,11 +268,18 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
         uint32_t r[16];
         tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+        for (int a = 1; a < MEGA_NACC; ++a) {              // K >= 64 per item: every accumulator has been written
+          tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c0), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+        }
         if (row < p.B) {
           const int n0 = tile * g.bn + c0;
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
           if (g.epi == EPI_STORE_BF16) {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + n0);
             op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -1344,7 +1354,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);
     fence_barrier_init();
   }
-  constexpr uint32_t TMEM_COLS = GM == 0 ? 64 : 128;     // accumulator columns: tile width <= 64 (mode 0) / a_rows <= 128 (mode 1)
+  constexpr uint32_t TMEM_COLS = GM == 0 ? (MEGA_NACC <= 1 ? 64 : (MEGA_NACC == 2 ? 128 : 256)) : 128;   // mode 0: MEGA_NACC accumulators of <= 64 columns; mode 1: a_rows <= 128
   if (warp == 1) { tmem_alloc(c.sm.tmem_holder, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();

@@ -6,6 +6,10 @@ namespace ivg {
 
 constexpr int MEGA_THREADS = 256;   // 256: one warp per attention item (fastest measured); 512: warp pairs
 constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
+#ifndef IVG_MEGA_NACC
+#define IVG_MEGA_NACC 1
+#endif
+constexpr int MEGA_NACC = IVG_MEGA_NACC;    // gemm_mode 0: independent TMEM accumulators per work item (1, 2 or 4), k-steps dealt round-robin
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
 constexpr int MEGA_B_BYTES = MEGA_BN * MEGA_MAXK * 2;   // 32 KB per slab

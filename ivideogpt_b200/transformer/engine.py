@@ -285,8 +285,8 @@ class LlamaEngine:
                 pick(w.hidden, w.inter, 12, ov[2]))
 
     def _mega_bn_wide(self, B: int, sms: int = 148) -> int:
-        """gemm_mode 0: weight rows per work item of the gate/up and lm_head phases -- the smallest multiple of 16 that covers
-        gate/up in one round over the SMs, capped by what fits in shared memory next to the K = hidden activation slab."""
+        """gemm_mode 0: weight rows per work item of the gate/up and lm_head phases (a multiple of 16): as wide as
+        what fits in shared memory next to the K = hidden activation slab (at most 64)."""
         ov = int(getattr(self, "mega_bn_wide", int(os.environ.get("IVGPT_MEGA_BNWIDE", "0"))))
         w = self.w
         a_rows = 64 if B <= 64 else 128
@@ -294,8 +294,11 @@ class LlamaEngine:
         if ov:
             assert ov % 16 == 0 and 16 <= ov <= fit, f"mega_bn_wide {ov} does not fit (max {fit})"
             return ov
-        want = next((bn for bn in (16, 32, 48, 64) if -(-2 * w.inter // bn) <= sms), 64)
-        return max(16, min(fit, want))
+        if -(-2 * w.inter // 16) <= sms:      # gate/up already is one round of 16-row items: nothing to gain
+            return 16
+        # the widest that fits: same-box A/B at B=64, hidden 768 (profiles/r01/mega_build_variants_ab4_wide_tiles.txt):
+        # 16 -> 228.2 ms per rollout, 32 -> 220.9, 48 -> 215.5, 64 -> 213.7 (96 gate/up items, 2 lm_head rounds)
+        return max(16, fit)
 
     def _mega_tables(self, bn_wide: int = 16):
         """Packed weight copies (swizzled slab images: 16 rows per work item in mode 0, ivgpt_mega_pack_weight; 64 rows in
