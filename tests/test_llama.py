@@ -272,3 +272,30 @@ def test_training_with_bucketed_grad_reducer_matches_plain_backward(cuda):
             assert torch.allclose(p.grad, plain[n], rtol=1e-3, atol=1e-6), n
         else:
             assert torch.equal(p.grad, plain[n]), n
+
+
+def test_megakernel_host_geometry_for_the_baseline_configs():
+    """CPU: split-K factors, wide-tile width and shared-memory budget the engine derives for the BASELINE.json transformer
+    configs (138M at B=64 / B=16, 436M at B=32) -- the constraints ivgpt_decode_mega checks on the device side."""
+    from types import SimpleNamespace
+    from ivideogpt_b200.transformer.engine import LlamaEngine
+    for hidden, inter, heads, layers, B, want_bn in ((768, 3072, 12, 12, 64, 64), (768, 3072, 12, 12, 16, 64),
+                                                     (1024, 4096, 16, 24, 32, 32)):
+        w = SimpleNamespace(hidden=hidden, inter=inter, heads=heads, layers_n=layers, vocab=16386, dtype=torch.bfloat16,
+                            embed=torch.zeros(1))
+        eng = LlamaEngine(w)
+        eng.mega_gemm_mode = 0
+        o_s, d_s = eng._mega_splits()
+        a_rows = 64
+        assert hidden % (64 * o_s) == 0 and inter % (64 * d_s) == 0 and inter // d_s <= 1024
+        assert a_rows * max(hidden, inter // d_s) * 2 <= 128 * 1024                      # activation slab
+        bn = eng._mega_bn_wide(B)
+        assert bn == want_bn and bn % 16 == 0 and (a_rows + bn) * hidden * 2 <= 192 * 1024   # wide slab next to the K=hidden slab
+        assert eng.mega_supported(B, 752)
+        eng.mega_gemm_mode = 1
+        q_s, o_s, d_s = eng._mega_splits64()
+        for rows, K, s in ((3 * hidden, hidden, q_s), (hidden, hidden, o_s), (hidden, inter, d_s)):
+            assert K % (64 * s) == 0 and ((rows + 63) // 64) * s <= 148 and s <= 12
+        assert q_s <= 4 and eng.mega_supported(B, 752) and not eng.mega_supported(100, 752)
+    eng.dtype = torch.float32
+    assert not eng.mega_supported(64, 752)          # the TF32 parity path keeps the multi-kernel CUDA-graph step
