@@ -980,141 +980,8 @@ __device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, 
   attention_store(p, bh, o, 1.0f / L);
 }
 
-// ---- RoPE + KV append + attention over the cache: a PAIR of warps per (b, head) item ----
-// v1 gave each item a whole CTA: with one CTA per SM an item's loads form a latency chain (~10 us/item, 2.5 TB/s).
-// v2 used one warp per item (6 of 8 warps busy).  v3: 16 warps per CTA, each item split along the sequence between two
-// warps (flash-decoding style partial softmax, combined through shared memory): ~11 warps per SM keep 12-16
-// independent 16-byte loads per lane in flight.  Arithmetic per position equals decode_attn_fused_kernel.
-constexpr int ATT_QB = 12;    // K rows in flight per 8-lane group (4 rows per pass)
-constexpr int ATT_DB = 8;     // V^T rows in flight per lane (register budget: 128 / thread at 512 threads)
-constexpr int ATT_WS = 64 + 64 + 4;   // per-pair combine scratch: acc[2][64] ... laid out as [half][66]
-
-__device__ __forceinline__ void pair_barrier(int pair) {   // named barrier 1 + pair, 64 threads
-  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
-}
-
-template <int GM>
-__device__ void attention_pair(const MegaParams& p, int layer, int bh, int pos, float* psm, int half, int pair) {
-  // psm: per-PAIR scratch: sc[Lmax + 16] | q[64] | comb[2][66]
-  const int heads = p.heads, Lmax = p.Lmax, Hd = p.hidden;
-  const int Lcur = pos + 1;
-  const int Lh = min(Lcur, ((Lcur / 2 + 7) / 8) * 8);          // split point, multiple of 8 (vector loads on V^T)
-  const int lbeg = half == 0 ? 0 : Lh, lend = half == 0 ? Lh : Lcur;
-  float* sc = psm;
-  float* qs = psm + Lmax + 16;
-  float* comb = qs + 64;                                        // [2][66]: m, s, acc[64]
-  const int b = bh / heads, hh = bh - b * heads;
-  const int lane = threadIdx.x & 31;
-  __nv_bfloat16* kslab = p.kcache + ((size_t)layer * p.B * heads + bh) * Lmax * 64;
-  __nv_bfloat16* vslab = p.vcache + ((size_t)layer * p.B * heads + bh) * 64 * Lmax;
-  if (half == 1) {   // the warp that owns position `pos` appends K/V (it is the one that reads them back) and stages q
-    const float cs = __ldg(p.cos_tab + (size_t)pos * 32 + lane), sn = __ldg(p.sin_tab + (size_t)pos * 32 + lane);
-    const float q0 = qkv_in<GM>(p, b, hh * 64 + lane), q1 = qkv_in<GM>(p, b, hh * 64 + lane + 32);
-    const float k0 = qkv_in<GM>(p, b, Hd + hh * 64 + lane), k1 = qkv_in<GM>(p, b, Hd + hh * 64 + lane + 32);
-    const __nv_bfloat16 v0 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane));
-    const __nv_bfloat16 v1 = __float2bfloat16_rn(qkv_in<GM>(p, b, 2 * Hd + hh * 64 + lane + 32));
-    qs[lane] = __bfloat162float(__float2bfloat16_rn(q0 * cs - q1 * sn)) * 0.125f;
-    qs[lane + 32] = __bfloat162float(__float2bfloat16_rn(q1 * cs + q0 * sn)) * 0.125f;
-    kslab[(size_t)pos * 64 + lane] = __float2bfloat16_rn(k0 * cs - k1 * sn);
-    kslab[(size_t)pos * 64 + lane + 32] = __float2bfloat16_rn(k1 * cs + k0 * sn);
-    vslab[(size_t)lane * Lmax + pos] = v0;
-    vslab[(size_t)(lane + 32) * Lmax + pos] = v1;
-  }
-  pair_barrier(pair);                 // q visible to both warps; K/V writes ordered before the owner warp's reads
-  const int sub = lane & 7, rslot = lane >> 3;
-  float qreg[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qreg[i] = qs[sub * 8 + i];
-  float mx = -INFINITY;
-  for (int l0 = lbeg; l0 < lend; l0 += 4 * ATT_QB) {
-    uint4 kv[ATT_QB];
-#pragma unroll
-    for (int u = 0; u < ATT_QB; ++u) {
-      const int l = l0 + u * 4 + rslot;
-      kv[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (l < lend) kv[u] = ldg_cg_v4(kslab + (size_t)l * 64 + sub * 8);
-    }
-#pragma unroll
-    for (int u = 0; u < ATT_QB; ++u) {
-      const int l = l0 + u * 4 + rslot;
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
-      float part = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h2[i]);
-        part = fmaf(qreg[2 * i], f.x, part);
-        part = fmaf(qreg[2 * i + 1], f.y, part);
-      }
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (l < lend) {
-        mx = fmaxf(mx, part);
-        if (sub == 0) sc[l] = part;
-      }
-    }
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  __syncwarp();
-  float sum = 0.f;
-  const int lend8 = half == 0 ? lend : lend + 8;                // owner of the tail clears 8 entries past Lcur
-  for (int l = lbeg + lane; l < lend8; l += 32) {
-    const float e = l < lend ? __expf(sc[l] - mx) : 0.f;
-    sc[l] = e;
-    sum += e;
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  __syncwarp();
-  float* my = comb + half * 66;
-  if (lane == 0) { my[0] = mx; my[1] = sum; }
-  for (int d0 = 0; d0 < 64; d0 += ATT_DB) {
-    float acc[ATT_DB];
-#pragma unroll
-    for (int r = 0; r < ATT_DB; ++r) acc[r] = 0.f;
-    for (int l = lbeg + lane * 8; l < lend; l += 256) {
-      uint4 vv[ATT_DB];
-#pragma unroll
-      for (int r = 0; r < ATT_DB; ++r) vv[r] = ldg_cg_v4(vslab + (size_t)(d0 + r) * Lmax + l);
-      float pr[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pr[i] = sc[l + i];
-      const int nvalid = lend - l;    // beyond the range: other half's entries / uninitialised cache -> select, never multiply
-#pragma unroll
-      for (int r = 0; r < ATT_DB; ++r) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[r]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h2[i]);
-          acc[r] += (2 * i < nvalid) ? pr[2 * i] * f.x : 0.f;
-          acc[r] += (2 * i + 1 < nvalid) ? pr[2 * i + 1] * f.y : 0.f;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < ATT_DB; ++r) {
-      float a = acc[r];
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == r) my[2 + d0 + r] = a;
-    }
-  }
-  pair_barrier(pair);
-  if (half == 0) {                    // combine the two partial softmaxes: lanes own output dims lane, lane + 32
-    const float m0 = comb[0], s0 = comb[1], m1 = comb[66], s1 = comb[67];
-    const float M = fmaxf(m0, m1);
-    const float e0 = (s0 > 0.f) ? __expf(m0 - M) : 0.f, e1 = (s1 > 0.f) ? __expf(m1 - M) : 0.f;
-    const float inv = 1.0f / (s0 * e0 + s1 * e1);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int d = lane + 32 * k;
-      const float o = (comb[2 + d] * e0 + comb[66 + 2 + d] * e1) * inv;
-      p.ao[a_off(p, b, hh * 64 + d, Hd)] = __float2bfloat16_rn(o);
-    }
-  }
-  pair_barrier(pair);                 // scratch reusable by the pair's next item
-}
+// (History: v3 ran 512 threads with a PAIR of warps per item, flash-decoding style halves combined through shared memory:
+// 55 us per layer against 51-53 for one warp per item; removed.)
 
 // ---- sampling of one logits row by one CTA (argmax, or top-k radix select + inverse CDF as topk_sample_kernel) ----
 __device__ __forceinline__ uint32_t mega_fkey(float f) {
@@ -1363,7 +1230,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   const int H = p.hidden;
   const int pos0 = *p.dpos;
-  float* smem_f = reinterpret_cast<float*>(c.sm.a);
   uint32_t* smem_u = reinterpret_cast<uint32_t*>(c.sm.a);
   bool ok = true;
   // phase timing (CTA 0, thread 0): slots 0 norm, 1 qkv, 2 attention, 3 o-proj, 4 gate/up, 5 down, 6 lm_head,
@@ -1397,7 +1263,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H, MEGA_BN, narrow_off, narrow_bytes, narrow_nbuf};
       prefetch_phase<GM>(p, c, o_g);
-      const bool ring_prefetch = MEGA_THREADS == 256 && AM == 0 && p.attn_mode == 0 && att_even_deal(p);
+      const bool ring_prefetch = AM == 0 && p.attn_mode == 0 && att_even_deal(p);
       if (ring_prefetch) {
         // the activation slab is dead (this CTA's MMAs have retired): start filling the attention ring with old K/V rows.
         // The region was last written through the generic proxy (cp.async), the copies below are async-proxy writes.
@@ -1406,7 +1272,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         attention_prefetch(p, l, pos, w, c.sm.a + (size_t)warp * w.nslot * MEGA_RING_SLOT, c.sm.ring_bar + warp * 8);
       }
       MEGA_BARRIER(false); if (!ok) break;
-      if constexpr (MEGA_THREADS == 256) {
+      static_assert(MEGA_THREADS == 256, "the attention phase deals one warp per item over 8 warps");
+      {
         if constexpr (AM != 1) {
           // the ring lives in the activation region, last written through the generic proxy (cp.async / scratch)
           fence_proxy_async();
@@ -1445,11 +1312,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           for (int bh = blockIdx.x + (int)gridDim.x * warp; bh < p.B * p.heads; bh += (int)gridDim.x * (MEGA_THREADS / 32))
             attention_warp<GM>(p, l, bh, pos, c.sm.sc + (size_t)warp * (p.Lmax + 8 + 64));
         }
-      } else {
-        const int pair = warp >> 1, half = warp & 1, npairs = MEGA_THREADS / 64;
-        float* psm = smem_f + (size_t)pair * (p.Lmax + 16 + 64 + 2 * 66);
-        for (int bh = blockIdx.x + (int)gridDim.x * pair; bh < p.B * p.heads; bh += (int)gridDim.x * npairs)
-          attention_pair<GM>(p, l, bh, pos, psm, half, pair);
       }
       MEGA_MARK(2);
       MEGA_BARRIER(true); if (!ok) break;
@@ -1599,8 +1461,7 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
     IVG_CHECK(a_floor + 2 * MEGA_WM * MEGA_W_CHUNK * 2 <= MEGA_A_BYTES + 2 * MEGA_B_BYTES,
               "decode_mega: batch %d with K %d leaves no room for two weight slabs", p.B, p.hidden);
   }
-  IVG_CHECK((size_t)(p.Lmax + 16 + 64 + 2 * 66) * 4 * (MEGA_THREADS / 64) <= MEGA_A_BYTES &&
-                (size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
+  IVG_CHECK((size_t)(p.Lmax + 8 + 64) * 4 * (MEGA_THREADS / 32) <= MEGA_SC_BYTES && (size_t)(p.vocab + 256) * 4 <= MEGA_A_BYTES,
             "decode_mega: Lmax/vocab too large for the scratch region");
   IVG_CHECK(p.Lmax % 8 == 0, "decode_mega: Lmax must be a multiple of 8");
   // one instantiation per (GEMM mode, attention mode, profiling): the timed kernels carry no timing code at all (cycle
