@@ -28,7 +28,9 @@ def _worker(rank, world, port, out, min_bytes):
     for names in ORDER:
         red.on_grads(grads, names)
     red.finish(grads)
-    out.put((rank, {k: v.clone() for k, v in grads.items()}, red.buckets_launched))
+    # numpy, not tensors: a tensor travels through the queue as a shared-memory handle served by THIS process, which may
+    # have exited before the parent opens it
+    out.put((rank, {k: v.numpy().copy() for k, v in grads.items()}, red.buckets_launched))
     dist.destroy_process_group()
 
 
@@ -52,7 +54,7 @@ def test_bucketed_reducer_equals_plain_sum_gloo():
             assert buckets == nb
             assert set(got) == set(want)
             for k in want:
-                assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), (rank, k)
+                assert tuple(got[k].shape) == tuple(want[k].shape) and torch.equal(torch.from_numpy(got[k]), want[k]), (rank, k)
 
 
 def test_reducer_single_process_is_identity():
