@@ -39,19 +39,24 @@ __device__ __forceinline__ void gn_store(T* p, const float (&f)[16 / sizeof(T)])
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+constexpr int GN_PART_ROWS = 256;  // pixels per CTA of the stand-alone statistics pass (64 KB of bf16 at C = 128)
+
 template <typename T>
 __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int rows, int C, int G,
                                   int slabs) {
   // grid: (slabs, N), 256 threads = (C/VN channel vectors) x (row lanes).  part layout [N][slabs][G][2].
-  // Bit-reproducible: per-thread channel sums go to shared memory and every group is reduced by ONE thread in a fixed
-  // order (the atomics of the first vectorised version made the statistics differ in the last ulp from run to run, and
-  // ~40 TF32 layers amplified that to 4e-3 in pixel space -- caught by the batch-independence test).
+  // Bit-reproducible: per-thread channel sums go to shared memory and are reduced in a fixed order (the atomics of the
+  // first vectorised version made the statistics differ in the last ulp from run to run, and ~40 TF32 layers amplified
+  // that to 4e-3 in pixel space -- caught by the batch-independence test).
+  // Round-1 v2: 256-row slabs with four 16-byte loads in flight per thread and a two-stage reduction (channel over row
+  // lanes by C threads, then group over its channels) -- the 64-row version with a 64-step single-thread tail per group
+  // streamed at ~1.9 TB/s (profiles/r01/launches_cfg64_v9.txt).
   constexpr int VN = GnVec<T>::N;
-  extern __shared__ float gn_sm[];  // [rlanes][C][2]
+  extern __shared__ float gn_sm[];  // [rlanes][C][2], then [C][2] reduced over the row lanes (aliases lane 0)
   const int n = blockIdx.y, slab = blockIdx.x;
   const int cpg = C / G;
-  const int r0 = slab * GN_SLAB_ROWS;
-  const int r1 = min(rows, r0 + GN_SLAB_ROWS);
+  const int r0 = slab * GN_PART_ROWS;
+  const int r1 = min(rows, r0 + GN_PART_ROWS);
   const T* base = x + ((size_t)n * rows) * C;
   const int cvecs = C / VN;
   const int rlanes = blockDim.x / cvecs;          // >= 1 (C/VN <= 256)
@@ -60,7 +65,22 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
     float s[VN], q[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    for (int r = r0 + rl; r < r1; r += rlanes) {
+    int r = r0 + rl;
+    for (; r + 3 * rlanes < r1; r += 4 * rlanes) {          // four independent loads, then the (ordered) accumulation
+      float f0[VN], f1[VN], f2[VN], f3[VN];
+      gn_load<T>(base + (size_t)r * C + cv * VN, f0);
+      gn_load<T>(base + (size_t)(r + rlanes) * C + cv * VN, f1);
+      gn_load<T>(base + (size_t)(r + 2 * rlanes) * C + cv * VN, f2);
+      gn_load<T>(base + (size_t)(r + 3 * rlanes) * C + cv * VN, f3);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        s[i] += f0[i]; q[i] = fmaf(f0[i], f0[i], q[i]);
+        s[i] += f1[i]; q[i] = fmaf(f1[i], f1[i], q[i]);
+        s[i] += f2[i]; q[i] = fmaf(f2[i], f2[i], q[i]);
+        s[i] += f3[i]; q[i] = fmaf(f3[i], f3[i], q[i]);
+      }
+    }
+    for (; r < r1; r += rlanes) {
       float f[VN];
       gn_load<T>(base + (size_t)r * C + cv * VN, f);
 #pragma unroll
@@ -71,14 +91,23 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
     for (int i = 0; i < VN; ++i) { dst[2 * i] = s[i]; dst[2 * i + 1] = q[i]; }
   }
   __syncthreads();
-  if ((int)threadIdx.x < G) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {      // stage 1: channel c over the row lanes, fixed order
+    float ss = 0.f, qq = 0.f;
+    for (int l = 0; l < rlanes; ++l) {
+      ss += gn_sm[((size_t)l * C + c) * 2];
+      qq += gn_sm[((size_t)l * C + c) * 2 + 1];
+    }
+    gn_sm[(size_t)c * 2] = ss;                              // lane 0's slot of channel c: only this thread touches it
+    gn_sm[(size_t)c * 2 + 1] = qq;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < G) {                               // stage 2: group over its channels, fixed order
     const int g = threadIdx.x;
     float ss = 0.f, qq = 0.f;
-    for (int l = 0; l < rlanes; ++l)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ss += gn_sm[((size_t)l * C + c) * 2];
-        qq += gn_sm[((size_t)l * C + c) * 2 + 1];
-      }
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      ss += gn_sm[(size_t)c * 2];
+      qq += gn_sm[(size_t)c * 2 + 1];
+    }
     float* o = part + (((size_t)n * slabs + slab) * G + g) * 2;
     o[0] = ss; o[1] = qq;
   }
@@ -123,42 +152,63 @@ __global__ void gn_coeff_kernel(const float* __restrict__ stats, const float* __
   shift[i] = beta[c] - st[0] * sc;
 }
 
-// y = x * scale + shift ; optional SiLU ; optional + pos[(row % pos_rows)][C].  16 bytes per thread.
+// y = x * scale + shift ; optional SiLU ; optional + pos[(row % pos_rows)][C].
+// grid (row chunks, samples); a thread owns ONE 16-byte channel vector (its scale / shift live in registers) and walks the
+// chunk's rows with four loads in flight.  (Round-1 v1 was a flat grid-stride loop with two 64-bit divisions and four
+// coefficient loads per 16 bytes: ~2.8 TB/s on the decoder tensors.)
+constexpr int GN_APPLY_ROWS = 256;
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const float* __restrict__ pos, long long total_rows,
-                                int rows_per_sample, int C, int silu, int pos_rows) {
+                                const float* __restrict__ shift, const float* __restrict__ pos, int rows_per_sample, int C,
+                                int silu, int pos_rows) {
   constexpr int VN = GnVec<T>::N;
   const int vecC = C / VN;
-  const long long total = total_rows * vecC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / vecC;
-    const int c = (int)(i - row * vecC) * VN;
-    const int n = (int)(row / rows_per_sample);
-    float f[VN];
-    gn_load<T>(x + row * C + c, f);
-    const float4* sc4 = reinterpret_cast<const float4*>(scale + (size_t)n * C + c);
-    const float4* sh4 = reinterpret_cast<const float4*>(shift + (size_t)n * C + c);
+  const int rlanes = blockDim.x / vecC;
+  const int cv = threadIdx.x % vecC, rl = threadIdx.x / vecC;
+  if (rl >= rlanes) return;
+  const int n = blockIdx.y;
+  const int c = cv * VN;
+  float sc[VN], sh[VN];
 #pragma unroll
-    for (int k = 0; k < VN / 4; ++k) {
-      const float4 a = __ldg(sc4 + k), b = __ldg(sh4 + k);
-      f[4 * k] = fmaf(f[4 * k], a.x, b.x); f[4 * k + 1] = fmaf(f[4 * k + 1], a.y, b.y);
-      f[4 * k + 2] = fmaf(f[4 * k + 2], a.z, b.z); f[4 * k + 3] = fmaf(f[4 * k + 3], a.w, b.w);
-    }
+  for (int k = 0; k < VN / 4; ++k) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * C + c) + k);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * C + c) + k);
+    sc[4 * k] = a.x; sc[4 * k + 1] = a.y; sc[4 * k + 2] = a.z; sc[4 * k + 3] = a.w;
+    sh[4 * k] = b.x; sh[4 * k + 1] = b.y; sh[4 * k + 2] = b.z; sh[4 * k + 3] = b.w;
+  }
+  const int r0 = blockIdx.x * GN_APPLY_ROWS;
+  const int r1 = min(rows_per_sample, r0 + GN_APPLY_ROWS);
+  const size_t sbase = (size_t)n * rows_per_sample;
+  auto finish = [&](float (&f)[VN], int r) {
+#pragma unroll
+    for (int k = 0; k < VN; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
     if (silu) {
 #pragma unroll
       for (int k = 0; k < VN; ++k) f[k] = silu_f(f[k]);
     }
     if (pos) {
-      const float4* pr = reinterpret_cast<const float4*>(pos + (row % pos_rows) * C + c);
+      const float4* pr = reinterpret_cast<const float4*>(pos + ((sbase + r) % pos_rows) * C + c);
 #pragma unroll
       for (int k = 0; k < VN / 4; ++k) {
         const float4 a = __ldg(pr + k);
         f[4 * k] += a.x; f[4 * k + 1] += a.y; f[4 * k + 2] += a.z; f[4 * k + 3] += a.w;
       }
     }
-    gn_store<T>(y + row * C + c, f);
+    gn_store<T>(y + (sbase + r) * C + c, f);
+  };
+  int r = r0 + rl;
+  for (; r + 3 * rlanes < r1; r += 4 * rlanes) {
+    float f0[VN], f1[VN], f2[VN], f3[VN];
+    gn_load<T>(x + (sbase + r) * C + c, f0);
+    gn_load<T>(x + (sbase + r + rlanes) * C + c, f1);
+    gn_load<T>(x + (sbase + r + 2 * rlanes) * C + c, f2);
+    gn_load<T>(x + (sbase + r + 3 * rlanes) * C + c, f3);
+    finish(f0, r); finish(f1, r + rlanes); finish(f2, r + 2 * rlanes); finish(f3, r + 3 * rlanes);
+  }
+  for (; r < r1; r += rlanes) {
+    float f[VN];
+    gn_load<T>(x + (sbase + r) * C + c, f);
+    finish(f, r);
   }
 }
 
@@ -175,7 +225,7 @@ int gn_finalize_launch(const float* part, float* stats, int N, int slabs, int G,
 template <typename T>
 int gn_stats_launch_t(const T* x, float* part_ws, float* stats, int N, int rows, int C, int G, float eps,
                       cudaStream_t st) {
-  const int slabs = cdiv(rows, GN_SLAB_ROWS);
+  const int slabs = cdiv(rows, GN_PART_ROWS);
   dim3 grid(slabs, N);
   const size_t smem = (size_t)(256 / (C / GnVec<T>::N)) * C * 2 * sizeof(float);
   gn_partial_kernel<T><<<grid, 256, smem, st>>>(x, part_ws, rows, C, G, slabs);
@@ -203,14 +253,17 @@ int gn_apply_launch(int dtype, const void* x, void* y, const float* stats, const
   float* scale = coef_ws;
   float* shift = coef_ws + (size_t)N * C;
   gn_coeff_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(stats, gamma, beta, scale, shift, N, C, G);
-  long long work = total_rows * (C / (dtype == DT_BF16 ? 8 : 4));
-  int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  const int vecC = C / (dtype == DT_BF16 ? 8 : 4);
+  IVG_CHECK(vecC >= 1 && vecC <= 256 && C % (dtype == DT_BF16 ? 8 : 4) == 0, "groupnorm_apply: bad C=%d", C);
+  IVG_CHECK((long long)N * rows_per_sample == total_rows && N <= 65535, "groupnorm_apply: rows %lld / samples %d", total_rows, N);
+  const int threads = (256 / vecC) * vecC;               // (row lanes) x (channel vectors), <= 256
+  dim3 grid(cdiv(rows_per_sample, GN_APPLY_ROWS), N);
   if (dtype == DT_BF16)
-    gn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, scale, shift, pos,
-                                                           total_rows, rows_per_sample, C, silu, pos_rows);
+    gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, scale, shift, pos,
+                                                             rows_per_sample, C, silu, pos_rows);
   else
-    gn_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, scale, shift, pos, total_rows,
-                                                   rows_per_sample, C, silu, pos_rows);
+    gn_apply_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, scale, shift, pos, rows_per_sample, C, silu,
+                                                     pos_rows);
   count_launch(2);
   IVG_LAUNCH_CHECK();
   return 0;
