@@ -243,6 +243,9 @@ typedef struct ivgpt_mega_desc {
   int bn_wide;     /* gemm_mode 0: weight rows per work item of the gate/up and lm_head phases (multiple of 16, <= 64; 0 = 16).
                       wgu and lm_head must be packed with the same width (ivgpt_mega_pack_weight_bn); wider items cut those
                       phases from 3 / 7 rounds of 48 tcgen05.mma issues over the SMs to 1 / 3 */
+  int bn_down;     /* gemm_mode 0: weight rows per work item of the down projection (multiple of 16, <= 64; 0 = 16); wd must be
+                      packed with the same width.  Wider tiles x more K splits keep one round over the SMs with fewer
+                      tcgen05.mma issues per CTA (32-row tiles x 6 splits: 32 instead of 64 for the 138 M model) */
 } ivgpt_mega_desc;
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);

@@ -80,6 +80,7 @@ class MegaDesc(C.Structure):
         ("gemm_mode", C.c_int), ("qkv_splits", C.c_int), ("a_rows", C.c_int),
         ("qkvp", C.c_void_p),
         ("bn_wide", C.c_int),
+        ("bn_down", C.c_int),
     ]
 
 

@@ -519,6 +519,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.a_bulk = 1;
   IVG_CHECK(d->a_bulk == 1, "decode_mega: a_bulk must be 1 (xn / ao / act are swizzled activation images)");
   p.bn_wide = d->bn_wide > 0 ? d->bn_wide : ivg::MEGA_BN;
+  p.bn_down = d->bn_down > 0 ? d->bn_down : ivg::MEGA_BN;
   p.gemm_mode = d->gemm_mode; p.qkv_splits = d->qkv_splits; p.qkvp = (float*)d->qkvp;
   p.a_rows = d->gemm_mode == 0 ? (d->B <= 64 ? 64 : 128) : d->a_rows;
   IVG_CHECK(p.slot_period >= 0 && (p.slot_period == 0 || p.nslots >= 1), "decode_mega: bad slot layout");

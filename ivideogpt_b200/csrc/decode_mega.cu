@@ -1184,10 +1184,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   c.sm.a = base;
   if constexpr (GM == 0) {   // activation slab sized for this model, the rest of the 192 KB operand area holds 2-4 weight slab buffers
     const int a_rows = p.B <= 64 ? 64 : 128;
-    const int kmax = p.hidden > p.inter / p.d_splits ? p.hidden : p.inter / p.d_splits;
+    const int kd = p.inter / p.d_splits;
+    const int kmax = p.hidden > kd ? p.hidden : kd;
+    // narrow phases: qkv / o-proj items are 16 rows x <= hidden, down-proj items bn_down rows x inter / d_splits
+    const uint32_t s_qkv = (uint32_t)(MEGA_BN * p.hidden * 2), s_down = (uint32_t)(p.bn_down * kd * 2);
+    c.sm.slab_bytes = s_qkv > s_down ? s_qkv : s_down;
     c.sm.a_bytes = (uint32_t)(a_rows * kmax * 2);
-    if (c.sm.a_bytes < 64u * 1024u) c.sm.a_bytes = 64u * 1024u;      // attention ring / sampler scratch floor
-    c.sm.slab_bytes = (uint32_t)(MEGA_BN * kmax * 2);
+    // floor: the attention ring and the sampler scratch live in this region too -- as much of 128 KB as leaves two slabs
+    uint32_t floor_b = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES) - 2u * c.sm.slab_bytes;
+    floor_b = floor_b > (uint32_t)MEGA_A_BYTES ? (uint32_t)MEGA_A_BYTES : floor_b;
+    if (c.sm.a_bytes < floor_b) c.sm.a_bytes = floor_b;
     const uint32_t nb = (uint32_t)(MEGA_A_BYTES + 2 * MEGA_B_BYTES - c.sm.a_bytes) / c.sm.slab_bytes;
     c.sm.nbuf = nb > 4u ? 4u : nb;
     c.sm.b0 = base + c.sm.a_bytes;
@@ -1325,7 +1331,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, gu_g);
       MEGA_MARK(4);
-      GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H, MEGA_BN, narrow_off, narrow_bytes,
+      GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H, p.bn_down, narrow_off, narrow_bytes,
                     narrow_nbuf};
       prefetch_phase<GM>(p, c, d_g);
       MEGA_BARRIER(true); if (!ok) break;
@@ -1445,6 +1451,10 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
     IVG_CHECK(p.a_rows == a_rows, "decode_mega: a_rows must be %d in gemm_mode 0", a_rows);
     IVG_CHECK((long long)a_rows * p.hidden * 2 <= MEGA_A_BYTES && (long long)a_rows * (p.inter / p.d_splits) * 2 <= MEGA_A_BYTES,
               "decode_mega: batch %d with K %d does not fit the shared-memory activation slab", p.B, p.hidden);
+    IVG_CHECK(p.bn_down >= 16 && p.bn_down <= 64 && p.bn_down % 16 == 0 &&
+                  (long long)a_rows * (p.inter / p.d_splits) * 2 + 2ll * p.bn_down * (p.inter / p.d_splits) * 2 <=
+                      MEGA_A_BYTES + 2 * MEGA_B_BYTES,
+              "decode_mega: down-proj tile width %d with %d splits does not leave two weight slabs", p.bn_down, p.d_splits);
     IVG_CHECK(p.bn_wide >= 16 && p.bn_wide <= 64 && p.bn_wide % 16 == 0 &&
                   (long long)(a_rows + p.bn_wide) * p.hidden * 2 <= MEGA_A_BYTES + 2 * MEGA_B_BYTES,
               "decode_mega: wide tile width %d (gate/up, lm_head) must be a multiple of 16 in [16, 64] whose slab fits next to the "

@@ -61,6 +61,7 @@ struct MegaParams {
   float* attn_part;             // [SMs][4][72] flash-decoding partials of the items cut along the sequence (attn_mode 0)
   unsigned int* attn_cnt;       // [SMs] zero-initialised arrival counters of those items
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
+  int bn_down;                  // gemm_mode 0: weight rows per work item of the down projection (16..64); wd is packed with it
   int bn_wide;                  // gemm_mode 0: weight rows per work item of the gate/up and lm_head phases (16..64); wgu and lm_head are packed with it
   int gemm_mode;                // 0: activations are the MMA's M side, 16 weight rows per item; 1: weight-stationary (see decode_mega.cu)
   int qkv_splits;               // gemm_mode 1: split-K of the qkv projection (partials in qkvp, summed by the attention prologue)

@@ -254,7 +254,10 @@ class LlamaEngine:
         o_s, d_s = self._mega_splits()
         if o_s is None:
             return False
-        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * (w.inter // d_s) * 2 <= 128 * 1024 and common)
+        kd = w.inter // d_s
+        slab = max(16 * w.hidden * 2, self._mega_down(d_s)[0] * kd * 2)
+        return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * kd * 2 <= 128 * 1024 and
+                a_rows * max(w.hidden, kd) * 2 + 2 * slab <= 192 * 1024 and common)
 
     def _mega_splits(self):
         w = self.w
@@ -262,7 +265,21 @@ class LlamaEngine:
         d_s = next((s for s in range(1, 9) if w.inter % (64 * s) == 0 and w.inter // s <= 1024), None)
         if o_s is None or d_s is None:
             return None, None
-        return o_s, d_s
+        return o_s, self._mega_down(d_s)[1]
+
+    def _mega_down(self, d_s_default: int, sms: int = 148):
+        """gemm_mode 0 down projection: (tile width, split-K).  Default (16, first split with K <= 1024); `mega_down = (bn, s)` /
+        IVGPT_MEGA_DOWN=bn:s selects wider tiles with more splits (same number of work items, fewer tcgen05.mma issues per
+        CTA, more fp32 partials for the norm phase to add)."""
+        ov = getattr(self, "mega_down", None)
+        if ov is None and os.environ.get("IVGPT_MEGA_DOWN"):
+            ov = tuple(int(v) for v in os.environ["IVGPT_MEGA_DOWN"].split(":"))
+        if ov:
+            bn, s = int(ov[0]), int(ov[1])
+            w = self.w
+            assert bn % 16 == 0 and 16 <= bn <= 64 and 1 <= s <= 8 and w.inter % (64 * s) == 0 and w.inter // s <= 1024, ov
+            return bn, s
+        return 16, d_s_default
 
     def _mega_splits64(self, sms: int = 148):
         """Split-K factors of the weight-stationary phases: the largest s <= 12 with (rows / 64) * s <= #SMs work items
@@ -300,7 +317,7 @@ class LlamaEngine:
         # 16 -> 228.2 ms per rollout, 32 -> 220.9, 48 -> 215.5, 64 -> 213.7 (96 gate/up items, 2 lm_head rounds)
         return max(16, fit)
 
-    def _mega_tables(self, bn_wide: int = 16):
+    def _mega_tables(self, bn_wide: int = 16, bn_down: int = 16):
         """Packed weight copies (swizzled slab images: 16 rows per work item in mode 0, ivgpt_mega_pack_weight; 64 rows in
         the weight-stationary mode 1, ivgpt_mega_pack_weight64) and the device-resident array of per-layer pointer
         records, built once per engine and mode."""
@@ -308,7 +325,7 @@ class LlamaEngine:
         cache = getattr(self, "_mega_dev", None)
         if cache is None:
             cache = self._mega_dev = {}
-        key = (mode, bn_wide if mode == 0 else 0)
+        key = (mode, bn_wide if mode == 0 else 0, bn_down if mode == 0 else 0)
         if key in cache:
             return cache[key]
         import ctypes as C
@@ -341,7 +358,7 @@ class LlamaEngine:
         base_al = (C.addressof(host) + 63) // 64 * 64
         for i, lw in enumerate(w.layers):
             _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"], 1, bn_wide),
-                                                 pack(lw["wd"]), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
+                                                 pack(lw["wd"], 0, bn_down), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
                        "mega_fill_layer")
         lm_head = pack(w.lm_head, 0, bn_wide)
         raw = bytes((C.c_uint8 * (nbytes * w.layers_n)).from_address(base_al))
@@ -356,7 +373,8 @@ class LlamaEngine:
         h = w.hidden
         mode = self.mega_mode()
         bn_wide = self._mega_bn_wide(B) if mode == 0 else 16
-        dev_tab, lm_head_packed, _ = self._mega_tables(bn_wide)
+        bn_down = self._mega_down(1)[0] if mode == 0 else 16
+        dev_tab, lm_head_packed, _ = self._mega_tables(bn_wide, bn_down)
         if mode == 1:
             q_s, o_s, d_s = self._mega_splits64()
         else:
@@ -373,7 +391,7 @@ class LlamaEngine:
         d.x = self.buf("xd", (B, h), torch.float32).data_ptr()
         # rows of the swizzled activation images: the MMA's N in the weight-stationary mode, 64 / 128 MMA rows in mode 0
         a_rows = (B + 7) // 8 * 8 if mode == 1 else (64 if B <= 64 else 128)
-        d.gemm_mode, d.qkv_splits, d.a_rows, d.bn_wide = mode, q_s, a_rows, bn_wide
+        d.gemm_mode, d.qkv_splits, d.a_rows, d.bn_wide, d.bn_down = mode, q_s, a_rows, bn_wide, bn_down
         if mode == 1:
             d.qkvp = self.buf("mega_qkvp", (q_s, B, 3 * h), torch.float32).data_ptr()
         d.xn = self.buf("mega_xn", (a_rows, h), self.dtype).data_ptr()

@@ -105,13 +105,15 @@ def test_full_size_138m_prefill_logits(cuda):
     assert rel_err(got, want) < 3e-3
 
 
-def _mega_vs_graph(cuda, cfg, B, L, new, mode, seed=9, min_agree=0.6):
+def _mega_vs_graph(cuda, cfg, B, L, new, mode, seed=9, min_agree=0.6, setup=None):
     """Greedy rollout of the megakernel (GEMM mode `mode`) against the per-kernel CUDA-graph path on the same bf16 weights;
     a row may leave the graph path's tokens only where the HF oracle's own top-2 logit margin is tiny."""
     ref, mine = _pair(cfg, cuda, torch.bfloat16, scale=3.0)
     ids = torch.randint(0, cfg["vocab_size"], (B, L), generator=torch.Generator().manual_seed(seed)).to(cuda)
     eng = mine.b200_engine()
     eng.mega_gemm_mode = mode
+    if setup is not None:
+        setup(eng)
     assert eng.mega_supported(B, (L + new + 7) // 8 * 8)
     V = cfg["vocab_size"]
     a = eng.generate(ids, None, new, False, 0, 1.0, 0, use_mega=False)
@@ -173,6 +175,17 @@ def test_decode_megakernel_wide_tiles(cuda, bn_wide, hidden, inter, B):
     # same products, same per-element summation order: identical rollouts, greedy and seeded sampling
     assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] != outs[1][0]).nonzero()[:5]
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hidden,inter,B,down", [(192, 768, 5, (32, 6)), (768, 3072, 16, (32, 6)), (128, 256, 64, (64, 4))])
+def test_decode_megakernel_down_projection_tiles(cuda, hidden, inter, B, down):
+    """gemm_mode 0 down projection with wider tiles and more K splits (fewer tcgen05.mma issues per CTA, more fp32 partials
+    summed by the norm phase) against the multi-kernel path."""
+    from oracle.llama_ref import TINY_LLAMA
+    cfg = dict(TINY_LLAMA, hidden_size=hidden, intermediate_size=inter, num_attention_heads=hidden // 64,
+               num_key_value_heads=hidden // 64)
+    _mega_vs_graph(cuda, cfg, B, 30, 12, 0, seed=17, setup=lambda eng: setattr(eng, "mega_down", down))
 
 
 @pytest.mark.gpu

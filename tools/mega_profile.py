@@ -29,9 +29,10 @@ for spec in os.environ.get("VARIANTS", "0:0:1").split(","):
     f = [int(v) for v in spec.split(":")]
     eng.mega_gemm_mode = f[0]
     eng.mega_bn_wide = f[1] if f[1] >= 16 else 0
+    eng.mega_down = (f[2] // 100, f[2] % 100) if f[2] >= 100 else None      # third field: 100 * bn_down + d_splits (e.g. 3206)
     eng.mega_attn_mode = f[3] if len(f) > 3 else 0
     eng.mega_splits_override = tuple(f[4:7]) if len(f) >= 7 else None
-    tag = f"gemm={f[0]},bn_wide={eng.mega_bn_wide or 'auto'},attn={eng.mega_attn_mode},splits={eng.mega_splits_override}"
+    tag = f"gemm={f[0]},bn_wide={eng.mega_bn_wide or 'auto'},down={eng.mega_down},attn={eng.mega_attn_mode},splits={eng.mega_splits_override}"
     PROFILE = os.environ.get("PHASES", "1") == "1"
     eng.mega_profile = False
     try:
