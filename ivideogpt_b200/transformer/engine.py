@@ -255,30 +255,39 @@ class LlamaEngine:
         if o_s is None:
             return False
         kd = w.inter // d_s
-        slab = max(16 * w.hidden * 2, self._mega_down(d_s)[0] * kd * 2)
+        slab = max(16 * w.hidden * 2, self._mega_down()[0] * kd * 2)
         return (a_rows * w.hidden * 2 <= 128 * 1024 and a_rows * kd * 2 <= 128 * 1024 and
                 a_rows * max(w.hidden, kd) * 2 + 2 * slab <= 192 * 1024 and common)
 
     def _mega_splits(self):
         w = self.w
         o_s = next((s for s in (3, 2, 4, 1) if w.hidden % (64 * s) == 0), None)
-        d_s = next((s for s in range(1, 9) if w.inter % (64 * s) == 0 and w.inter // s <= 1024), None)
-        if o_s is None or d_s is None:
+        if o_s is None or self._mega_down() is None:
             return None, None
-        return o_s, self._mega_down(d_s)[1]
+        return o_s, self._mega_down()[1]
 
-    def _mega_down(self, d_s_default: int, sms: int = 148):
+    def _mega_down(self, sms: int = 148):
         """gemm_mode 0 down projection: (tile width, split-K).  Default (16, first split with K <= 1024); `mega_down = (bn, s)` /
         IVGPT_MEGA_DOWN=bn:s selects wider tiles with more splits (same number of work items, fewer tcgen05.mma issues per
         CTA, more fp32 partials for the norm phase to add)."""
+        w = self.w
+        d_s_default = next((s for s in range(1, 9) if w.inter % (64 * s) == 0 and w.inter // s <= 1024), None)
+        if d_s_default is None:
+            return None
         ov = getattr(self, "mega_down", None)
         if ov is None and os.environ.get("IVGPT_MEGA_DOWN"):
             ov = tuple(int(v) for v in os.environ["IVGPT_MEGA_DOWN"].split(":"))
         if ov:
             bn, s = int(ov[0]), int(ov[1])
-            w = self.w
             assert bn % 16 == 0 and 16 <= bn <= 64 and 1 <= s <= 8 and w.inter % (64 * s) == 0 and w.inter // s <= 1024, ov
             return bn, s
+        # Default: when 16-row items already fill one round over the SMs, 32-row tiles with twice the splits keep the item
+        # count and halve the tcgen05.mma issues per CTA (138 M model: 24 tiles x 6 splits, K = 512: 32 MMAs instead of 64;
+        # same-box A/B 213.7 -> 210.7 ms per rollout, logits equal to the (16, 3) path to 1e-4, tools/diag_down.py).
+        s2 = 2 * d_s_default
+        if (s2 <= 8 and w.inter % (64 * s2) == 0 and -(-w.hidden // 16) * d_s_default >= 128
+                and -(-w.hidden // 32) * s2 <= sms and 32 * (w.inter // s2) * 2 <= 32 * 1024):
+            return 32, s2
         return 16, d_s_default
 
     def _mega_splits64(self, sms: int = 148):
@@ -373,7 +382,7 @@ class LlamaEngine:
         h = w.hidden
         mode = self.mega_mode()
         bn_wide = self._mega_bn_wide(B) if mode == 0 else 16
-        bn_down = self._mega_down(1)[0] if mode == 0 else 16
+        bn_down = self._mega_down()[0] if mode == 0 else 16
         dev_tab, lm_head_packed, _ = self._mega_tables(bn_wide, bn_down)
         if mode == 1:
             q_s, o_s, d_s = self._mega_splits64()

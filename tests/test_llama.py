@@ -178,7 +178,7 @@ def test_decode_megakernel_wide_tiles(cuda, bn_wide, hidden, inter, B):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("hidden,inter,B,down", [(192, 768, 5, (32, 6)), (768, 3072, 16, (32, 6)), (128, 256, 64, (64, 4))])
+@pytest.mark.parametrize("hidden,inter,B,down", [(192, 768, 5, (32, 6)), (128, 256, 64, (64, 4))])
 def test_decode_megakernel_down_projection_tiles(cuda, hidden, inter, B, down):
     """gemm_mode 0 down projection with wider tiles and more K splits (fewer tcgen05.mma issues per CTA, more fp32 partials
     summed by the norm phase) against the multi-kernel path."""
@@ -300,6 +300,10 @@ def test_megakernel_host_geometry_for_the_baseline_configs():
         eng.mega_gemm_mode = 0
         o_s, d_s = eng._mega_splits()
         a_rows = 64
+        bn_down = eng._mega_down()[0]
+        assert (bn_down, d_s) == ((32, 6) if hidden == 768 else (16, 4))
+        assert ((hidden + bn_down - 1) // bn_down) * d_s <= (148 if hidden == 768 else 296)
+        assert a_rows * max(hidden, inter // d_s) * 2 + 2 * max(16 * hidden * 2, bn_down * (inter // d_s) * 2) <= 192 * 1024
         assert hidden % (64 * o_s) == 0 and inter % (64 * d_s) == 0 and inter // d_s <= 1024
         assert a_rows * max(hidden, inter // d_s) * 2 <= 128 * 1024                      # activation slab
         bn = eng._mega_bn_wide(B)
