@@ -5,11 +5,18 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this file.  The product package ``ivideogpt_b200``
 never does.
 
-PARITY UNPINNED: the reference ships no golden vectors for this path and the arithmetic
-lives in ``diffusers==0.27.0`` (requirements.txt:5), which is installed neither here nor on
-the GPU box.  The blocks below restate that library's published algorithm; the structure is
-pinned by (a) exact state-dict key/shape agreement with the reference's module tree and (b)
-the README's parameter counts (114.2 M / 310.5 M), see tests/test_oracle.py.
+PARITY, what is pinned and what is not.  The reference ships no golden vectors for this path and the block-level
+arithmetic lives in ``diffusers==0.27.0`` (requirements.txt:5), which is installed neither here nor on the GPU box.
+  * PINNED -- the reference's own code: tests/golden/make_golden_tokenizer_ref.py imports and RUNS the reference's
+    vae.py / conditional_vae.py / compressive_vq_model.py unmodified (on top of oracle/diffusers_stub, stand-ins for the
+    diffusers symbols they import) for the tiny config and the full ctx_vae64 / ctx_vae256 configs; this restatement
+    reproduces those runs exactly (state-dict keys, tokens, labels, reconstructed pixels: max abs diff 0.0), see
+    tests/golden/tokenizer_refglue.npz and tests/test_tokenizer.py.
+  * STILL RESTATED ("parity unpinned" at block level) -- the diffusers building blocks themselves (ResnetBlock2D,
+    Down/UpDecoderBlock2D, UNetMidBlock2D, Attention, VectorQuantizer): the classes below restate the library's published
+    algorithm and are the same classes the stub hands to the reference's code; their structure is pinned by
+    exact state-dict key/shape agreement with the reference's module tree and the README's parameter counts
+    (114.2 M / 310.5 M).
 
 What is restated, with the reference lines it follows:
   * ResnetBlock2D / DownEncoderBlock2D / Downsample2D / UpDecoderBlock2D / Upsample2D /

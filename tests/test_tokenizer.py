@@ -133,3 +133,30 @@ def test_detokenize_batch_independence_and_cache(cuda):
     rec, cache = mine.detokenize(tok, 2, return_cache=True)
     again = mine.detokenize(tok, 2, cache=cache)
     assert torch.equal(rec, full) and rel_err(again, full) < 1e-6
+
+
+def test_oracle_reproduces_vectors_of_the_reference_own_tokenizer_code():
+    """tests/golden/tokenizer_refglue.npz was produced by RUNNING the reference's own vae.py / conditional_vae.py /
+    compressive_vq_model.py (unmodified, imported from /root/reference) on top of oracle/diffusers_stub (stand-ins for the
+    diffusers 0.27.0 building blocks, which cannot be installed offline) -- tests/golden/make_golden_tokenizer_ref.py.
+    The oracle must reproduce those vectors: tokens and labels exactly, pixels to fp32 rounding.  (At generation time the
+    same comparison also ran for the full ctx_vae256 model; its summary is stored in the fixture.)"""
+    import json
+    import numpy as np
+    from oracle.vq_model_ref import TINY_CFG, RefCompressiveVQModel, config_path, seeded_init_
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_refglue.npz"))
+    summary = json.loads(str(z["summary"]))
+    assert set(summary) == {"tiny", "cfg64", "cfg256_not_stored"}
+    assert all(d["tokens_equal"] and d["labels_equal"] and d["recon_max_abs_diff"] < 1e-5 for d in summary.values())
+    with open(config_path("ctx_vae64")) as fh:
+        cfg64 = {k: v for k, v in json.load(fh).items() if not k.startswith("_") and k not in ("down_block_types", "up_block_types")}
+    for name, cfg in (("tiny", TINY_CFG), ("cfg64", cfg64)):
+        oracle = seeded_init_(RefCompressiveVQModel(**cfg).eval())
+        px = torch.from_numpy(z[f"{name}_pixels"])
+        with torch.no_grad():
+            tok, lab = oracle.tokenize(px, cfg["context_length"])
+            rec = oracle.detokenize(tok, cfg["context_length"])
+        assert np.array_equal(tok.numpy(), z[f"{name}_tokens"]) and np.array_equal(lab.numpy(), z[f"{name}_labels"]), name
+        assert float(np.abs(rec.numpy() - z[f"{name}_recon"]).max()) < 1e-4, name
+    assert z["tiny_recon_cached"].shape == (1, 3, 3, 64, 64)      # context (2) + the one future frame decoded from the cache
