@@ -130,3 +130,33 @@ def test_persistent_rollout_bf16_megakernel_matches_reprefill(cuda):
     # sampling mode: shapes, separators and vocabulary range
     s = mine.generate(prompt, do_sample=True, top_k=50, max_new_tokens=max_new, action=action).cpu()
     assert s.shape == a.shape and all(bool((s[:, k] == sdf).all()) for k in slots) and int(s.max()) <= sdf
+
+
+def test_persistent_rollout_layout_matches_the_reference_append_positions():
+    """CPU, host logic only: the forced-separator layout handed to the decode kernels must reproduce where the reference's
+    loop puts separators (one after every `per_frame` generated tokens, action_model.py:109-110) and where it adds action
+    embeddings (prelude + i * (n + 1), :80-81); layouts the single-cache rollout cannot express fall back (None)."""
+    from types import SimpleNamespace
+    from ivideogpt_b200.transformer import HeadModelWithAction
+    llm = torch.nn.Module()
+    llm.config = SimpleNamespace(vocab_size=1026, hidden_size=128)
+    llm.b200_engine = lambda: None
+    P, n, ctx, seg = 21, 4, 2, 5
+    m = HeadModelWithAction(llm, action_dim=3, prelude_tokens_num=P, tokens_num_per_dyna=n, context=ctx, segment_length=seg)
+    frames = seg - ctx
+    max_new = frames * (n + 1) - 1
+    per_frame = (max_new + 1) // frames - 1
+    assert per_frame == n
+    T = P + 1
+    # reference: separators land at T + per_frame + j * (per_frame + 1); action slots at P + i * (n + 1)
+    ref_sep = [T + per_frame + j * (per_frame + 1) for j in range(frames - 1)]
+    slot0, period = m._persistent_layout(T, per_frame, True)
+    assert (slot0, period) == (P, n + 1)
+    assert [q for q in range(T, T + max_new) if (q - slot0) % period == 0] == ref_sep
+    assert [slot0 + i * period for i in range(frames)] == [P + i * (n + 1) for i in range(frames)]
+    s0, per = m._persistent_layout(T, per_frame, False)            # generate_without_action: separators only
+    assert [q for q in range(T, T + max_new) if q >= s0 and (q - s0) % per == 0] == ref_sep
+    assert m._persistent_layout(T + 2, per_frame, True) is None     # prompt does not end on the first separator slot
+    assert m._persistent_layout(T, per_frame + 1, True) is None     # frame length differs from tokens_num_per_dyna
+    m.persistent_cache = False
+    assert m._persistent_layout(T, per_frame, True) is None
