@@ -160,3 +160,67 @@ def test_oracle_reproduces_vectors_of_the_reference_own_tokenizer_code():
         assert np.array_equal(tok.numpy(), z[f"{name}_tokens"]) and np.array_equal(lab.numpy(), z[f"{name}_labels"]), name
         assert float(np.abs(rec.numpy() - z[f"{name}_recon"]).max()) < 1e-4, name
     assert z["tiny_recon_cached"].shape == (1, 3, 3, 64, 64)      # context (2) + the one future frame decoded from the cache
+
+
+def test_legacy_checkpoint_keys_bin_fallback_and_mismatched_sizes(tmp_path):
+    """Host-side checkpoint I/O (hub_io.py): old diffusers attention key names are converted on load, the .bin fallback is
+    read when no safetensors file exists, ignore_mismatched_sizes drops tensors whose shape changed."""
+    from ivideogpt_b200.vq_model import CompressiveVQModel
+    from ivideogpt_b200.vq_model.hub_io import WEIGHTS_BIN
+    from oracle.vq_model_ref import TINY_CFG
+    _, mine = _pair(TINY_CFG)
+    sd = mine.state_dict()
+    ren = {".to_q.": ".query.", ".to_k.": ".key.", ".to_v.": ".value.", ".to_out.0.": ".proj_attn."}
+    legacy = {}
+    for k, v in sd.items():
+        if ".attentions." in k:
+            for a, b in ren.items():
+                k = k.replace(a, b)
+        legacy[k] = v.clone()
+    assert any(".query." in k for k in legacy), "the tiny config has a mid-block attention (cond encoder / decoder)"
+    d = tmp_path / "tokenizer"
+    mine.save_pretrained(str(d), save_function=lambda state, path: torch.save(legacy, path))     # writes the .bin name
+    assert os.path.exists(d / WEIGHTS_BIN) and not os.path.exists(d / "diffusion_pytorch_model.safetensors")
+    again = CompressiveVQModel.from_pretrained(str(tmp_path), subfolder="tokenizer")
+    assert all(torch.equal(v, again.state_dict()[k]) for k, v in sd.items())
+    # a codebook of another size: strict load refuses, ignore_mismatched_sizes keeps the model's own tensor
+    legacy["quantize.embedding.weight"] = torch.zeros(7, legacy["quantize.embedding.weight"].shape[1])
+    torch.save(legacy, d / WEIGHTS_BIN)
+    with pytest.raises(RuntimeError):
+        CompressiveVQModel.from_pretrained(str(tmp_path), subfolder="tokenizer")
+    loose = CompressiveVQModel.from_pretrained(str(tmp_path), subfolder="tokenizer", ignore_mismatched_sizes=True)
+    assert loose.state_dict()["quantize.embedding.weight"].shape == sd["quantize.embedding.weight"].shape
+    assert torch.equal(loose.state_dict()["quant_conv.weight"], sd["quant_conv.weight"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ivideogpt/vq_model"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("config", ["ctx_vae64", "ctx_vae256"])
+def test_module_tree_equals_the_reference_own_class(config):
+    """The product's parameter names and shapes against the REFERENCE'S OWN CompressiveVQModel class (its three files run on
+    oracle/diffusers_stub) for the released configs: a released checkpoint loads with strict=True."""
+    import importlib.util
+    import sys
+    from ivideogpt_b200.vq_model import CompressiveVQModel
+    from oracle.vq_model_ref import config_path
+    stub = os.path.join(ROOT, "oracle", "diffusers_stub")
+    sys.path.insert(0, stub)
+    try:
+        ref_dir = "/root/reference/ivideogpt/vq_model"
+        spec = importlib.util.spec_from_file_location("ref_vq_model_t", ref_dir + "/__init__.py", submodule_search_locations=[ref_dir])
+        pkg = importlib.util.module_from_spec(spec)
+        sys.modules["ref_vq_model_t"] = pkg
+        spec.loader.exec_module(pkg)
+        with open(config_path(config)) as fh:
+            cfg = {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+        with torch.device("meta"):
+            ref = pkg.CompressiveVQModel(**cfg)
+            mine = CompressiveVQModel.from_config(cfg)
+        a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+        assert a == b, sorted(set(a.items()) ^ set(b.items()))[:6]
+        # README.md:53-57 of the reference: 114.16 M / 310.47 M tokenizer parameters
+        assert sum(int(np.prod(s)) for s in a.values()) == {"ctx_vae64": 114_159_174, "ctx_vae256": 310_472_774}[config]
+    finally:
+        sys.path.remove(stub)
+        for k in [k for k in sys.modules if k == "diffusers" or k.startswith("diffusers.") or k.startswith("ref_vq_model_t")]:
+            del sys.modules[k]
