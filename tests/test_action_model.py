@@ -160,3 +160,27 @@ def test_persistent_rollout_layout_matches_the_reference_append_positions():
     assert m._persistent_layout(T, per_frame + 1, True) is None     # frame length differs from tokens_num_per_dyna
     m.persistent_cache = False
     assert m._persistent_layout(T, per_frame, True) is None
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/ivideogpt/transformer/action_model.py"),
+                    reason="needs the reference checkout (build container only)")
+def test_state_dict_keys_equal_the_reference_own_class():
+    """Parameter names / shapes of HeadModelWithAction (with reward and action-reconstruction heads) against the reference's
+    own class around the HF Llama: released action-conditioned checkpoints load with strict=True."""
+    import importlib.util
+    from ivideogpt_b200.transformer import B200LlamaForCausalLM, HeadModelWithAction
+    from oracle.llama_ref import TINY_LLAMA, build_hf_llama
+    spec = importlib.util.spec_from_file_location("ref_action_model_t", "/root/reference/ivideogpt/transformer/action_model.py")
+    ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_mod)
+    hf = build_hf_llama(TINY_LLAMA)
+    kw = dict(action_dim=3, prelude_tokens_num=21, tokens_num_per_dyna=4, context=2, segment_length=5,
+              model_type="llama", reward_prediction=True, action_recon=0.1)
+    ref = ref_mod.HeadModelWithAction(hf, **kw)
+    mine = HeadModelWithAction(B200LlamaForCausalLM(hf.config), **kw)
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert a == b, sorted(set(a.items()) ^ set(b.items()))[:6]
+    assert mine.token_for_sdf == ref.token_for_sdf == 1025
+    with pytest.raises(ValueError):
+        HeadModelWithAction(B200LlamaForCausalLM(hf.config), **dict(kw, model_type="gpt2"))
