@@ -51,3 +51,27 @@ def test_descriptor_structs_match_the_c_layout(tmp_path):
     assert sizes == [C.sizeof(_lib.GemmDesc), C.sizeof(_lib.ConvDesc), C.sizeof(_lib.MegaDesc)]
     M = _lib.MegaDesc
     assert offs == [M.kcache.offset, M.prof.offset, M.slot_emb.offset, M.qkvp.offset, M.bn_down.offset]
+
+
+def test_product_never_imports_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under ivideogpt_b200/ or ivideogpt/ may import oracle/ (or diffusers), and the
+    library loader must raise -- not fall back -- when the .so is missing."""
+    bad = []
+    for base in ("ivideogpt_b200", "ivideogpt"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    if re.search(r"^\s*(from|import)\s+(oracle|diffusers)\b", src, flags=re.M):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    import importlib
+    from ivideogpt_b200 import _lib
+    saved_path, saved_handle = _lib.LIB_PATH, _lib._lib
+    try:
+        _lib.LIB_PATH, _lib._lib = os.path.join(ROOT, "ivideogpt_b200", "no_such_library.so"), None
+        with pytest.raises(_lib.B200LibraryError, match="no CPU or PyTorch fallback"):
+            _lib.load()
+    finally:
+        _lib.LIB_PATH, _lib._lib = saved_path, saved_handle
+    importlib.import_module("ivideogpt_b200")       # importing the package never needs the GPU
