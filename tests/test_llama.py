@@ -316,3 +316,26 @@ def test_megakernel_host_geometry_for_the_baseline_configs():
         assert q_s <= 4 and eng.mega_supported(B, 752) and not eng.mega_supported(100, 752)
     eng.dtype = torch.float32
     assert not eng.mega_supported(64, 752)          # the TF32 parity path keeps the multi-kernel CUDA-graph step
+
+
+def test_unsupported_generate_and_forward_arguments_fail_loudly():
+    """CPU: API deviations raise instead of silently doing something else; CPU tensors are refused."""
+    from transformers import LlamaConfig
+    from ivideogpt_b200.transformer import B200LlamaForCausalLM
+    from oracle.llama_ref import TINY_LLAMA
+    m = B200LlamaForCausalLM(LlamaConfig(**TINY_LLAMA)).eval()
+    ids = torch.zeros(1, 4, dtype=torch.int64)
+    for kw in (dict(return_dict_in_generate=True), dict(output_hidden_states=True), dict(num_beams=4), dict(top_p=0.9)):
+        with pytest.raises(NotImplementedError):
+            m.generate(ids, max_new_tokens=2, **kw)
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, max_new_tokens=2, attention_mask=torch.tensor([[1, 1, 0, 0]]))
+    with pytest.raises(ValueError):
+        m.generate(None, max_new_tokens=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.generate(ids, max_new_tokens=2)
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids, past_key_values=object())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(input_ids=ids)
+    assert m.gradient_checkpointing_enable() is None          # accepted and ignored (train_gpt.py:598-600)
