@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=1)
     ap.add_argument("--quick", action="store_true", help="profiling aid: exact --warmup, no e2e / cpu legs")
+    ap.add_argument("--no-legs", action="store_true", help="skip the nested tf32 / cfg256 / cfg64_medium / train64 legs")
     return ap.parse_args()
 
 
@@ -215,26 +216,58 @@ def workload_config(args, batch, res):
 # ----------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------
-def run_b200(args):
+class Dist:
+    """Rank / device / barrier plumbing shared by every leg of one bench process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def measure_inference(args, D, workload, dtype_name, steps, warmup, with_e2e, with_clocks, keep_oracle=False):
+    """One inference workload on this process's GPU (all ranks call it together): returns the record of the leg
+    (rank 0: full dict; other ranks: None) and, when asked, the oracle models for the CPU baseline."""
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     from ivideogpt_b200 import _lib
     lib = _lib.load()
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    _, _, res, default_b = WORKLOADS[args.workload]
+    dev = D.dev
+    dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float32
+    _, _, res, default_b = WORKLOADS[workload]
     B = args.batch or default_b
     ctx, seg = args.context_length, args.segment_length
     fut = seg - ctx
     max_new = 17 * fut - 1
-    tok, llm, ref_tok, ref_llm = build_b200_models(args.workload, dev, dtype)
-    clips_host = synthetic_clips(B, seg, res, seed=rank).pin_memory()
+    tok, llm, ref_tok, ref_llm = build_b200_models(workload, dev, dtype)
+    if not keep_oracle:
+        ref_tok = ref_llm = None
+    clips_host = synthetic_clips(B, seg, res, seed=D.rank).pin_memory()
     clips_dev = clips_host.to(dev)
     gen_kw = dict(do_sample=not args.greedy, temperature=1.0, top_k=100, max_new_tokens=max_new, pad_token_id=50256)
 
@@ -253,40 +286,31 @@ def run_b200(args):
         frames_host.copy_(frames, non_blocking=True)                  # D2H of the result into pinned memory (stream-ordered:
         return frames_host                                            # the closing CUDA event of the step waits for it)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, profile=False):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
+    def timed(fn, n, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        D.barrier()
         n0 = _lib.launch_count()
         if profile:
             lib.ivgpt_profile_enable(1)
         e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_all0.record()
-        for i in range(steps):
+        for i in range(n):
             ev[i][0].record()
             fn()
             ev[i][1].record()
         e_all1.record()
-        barrier()
+        D.barrier()
         if profile:
             lib.ivgpt_profile_enable(0)
-        total_ms = e_all0.elapsed_time(e_all1)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), [a.elapsed_time(b) for a, b in ev], _lib.launch_count() - n0
+        return D.max_ms(e_all0.elapsed_time(e_all1)), [a.elapsed_time(b) for a, b in ev], _lib.launch_count() - n0
 
-    for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
+    for _ in range(warmup):
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(D.local) if (D.rank == 0 and with_clocks) else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    total_ms, per_step, launches = timed(step_resident, args.steps, profile=True)
+    total_ms, per_step, launches = timed(step_resident, steps, profile=True)
     clocks = sampler.finish() if sampler else None
     # where the step goes (one extra, untimed-for-the-headline pass with events between the three API calls)
     sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -306,53 +330,108 @@ def run_b200(args):
         ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
         lib.ivgpt_profile_collect(bucket, C.byref(ms), C.byref(fl), C.byref(n))
         prof[name] = (ms.value, fl.value, n.value)
-    # end-to-end arm through the reference-facing API
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = max(2, min(steps, 3))
     e2e_ms = float("nan")
-    if not args.quick:
+    if with_e2e:
         step_e2e()
         e2e_ms, _, _ = timed(step_e2e, e2e_steps)
+    rec = None
+    if D.rank == 0:
+        frames_per_step = D.world * B * fut
+        ms_per_step = total_ms / steps
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        px_bytes = clips_host.numel() * 4
+        rec = {"value": frames_per_step / (ms_per_step / 1e3), "unit": "frames/s", "ms_per_step": ms_per_step,
+               "dtype": dtype_name, "per_step_ms": per_step, "stages_ms": stages, "gpu_launches": launches, "clocks": clocks,
+               "roofline": build_roofline(args, dtype_name, steps, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src),
+               "e2e": {"value": frames_per_step / (e2e_ms / e2e_steps / 1e3) if with_e2e else None, "unit": "frames/s",
+                       "h2d_bytes_per_step": px_bytes, "d2h_bytes_per_step": px_bytes,
+                       "ms_per_step": e2e_ms / e2e_steps if with_e2e else None,
+                       "api": "CompressiveVQModel.tokenize(all frames) -> B200LlamaForCausalLM.generate -> detokenize -> .cpu()"},
+               "B": B, "res": res}
+    del tok, llm, clips_dev
+    torch.cuda.empty_cache()
+    return rec, (ref_tok, ref_llm)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    frames_per_step = world * B * fut
-    ms_per_step = total_ms / args.steps
-    value = frames_per_step / (ms_per_step / 1e3)
-    peak_tf, peak_gbs, peak_src = measured_peaks()
-    roofline = build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src)
-    px_bytes = clips_host.numel() * 4
-    out = {
-        "metric": "predicted_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (U[0,1) pixels, seeded random weights in the reference state-dict layout)",
-        "config": workload_config(args, B, res),
-        "per_step_ms": per_step, "stages_ms": stages, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "e2e": {"value": None if args.quick else frames_per_step / (e2e_ms / e2e_steps / 1e3), "unit": "frames/s",
-                "h2d_bytes_per_step": px_bytes, "d2h_bytes_per_step": px_bytes,
-                "ms_per_step": None if args.quick else e2e_ms / e2e_steps,
-                "api": "CompressiveVQModel.tokenize(all frames) -> B200LlamaForCausalLM.generate -> detokenize -> .cpu()"},
-    }
+
+def leg(name, fn):
+    """Secondary legs never take the headline line down with them."""
+    try:
+        return fn()
+    except Exception as e:        # noqa: BLE001 -- reported in the JSON line
+        return {"error": f"{name}: {repr(e)[:300]}"}
+
+
+def run_b200(args):
+    import torch
+    D = Dist()
+    _, _, res, default_b = WORKLOADS[args.workload]
+    B = args.batch or default_b
+    ctx, seg = args.context_length, args.segment_length
+    fut = seg - ctx
+    warmup = args.warmup if args.quick else max(args.warmup, 3)
+    main, (ref_tok, ref_llm) = measure_inference(args, D, args.workload, args.dtype, args.steps, warmup, not args.quick, True,
+                                                 keep_oracle=(D.world == 1 and not args.no_cpu_baseline and not args.quick))
+    out = None
+    if D.rank == 0:
+        out = {
+            "metric": "predicted_frames_per_sec", "value": main["value"], "unit": "frames/s", "n_gpus": D.world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic (U[0,1) pixels, seeded random weights in the reference state-dict layout)",
+            "config": workload_config(args, B, res),
+            "per_step_ms": main["per_step_ms"], "stages_ms": main["stages_ms"], "gpu_launches": main["gpu_launches"],
+            "clocks": main["clocks"], "roofline": main["roofline"], "e2e": main["e2e"],
+        }
+    legs = not args.quick and not args.no_legs and args.workload == "cfg64" and args.dtype == "bf16" and not args.batch
     if not args.quick:
-        try:      # BASELINE.json's second metric: VQ-argmin GB/s on algorithmic bytes (4ND + 4KD + 8N), this workload's context shape
-            out["vq_argmin"] = vq_argmin_leg(dev, 2 * B * 256, peak_gbs)
-        except Exception as e:     # never lose the headline line to a secondary leg
-            out["vq_argmin"] = {"error": repr(e)[:200]}
-    if not args.no_cpu_baseline and not args.quick and world == 1:
+        r = leg("vq_argmin", lambda: vq_argmin_leg(D.dev, 2 * B * 256, measured_peaks()[1]))
+        if out is not None:
+            out["vq_argmin"] = r      # BASELINE.json's second metric: GB/s on algorithmic bytes + fp32-pipe fraction
+    if legs:
+        # The same bench at the parity-grade arithmetic (TF32 tensor cores, fp32 storage: what the reference's predict.py runs
+        # on a GPU) and on the other BASELINE.json configurations, as nested records: every driver-run line carries them.
+        def short(workload, dtype_name):
+            rec, _ = measure_inference(args, D, workload, dtype_name, 2, 3, True, False)
+            if rec is None:
+                return None
+            keep = ("value", "unit", "ms_per_step", "dtype", "stages_ms", "gpu_launches", "B", "res")
+            o = {k: rec[k] for k in keep}
+            o["e2e"] = {k: rec["e2e"][k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+            o["roofline"] = {k: rec["roofline"].get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "share_of_step")}
+            o["roofline"]["other"] = rec["roofline"].get("other")
+            o["steps"], o["warmup"] = 2, 3
+            return o
+        for key, wl, dt in (("tf32", "cfg64", "tf32"), ("cfg256", "cfg256", "bf16"), ("cfg64_medium", "cfg64-medium", "bf16")):
+            r = leg(key, lambda wl=wl, dt=dt: short(wl, dt))
+            if out is not None:
+                out[key] = r
+        r = leg("train64", lambda: train_record(args, D, "train64", 3, 3))
+        if out is not None:
+            out["train64"] = r
+    if out is not None and ref_tok is not None:
+        cores = host_threads()
+        torch.set_num_threads(cores)
         try:
-            cores = host_threads()
-            torch.set_num_threads(cores)
             clips = synthetic_clips(args.cpu_clips, seg, res)
             t_cpu, _ = cpu_rollout(ref_tok, ref_llm, clips, ctx, seg)
             out["cpu_baseline"] = {"value": args.cpu_clips * fut / t_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": f"{args.cpu_clips} clip {res}x{res}x{seg}, greedy, fp32 (oracle tokenizer + HF Llama), {t_cpu:.1f} s"}
-        except Exception as e:
-            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": host_threads(), "kind": "port",
+        except Exception as e:     # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": f"failed: {repr(e)[:200]}"}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        if legs:
+            # SURVEY 8(d) asks for the CPU path at B = 1 and B = 8; a full B = 8 rollout is minutes of CPU time, so the B = 8
+            # sample is bounded: 8 clips, context 2 + 2 predicted frames (33 new tokens per clip)
+            def cpu_b8():
+                clips8 = synthetic_clips(8, ctx + 2, res)
+                t8, _ = cpu_rollout(ref_tok, ref_llm, clips8, ctx, ctx + 2)
+                return {"value": 8 * 2 / t8, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"8 clips {res}x{res}x{ctx + 2} (2 predicted frames each), greedy, fp32, {t8:.1f} s"}
+            out["cpu_baseline_b8"] = leg("cpu_baseline_b8", cpu_b8)
+    if out is not None:
+        print(json.dumps(out))
+    D.close()
 
 
 def vq_argmin_leg(dev, N, peak_gbs, K=8192, D=64, iters=10):
@@ -387,7 +466,7 @@ def mega_traffic():
     return None
 
 
-def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src):
+def build_roofline(args, dtype_name, nsteps, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs, peak_src):
     """Roofline of the DOMINANT kernel (largest summed device time in the timed region).
 
     decode_mega_kernel is HBM-bound: algorithmic bytes per launch = per decode step the bf16 block
@@ -398,14 +477,14 @@ def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs
     conv_ms, conv_fl, conv_n = prof["conv"]
     gemm_ms, gemm_fl, gemm_n = prof["gemm"]
     mega_ms, mega_steps, mega_n = prof["mega"]
-    dense_peak = peak_tf if args.dtype == "bf16" else peak_tf / 2.0    # tf32 runs at half the bf16 rate
-    tsrc = f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})" + ("" if args.dtype == "bf16" else " / 2 for tf32")
+    dense_peak = peak_tf if dtype_name == "bf16" else peak_tf / 2.0    # tf32 runs at half the bf16 rate
+    tsrc = f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})" + ("" if dtype_name == "bf16" else " / 2 for tf32")
     for name, ms, fl, n, label in (("conv", conv_ms, conv_fl, conv_n, "implicit-GEMM 3x3 conv"),
                                    ("gemm", gemm_ms, gemm_fl, gemm_n, "plain/batched GEMM")):
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        fam[name] = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{args.dtype}> ({label})", "achieved": ach,
+        fam[name] = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{dtype_name}> ({label})", "achieved": ach,
                      "peak": dense_peak, "unit": "TFLOP/s", "frac": ach / dense_peak, "peak_source": tsrc,
-                     "launches_per_step": n / args.steps, "kernel_ms_per_step": ms / args.steps,
+                     "launches_per_step": n / nsteps, "kernel_ms_per_step": ms / nsteps,
                      "share_of_step": ms / total_ms, "traffic": None}
     if mega_n > 0 and mega_ms > 0:
         w = llm.b200_engine().w
@@ -418,7 +497,7 @@ def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs
         fam["mega"] = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent decode rollout, one launch per step of the bench)",
                        "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
-                       "launches_per_step": mega_n / args.steps, "kernel_ms_per_step": mega_ms / args.steps,
+                       "launches_per_step": mega_n / nsteps, "kernel_ms_per_step": mega_ms / nsteps,
                        "share_of_step": mega_ms / total_ms, "algorithmic_bytes_per_launch": per_launch,
                        "decode_steps_per_launch": steps, "traffic": None}
         cap = mega_traffic()
@@ -433,36 +512,37 @@ def build_roofline(args, prof, total_ms, B, ctx, max_new, llm, peak_tf, peak_gbs
     return roofline
 
 
-def run_train(args):
-    """One training step of reference train_gpt.py:766-804 per bench step; metric = clips/s."""
+def train_record(args, D, workload, steps, warmup):
+    """One training step of reference train_gpt.py:766-804 per bench step; metric = clips/s.
+    All ranks call it together; rank 0 returns the record."""
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from ivideogpt_b200 import _lib, ops
-    base = "tiny" if args.workload == "train-tiny" else "cfg64"
-    _, _, res, default_b = WORKLOADS[args.workload]
+    from ivideogpt_b200 import _lib
+    from ivideogpt_b200.optim import FusedAdamW
+    world, rank, dev = D.world, D.rank, D.dev
+    base = "tiny" if workload == "train-tiny" else "cfg64"
+    _, _, res, default_b = WORKLOADS[workload]
     B = args.batch or default_b
     ctx, seg = args.context_length, args.segment_length
     tok, llm, _, _ = build_b200_models(base, dev, torch.bfloat16)
     tok.set_compute_dtype(torch.float32)          # train_gpt.py runs the frozen tokenizer in fp32 (TF32 convs)
     llm.train()
+    p_drop = float(os.environ.get("IVGPT_TRAIN_ATTN_DROPOUT", "0.0"))    # 0.1 = as scripted (oxe-64-act-free.sh:31); 0 = parity config
+    llm.config.attention_dropout = p_drop
     params = [p for p in llm.parameters()]
-    m_state = [torch.zeros_like(p) for p in params]
-    v_state = [torch.zeros_like(p) for p in params]
+    decay = [p for p in params if p.dim() >= 2]
+    no_decay = [p for p in params if p.dim() < 2]
+    # train_gpt.py:640-646: AdamW, weight decay on the matrices only; the exchange is a SUM, the mean is the optimizer's scale
+    opt = FusedAdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-4,
+                     betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0 / world)
     clips = synthetic_clips(B, seg, res, seed=rank).to(dev)
-    step_no = [0]
 
     overlap = os.environ.get("IVGPT_TRAIN_OVERLAP", "1") == "1"
+    reducer = None
     if world > 1 and overlap:
         # gradient exchange launched bucket by bucket from inside the backward (sum; the mean is AdamW's gscale = 1/world)
         from ivideogpt_b200.grad_reduce import BucketedGradReducer
-        llm.b200_grad_reducer = BucketedGradReducer()
+        reducer = llm.b200_grad_reducer = BucketedGradReducer()
 
     def train_step():
         with torch.no_grad():
@@ -477,58 +557,67 @@ def run_train(args):
                 n = p.numel()
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
-        step_no[0] += 1
-        for p, m, v in zip(params, m_state, v_state):                     # :803 AdamW (lr 1e-4, wd 0.01 on matrices)
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            ops.adamw(p.data, g, m, v, 1e-4, 0.9, 0.999, 1e-8, 0.01 if p.dim() >= 2 else 0.0, step_no[0], 1.0 / world)
-            p.grad = None
-        return loss
+        opt.step()                                                        # :803 (fused AdamW; bumps every parameter's version:
+        opt.zero_grad(set_to_none=True)                                   #  the packed weight copies are rebuilt next step)
+        return loss.detach()                                              # :794 gather(loss) deferred: read after the timed region
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         train_step()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(D.local) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)
-    barrier()
+    D.barrier()
     n0 = _lib.launch_count()
+    b0 = reducer.bytes_reduced if reducer is not None else 0
+    k0 = reducer.buckets_launched if reducer is not None else 0
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    losses = [train_step() for _ in range(args.steps)]
+    losses = [train_step() for _ in range(steps)]
     b.record()
-    barrier()
-    ms = a.elapsed_time(b)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    D.barrier()
+    ms_step = D.max_ms(a.elapsed_time(b)) / steps
     clocks = sampler.finish() if sampler else None
+    rec = None
     if rank == 0:
-        ms_step = float(t.item()) / args.steps
         tokens_per_clip = ctx * 257 + 17 * (seg - ctx) - 1
         flops_clip = 6.0 * 125.8e6 * tokens_per_clip + 31e9            # ~567 + 31 GFLOP per clip (fwd+bwd)
         peak_tf, _, src = measured_peaks()
-        ach = world * B * flops_clip / (ms_step * 1e-3) / 1e12 / world
-        print(json.dumps({
+        ach = B * flops_clip / (ms_step * 1e-3) / 1e12
+        if world == 1:
+            exch = {"algorithm": "none (1 GPU)"}
+        elif reducer is not None:
+            exch = {"algorithm": "bucketed NCCL all-reduce (SUM), one bucket per layer launched from inside the backward, overlapped",
+                    "buckets_per_step": (reducer.buckets_launched - k0) / steps,
+                    "bytes_per_step": (reducer.bytes_reduced - b0) / steps,
+                    "bucket_bytes": {"lm_head+final_norm": 4 * (16386 * 768 + 768), "layer": 4 * (12 * 768 * 768 + 2 * 768),
+                                     "embedding": 4 * 16386 * 768}}
+        else:
+            exch = {"algorithm": "one flat NCCL all-reduce after the backward"}
+        rec = {
             "metric": "train_clips_per_sec", "value": world * B / (ms_step / 1e3), "unit": "clips/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: train_gpt.py step, {B} clips/GPU of {res}x{res}x{seg}, frozen fp32 "
+            "config": {"workload": f"{workload}: train_gpt.py step, {B} clips/GPU of {res}x{res}x{seg}, frozen fp32 "
                                    f"tokenizer -> Llama fwd+bwd bf16 -> all-reduce -> AdamW", "per_gpu_batch": B,
-                       "parallelism": f"dp{world}", "attention_dropout": 0.0,
-                       "grad_exchange": ("none" if world == 1 else "bucketed NCCL all-reduce overlapped with backward" if overlap
-                                         else "one flat NCCL all-reduce after backward")},
-            "loss_first_last": [float(losses[0].detach()), float(losses[-1].detach())], "gpu_launches": _lib.launch_count() - n0,
+                       "parallelism": f"dp{world}", "attention_dropout": p_drop},
+            "grad_exchange": exch,
+            "loss_first_last": [float(losses[0]), float(losses[-1])], "gpu_launches": _lib.launch_count() - n0,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "training step (all tcgen05 GEMMs)", "achieved": ach, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": f"bf16_tflops_sustained ({src})",
-                         "traffic": None, "note": "model-FLOPs utilisation of the transformer fwd+bwd only"},
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+                         "traffic": None, "note": "model-FLOPs utilisation (MFU) of the transformer fwd+bwd only, per GPU"},
+        }
+    del tok, llm, opt, params
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args):
+    D = Dist()
+    rec = train_record(args, D, args.workload, args.steps, args.warmup)
+    if rec is not None:
+        print(json.dumps(rec))
+    D.close()
 
 
 if __name__ == "__main__":

@@ -139,9 +139,11 @@ int ivgpt_convert(int src_dtype, const void* x, int dst_dtype, void* y, long lon
 /* token (de)serialisation, compressive_vq_model.py:205-220 / :227-245 */
 int ivgpt_tokens_serialise(const long long* idx_ctx, const long long* idx_dyn, long long* tokens, long long* labels,
                            int B, int t, int f, int cr, int dr, long long n_vq, long long n_dyn, void* stream);
+/* bad_ctx (device int, may be NULL): set to 1 when a CONTEXT position holds an id outside [0, n_vq) -- the reference's
+ * `self.quantize.embedding(...)` (:238) raises on such input; dynamics ids are clamped as the reference does (:236). */
 int ivgpt_tokens_gather(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* q_ctx,
                         void* q_dyn, int B, int t, int f, int cr, int dr, int D, long long n_vq, long long n_dyn,
-                        int L, void* stream);
+                        int L, int* bad_ctx, void* stream);
 
 /* ---- input pipeline -----------------------------------------------------------------------------------
  * Replaces inference/utils.py:12-16 NPZParser.preprocess (and ivideogpt/data/simple_dataloader.py:394,510):
@@ -276,6 +278,10 @@ int ivgpt_embed_bwd(const long long* ids, const float* dx, float* dE, long long 
 int ivgpt_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int step, float gscale, void* stream);
 int ivgpt_add_to_f32(int dtype, float* y, const void* x, long long n, void* stream);
+/* Attention dropout of the training step (HF LlamaAttention, `attention_dropout` of the Llama config;
+ * scripts/pretrain/oxe-64-act-free.sh:31 uses 0.1): y[i] = keep(seed, i) ? x[i] / (1 - p) : 0, counter-based so that the
+ * backward pass regenerates the forward mask from the seed.  y may alias x. */
+int ivgpt_dropout(int dtype, const void* x, void* y, long long n, float p, unsigned long long seed, void* stream);
 /* Programmatic dependent launch for the kernels of the decode step (prologue overlap inside CUDA graphs). */
 int ivgpt_set_pdl(int on);
 

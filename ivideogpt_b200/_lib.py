@@ -106,7 +106,7 @@ SIGNATURES = {
     "ivgpt_patchify": [_I, _P, _P, _I, _I, _I, _I, _I, _P],
     "ivgpt_convert": [_I, _P, _I, _P, _L, _P],
     "ivgpt_tokens_serialise": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P],
-    "ivgpt_tokens_gather": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P],
+    "ivgpt_tokens_gather": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P],
     "ivgpt_embed": [_P, _L, _I, _P, _P, _P, _L, _I, _L, _P],
     "ivgpt_add_rows": [_P, _P, _L, _P],
     "ivgpt_rmsnorm": [_I, _P, _P, _P, _L, _I, _F, _P],
@@ -131,6 +131,7 @@ SIGNATURES = {
     "ivgpt_embed_bwd": [_P, _P, _P, _L, _I, _L, _P],
     "ivgpt_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "ivgpt_add_to_f32": [_I, _P, _P, _L, _P],
+    "ivgpt_dropout": [_I, _P, _P, _L, _F, _U, _P],
     "ivgpt_vq_set_order": [_I],
     "ivgpt_vq_get_order": [],
     "ivgpt_mega_layer_bytes": [],

@@ -62,15 +62,17 @@ int make_tensor_map(CUtensorMap* out, int dtype, const void* base, int rank, con
   return 0;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[64] = {0};      // per device ordinal (a process may drive several GPUs)
 static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = g_num_sms[dev & 63];
+  if (!n) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
   }
-  return g_num_sms;
+  return n;
 }
 
 // ---- forward declarations of launchers defined in the other translation units -----------------
@@ -96,7 +98,7 @@ int convert_launch(int, const void*, int, void*, long long, cudaStream_t);
 int serialise_launch(const long long*, const long long*, long long*, long long*, int, int, int, int, int, long long,
                      long long, cudaStream_t);
 int detok_gather_launch(int, const long long*, const float*, const float*, void*, void*, int, int, int, int, int, int,
-                        long long, long long, int, cudaStream_t);
+                        long long, long long, int, int*, cudaStream_t);
 int embed_launch(const long long*, long long, int, const int*, const float*, float*, long long, int, long long,
                  cudaStream_t);
 int add_rows_launch(float*, const float*, long long, cudaStream_t);
@@ -128,6 +130,7 @@ int embed_bwd_launch(const long long*, const float*, float*, long long, int, lon
 int adamw_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float,
                  cudaStream_t);
 int add_to_f32_launch(int, float*, const void*, long long, cudaStream_t);
+int dropout_launch(int, const void*, void*, long long, float, unsigned long long, cudaStream_t);
 int decode_attn_fused_launch(int, const void*, void*, void*, void*, int, int, int, int, const int*, const float*,
                              const float*, float, cudaStream_t);
 
@@ -355,8 +358,8 @@ int ivgpt_tokens_serialise(const long long* ic, const long long* id, long long* 
 }
 int ivgpt_tokens_gather(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* qc,
                         void* qd, int B, int t, int f, int cr, int dr, int D, long long n_vq, long long n_dyn, int L,
-                        void* stream) {
-  return detok_gather_launch(dtype, tokens, cb_ctx, cb_dyn, qc, qd, B, t, f, cr, dr, D, n_vq, n_dyn, L, S(stream));
+                        int* bad_ctx, void* stream) {
+  return detok_gather_launch(dtype, tokens, cb_ctx, cb_dyn, qc, qd, B, t, f, cr, dr, D, n_vq, n_dyn, L, bad_ctx, S(stream));
 }
 int ivgpt_embed(const long long* ids, long long ids_stride, int L, const int* dpos, const float* table, float* x,
                 long long M, int hidden, long long vocab, void* stream) {
@@ -451,6 +454,9 @@ int ivgpt_adamw(float* p, const float* g, float* m, float* v, long long n, float
 }
 int ivgpt_add_to_f32(int dtype, float* y, const void* x, long long n, void* stream) {
   return add_to_f32_launch(dtype, y, x, n, S(stream));
+}
+int ivgpt_dropout(int dtype, const void* x, void* y, long long n, float p, unsigned long long seed, void* stream) {
+  return dropout_launch(dtype, x, y, n, p, seed, S(stream));
 }
 int ivgpt_vq_set_order(int order) {
   IVG_CHECK(order == 0 || order == 1, "vq order must be 0 or 1");

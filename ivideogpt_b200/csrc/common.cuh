@@ -34,6 +34,15 @@ const char* last_error();
 
 #define IVG_LAUNCH_CHECK() IVG_CUDA(cudaGetLastError())
 
+// Function attributes (cudaFuncSetAttribute) and device properties are PER DEVICE: "done once" flags are bit masks over
+// the device ordinal, so a process that drives several GPUs (or a model living on cuda:1) sets them on each device it uses.
+struct PerDeviceOnce {
+  unsigned long long mask = 0ull;
+  // true when the current device has not been marked yet (call mark() after the one-off work succeeded)
+  bool pending() const { int d = 0; cudaGetDevice(&d); return !((mask >> (d & 63)) & 1ull); }
+  void mark() { int d = 0; cudaGetDevice(&d); __atomic_fetch_or(&mask, 1ull << (d & 63), __ATOMIC_RELAXED); }
+};
+
 // launch counter (bench.py reports gpu_launches from it)
 extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }

@@ -1486,10 +1486,10 @@ int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
       (const void*)decode_mega_kernel<1, 1, false>, (const void*)decode_mega_kernel<1, 1, true>};
   const int vi = (p.gemm_mode != 0 ? 4 : 0) + am * 2 + pf;
   fn = table[vi];
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  if (!attr_set[vi]) {
+  static PerDeviceOnce attr_once[8];
+  if (attr_once[vi].pending()) {
     IVG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM));
-    attr_set[vi] = true;
+    attr_once[vi].mark();
   }
   int max_blocks = 0;
   IVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, fn, MEGA_THREADS, MEGA_SMEM));

@@ -497,11 +497,11 @@ int conv_out3_launch(int dtype, const void* x, const float* stats, const float* 
   if (N == 0) return 0;
   if (C <= 128 && C % 4 == 0 && C % (dtype == DT_BF16 ? 8 : 4) == 0 && H % CO3_TH == 0 && W % CO3_TW == 0) {
     const size_t tsm = (size_t)((CO3_TH + 2) * (CO3_TW + 2) * C + 27 * C) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
       IVG_CUDA(cudaFuncSetAttribute(conv_out3_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
       IVG_CUDA(cudaFuncSetAttribute(conv_out3_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-      attr_set = true;
+      attr_once.mark();
     }
     const long long tiles = (long long)N * (H / CO3_TH) * (W / CO3_TW);
     IVG_CHECK(tiles < 0x7fffffffLL && tsm <= 110 * 1024, "conv_out3: tile count / shared memory out of range");
@@ -662,7 +662,8 @@ int serialise_launch(const long long* ic, const long long* id, long long* tokens
 template <typename T>
 __global__ void detok_gather_kernel(const long long* __restrict__ tokens, const float* __restrict__ cb_ctx,
                                     const float* __restrict__ cb_dyn, T* __restrict__ qc, T* __restrict__ qd, int B,
-                                    int t, int f, int cr, int dr, int D, long long nvq, long long ndyn, int L) {
+                                    int t, int f, int cr, int dr, int D, long long nvq, long long ndyn, int L,
+                                    int* __restrict__ bad_ctx) {
   const long long nctx = (long long)B * t * cr, ndy = (long long)B * f * dr;
   const int ctx_len = t * (cr + 1) - 1;
   const long long total = (nctx + ndy) * D;
@@ -675,7 +676,10 @@ __global__ void detok_gather_kernel(const long long* __restrict__ tokens, const 
       const int r = (int)(row % ((long long)t * cr));
       const int fr = r / cr, k = r % cr;
       long long id = tokens[(size_t)b * L + fr * (cr + 1) + k];
-      id = id < 0 ? 0 : (id >= nvq ? nvq - 1 : id);  // the reference would raise on out-of-range ctx ids
+      if (id < 0 || id >= nvq) {       // the reference's embedding lookup raises here (:238): flag it, the host raises
+        if (bad_ctx != nullptr && d == 0) *bad_ctx = 1;
+        id = id < 0 ? 0 : nvq - 1;     // stay in bounds; the output of this call is discarded by the caller
+      }
       qc[row * D + d] = from_f32<T>(cb_ctx[id * D + d]);
     } else {
       const long long r2 = row - nctx;
@@ -691,16 +695,16 @@ __global__ void detok_gather_kernel(const long long* __restrict__ tokens, const 
 
 int detok_gather_launch(int dtype, const long long* tokens, const float* cb_ctx, const float* cb_dyn, void* qc,
                         void* qd, int B, int t, int f, int cr, int dr, int D, long long nvq, long long ndyn, int L,
-                        cudaStream_t st) {
+                        int* bad_ctx, cudaStream_t st) {
   if (B == 0) return 0;
   const long long total = ((long long)B * t * cr + (long long)B * f * dr) * D;
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (dtype == DT_BF16)
     detok_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, cb_ctx, cb_dyn, (__nv_bfloat16*)qc,
-                                                               (__nv_bfloat16*)qd, B, t, f, cr, dr, D, nvq, ndyn, L);
+                                                               (__nv_bfloat16*)qd, B, t, f, cr, dr, D, nvq, ndyn, L, bad_ctx);
   else
     detok_gather_kernel<float><<<blocks, 256, 0, st>>>(tokens, cb_ctx, cb_dyn, (float*)qc, (float*)qd, B, t, f, cr, dr,
-                                                       D, nvq, ndyn, L);
+                                                       D, nvq, ndyn, L, bad_ctx);
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;

@@ -330,10 +330,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 template <typename T, int BN>
 static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
   using SM = GemmSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     IVG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr_set = true;
+    attr_once.mark();
   }
   long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
   int grid = (int)(total < num_sms ? total : num_sms);

@@ -574,10 +574,10 @@ int topk_sample_launch(const float* logits, long long ld, int rows, int V, int k
   IVG_CHECK(k >= 1 && temperature > 0.f, "topk_sample: bad k=%d / temperature=%f", k, temperature);
   if (rows == 0) return 0;
   size_t smem = (size_t)(V + 256) * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     IVG_CUDA(cudaFuncSetAttribute(topk_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_once.mark();
   }
   IVG_CHECK(smem <= 200 * 1024, "topk_sample: vocab %d too large for the shared-memory select", V);
   IVG_CUDA(launch_k(topk_sample_kernel, dim3(rows), dim3(512), smem, st, logits, ld, V, k, 1.0f / temperature, seed, step,

@@ -357,4 +357,35 @@ int add_to_f32_launch(int dtype, float* y, const void* x, long long n, cudaStrea
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Attention dropout (HF LlamaAttention: nn.functional.dropout(attn_weights, p=attention_dropout, training=True);
+// reference scripts/pretrain/oxe-64-act-free.sh:31 trains with 0.1).  y[i] = keep(i) ? x[i] / (1 - p) : 0 with a
+// counter-based generator: keep(i) depends only on (seed, element index), so the backward pass regenerates the mask of
+// the forward pass from the seed instead of storing it (dP is masked in place, P' = dropout(P) is recomputed for dV).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dropout_uniform(unsigned long long seed, unsigned long long i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);      // [0, 1)
+}
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p, float inv_keep,
+                               unsigned long long seed) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = dropout_uniform(seed, (unsigned long long)i) >= p ? from_f32<T>(to_f32(x[i]) * inv_keep) : from_f32<T>(0.f);
+}
+int dropout_launch(int dtype, const void* x, void* y, long long n, float p, unsigned long long seed, cudaStream_t st) {
+  IVG_CHECK(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0, 1)", p);
+  if (n <= 0) return 0;
+  const float inv_keep = 1.0f / (1.0f - p);
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (dtype == DT_BF16) dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, inv_keep, seed);
+  else dropout_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, n, p, inv_keep, seed);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ivg

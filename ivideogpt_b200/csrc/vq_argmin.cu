@@ -299,13 +299,13 @@ int vq_argmin_launch(const float* z, const float* e, float* enorm_ws, unsigned l
   IVG_CHECK(N >= 0 && K > 0 && K < 0x7fffffff, "vq_argmin: bad N=%d K=%d", N, K);
   if (N == 0) return 0;
   IVG_CHECK(((uintptr_t)z & 15) == 0 && ((uintptr_t)e & 15) == 0, "vq_argmin: z/e must be 16-byte aligned");
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once;
   const size_t smem = (size_t)(VQ_TN * VQ_PITCH + 2 * VQ_TK * VQ_PITCH + 2 * VQ_TK) * sizeof(float);
   const size_t smem2 = (size_t)(VQ_TN * VQ_PITCH + 2 * VQ2_TK * VQ_PITCH + 2 * VQ2_TK) * sizeof(float);
-  if (!attr_set) {
+  if (attr_once.pending()) {
     IVG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IVG_CUDA(cudaFuncSetAttribute(vq_argmin_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    attr_set = true;
+    attr_once.mark();
   }
   vq_enorm_kernel<<<cdiv(K, 256), 256, 0, stream>>>(e, enorm_ws, K);
   vq_fill_kernel<<<cdiv(N, 256), 256, 0, stream>>>(packed_ws, N);

@@ -7,6 +7,8 @@ torch.cuda.current_stream().  Nothing in this file computes with torch ops.
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import types
 from typing import Optional
 
 import torch
@@ -275,8 +277,10 @@ def tokens_serialise(idx_ctx, idx_dyn, B, t, f, cr, dr, n_vq, n_dyn, want_labels
     return tokens, labels
 
 
-def tokens_gather(tokens, cb_ctx, cb_dyn, t, f, cr, dr, dtype):
-    _cuda(tokens, cb_ctx, cb_dyn)
+def tokens_gather(tokens, cb_ctx, cb_dyn, t, f, cr, dr, dtype, bad_ctx=None):
+    """bad_ctx: optional int32 [1] device flag, set to 1 by the kernel when a context position holds an id outside the
+    context codebook (the reference's embedding lookup raises there, compressive_vq_model.py:238)."""
+    _cuda(tokens, cb_ctx, cb_dyn, bad_ctx)
     assert tokens.dtype == torch.int64 and tokens.is_contiguous()
     B, L = tokens.shape
     D = cb_ctx.shape[1]
@@ -284,7 +288,7 @@ def tokens_gather(tokens, cb_ctx, cb_dyn, t, f, cr, dr, dtype):
     qd = torch.empty(B * f * dr, D, dtype=dtype, device=tokens.device)
     _lib.check(_lib.load().ivgpt_tokens_gather(_dt(qc), tokens.data_ptr(), cb_ctx.data_ptr(), cb_dyn.data_ptr(),
                                                qc.data_ptr(), qd.data_ptr(), B, t, f, cr, dr, D, cb_ctx.shape[0],
-                                               cb_dyn.shape[0], L, _stream()), "tokens_gather")
+                                               cb_dyn.shape[0], L, _ptr(bad_ctx), _stream()), "tokens_gather")
     return qc, qd
 
 
@@ -448,10 +452,27 @@ def embed_bwd(ids, dx, dE):
 
 
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0):
+    """Fused AdamW update of `p` in place (raw-pointer kernel).  Pass the Parameter itself (or a tensor sharing its
+    version counter, e.g. p.detach()), NOT p.data: the write is announced with increment_version so that every cache
+    keyed on (data_ptr, _version) -- the packed kernel-layout weight copies of LlamaWeights / PackedWeights -- is
+    rebuilt before the next forward."""
     _cuda(p, g, m, v)
     assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (p, g, m, v))
     _lib.check(_lib.load().ivgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                                        eps, weight_decay, step, gscale, _stream()), "adamw")
+    torch.autograd.graph.increment_version(p)
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = keep(seed, i) ? x / (1 - p) : 0 over the flattened contiguous x (out may be x itself)."""
+    _cuda(x, out)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.dtype == x.dtype and out.numel() == x.numel()
+    _lib.check(_lib.load().ivgpt_dropout(_dt(x), x.data_ptr(), out.data_ptr(), x.numel(), float(p),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "dropout")
+    return out
 
 
 def add_to_f32(y, x):
@@ -487,3 +508,44 @@ def preprocess_resize(frames: torch.Tensor, size_hw, channels_last: bool = True,
                                                    T, H, W, Cc, out.data_ptr(), oh, ow, float(divisor), _stream()),
                "preprocess_resize")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# device guard: every launch above goes to torch.cuda.current_stream() of the CURRENT device, and the C side keeps
+# per-device state keyed by cudaGetDevice().  A tensor living on another GPU (model on cuda:1 while cuda:0 is current)
+# therefore switches the current device for the duration of the call.
+# ------------------------------------------------------------------------------------------------
+def _first_cuda_device(args, kwargs):
+    for x in args:
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.device
+    for x in kwargs.values():
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.device
+    return None
+
+
+def _device_guarded(fn):
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+def on_device_of(t: torch.Tensor):
+    """Context manager: make t's GPU the current device (no-op when it already is).  Used by the model-level entry points
+    (tokenize / detokenize / generate / forward) so that descriptor-only launches (gemm_raw) follow the model's device."""
+    return torch.cuda.device(t.device)
+
+
+device_scoped = _device_guarded      # decorator for model-level methods (first CUDA tensor argument decides)
+
+for _name, _fn in list(globals().items()):
+    if isinstance(_fn, types.FunctionType) and not _name.startswith("_") and _fn.__module__ == __name__ and \
+            _name not in ("gemm_desc", "gemm_raw", "torch_dtype", "set_pdl", "on_device_of", "device_scoped"):
+        globals()[_name] = _device_guarded(_fn)
+del _name, _fn

@@ -23,6 +23,34 @@ from typing import Optional
 import torch
 from torch import nn
 
+from .. import ops
+
+
+def _embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    B, L = ids.shape
+    out = torch.empty(B * L, table.shape[1], dtype=torch.float32, device=ids.device)
+    ops.embed(ids, ids.stride(0), L, None, table.detach().float().contiguous(), out, B * L)
+    return out.view(B, L, -1)
+
+
+class _EmbedFn(torch.autograd.Function):
+    """Embedding lookup on the B200 kernels with a gradient for the table (scatter-add of the row gradients)."""
+
+    @staticmethod
+    def forward(ctx, ids, table):
+        ctx.save_for_backward(ids)
+        ctx.shape = tuple(table.shape)
+        ctx.tdtype = table.dtype
+        return _embed_rows(ids, table)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ids,) = ctx.saved_tensors
+        dE = torch.zeros(ctx.shape, dtype=torch.float32, device=gout.device)
+        g = gout.to(torch.float32).contiguous().view(-1, ctx.shape[1])
+        ops.embed_bwd(ids, g, dE)
+        return None, dE.to(ctx.tdtype)
+
 
 class HeadModelWithAction(nn.Module):
     def __init__(self, llm, action_dim, prelude_tokens_num, tokens_num_per_dyna, context, segment_length,
@@ -67,21 +95,22 @@ class HeadModelWithAction(nn.Module):
 
     # ------------------------------------------------------------------------------------------------------
     def get_input_embeddings(self, input_ids):
-        """fp32 token embeddings [B, L, hidden], gathered by the B200 embed kernel."""
-        from .. import ops
+        """fp32 token embeddings [B, L, hidden], gathered by the B200 embed kernel.  Differentiable w.r.t. the embedding
+        table when autograd is recording (training from inputs_embeds, reference :160-186): the backward is the
+        scatter-add kernel ivgpt_embed_bwd."""
         table = self.llm.get_input_embeddings().weight
         if not input_ids.is_cuda:
             raise RuntimeError("HeadModelWithAction requires CUDA tensors (no CPU fallback)")
         ids = input_ids.to(torch.int64).contiguous()
-        B, L = ids.shape
-        out = torch.empty(B * L, table.shape[1], dtype=torch.float32, device=ids.device)
-        ops.embed(ids, ids.stride(0), L, None, table.detach().float().contiguous(), out, B * L)
-        return out.view(B, L, -1)
+        if torch.is_grad_enabled() and table.requires_grad:
+            return _EmbedFn.apply(ids, table)
+        return _embed_rows(ids, table)
 
     def _frames(self):
         return self.segment_length - self.context
 
     @torch.no_grad()
+    @ops.device_scoped
     def generate(self, inputs_token, do_sample=True, temperature=1.0, top_k=100, max_new_tokens=None,
                  pad_token_id=50256, action: Optional[torch.FloatTensor] = None):
         if self.reward_prediction:
@@ -100,6 +129,12 @@ class HeadModelWithAction(nn.Module):
             for i in range(n_prompt_slots):
                 embeds[:, slot0 + i * period, :] += act[:, i + self.context - 1, :]
             nslots = n_prompt_slots + self._frames()
+            # the reference indexes action[:, i + context - 1] for every generated frame (:80-81) and raises IndexError when
+            # the action tensor is too short; only the slot after the LAST frame (forced separator, dropped) may be missing
+            need = self.context - 1 + n_prompt_slots - 1 + self._frames()
+            if act.shape[1] < need:
+                raise IndexError(f"HeadModelWithAction.generate: action has {act.shape[1]} timesteps, the rollout of "
+                                 f"{self._frames()} frames with context {self.context} needs at least {need}")
             slot_emb = torch.zeros(B, nslots, act.shape[-1], dtype=torch.float32, device=act.device)
             avail = min(nslots, act.shape[1] - (self.context - 1))
             slot_emb[:, :avail] = act[:, self.context - 1: self.context - 1 + avail]
@@ -122,6 +157,7 @@ class HeadModelWithAction(nn.Module):
         return tokens[:, :-1]
 
     @torch.no_grad()
+    @ops.device_scoped
     def generate_without_action(self, inputs_token, do_sample=True, temperature=1.0, top_k=100,
                                 max_new_tokens=None):
         per_frame = ((max_new_tokens + 1) // self._frames()) - 1
@@ -141,6 +177,7 @@ class HeadModelWithAction(nn.Module):
         assert tokens.size(1) == T + max_new_tokens + 1
         return tokens[:, :-1]
 
+    @ops.device_scoped
     def forward(self, input_ids=None, attention_mask=None, labels=None, position_ids=None, action=None):
         embeds = self.get_input_embeddings(input_ids)
         act = torch.nn.functional.linear(action.float(), self.action_linear.weight.float(),

@@ -152,7 +152,7 @@ class LlamaEngine:
 
     # ---- prefill ------------------------------------------------------------------------------------------
     def prefill(self, B, L, Lmax, ids: Optional[torch.Tensor], embeds: Optional[torch.Tensor], all_logits: bool,
-                logits_out: Optional[torch.Tensor] = None, want_hidden: bool = False):
+                logits_out: Optional[torch.Tensor] = None, want_hidden: bool = False, hidden_only: bool = False):
         """Runs L prompt positions, fills the KV cache.  Returns logits: [B, V] of the last position, or
         [B, L, Vpad] of every position when all_logits."""
         w = self.w
@@ -173,6 +173,8 @@ class LlamaEngine:
         xn = self.buf("xn", (M, h), self.dtype)
         ops.rmsnorm(x, w.norm, xn, M, w.eps)
         V = w.vocab
+        if hidden_only:                                  # final-norm states of every position, no lm_head
+            return None, xn.view(B, L, h)
         if all_logits:
             vpad = (V + 3) // 4 * 4
             logits = logits_out if logits_out is not None else torch.empty(B, L, vpad, dtype=torch.float32,

@@ -65,6 +65,7 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
             raise NotImplementedError(f"B200LlamaForCausalLM: argument `{name}` is not supported by the sm_100a path")
 
     # ---- forward: full-sequence logits (+ shifted CE loss) ---------------------------------------------------------
+    @ops.device_scoped
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
                 inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, cache_position=None, logits_to_keep=0, **kwargs):
@@ -85,14 +86,14 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
         if torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters()):
             # training step (train_gpt.py:792-798): forward + backward on the B200 kernels; the returned loss carries a
             # grad_fn whose backward hands the already-computed parameter gradients to autograd (DDP hooks included).
-            if input_ids is None:
-                raise NotImplementedError("training from inputs_embeds (action-conditioned fine-tuning) is not built yet")
-            if float(getattr(self.config, "attention_dropout", 0.0) or 0.0) > 0.0 and self.training:
-                import warnings
-                warnings.warn("B200LlamaForCausalLM: attention_dropout > 0 is ignored (dropout 0 is what loss parity "
-                              "is defined on; see DESIGN.md)", stacklevel=2)
+            if output_hidden_states:
+                raise NotImplementedError("training with output_hidden_states (reward / action-reconstruction heads of "
+                                          "HeadModelWithAction) is not implemented on the sm_100a path")
+            p_drop = float(getattr(self.config, "attention_dropout", 0.0) or 0.0) if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0.0 else 0      # torch's CPU generator: seedable
             names, params = zip(*self.named_parameters())
-            loss = _TrainLossFn.apply(self, input_ids, labels, names, *params)
+            emb = inputs_embeds if input_ids is None else None
+            loss = _TrainLossFn.apply(self, input_ids, emb, labels, names, p_drop, seed, *params)
             return CausalLMOutputWithPast(loss=loss, logits=None, past_key_values=None, hidden_states=None,
                                           attentions=None)
         eng = self.b200_engine()
@@ -114,14 +115,18 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
 
     # ---- generate: prefill + CUDA-graph decode loop -----------------------------------------------------------------
     @torch.no_grad()
+    @ops.device_scoped
     def generate(self, inputs=None, generation_config=None, do_sample=None, temperature=None, top_k=None,
                  top_p=None, max_new_tokens=None, max_length=None, pad_token_id=None, eos_token_id=None,
                  use_cache=True, inputs_embeds=None, input_ids=None, attention_mask=None,
                  return_dict_in_generate=False, output_hidden_states=False, num_beams=1, seed=None, **kwargs):
         if inputs is None:
             inputs = input_ids
-        self._reject("return_dict_in_generate", return_dict_in_generate)
-        self._reject("output_hidden_states", output_hidden_states)
+        if output_hidden_states and not return_dict_in_generate:
+            raise NotImplementedError("generate(output_hidden_states=True) needs return_dict_in_generate=True "
+                                      "(mbrl/video_predictor.py:293-303 passes both)")
+        for _k in ("output_scores", "output_logits", "output_attentions"):
+            self._reject(_k, kwargs.get(_k))
         if num_beams not in (None, 1):
             raise NotImplementedError("beam search is not supported")
         if top_p is not None and top_p < 1.0:
@@ -149,9 +154,44 @@ class B200LlamaForCausalLM(LlamaForCausalLM):
                               inputs_embeds if inputs is None else None, int(max_new_tokens), do_sample, top_k,
                               temperature, seed)
         # eos_token_id 50256 is outside the 16386-token vocabulary (configs/llama/config.json) -> never stops early.
-        if inputs is None:
-            return tokens[:, L:]      # HF returns only the new tokens when fed inputs_embeds (action_model.py:101-114)
-        return tokens
+        # HF returns only the new tokens when fed inputs_embeds (action_model.py:101-114)
+        sequences = tokens[:, L:] if inputs is None else tokens
+        if not return_dict_in_generate:
+            return sequences
+        from transformers.generation.utils import GenerateDecoderOnlyOutput
+        hidden_states = None
+        if output_hidden_states:
+            hidden_states = self._generation_hidden_states(eng, inputs, inputs_embeds if inputs is None else None, tokens,
+                                                           L, int(max_new_tokens))
+        return GenerateDecoderOnlyOutput(sequences=sequences, hidden_states=hidden_states)
+
+    def _generation_hidden_states(self, eng, inputs, inputs_embeds, tokens, L, new):
+        """`result.hidden_states` of HF generate(return_dict_in_generate=True, output_hidden_states=True), as far as the
+        reference reads it (mbrl/video_predictor.py:305-308: hidden_states[-1][-1] -> reward head): a tuple over the `new`
+        generation steps, each a tuple whose LAST entry is the final-norm output of the positions fed at that step
+        ([B, L, h] for the prompt step, [B, 1, h] afterwards).  HF's tuples also hold the embedding output and every
+        intermediate layer; only the last entry is provided here (1-tuples).  The states come from ONE teacher-forced pass
+        over prompt + generated tokens on the prefill kernels after the rollout (same quantities as the decode steps up to
+        rounding), so the decode kernels carry no per-step hidden-state traffic."""
+        B = tokens.shape[0]
+        fed = L + new - 1                                    # positions that were fed to the model
+        if fed <= 0:
+            return ()
+        Lmax = (fed + 7) // 8 * 8
+        if inputs is not None:
+            _, hidden = eng.prefill(B, fed, Lmax, tokens[:, :fed].contiguous(), None, True, hidden_only=True)
+        else:
+            emb = inputs_embeds.to(torch.float32)
+            if new > 1:
+                ids_new = tokens[:, L:fed].contiguous()
+                table = eng.w.embed
+                rows = torch.empty(B * (fed - L), table.shape[1], dtype=torch.float32, device=tokens.device)
+                ops.embed(ids_new, ids_new.stride(0), fed - L, None, table, rows, B * (fed - L))
+                emb = torch.cat([emb, rows.view(B, fed - L, -1)], dim=1)
+            _, hidden = eng.prefill(B, fed, Lmax, None, emb.contiguous(), True, hidden_only=True)
+        hidden = hidden.to(torch.float32).clone()
+        steps = [(hidden[:, :L],)] + [(hidden[:, L + i - 1: L + i],) for i in range(1, new)]
+        return tuple(steps)
 
     def gradient_checkpointing_enable(self, *a, **k):  # accepted and ignored (train_gpt.py:598-600)
         return None
@@ -162,26 +202,31 @@ class _TrainLossFn(torch.autograd.Function):
     call (activations never outlive it) and released to autograd in backward."""
 
     @staticmethod
-    def forward(ctx, model, input_ids, labels, names, *params):
+    def forward(ctx, model, input_ids, inputs_embeds, labels, names, p_drop, seed, *params):
         from .train_engine import LlamaTrainEngine
         eng = model.b200_engine()
         train = LlamaTrainEngine(eng.w)
         # model.b200_grad_reducer (grad_reduce.BucketedGradReducer, optional): the data-parallel exchange, launched bucket
         # by bucket from inside the backward so that it overlaps the remaining layers (row a13, train_gpt.py:672,798)
         reducer = getattr(model, "b200_grad_reducer", None)
-        loss, grads = train.forward_backward(input_ids, labels, on_grads=reducer.on_grads if reducer is not None else None)
+        loss, grads = train.forward_backward(input_ids, labels, on_grads=reducer.on_grads if reducer is not None else None,
+                                             embeds=inputs_embeds, attn_dropout=p_drop, seed=seed)
         if reducer is not None:
             reducer.finish(grads)
-        ctx.grads = [grads[n] for n in names]
+        # trained from inputs_embeds: the embedding table is reached through the caller's own lookup (autograd), not here
+        ctx.grads = [grads.get(n) for n in names]
+        ctx.d_embeds = grads.get("inputs_embeds")
         return loss.clone()
 
     @staticmethod
     def backward(ctx, gout):
         out = []
         for g in ctx.grads:
-            out.append(g.mul_(gout) if g.is_contiguous() else g * gout)
+            out.append(None if g is None else (g.mul_(gout) if g.is_contiguous() else g * gout))
+        d_emb = None if ctx.d_embeds is None else ctx.d_embeds * gout
         ctx.grads = None
-        return (None, None, None, None) + tuple(out)
+        ctx.d_embeds = None
+        return (None, None, d_emb, None, None, None, None) + tuple(out)
 
 
 def register():

@@ -4,8 +4,10 @@ train_gpt.py:766-804: `outputs = model(input_ids, labels)` -> `accelerator.backw
 Every contraction -- forward projections, dgrad, wgrad, the four attention-backward products -- is a launch of the
 tcgen05 GEMM (gemm_tc.cu); both operands of that kernel are K-major, so wgrad / attention-backward operands are first
 re-laid out by the batched transpose kernel.  Activations needed by the backward pass are kept per layer (B = 16 clips
-of 751 tokens: ~0.6 GB per layer).  Attention dropout is not implemented (dropout 0 == what loss parity is defined on,
-SURVEY.md section 7); a configured attention_dropout > 0 is ignored with a warning.
+of 751 tokens: ~0.6 GB per layer).  Attention dropout (config.attention_dropout, 0.1 in the reference's pre-training
+scripts) is applied to the attention probabilities in training mode with a counter-based mask (ivgpt_dropout) that the
+backward pass regenerates from the seed; loss/gradient parity with HF is defined at dropout 0 and, for dropout > 0,
+against a torch restatement fed the SAME mask (tests/test_llama.py).
 """
 from __future__ import annotations
 
@@ -21,6 +23,11 @@ from .engine import LlamaWeights
 
 def _r8(n: int) -> int:
     return (n + 7) // 8 * 8
+
+
+def dropout_layer_seed(seed: int, layer: int) -> int:
+    """Seed of the attention-dropout mask of `layer` for a forward call that drew `seed`."""
+    return (int(seed) * 1000003 + layer * 7919 + 1) & 0x7FFFFFFFFFFFFFFF
 
 
 class LlamaTrainEngine:
@@ -52,21 +59,35 @@ class LlamaTrainEngine:
 
     # ---- forward + backward --------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, on_grads=None):
+    def forward_backward(self, ids: Optional[torch.Tensor], labels: torch.Tensor, grad_scale: float = 1.0, on_grads=None,
+                         embeds: Optional[torch.Tensor] = None, attn_dropout: float = 0.0, seed: int = 0):
         """Returns (loss 0-d fp32 tensor, grads dict keyed by HF parameter name -> fp32 tensor).
+
+        embeds [B, L, hidden] instead of ids: the action-conditioned training entry (HeadModelWithAction.forward,
+        reference action_model.py:171-186); the gradient w.r.t. the embeddings is returned as grads["inputs_embeds"]
+        (fp32 [B, L, hidden]) and no embedding-table gradient is produced here (autograd routes it through the caller's
+        embedding lookup).  attn_dropout > 0: dropout on the attention probabilities (HF LlamaAttention in training mode),
+        mask regenerated from (seed, layer) in the backward pass.
 
         on_grads(grads, names): called as soon as the gradients `names` are final, in backward order ([lm_head, final norm],
         layer L-1 ... layer 0, [embedding]) -- the hook of the data-parallel exchange (grad_reduce.BucketedGradReducer
         launches that bucket's all-reduce while the next layer's backward is computed).  The hook may replace entries."""
         w, dt, code = self.w, self.dt, self.code
-        B, L = ids.shape
+        src = ids if ids is not None else embeds
+        B, L = src.shape[0], src.shape[1]
         M, h, H, I, V = B * L, w.hidden, w.heads, w.inter, w.vocab
         Lp = _r8(L)
-        dev = ids.device
-        ids = ids.contiguous()
+        dev = src.device
         labels = labels.contiguous()
-        x = torch.empty(M, h, dtype=torch.float32, device=dev)
-        ops.embed(ids, ids.stride(0), L, None, w.embed, x, M)
+        if ids is not None:
+            ids = ids.contiguous()
+            x = torch.empty(M, h, dtype=torch.float32, device=dev)
+            ops.embed(ids, ids.stride(0), L, None, w.embed, x, M)
+        else:
+            assert embeds.shape == (B, L, h), (embeds.shape, (B, L, h))
+            x = embeds.detach().to(torch.float32).reshape(M, h).clone()
+        p_drop = float(attn_dropout)
+        layer_seed = lambda li: dropout_layer_seed(seed, li)
         saved: List[Dict[str, torch.Tensor]] = []
         kc = torch.zeros(B, H, Lp, 64, dtype=dt, device=dev)
         vc = torch.zeros(B, H, 64, Lp, dtype=dt, device=dev)
@@ -87,9 +108,10 @@ class LlamaTrainEngine:
                 out=sc.data_ptr(), ldo=Lp, out_bstride=L * Lp, out_dtype=F32, alpha=0.125))
             P = torch.empty(B * H, L, Lp, dtype=dt, device=dev)
             ops.softmax(sc, P, B * H * L, L, L, Lp, Lp, True, 0)
+            Pd = ops.dropout(P, p_drop, layer_seed(li)) if p_drop > 0.0 else P      # P' = dropout(P); P itself is kept
             ao = torch.empty(M, h, dtype=dt, device=dev)
             ops.gemm_raw(ops.gemm_desc(
-                dtype=code, a=P.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
+                dtype=code, a=Pd.data_ptr(), lda=Lp, a_bstride=L * Lp, a_rows=L, a_cols=L, a_batches=B * H,
                 b=vt.data_ptr(), ldb=Lp, b_bstride=64 * Lp, b_rows=64, b_cols=L, b_batches=B * H,
                 M=L, N=64, K=L, batch=B * H, heads=H, a_bsel=2, b_bsel=2, o_bsel=1, o_nhead=64,
                 out=ao.data_ptr(), ldo=h, out_bstride=L * h, out_dtype=code))
@@ -100,6 +122,7 @@ class LlamaTrainEngine:
             gu = ops.gemm(xn2, lw["wgu"])
             act = ops.swiglu(gu)
             ops.gemm(act, lw["wd"], residual=x, out=x)
+            del Pd
             s.update(xn1=xn1, qkv=qkv, q=q, k=k, P=P, ao=ao, xn2=xn2, gu=gu, act=act)
             saved.append(s)
         xnf = torch.empty(M, h, dtype=dt, device=dev)
@@ -146,11 +169,15 @@ class LlamaTrainEngine:
                 M=L, N=L, K=64, batch=B * H, heads=H, a_bsel=1, a_bdiv=1, b_bsel=1, b_bdiv=1, o_bsel=2,
                 a_khead=64, b_kbase=2 * h, b_khead=64, causal_skip=1,
                 out=dP.data_ptr(), ldo=Lp, out_bstride=L * Lp, out_dtype=F32))
+            if p_drop > 0.0:
+                ops.dropout(dP, p_drop, layer_seed(li), out=dP)          # dP = dP' * mask / (1 - p), same mask as the forward
             dS = torch.empty(B * H, L, Lp, dtype=dt, device=dev)
             ops.softmax_bwd(P, dP, dS, B * H * L, L, L, Lp, True, 0.125)
             del dP
             Pt = torch.zeros(B * H, L, Lp, dtype=dt, device=dev)
-            ops.transpose_raw(P, 0, Pt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
+            Pd = ops.dropout(P, p_drop, layer_seed(li)) if p_drop > 0.0 else P      # dV = P'^T . dO
+            ops.transpose_raw(Pd, 0, Pt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
+            del Pd
             d_aoT = torch.zeros(B, h, Lp, dtype=dt, device=dev)
             ops.transpose_raw(d_ao, 0, d_aoT, B, L, h, h, Lp, L * h, h * Lp)
             dV = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
@@ -193,9 +220,12 @@ class LlamaTrainEngine:
                     "mlp.down_proj.weight", "mlp.gate_proj.weight", "mlp.up_proj.weight", "post_attention_layernorm.weight",
                     "self_attn.o_proj.weight", "self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
                     "input_layernorm.weight")])
-        dE = torch.zeros(V, h, dtype=torch.float32, device=dev)
-        ops.embed_bwd(ids, dx, dE)
-        grads["model.embed_tokens.weight"] = dE
-        if on_grads is not None:
-            on_grads(grads, ["model.embed_tokens.weight"])
+        if ids is not None:
+            dE = torch.zeros(V, h, dtype=torch.float32, device=dev)
+            ops.embed_bwd(ids, dx, dE)
+            grads["model.embed_tokens.weight"] = dE
+            if on_grads is not None:
+                on_grads(grads, ["model.embed_tokens.weight"])
+        else:
+            grads["inputs_embeds"] = dx.view(B, L, h)
         return loss, grads

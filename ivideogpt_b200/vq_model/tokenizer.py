@@ -132,6 +132,7 @@ class CompressiveVQModel(HubMixin, nn.Module):
 
     # ---- tokenize -----------------------------------------------------------------------------------
     @torch.no_grad()
+    @ops.device_scoped
     def encode_latents(self, pixel_values: torch.Tensor, with_dynamics: bool = True):
         """Pre-quantisation latents in fp32: z_ctx [B*t*256, D], z_dyn [B*f*16, D] (None if not requested)."""
         self._require_cuda(pixel_values, "tokenize")
@@ -152,6 +153,7 @@ class CompressiveVQModel(HubMixin, nn.Module):
         return z_ctx, z_dyn
 
     @torch.no_grad()
+    @ops.device_scoped
     def tokenize(self, pixel_values: torch.FloatTensor, context_length: int = 0):
         assert context_length == self.context_length  # same contract as the reference (:166)
         t = self.context_length
@@ -168,6 +170,7 @@ class CompressiveVQModel(HubMixin, nn.Module):
         return tokens, labels
 
     @torch.no_grad()
+    @ops.device_scoped
     def tokenize_context(self, pixel_values: torch.FloatTensor):
         """Prediction-minimal entry: tokens of the context frames only (what predict.py:54 keeps)."""
         t = self.context_length
@@ -183,6 +186,7 @@ class CompressiveVQModel(HubMixin, nn.Module):
 
     # ---- detokenize ---------------------------------------------------------------------------------
     @torch.no_grad()
+    @ops.device_scoped
     def detokenize(self, indices, context_length: int = 0, cache=None, return_cache=False):
         assert context_length == self.context_length
         self._require_cuda(indices, "detokenize")
@@ -192,9 +196,10 @@ class CompressiveVQModel(HubMixin, nn.Module):
         assert (L + 1 - (1 + cr * cr) * t) % (1 + dr * dr) == 0
         f = (L + 1 - (1 + cr * cr) * t) // (1 + dr * dr)
         D = self.vq_embed_dim
+        bad_ctx = torch.zeros(1, dtype=torch.int32, device=indices.device)
         qc, qd = ops.tokens_gather(indices.contiguous(), self.quantize.embedding.weight.detach().float(),
                                    self.dynamics_quantize.embedding.weight.detach().float(), t, f, cr * cr, dr * dr,
-                                   plan.dtype)
+                                   plan.dtype, bad_ctx=bad_ctx)
         H = W = self.config["resolution"] if "resolution" in self.config else None
         out = None
         if cache is not None:
@@ -215,6 +220,12 @@ class CompressiveVQModel(HubMixin, nn.Module):
             pd = ops.gemm(qd, wpl, bpl)                                       # [B*f*16, p*p*latent]
             lat_d = ops.patchify(pd, self.patch_size, inverse=True, frames=B * f, res=cr, ch=self.latent_channels)
             plan.decode(lat_d, self.cond_decoder, out, t, f, ctx_feats=ctx_feats)
+        # every kernel of the call is enqueued: now look at the flag (one host sync at the END of the call; the reference's
+        # embedding lookup raises on such ids, a mis-sliced prompt must not decode silently to wrong frames)
+        if int(bad_ctx.item()) != 0:
+            raise IndexError("detokenize: a context position holds a token id outside the context codebook "
+                             f"[0, {self.num_vq_embeddings}) -- separator or dynamics ids in a context slot "
+                             "(reference compressive_vq_model.py:238 raises in the embedding lookup)")
         if return_cache:
             return out, {"context_dec": out[:, :t].clone(), "cond_features": ctx_feats}
         return out

@@ -22,7 +22,7 @@ def test_roofline_reports_the_dominant_kernel_and_its_algorithmic_bytes():
     args = SimpleNamespace(dtype="bf16", steps=5)
     # (summed ms, summed work, launches) over 5 steps: decode megakernel dominates
     prof = {"conv": (225.0, 2.1e14, 345), "gemm": (105.0, 4.5e13, 600), "mega": (950.0, 5 * 236.0, 5)}
-    r = bench.build_roofline(args, prof, 1450.0, 64, 2, 237, _llm(), 1349.9, 6530.3, "measured")
+    r = bench.build_roofline(args, "bf16", 5, prof, 1450.0, 64, 2, 237, _llm(), 1349.9, 6530.3, "measured")
     assert r["bound"] == "hbm" and r["kernel"].startswith("decode_mega_kernel") and r["unit"] == "GB/s"
     # 236 steps from a 514-token prompt at B=64: 59.4 GB of weights + 351.6 GB of K/V
     assert abs(r["algorithmic_bytes_per_launch"] - 411.0e9) < 0.5e9
@@ -32,7 +32,7 @@ def test_roofline_reports_the_dominant_kernel_and_its_algorithmic_bytes():
     assert abs(r["other"]["conv"]["achieved"] - 2.1e14 / 0.225 / 1e12) < 1e-6
     # without the megakernel (TF32 parity path) the conv family is reported, against half the bf16 peak
     args32 = SimpleNamespace(dtype="tf32", steps=5)
-    r2 = bench.build_roofline(args32, dict(prof, mega=(0.0, 0.0, 0)), 1450.0, 64, 2, 237, _llm(), 1349.9, 6530.3, "measured")
+    r2 = bench.build_roofline(args32, "tf32", 5, dict(prof, mega=(0.0, 0.0, 0)), 1450.0, 64, 2, 237, _llm(), 1349.9, 6530.3, "measured")
     assert r2["bound"] == "tensor" and "conv" in r2["kernel"] and abs(r2["peak"] - 1349.9 / 2) < 1e-9
 
 

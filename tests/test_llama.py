@@ -325,7 +325,8 @@ def test_unsupported_generate_and_forward_arguments_fail_loudly():
     from oracle.llama_ref import TINY_LLAMA
     m = B200LlamaForCausalLM(LlamaConfig(**TINY_LLAMA)).eval()
     ids = torch.zeros(1, 4, dtype=torch.int64)
-    for kw in (dict(return_dict_in_generate=True), dict(output_hidden_states=True), dict(num_beams=4), dict(top_p=0.9)):
+    for kw in (dict(output_hidden_states=True), dict(num_beams=4), dict(top_p=0.9),
+               dict(return_dict_in_generate=True, output_scores=True)):
         with pytest.raises(NotImplementedError):
             m.generate(ids, max_new_tokens=2, **kw)
     with pytest.raises(NotImplementedError):
@@ -339,3 +340,186 @@ def test_unsupported_generate_and_forward_arguments_fail_loudly():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(input_ids=ids)
     assert m.gradient_checkpointing_enable() is None          # accepted and ignored (train_gpt.py:598-600)
+
+
+def test_masked_llama_oracle_equals_hf():
+    """CPU: the explicit-mask restatement used by the dropout test reproduces the unmodified HF model (no mask)."""
+    from oracle.llama_masked_ref import masked_llama_loss
+    from oracle.llama_ref import TINY_LLAMA, build_hf_llama
+    hf = build_hf_llama(TINY_LLAMA, init_scale=2.0)
+    ids = torch.randint(0, 1026, (2, 30), generator=torch.Generator().manual_seed(0))
+    labels = ids.clone()
+    labels[:, :10] = -100
+    with torch.no_grad():
+        want = hf(input_ids=ids, labels=labels)
+        loss, logits = masked_llama_loss(hf.state_dict(), hf.config, ids, labels)
+    assert abs(float(loss) - float(want.loss)) < 1e-6 and float((logits - want.logits).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_optimizer_steps_refresh_packed_weights_and_match_hf_adamw(cuda):
+    """the fused AdamW writes parameters through raw pointers; the packed kernel-layout copies must be
+    rebuilt for the next forward.  Three optimizer steps of the product (TF32 compute, FusedAdamW) against HF autograd +
+    torch.optim.AdamW on the same data: the loss trajectory must follow HF's (a stale engine repeats step 1's loss)."""
+    from oracle.llama_ref import TINY_LLAMA
+    from ivideogpt_b200.optim import FusedAdamW
+    ref, mine = _pair(TINY_LLAMA, cuda, torch.float32, scale=2.0)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(0, 1026, (4, 60), generator=g)
+    labels = ids.clone()
+    labels[:, :20] = -100
+    ref.train(), mine.train()
+    start = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    kw = dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    o_ref, o_mine = torch.optim.AdamW(ref.parameters(), **kw), FusedAdamW(mine.parameters(), **kw)
+    l_ref, l_mine = [], []
+    for _ in range(3):
+        o_ref.zero_grad()
+        lr_ = ref(input_ids=ids, labels=labels).loss
+        lr_.backward()
+        o_ref.step()
+        l_ref.append(float(lr_))
+        o_mine.zero_grad()
+        lm_ = mine(input_ids=ids.to(cuda), labels=labels.to(cuda)).loss
+        lm_.backward()
+        o_mine.step()
+        l_mine.append(float(lm_))
+    assert l_ref[0] - l_ref[2] > 0.05, f"the reference itself did not move: {l_ref}"
+    for a, b in zip(l_mine, l_ref):
+        assert abs(a - b) / b < 2e-3, (l_mine, l_ref)
+    # the parameter UPDATE (not just the parameter) points the same way
+    for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+        da = (q.detach().cpu() - start[n]).flatten().double()
+        db = (p.detach() - start[n]).flatten().double()
+        cos = float((da @ db) / (da.norm() * db.norm()).clamp_min(1e-30))
+        assert cos > 0.97, f"{n}: update cosine {cos}"
+
+
+@pytest.mark.gpu
+def test_action_conditioned_training_from_inputs_embeds(cuda):
+    """ADVICE r1 (medium) / VERDICT missing 7: HeadModelWithAction.forward under autograd (train_gpt.py
+    --action_conditioned; reference action_model.py:160-186): loss and the gradients of action_linear, the embedding
+    table and the transformer against the oracle restatement around the unmodified HF Llama."""
+    from oracle.action_model_ref import RefActionModel, seeded_heads_
+    from oracle.llama_ref import TINY_LLAMA, build_hf_llama
+    from ivideogpt_b200.transformer import B200LlamaForCausalLM, HeadModelWithAction
+    layout = dict(action_dim=3, prelude_tokens_num=21, tokens_num_per_dyna=4, context=2, segment_length=5)
+    hf = build_hf_llama(TINY_LLAMA, seed=11, init_scale=2.0)
+    ref = seeded_heads_(RefActionModel(hf, **layout), 5)
+    llm = B200LlamaForCausalLM(hf.config).to(torch.float32)
+    llm.load_state_dict(hf.state_dict(), strict=True)
+    mine = HeadModelWithAction(llm, model_type="llama", **layout)
+    mine.load_state_dict({k: v for k, v in ref.state_dict().items() if not k.startswith("llm.")}, strict=False)
+    mine = mine.to(cuda).train()
+    mine.llm.set_compute_dtype(torch.float32)
+    ref.train()
+    g = torch.Generator().manual_seed(2)
+    L = layout["prelude_tokens_num"] + 3 * 5
+    ids = torch.randint(0, 1024, (3, L), generator=g)
+    labels = ids.clone()
+    labels[:, :layout["prelude_tokens_num"] + 1] = -100
+    action = torch.randn(3, layout["segment_length"], 3, generator=g)
+    for p in ref.parameters():
+        p.grad = None
+    loss_ref = ref(ids, labels, action)[0]
+    loss_ref.backward()
+    out = mine(input_ids=ids.to(cuda), labels=labels.to(cuda), action=action.to(cuda))
+    assert out.loss.requires_grad
+    out.loss.backward()
+    assert abs(float(out.loss) - float(loss_ref)) / float(loss_ref) < 1e-3
+    want = dict(ref.named_parameters())
+    checked = 0
+    for n, q in mine.named_parameters():
+        p = want[n]
+        if p.grad is None:
+            continue
+        assert q.grad is not None, n
+        a, b = q.grad.detach().float().cpu().flatten().double(), p.grad.flatten().double()
+        if float(b.norm()) == 0.0:
+            continue
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        assert cos > 0.999, f"{n}: cos {cos}"
+        assert abs(float(a.norm() / b.norm()) - 1.0) < 0.02, n
+        checked += 1
+    assert checked >= 4 + 9 * TINY_LLAMA["num_hidden_layers"]
+    assert mine.action_linear.weight.grad is not None and float(mine.action_linear.weight.grad.abs().sum()) > 0.0
+    assert mine.llm.model.embed_tokens.weight.grad is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol_loss,min_cos", [(torch.float32, 1e-3, 0.999), (torch.bfloat16, 8e-3, 0.985)])
+def test_attention_dropout_training_matches_torch_given_the_same_mask(cuda, dtype, tol_loss, min_cos):
+    """VERDICT missing 7: attention dropout (0.1 in the reference's scripts).  The kernel's counter-based mask is read back
+    (dropout of a ones tensor), handed to the explicit-mask torch restatement (oracle/llama_masked_ref.py, pinned to HF
+    at mask = 1), and loss + every gradient are compared.  Also: ~10 % of the probabilities are dropped, eval mode and
+    p = 0 ignore the mask."""
+    from ivideogpt_b200 import ops
+    from ivideogpt_b200.transformer.train_engine import dropout_layer_seed
+    from oracle.llama_masked_ref import masked_llama_loss
+    from oracle.llama_ref import TINY_LLAMA
+    cfg = dict(TINY_LLAMA, attention_dropout=0.1)
+    ref, mine = _pair(cfg, cuda, dtype, scale=2.0)
+    B, L, H = 3, 45, cfg["num_attention_heads"]
+    g = torch.Generator().manual_seed(8)
+    ids = torch.randint(0, 1026, (B, L), generator=g)
+    labels = ids.clone()
+    labels[:, :15] = -100
+    mine.train()
+    torch.manual_seed(1234)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # what forward() will draw
+    torch.manual_seed(1234)
+    out = mine(input_ids=ids.to(cuda), labels=labels.to(cuda))
+    out.loss.backward()
+    Lp = (L + 7) // 8 * 8
+    masks = []
+    for li in range(cfg["num_hidden_layers"]):
+        ones = torch.ones(B * H, L, Lp, dtype=dtype, device=cuda)
+        m = ops.dropout(ones, 0.1, dropout_layer_seed(seed, li)).float().cpu()[:, :, :L].reshape(B, H, L, L)
+        masks.append(m)
+    kept = torch.stack(masks).ne(0).float().mean().item()
+    assert 0.88 < kept < 0.92, kept
+    assert abs(float(torch.stack(masks).max()) - 1.0 / 0.9) < 1e-2
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in ref.state_dict().items()}
+    loss_ref, _ = masked_llama_loss(sd, ref.config, ids, labels, masks)
+    loss_ref.backward()
+    assert abs(float(out.loss) - float(loss_ref)) / float(loss_ref) < tol_loss
+    for n, q in mine.named_parameters():
+        a, b = q.grad.detach().float().cpu().flatten().double(), sd[n].grad.flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        assert cos > min_cos, f"{n}: cos {cos}"
+    # the mask matters (loss differs from the no-dropout loss) and is off in eval mode
+    with torch.no_grad():
+        plain = float(ref(input_ids=ids, labels=labels).loss)
+    assert abs(plain - float(loss_ref)) > 1e-4
+    mine.eval()
+    with torch.no_grad():
+        ev = mine(input_ids=ids.to(cuda), labels=labels.to(cuda)).loss
+    assert abs(float(ev) - plain) / plain < (2e-3 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.gpu
+def test_generate_return_dict_with_hidden_states_like_mbrl_rollout(cuda):
+    """VERDICT missing 6: `llm.generate(inputs_embeds=..., return_dict_in_generate=True, output_hidden_states=True)` as
+    mbrl/video_predictor.py:293-308 drives it: `.sequences` are the new tokens, `.hidden_states[-1][-1]` is the final-norm
+    state of the last fed position ([B, 1, h]) -- compared with HF's own generate output on the same greedy rollout."""
+    from oracle.llama_ref import TINY_LLAMA
+    ref, mine = _pair(TINY_LLAMA, cuda, torch.float32, scale=4.0)
+    ids = torch.randint(0, 1026, (3, 19), generator=torch.Generator().manual_seed(21))
+    emb_ref = ref.get_input_embeddings()(ids).detach()
+    with torch.no_grad():
+        want = ref.generate(inputs_embeds=emb_ref, do_sample=False, max_new_tokens=6, pad_token_id=50256,
+                            return_dict_in_generate=True, output_hidden_states=True, use_cache=True)
+    got = mine.generate(inputs_embeds=emb_ref.to(cuda), do_sample=False, max_new_tokens=6, pad_token_id=50256,
+                        return_dict_in_generate=True, output_hidden_states=True, use_cache=True)
+    assert got.sequences.shape == want.sequences.shape == (3, 6)
+    same = (got.sequences.cpu() == want.sequences).all(dim=1)
+    assert int(same.sum()) >= 2, "greedy rollouts diverged on most rows (near-ties are expected to be rare at this scale)"
+    assert len(got.hidden_states) == len(want.hidden_states) == 6
+    assert got.hidden_states[0][-1].shape == want.hidden_states[0][-1].shape == (3, 19, 128)
+    last_got, last_want = got.hidden_states[-1][-1], want.hidden_states[-1][-1]
+    assert last_got.shape == last_want.shape == (3, 1, 128)
+    assert rel_err(last_got[same], last_want[same]) < 3e-3
+    assert rel_err(got.hidden_states[0][-1], want.hidden_states[0][-1]) < 3e-3
+    # ids path: sequences include the prompt
+    got2 = mine.generate(ids.to(cuda), do_sample=False, max_new_tokens=6, return_dict_in_generate=True)
+    assert got2.sequences.shape == (3, 25) and got2.hidden_states is None
