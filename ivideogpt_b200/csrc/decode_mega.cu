@@ -190,9 +190,9 @@ __device__ __forceinline__ void issue_items(MegaCtx& c, const GemmPhase& g, int 
 
 // called before the barrier that precedes phase g: weights do not depend on anything, start fetching them now
 __device__ __forceinline__ void prefetch_phase0(MegaCtx& c, const GemmPhase& g) {
+  c.phase_consumed = 0;                   // every issuing thread keeps its own copy of the consumer-side counters
   if (threadIdx.x != 0) return;
   c.phase_issued = 0;
-  c.phase_consumed = 0;
   issue_items(c, g, (int)g.nbuf);         // every buffer is free here: the previous GEMM phase has retired
 }
 
@@ -234,8 +234,9 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       loaded_split = split;
     }
     GEMM_MARK(14);
-    if (threadIdx.x == 0) {
-      issue_items(c, g, it + (int)g.nbuf);      // this item (if not prefetched) and the following nbuf - 1
+    if (threadIdx.x == 0) issue_items(c, g, it + (int)g.nbuf);      // this item (if not prefetched) and the following nbuf - 1
+    if (lane == 0 && warp < MEGA_NISSUE) {
+      // every issuing thread walks the same sequence of operand barriers (own copies of the parities)
       const uint32_t buf = (uint32_t)c.phase_consumed % g.nbuf;
       const uint32_t par = (c.wait_par >> buf) & 1u;
       c.wait_par ^= 1u << buf;
@@ -245,15 +246,16 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       tc_fence_after();
       GEMM_MARK(15);
       const uint32_t a0 = smem_u32(c.sm.a), b0 = smem_u32(c.sm.a + g.slab_off + (size_t)buf * g.slab_bytes);
-      // MEGA_NACC independent accumulators, k-step t -> accumulator t % MEGA_NACC (64 TMEM columns apart), summed in a fixed
-      // order by the epilogue: consecutive MMAs no longer form one dependent chain on a single accumulator
+      // k-step t = 4 j + k goes to issuer / accumulator t % MEGA_NISSUE (64 TMEM columns apart); the epilogue adds the
+      // accumulators in a fixed order.  Each issuer commits separately: mma_done counts MEGA_NISSUE arrivals.
+      const uint32_t acc = c.tmem_base + (uint32_t)(warp * 64);
       for (int j = 0; j < nkb; ++j) {
         const uint64_t adesc = umma_desc_sw128_kmajor(a0 + (uint32_t)(j * a_rows * 128));
         const uint64_t bdesc = umma_desc_sw128_kmajor(b0 + (uint32_t)(j * g.bn * 128));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss<false>(c.tmem_base + (uint32_t)(((j * 4 + k) % MEGA_NACC) * 64), adesc + (uint64_t)(k * 2),
-                         bdesc + (uint64_t)(k * 2), IDESC, (j * 4 + k) >= MEGA_NACC ? 1u : 0u);
+          if ((k % MEGA_NISSUE) == warp)
+            umma_ss<false>(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (j * 4 + k) >= MEGA_NISSUE ? 1u : 0u);
       }
       umma_commit(c.sm.mma_done);
       GEMM_MARK(16);
@@ -265,18 +267,18 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       mbar_wait_bounded(p, c.sm.mma_done, c.mphase, 5);
       tc_fence_after();
       for (int c0 = 0; c0 < g.bn; c0 += 16) {          // 16 accumulator columns (weight rows) at a time
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        uint32_t r[MEGA_NACC][16];                          // all accumulators in flight, one wait
+#pragma unroll
+        for (int a = 0; a < MEGA_NACC; ++a)                // K >= 64 per item: every accumulator has been written
+          tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c0), r[a]);
         tmem_ld_wait();
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[0][i]);
 #pragma unroll
-        for (int a = 1; a < MEGA_NACC; ++a) {              // K >= 64 per item: every accumulator has been written
-          tmem_ld_32x32b_x16(c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c0), r);
-          tmem_ld_wait();
+        for (int a = 1; a < MEGA_NACC; ++a) {              // fixed order: reproducible
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[a][i]);
         }
         if (row < p.B) {
           const int n0 = tile * g.bn + c0;
@@ -1221,7 +1223,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(c.sm.bfull + i, 1);
-    mbar_init(c.sm.mma_done, 1);
+    mbar_init(c.sm.mma_done, GM == 0 ? MEGA_NISSUE : 1);   // gemm_mode 0: one commit per issuing warp
     mbar_init(c.sm.abar, 1);
     for (int i = 0; i < 4; ++i) mbar_init(c.sm.bempty + i, 1);
     for (int i = 0; i < 64; ++i) mbar_init(c.sm.ring_bar + i, 1);

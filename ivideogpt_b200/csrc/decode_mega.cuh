@@ -6,10 +6,16 @@ namespace ivg {
 
 constexpr int MEGA_THREADS = 256;   // 256: one warp per attention item (fastest measured); 512: warp pairs
 constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
-#ifndef IVG_MEGA_NACC
-#define IVG_MEGA_NACC 1
+// gemm_mode 0: MEGA_NISSUE warps issue the tcgen05.mma instructions of a work item (lane 0 of warps 0..MEGA_NISSUE-1), each
+// into its OWN TMEM accumulator; k-step t goes to issuer / accumulator t % MEGA_NISSUE and the epilogue adds the accumulators
+// in a fixed order.  Why: one thread issuing back to back is limited to one tcgen05.mma per ~112 cycles whatever the shape
+// (M <= 128, N <= 128); 4 issuing warps sustain ~40 cycles per instruction (tools/probes/mma_probe.cu,
+// profiles/r02/mma_issue_and_ffma_probe.json).  A step of the 138 M model issues ~1800 MMAs per CTA.
+#ifndef IVG_MEGA_NISSUE
+#define IVG_MEGA_NISSUE 4
 #endif
-constexpr int MEGA_NACC = IVG_MEGA_NACC;    // gemm_mode 0: independent TMEM accumulators per work item (1, 2 or 4), k-steps dealt round-robin
+constexpr int MEGA_NISSUE = IVG_MEGA_NISSUE;   // 1, 2 or 4
+constexpr int MEGA_NACC = MEGA_NISSUE;         // one accumulator (64 TMEM columns) per issuing warp
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
 constexpr int MEGA_B_BYTES = MEGA_BN * MEGA_MAXK * 2;   // 32 KB per slab

@@ -28,9 +28,9 @@ from .. import ops
 
 def _embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     B, L = ids.shape
-    out = torch.empty(B * L, table.shape[1], dtype=torch.float32, device=ids.device)
+    out = torch.empty(B, L, table.shape[1], dtype=torch.float32, device=ids.device)   # not a view: callers add to it in place
     ops.embed(ids, ids.stride(0), L, None, table.detach().float().contiguous(), out, B * L)
-    return out.view(B, L, -1)
+    return out
 
 
 class _EmbedFn(torch.autograd.Function):

@@ -72,9 +72,12 @@ def test_megakernel_138m_vs_hf_teacher_forced(cuda):
         o = eng.generate(ids, None, n, False, 0, 1.0, 0, use_mega=True).cpu()
         assert torch.equal(o, out[:, :L + n]), f"megakernel rollout of {n} tokens is not a prefix of the {NEW}-token one"
         last_logits[n] = eng.buf("logits", (B, (V + 3) // 4 * 4), torch.float32)[:, :V].float().cpu().clone()
-    # HF fp32 (eager attention, CPU), teacher-forced on the megakernel's OWN history: position p predicts token p + 1
+    # HF fp32 (eager attention, CPU), teacher-forced on the megakernel's OWN history: position p predicts token p + 1;
+    # and the same pass under autocast(bf16) -- the reference's own bf16 arithmetic -- as the yardstick for logit error
     with torch.no_grad():
         hf = ref(input_ids=out[:, :-1]).logits[:, L - 1:]                               # [B, NEW, V]
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            hf_bf16 = ref(input_ids=out[:, :-1]).logits[:, L - 1:].float()
     produced = out[:, L:]                                                               # [B, NEW]; [:, 0] is the prefill's token
     top2 = hf.topk(2, dim=-1)
     margin = top2.values[..., 0] - top2.values[..., 1]
@@ -96,9 +99,10 @@ def test_megakernel_138m_vs_hf_teacher_forced(cuda):
     # last-step logits (the buffer lm_head of the final megakernel step wrote) vs HF at that position
     for n, lg in last_logits.items():
         want = hf[:, n - 1]                                  # the step that produced token L + n - 1 (fed position L + n - 2)
-        e = rel_err(lg, want)
-        print(f"[mega vs HF 138M] last-step logits after {n} new tokens: rel err {e:.3e}")
-        assert e < 2.5e-2, f"megakernel logits after {n} tokens: rel err {e}"
+        e, e_auto = rel_err(lg, want), rel_err(hf_bf16[:, n - 1], want)
+        print(f"[mega vs HF 138M] last-step logits after {n} new tokens: rel err {e:.3e} (HF under autocast(bf16): {e_auto:.3e})")
+        assert e < 1.15 * e_auto + 1e-3, f"megakernel logits after {n} tokens: rel err {e} vs the reference's own bf16 deviation {e_auto}"
+        assert e < 4e-2
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -124,9 +128,9 @@ def test_bf16_llama_no_worse_than_hf_autocast(cuda):
     l_mine = abs(float(got.loss) - float(truth.loss)) / float(truth.loss)
     print(f"\n[bf16 llama] logits rel err vs fp32: ours {e_mine:.3e}, HF autocast {e_auto:.3e}; loss rel err ours {l_mine:.2e}, "
           f"autocast {l_auto:.2e}; ours vs autocast {rel_err(got.logits, auto.logits.float()):.3e}")
-    assert e_mine < 1.5 * e_auto + 1e-3
+    assert e_mine < 1.15 * e_auto + 1e-3                   # at least as accurate as the reference's own bf16 arithmetic
     assert l_mine < max(1.5 * l_auto, 2e-3)
-    assert e_mine < 2e-2                                   # absolute ceiling, tighter than round 1's 3e-2
+    assert e_mine < 4e-2
 
 
 @pytest.mark.gpu
@@ -298,36 +302,33 @@ def test_topk_sample_kernel_distribution(cuda, k, temperature, ties):
 
 @pytest.mark.gpu
 def test_megakernel_sampler_distribution(cuda):
-    """The megakernel's own sampler (sample_row in decode_mega.cu): every row gets the SAME prompt, so all rows share
-    one next-token distribution per first token; many seeds x 64 rows are pooled per first token and compared with
-    softmax(top-k(teacher-forced logits)) of the product's own bf16 forward (isolates the sampler from GEMM rounding)."""
+    """The megakernel's own sampler (sample_row in decode_mega.cu).  Every row gets the SAME prompt and the first new token
+    is FORCED (slot mechanism of the action-conditioned rollout), so all 64 rows x 160 seeds draw the second token from one
+    distribution; the expectation is HF's rule applied to the megakernel's OWN logits for that history (read back from a
+    greedy run) -- the sampler is isolated from GEMM rounding."""
     from oracle.llama_ref import TINY_LLAMA
     cfg = dict(TINY_LLAMA, hidden_size=192, intermediate_size=768, num_attention_heads=3, num_key_value_heads=3)
     ref, mine = _llama_pair(cfg, cuda, torch.bfloat16, scale=3.0)
-    B, L, k, T = 64, 24, 6, 0.8
+    B, L, k, T, first = 64, 24, 6, 0.8, 321
     one = torch.randint(0, 1026, (1, L), generator=torch.Generator().manual_seed(44))
     ids = one.expand(B, L).contiguous().to(cuda)
     eng = mine.b200_engine()
+    force = (L, 1 << 20, first, None)                        # position L holds `first` in every row; nothing else is forced
+    g = eng.generate(ids, None, 2, False, 0, 1.0, 0, use_mega=True, slot_cfg=force)
+    assert bool((g[:, L] == first).all())
+    lg = eng.buf("logits", (B, (1026 + 3) // 4 * 4), torch.float32)[:, :1026].float().cpu().clone()
+    assert float((lg - lg[0]).abs().max()) == 0.0, "identical rows must produce identical logits"
+    p = _hf_topk_probs(lg[0], k, T)
+    support = (p > 0).nonzero().flatten()
     draws = []
     for seed in range(160):
-        draws.append(eng.generate(ids, None, 2, True, k, T, 1000 + seed, use_mega=True)[:, L:].cpu())
-    draws = torch.cat(draws)                                  # [160*64, 2]: first token (prefill sampler), second (megakernel)
-    checked = 0
-    for first in draws[:, 0].unique().tolist():
-        sel = draws[draws[:, 0] == first, 1]
-        if len(sel) < 1500:
-            continue
-        with torch.no_grad():
-            lg = mine(input_ids=torch.cat([one, torch.tensor([[first]])], 1).to(cuda)).logits[0, -1].float().cpu()
-        p = _hf_topk_probs(lg, k, T)
-        support = (p > 0).nonzero().flatten()
-        assert bool(torch.isin(sel, support).all())
-        cnt = torch.bincount(sel, minlength=1026).double()[support]
-        exp = p[support] * len(sel)
-        chi = float(((cnt - exp) ** 2 / exp.clamp_min(1e-9)).sum())
-        print(f"\n[mega sampler] first token {first}: {len(sel)} draws, chi2 {chi:.1f} (dof {len(support) - 1})")
-        # the expected probabilities come from the prefill path's logits; the megakernel's differ by bf16 rounding (~1 %
-        # in p), which adds ~N * 1e-4 to the statistic -- well inside the slack of the 1e-6 critical value
-        assert chi < _chi2_crit(len(support) - 1) + 1e-4 * len(sel) * 4
-        checked += 1
-    assert checked >= 1
+        o = eng.generate(ids, None, 2, True, k, T, 1000 + seed, use_mega=True, slot_cfg=force)
+        assert bool((o[:, L] == first).all())
+        draws.append(o[:, L + 1].cpu())
+    draws = torch.cat(draws)
+    assert bool(torch.isin(draws, support).all()), "the megakernel sampled outside HF's top-k survivor set"
+    cnt = torch.bincount(draws, minlength=1026).double()[support]
+    exp = p[support] * len(draws)
+    chi = float(((cnt - exp) ** 2 / exp.clamp_min(1e-9)).sum())
+    print(f"\n[mega sampler] {len(draws)} draws over {len(support)} survivors: chi2 {chi:.1f} (crit {_chi2_crit(len(support) - 1):.1f})")
+    assert chi < _chi2_crit(len(support) - 1)

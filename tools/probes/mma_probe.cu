@@ -28,39 +28,44 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
-// mode 0: SS, one accumulator; 1: SS, two accumulators alternating; 2: TS (A in TMEM), one accumulator
-// kstep: 0 = every MMA reads the same 32-byte K slice of the 128-byte swizzled rows; 1 = slices 0..3 of successive k-blocks
+// mode 0: SS, one accumulator; 1: SS, two accumulators alternating; 2: TS (A in TMEM), one accumulator;
+// mode 3 / 4: SS with 2 / 4 ISSUING WARPS (lane 0 of warps 0..W-1), each with its own accumulator (N <= 128) and its own share
+// of the nmma instructions -- does the ~112-cycle floor belong to the issuing thread or to the tensor pipe?
 __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int M, int N, int nmma, int mode, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a = base;                       // 4 k-blocks x 128 rows x 128 B = 64 KB
   uint8_t* b = base + 64 * 1024;           // 4 k-blocks x 256 rows x 128 B = 128 KB
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[4];
   __shared__ uint32_t holder;
   for (int i = threadIdx.x; i < (192 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(bar + i, 1); fence_barrier_init(); }
   if (threadIdx.x < 32) { tmem_alloc(&holder, 512); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = holder;
-  if (threadIdx.x == 0) {
+  const int issuers = mode == 3 ? 2 : (mode == 4 ? 4 : 1);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < issuers) {
     const uint32_t idesc = umma_idesc(1, M, N);
     const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
+    const int mine = nmma / issuers;
     const long long t0 = clock64();
-    for (int i = 0; i < nmma; ++i) {
+    for (int i = 0; i < mine; ++i) {
       const int kb = (i >> 2) & 3, ks = i & 3;
       const uint64_t ad = umma_desc_sw128_kmajor(a0 + kb * (128 * 128)) + (uint64_t)(ks * 2);
       const uint64_t bd = umma_desc_sw128_kmajor(b0 + kb * (256 * 128)) + (uint64_t)(ks * 2);
       if (mode == 2) umma_ts(tm, tm + 256 + (uint32_t)((i & 15) * 8), bd, idesc, i > 0);
+      else if (mode >= 3) umma_ss<false>(tm + (uint32_t)(w * 128), ad, bd, idesc, i > 0 ? 1u : 0u);
       else umma_ss<false>(tm + (mode == 1 ? (uint32_t)((i & 1) * 256) : 0u), ad, bd, idesc, i > 1 ? 1u : 0u);
     }
     const long long t1 = clock64();
-    umma_commit(&bar);
-    mbar_wait(&bar, 0);
+    umma_commit(bar + w);
+    mbar_wait(bar + w, 0);
     const long long t2 = clock64();
-    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (blockIdx.x == 0 && w == issuers - 1) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
   tc_fence_before();
   __syncthreads();
@@ -102,12 +107,12 @@ int main() {
   const int Ms[2] = {64, 128};
   const int Ns[7] = {8, 16, 32, 64, 128, 256, 48};
   bool first = true;
-  for (int mode = 0; mode < 3; ++mode)
+  for (int mode = 0; mode < 5; ++mode)
     for (int mi = 0; mi < 2; ++mi)
       for (int ni = 0; ni < 7; ++ni) {
         const int M = Ms[mi], N = Ns[ni], nm = 512;
         if (mode == 2 && M == 64) continue;              // TS form: M = 128 only here
-        if (mode == 1 && N > 256) continue;
+        if (mode >= 3 && N > 128) continue;
         long long h[2] = {0, 0};
         for (int rep = 0; rep < 3; ++rep) {              // last repetition is reported (warm)
           mma_probe_kernel<<<sms, 128, smem>>>(M, N, nm, mode, out);
@@ -115,7 +120,7 @@ int main() {
           CK(cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost));
         }
         printf("%s  {\"mode\": \"%s\", \"M\": %d, \"N\": %d, \"issue_cycles_per_mma\": %.1f, \"complete_cycles_per_mma\": %.1f}",
-               first ? "" : ",\n", mode == 0 ? "SS" : (mode == 1 ? "SS-2acc" : "TS"), M, N, (double)h[0] / nm, (double)h[1] / nm);
+               first ? "" : ",\n", mode == 0 ? "SS" : (mode == 1 ? "SS-2acc" : (mode == 2 ? "TS" : (mode == 3 ? "SS-2warps" : "SS-4warps"))), M, N, (double)h[0] / nm, (double)h[1] / nm);
         first = false;
       }
   printf("\n ],\n");
