@@ -220,8 +220,10 @@ typedef struct ivgpt_mega_desc {
                       down, lm_head, sample, barriers); NULL to disable */
   void* vrows;     /* bf16 [layers][B][heads][Lmax][64]: V cache in K's layout (filled by ivgpt_rope_kv), used and
                       appended to when attn_mode == 0 */
-  void* attn_part; /* fp32 [SMs][4][72] scratch and */
-  void* attn_cnt;  /* uint32 [SMs] zeroed counters for attention items cut along the sequence (attn_mode 0) */
+  void* attn_part; /* fp32 [8 * SMs][72] scratch and */
+  void* attn_cnt;  /* uint32 [max(SMs, B * heads)] zeroed counters for attention items cut along the sequence (attn_mode 0:
+                      the left-over items of a large batch in 4 parts; every item in floor(8 * SMs / (B * heads)) <= 8
+                      parts when that is >= 2, e.g. B = 16) */
   int attn_mode;   /* attention phase: 0 = K/V streamed by 1-D bulk copies (TMA) into a shared-memory ring,
                       1 = register-staged loads */
   /* forced separator slots (action-conditioned rollout, action_model.py:78-114); slot_period == 0 disables.
@@ -248,7 +250,14 @@ typedef struct ivgpt_mega_desc {
   int bn_down;     /* gemm_mode 0: weight rows per work item of the down projection (multiple of 16, <= 64; 0 = 16); wd must be
                       packed with the same width.  Wider tiles x more K splits keep one round over the SMs with fewer
                       tcgen05.mma issues per CTA (32-row tiles x 6 splits: 32 instead of 64 for the 138 M model) */
+  void* tile_cnt;  /* uint32 [128] zeroed: arrival counters of the o-proj / down-proj output tiles.  Needed when
+                      ivgpt_mega_fused_norm() == 1 (gemm_mode 0): the add + RMSNorm phases are folded into their neighbours --
+                      the last split-K item of a tile adds the partials to x and writes bf16(x) into `xn`; wqkv / wgu /
+                      lm_head must then be packed from W (.) g (the RMSNorm weight of their input folded into the columns)
+                      and the kernel multiplies the per-row 1/rms in the consumers' epilogues (63 instead of 87 device-wide
+                      barriers per step of a 12-layer model). */
 } ivgpt_mega_desc;
+int ivgpt_mega_fused_norm(void);   /* compile-time property of gemm_mode 0, see tile_cnt */
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);

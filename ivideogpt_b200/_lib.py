@@ -81,6 +81,7 @@ class MegaDesc(C.Structure):
         ("qkvp", C.c_void_p),
         ("bn_wide", C.c_int),
         ("bn_down", C.c_int),
+        ("tile_cnt", C.c_void_p),
     ]
 
 
@@ -143,6 +144,7 @@ SIGNATURES = {
     "ivgpt_mega_packed_elems64": [_I, _I],
     "ivgpt_mega_pack_weight64": [_P, _P, _I, _I, _I, _P],
     "ivgpt_decode_mega": [C.POINTER(MegaDesc), _P],
+    "ivgpt_mega_fused_norm": [],
 }
 _RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong,
              "ivgpt_mega_packed_elems": C.c_longlong, "ivgpt_mega_packed_elems64": C.c_longlong,

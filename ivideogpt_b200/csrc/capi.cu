@@ -501,6 +501,8 @@ int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, co
   return 0;
 }
 
+int ivgpt_mega_fused_norm(void) { return ivg::mega_fused_norm(); }
+
 int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   IVG_CHECK(d != nullptr, "decode_mega: null descriptor");
   ivg::MegaParams p;
@@ -519,6 +521,7 @@ int ivgpt_decode_mega(const ivgpt_mega_desc* d, void* stream) {
   p.prof = d->prof;
   p.attn_mode = d->attn_mode;
   p.attn_part = (float*)d->attn_part; p.attn_cnt = (unsigned int*)d->attn_cnt;
+  p.tile_cnt = (unsigned int*)d->tile_cnt;
   p.slot_emb = d->slot_emb; p.slot0 = d->slot0; p.slot_period = d->slot_period; p.nslots = d->nslots;
   p.slot_token = d->slot_token;
   p.mma_m64 = 1;

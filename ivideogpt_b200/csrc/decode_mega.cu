@@ -152,6 +152,8 @@ __device__ __forceinline__ void issue_slab(MegaCtx& c, const GemmPhase& g, int t
 // (Until round-1 v10 the activation slab was row-major in global memory and laid out in shared memory by 24 cp.async per
 // thread + wait + __syncthreads: ~2 us per phase, 97 us per step; the bulk copy of a pre-swizzled image costs 24.)
 enum { EPI_STORE_BF16 = 0, EPI_PARTIAL_F32 = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
+// fused norms: EPI_PARTIAL_F32 phases carry `resid_cnt` (the tile's last arriver adds the partials to x and writes bf16(x));
+// phases whose A operand is that image carry `norm_a` (epilogue scales row b by rstd_b computed from the shared-memory slab)
 
 struct GemmPhase {
   const __nv_bfloat16* w;   // packed weights of [N, K]
@@ -164,6 +166,8 @@ struct GemmPhase {
   // gemm_mode 0 slab geometry (filled by phase_geometry); gemm_mode 1 ignores it
   int bn;                   // weight rows per work item (multiple of 16)
   uint32_t slab_off, slab_bytes, nbuf;
+  int norm_a;               // fused norms: A is bf16(x); multiply row b of the result by rsqrt(mean(x_b^2) + eps)
+  unsigned int* resid_cnt;  // fused norms: per-tile arrival counters of a split-K projection whose result is added to x
 };
 
 __device__ __forceinline__ int phase_items(const GemmPhase& g) { return ((g.N + g.bn - 1) / g.bn) * g.ksplits; }
@@ -212,6 +216,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
   const uint32_t IDESC = m64 ? umma_idesc(1, 64, g.bn) : umma_idesc(1, 128, g.bn);
   int loaded_split = -1;
   int it = 0;
+  float rstd = 1.0f;          // fused norms: 1 / rms of this thread's row of the activation slab
   const long long gt_entry = (PROF && p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
   for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
     const int tile = w % ntiles, split = w / ntiles;
@@ -241,7 +246,7 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       const uint32_t par = (c.wait_par >> buf) & 1u;
       c.wait_par ^= 1u << buf;
       ++c.phase_consumed;
-      if (a_pending) { mbar_wait_bounded(p, c.sm.abar, c.aphase, 3); c.aphase ^= 1u; }
+      if (a_pending) mbar_wait_bounded(p, c.sm.abar, c.aphase, 3);
       mbar_wait_bounded(p, c.sm.bfull + buf, par, 4);
       tc_fence_after();
       GEMM_MARK(15);
@@ -264,6 +269,27 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
     if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
       const int row = m64 ? (lane < 16 ? q * 16 + lane : p.B) : q * 32 + lane;
+      if (MEGA_FUSE_NORM && g.norm_a && a_pending) {
+        // rstd of this thread's row from the activation slab (bf16(x), K = hidden) while the tensor core works; with M = 64
+        // tiles only 16 lanes of a warp own rows, the other 16 take every second k-block of the same rows
+        mbar_wait_bounded(p, c.sm.abar, c.aphase, 3);
+        const int r = m64 ? q * 16 + (lane & 15) : q * 32 + lane;
+        float ssq = 0.f;
+        if (r < p.B) {
+          for (int j = m64 ? (lane >> 4) : 0; j < nkb; j += m64 ? 2 : 1) {
+            const uint4* rp = reinterpret_cast<const uint4*>(c.sm.a + (size_t)j * (size_t)(a_rows * 128) + (size_t)r * 128);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 u = rp[ch ^ (r & 7)];      // rows of a quarter-warp hit 8 different 16-byte columns: no bank conflicts
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); ssq = fmaf(f.x, f.x, ssq); ssq = fmaf(f.y, f.y, ssq); }
+            }
+          }
+        }
+        if (m64) ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+        rstd = rsqrtf(ssq / (float)g.K + p.eps);
+      }
       mbar_wait_bounded(p, c.sm.mma_done, c.mphase, 5);
       tc_fence_after();
       for (int c0 = 0; c0 < g.bn; c0 += 16) {          // 16 accumulator columns (weight rows) at a time
@@ -279,6 +305,10 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
         for (int a = 1; a < MEGA_NACC; ++a) {              // fixed order: reproducible
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[a][i]);
+        }
+        if (MEGA_FUSE_NORM && g.norm_a) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= rstd;
         }
         if (row < p.B) {
           const int n0 = tile * g.bn + c0;
@@ -308,8 +338,43 @@ __device__ void gemm_phase0(const MegaParams& p, MegaCtx& c, const GemmPhase& g)
       tc_fence_before();
     }
     c.mphase ^= 1;          // every thread tracks the parity (only warps 4..7 wait on it)
+    if (a_pending) c.aphase ^= 1u;   // ... and the parity of the activation-slab barrier (issuers and epilogue warps wait on it)
+    if (MEGA_FUSE_NORM && g.resid_cnt != nullptr && warp >= 4) __threadfence();   // partials of this item: released before the count
     __syncthreads();        // MMA retired (epilogue observed mma_done): TMEM accumulator, A slab and this weight
                             // buffer may be reused
+    if (MEGA_FUSE_NORM && g.resid_cnt != nullptr) {
+      // x += sum of the split-K partials of this output tile, by the LAST of its `ksplits` work items to arrive
+      __shared__ unsigned int s_last;
+      if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(g.resid_cnt + tile, 1u);
+        __threadfence();
+        s_last = ((old + 1u) % (unsigned int)g.ksplits == 0u) ? 1u : 0u;
+      }
+      __syncthreads();
+      if (s_last) {
+        const int f4_per_row = g.bn >> 2;                                   // float4 groups per row of the tile
+        for (int e = threadIdx.x; e < p.B * f4_per_row; e += MEGA_THREADS) {
+          const int rr = e / f4_per_row, cc = tile * g.bn + (e - rr * f4_per_row) * 4;
+          if (cc < g.N) {
+            float* xr = p.x + (size_t)rr * g.ldo + cc;
+            float4 v = __ldcg(reinterpret_cast<const float4*>(xr));           // past L1: another SM wrote it a phase ago
+            float4 q[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s)                                   // every load in flight before the first add; past L1
+              if (s < g.ksplits) q[s] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.out) + ((size_t)s * p.B + rr) * g.ldo + cc));
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              if (s < g.ksplits) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }   // split order: reproducible
+            *reinterpret_cast<float4*>(xr) = v;
+            uint2 o;
+            o.x = pack_bf16x2(v.x, v.y);
+            o.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(p.xn + a_off(p, rr, cc, g.ldo)) = o;  // un-normalised image: the consumer applies rstd
+          }
+        }
+      }
+      // (the device-wide barrier that follows orders these writes before the next phase; its proxy fence covers the image)
+    }
     GEMM_MARK(17);
 #undef GEMM_MARK
   }
@@ -482,8 +547,9 @@ __device__ __forceinline__ void gemm_phase(const MegaParams& p, MegaCtx& c, cons
 
 // ---- add split-K partials (fixed order) + RMSNorm -> xn ; or embedding gather + RMSNorm ----
 // One row per CTA, one float4 per thread (hidden <= 1024): every load of the row is in flight at once.
+// raw (fused norms): only x = E[token] (+ slot embedding) and its bf16 image; the consumer applies rstd, g is folded into its weights
 template <int MAXP>
-__device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col) {
+__device__ void norm_phase(const MegaParams& p, const float* w, int nparts, const long long* tok_row0, int tok_col, bool raw = false) {
   __shared__ float s_ss[MEGA_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.hidden;
@@ -517,6 +583,15 @@ __device__ void norm_phase(const MegaParams& p, const float* w, int nparts, cons
         if (s < nparts) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }   // fixed order: reproducible
       *reinterpret_cast<float4*>(xr + i) = v;
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    if (raw) {                 // CTA-uniform
+      if (i < H) {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(p.xn + a_off(p, m, i, H)) = o;
+      }
+      continue;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -700,6 +775,17 @@ __device__ __forceinline__ void ring_wait(const MegaParams& p, uint64_t* bar, ui
 // (History: V^T rows + a butterfly per row 61 us/layer; this layout 34.7; 5.5 TB/s is what the ring sustains in
 // isolation, tools/probes/ring_probe.cu.)
 constexpr int MEGA_ATT_SPLIT = 4;
+constexpr int MEGA_ATT_MAXSPLIT = 8;
+// Small batches (B * heads * 2 <= 8 * #CTAs, e.g. cfg256's B = 16: 192 items on 148 CTAs): one warp per item leaves most warps
+// idle and a single warp keeps only ~32 KB of K/V in flight (latency-bound: 22 us per layer for 37 MB).  Then EVERY item is
+// cut into P = floor(8 * #CTAs / items) <= 8 parts along the sequence, dealt round-robin over all warps of all CTAs, and
+// merged by the last part to arrive exactly like the left-over items of the large-batch deal.
+__device__ __forceinline__ int att_uniform_parts(const MegaParams& p) {
+  const int total = p.B * p.heads, G = (int)gridDim.x;
+  int P = (8 * G) / total;
+  P = P > MEGA_ATT_MAXSPLIT ? MEGA_ATT_MAXSPLIT : P;
+  return P >= 2 ? P : 0;
+}
 
 // unit u of the item's [u0, u0 + nU) K units followed by the same V units -> ring slot (lane 0 only; rows < pos were
 // written in earlier steps)
@@ -715,8 +801,9 @@ __device__ __forceinline__ void att_issue(const MegaParams& p, int layer, int bh
 
 // what a warp does in the attention phase of this step
 struct AttWork {
-  int kind;            // 0 nothing, 1 whole item, 2 part of a left-over item
+  int kind;            // 0 nothing, 1 whole item, 2 part of an item cut along the sequence
   int bh, u0, u1, extra, q, nslot;
+  int nsplit;          // parts per cut item (MEGA_ATT_SPLIT for the left-over items of the large-batch deal)
   bool tail;
 };
 
@@ -724,16 +811,35 @@ struct AttWork {
 __device__ __forceinline__ bool att_even_deal(const MegaParams& p) {
   const int total = p.B * p.heads, G = (int)gridDim.x;
   const int full = total / G, extras = total - full * G, free_w = 8 - full;
+  if (att_uniform_parts(p) != 0) return true;
   return full <= 8 && (extras == 0 || (free_w > 0 && extras * MEGA_ATT_SPLIT <= free_w * G));
 }
 __device__ __forceinline__ AttWork att_assign(const MegaParams& p, uint32_t a_bytes, int warp, int pos) {
   const int total = p.B * p.heads, G = (int)gridDim.x;
+  const int P = att_uniform_parts(p);
+  if (P != 0) {                       // every item in P parts, part pi = item * P + q on CTA pi % G, warp pi / G
+    AttWork w;
+    w.kind = 0;
+    const int nparts_u = total * P;
+    const int mine = nparts_u > (int)blockIdx.x ? (nparts_u - (int)blockIdx.x + G - 1) / G : 0;     // <= 8 by construction
+    w.nslot = mine > 0 ? (int)(a_bytes / MEGA_RING_SLOT) / mine : 1;
+    w.nslot = w.nslot > 8 ? 8 : w.nslot;
+    w.nsplit = P;
+    const int nK = (pos + 31) >> 5;
+    if (warp < mine) {
+      const int pi = (int)blockIdx.x + G * warp;
+      w.kind = 2; w.bh = pi / P; w.q = pi - w.bh * P; w.extra = w.bh;
+      w.u0 = (nK * w.q) / P; w.u1 = (nK * (w.q + 1)) / P; w.tail = w.q == P - 1;
+    }
+    return w;
+  }
   const int full = total / G, extras = total - full * G;
   const int nparts = extras * MEGA_ATT_SPLIT;
   const int my_parts = nparts > (int)blockIdx.x ? (nparts - (int)blockIdx.x + G - 1) / G : 0;
   const int active = full + my_parts;
   AttWork w;
   w.kind = 0;
+  w.nsplit = MEGA_ATT_SPLIT;
   w.nslot = active > 0 ? (int)(a_bytes / MEGA_RING_SLOT) / active : 1;     // o-proj slabs sit above a_bytes
   w.nslot = w.nslot > 8 ? 8 : w.nslot;
   const int nK = (pos + 31) >> 5;
@@ -941,12 +1047,12 @@ __device__ __forceinline__ void attention_store(const MegaParams& p, int bh, con
 // one left-over item cut along the sequence: every part publishes (max, sum, acc[64]); the part that arrives last
 // (monotonic counter, MEGA_ATT_SPLIT arrivals per item, layer and step) merges them and writes the output row.
 template <int GM, bool PROF>
-__device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, int u0, int u1, bool issued,
-                               float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
+__device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, int extra, int q, int nsplit, int u0, int u1,
+                               bool issued, float* wsm, uint8_t* ring, int nslot, uint64_t* bars, uint32_t& par) {
   const int lane = threadIdx.x & 31;
   float m, l, acc[8];
-  attention_stream<GM, PROF>(p, layer, bh, pos, u0, u1, q == MEGA_ATT_SPLIT - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
-  float* rec = p.attn_part + ((size_t)extra * MEGA_ATT_SPLIT + q) * 72;
+  attention_stream<GM, PROF>(p, layer, bh, pos, u0, u1, q == nsplit - 1, issued, wsm, ring, nslot, bars, par, m, l, acc);
+  float* rec = p.attn_part + ((size_t)extra * nsplit + q) * 72;
   if ((lane >> 3) == 0) {
     float4* dst = reinterpret_cast<float4*>(rec + 8 + (lane & 7) * 8);
     dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -961,17 +1067,18 @@ __device__ void attention_part(const MegaParams& p, int layer, int bh, int pos, 
     __threadfence();
   }
   old = __shfl_sync(0xffffffffu, old, 0);
-  if ((old + 1u) % MEGA_ATT_SPLIT != 0u) return;
+  if ((old + 1u) % (unsigned int)nsplit != 0u) return;
   // last arriver: merge (records are read past L1 -- the same addresses were read one layer ago)
-  const float* base = p.attn_part + (size_t)extra * MEGA_ATT_SPLIT * 72;
-  float mm[MEGA_ATT_SPLIT], M = -INFINITY;
+  const float* base = p.attn_part + (size_t)extra * nsplit * 72;
+  float mm[MEGA_ATT_MAXSPLIT], M = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < MEGA_ATT_SPLIT; ++k) { mm[k] = __ldcg(base + k * 72); M = fmaxf(M, mm[k]); }
+  for (int k = 0; k < MEGA_ATT_MAXSPLIT; ++k) { mm[k] = k < nsplit ? __ldcg(base + k * 72) : -INFINITY; M = fmaxf(M, mm[k]); }
   float L = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
 #pragma unroll
-  for (int k = 0; k < MEGA_ATT_SPLIT; ++k) {
+  for (int k = 0; k < MEGA_ATT_MAXSPLIT; ++k) {
+    if (k >= nsplit) break;
     const float w = __expf(mm[k] - M);
     L = fmaf(__ldcg(base + k * 72 + 1), w, L);
     const float4 a0 = __ldcg(reinterpret_cast<const float4*>(base + k * 72 + 8 + (lane & 7) * 8));
@@ -1260,8 +1367,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     wide_nbuf = wide_nbuf > 4u ? 4u : wide_nbuf;
     GemmPhase qkv_g{p.lw[0].wqkv, 3 * H, H, ws ? p.qkv_splits : 1, p.xn, H, ws ? EPI_PARTIAL_F32 : EPI_STORE_BF16,
                     ws ? (void*)p.qkvp : (void*)p.qkv, 3 * H, MEGA_BN, narrow_off, narrow_bytes, narrow_nbuf};
+    constexpr bool FN = GM == 0 && MEGA_FUSE_NORM;                          // fused norms (decode_mega.cuh)
+    qkv_g.norm_a = FN ? 1 : 0;
     prefetch_phase<GM>(p, c, qkv_g);
-    norm_phase<MAXP>(p, p.lw[0].n1, 0, p.tokens, pos);                       // x = E[token], xn = rmsnorm(x)
+    norm_phase<MAXP>(p, p.lw[0].n1, 0, p.tokens, pos, FN);                   // x = E[token], xn = rmsnorm(x) (FN: bf16(x))
     MEGA_MARK(0);
     MEGA_BARRIER(true); if (!ok) break;
     for (int l = 0; l < p.layers && ok; ++l) {
@@ -1270,6 +1379,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       gemm_phase<GM, PROF>(p, c, qkv_g);
       MEGA_MARK(1);
       GemmPhase o_g{L.wo, H, H, p.o_splits, p.ao, H, EPI_PARTIAL_F32, p.part, H, MEGA_BN, narrow_off, narrow_bytes, narrow_nbuf};
+      if (FN) o_g.resid_cnt = p.tile_cnt;
       prefetch_phase<GM>(p, c, o_g);
       const bool ring_prefetch = AM == 0 && p.attn_mode == 0 && att_even_deal(p);
       if (ring_prefetch) {
@@ -1296,7 +1406,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                                ring_par, m, lsum, acc);
               attention_store(p, w.bh, acc, 1.0f / lsum);
             } else if (w.kind == 2) {
-              attention_part<GM, PROF>(p, l, w.bh, pos, w.extra, w.q, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
+              attention_part<GM, PROF>(p, l, w.bh, pos, w.extra, w.q, w.nsplit, w.u0, w.u1, ring_prefetch, wsm, ring, w.nslot,
                              c.sm.ring_bar + warp * 8, ring_par);
             }
           } else {
@@ -1326,15 +1436,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       gemm_phase<GM, PROF>(p, c, o_g);
       MEGA_MARK(3);
       GemmPhase gu_g{L.wgu, 2 * p.inter, H, 1, p.xn, H, EPI_SWIGLU, p.act, p.inter, p.bn_wide, wide_off, wide_bytes, wide_nbuf};
+      gu_g.norm_a = FN ? 1 : 0;
       prefetch_phase<GM>(p, c, gu_g);
-      MEGA_BARRIER(false); if (!ok) break;
-      norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                    // x += o partials; xn = rmsnorm(x) * n2
-      MEGA_MARK(0);
+      if constexpr (!FN) {
+        MEGA_BARRIER(false); if (!ok) break;
+        norm_phase<MAXP>(p, L.n2, p.o_splits, nullptr, 0);                  // x += o partials; xn = rmsnorm(x) * n2
+        MEGA_MARK(0);
+      }
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, gu_g);
       MEGA_MARK(4);
       GemmPhase d_g{L.wd, H, p.inter, p.d_splits, p.act, p.inter, EPI_PARTIAL_F32, p.part, H, p.bn_down, narrow_off, narrow_bytes,
                     narrow_nbuf};
+      if (FN) d_g.resid_cnt = p.tile_cnt + 64;
       prefetch_phase<GM>(p, c, d_g);
       MEGA_BARRIER(true); if (!ok) break;
       gemm_phase<GM, PROF>(p, c, d_g);
@@ -1345,10 +1459,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                      last ? (void*)p.logits : (ws ? (void*)p.qkvp : (void*)p.qkv), last ? p.ldl : (long long)(3 * H),
                      last ? p.bn_wide : MEGA_BN, last ? wide_off : narrow_off, last ? wide_bytes : narrow_bytes,
                      last ? wide_nbuf : narrow_nbuf};
+      nx_g.norm_a = FN ? 1 : 0;
       prefetch_phase<GM>(p, c, nx_g);
-      MEGA_BARRIER(false); if (!ok) break;
-      norm_phase<MAXP>(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
-      MEGA_MARK(0);
+      if constexpr (!FN) {
+        MEGA_BARRIER(false); if (!ok) break;
+        norm_phase<MAXP>(p, last ? p.norm_f : p.lw[l + 1].n1, p.d_splits, nullptr, 0);   // x += down partials; next norm
+        MEGA_MARK(0);
+      }
       MEGA_BARRIER(true); if (!ok) break;
       if (last) {
         gemm_phase<GM, PROF>(p, c, nx_g);                                       // lm_head
@@ -1437,7 +1554,12 @@ int mega_pack_weight64_launch(const void* w, void* out, int rows, int cols, int 
   return 0;
 }
 
+int mega_fused_norm() { return MEGA_FUSE_NORM ? 1 : 0; }
+
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st) {
+  IVG_CHECK(!(MEGA_FUSE_NORM && p.gemm_mode == 0) || (p.tile_cnt != nullptr && p.hidden / MEGA_BN <= 64 && p.o_splits <= 8 &&
+                                                      p.d_splits <= 8),
+            "decode_mega: fused norms need tile_cnt [128 uints, zeroed], hidden <= 1024 and at most 8 splits");
   IVG_CHECK(p.B >= 1 && p.B <= 128, "decode_mega: batch %d not in [1,128]", p.B);
   IVG_CHECK(p.hidden % 64 == 0 && p.hidden <= MEGA_MAXK, "decode_mega: hidden %d unsupported", p.hidden);
   IVG_CHECK(p.gemm_mode == 0 || p.gemm_mode == 1, "decode_mega: gemm_mode %d", p.gemm_mode);

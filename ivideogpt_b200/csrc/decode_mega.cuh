@@ -15,6 +15,20 @@ constexpr int MEGA_BN = 16;                 // weight rows per GEMM work item
 #define IVG_MEGA_NISSUE 4
 #endif
 constexpr int MEGA_NISSUE = IVG_MEGA_NISSUE;   // 1, 2 or 4
+// gemm_mode 0, fused norms (default): the two add + RMSNorm phases of a layer (and their device-wide barriers) do not exist.
+//   * the residual add of a split-K projection (o, down) is done by the LAST work item of an output tile to arrive (monotonic
+//     counter per tile): it sums the fp32 partials in split order (fixed -> bit-reproducible), updates x and writes the bf16
+//     image of the UN-normalised row;
+//   * RMSNorm is linear up to the per-row scale: xn @ W^T = rstd * ((x (.) g) @ W^T) = rstd * (x @ (W (.) g)^T).  The norm
+//     weight g is folded into the columns of the consuming matrices when they are packed (wqkv, wgu, lm_head), the consumer's
+//     A operand is bf16(x), and every CTA computes rstd = rsqrt(mean(x^2) + eps) of the rows from the activation slab it has
+//     in shared memory anyway while the tensor core works, multiplying it in the epilogue.
+// 63 instead of 87 device-wide barriers per decode step of the 12-layer model.
+// MEASURED (profiles/r02/mega_fused_norm_ab.txt): not a win as built -- see DESIGN.md; kept as a compile-time variant, OFF.
+#ifndef IVG_MEGA_FUSE_NORM
+#define IVG_MEGA_FUSE_NORM 0
+#endif
+constexpr bool MEGA_FUSE_NORM = IVG_MEGA_FUSE_NORM != 0;
 constexpr int MEGA_NACC = MEGA_NISSUE;         // one accumulator (64 TMEM columns) per issuing warp
 constexpr int MEGA_MAXK = 1024;             // K handled by one work item (hidden or inter/3 ... all <= 1024)
 constexpr int MEGA_A_BYTES = 128 * 1024;    // 64 rows x 1024 k x 2 B, or 128 rows x 512 ...; see a_rows below
@@ -66,6 +80,7 @@ struct MegaParams {
   long long* prof;              // optional [24] cycle counters filled by CTA 0 (phase breakdown; 9..13 attention, 14..17 GEMM item), may be null
   float* attn_part;             // [SMs][4][72] flash-decoding partials of the items cut along the sequence (attn_mode 0)
   unsigned int* attn_cnt;       // [SMs] zero-initialised arrival counters of those items
+  unsigned int* tile_cnt;       // [2][64] zero-initialised arrival counters of the o-proj / down-proj output tiles (fused norms)
   int attn_mode;                // 0: TMA bulk-copy ring (default), 1: register-staged loads (round-1 v2 path)
   int bn_down;                  // gemm_mode 0: weight rows per work item of the down projection (16..64); wd is packed with it
   int bn_wide;                  // gemm_mode 0: weight rows per work item of the gate/up and lm_head phases (16..64); wgu and lm_head are packed with it
@@ -82,6 +97,7 @@ struct MegaParams {
 };
 
 int decode_mega_launch(const MegaParams& p, int num_sms, cudaStream_t st);
+int mega_fused_norm();        // 1 when gemm_mode 0 of this build folds the norms (the host packs g-folded weights)
 int mega_pack_weight_launch(const void* w, void* out, int rows, int cols, int bn, cudaStream_t st);
 int mega_pack_weight64_launch(const void* w, void* out, int rows, int cols, int swiglu_pairs, cudaStream_t st);
 

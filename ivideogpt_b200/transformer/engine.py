@@ -70,6 +70,9 @@ class LlamaWeights:
                 n2=lyr.post_attention_layernorm.weight.detach().float().contiguous()))
         self.norm = m.norm.weight.detach().float().contiguous()
         self.lm_head = _pack(hf_model.lm_head.weight, dtype)
+        import weakref
+        self._src = weakref.ref(hf_model)          # fp32 masters, for the norm-folded copies of the decode megakernel
+        self._folded = None
         # RoPE tables exactly as LlamaRotaryEmbedding computes them (fp32, theta from config)
         theta = float(getattr(cfg, "rope_theta", None) or (getattr(cfg, "rope_parameters", None) or {}).get("rope_theta", 10000.0))
         dev = self.embed.device
@@ -78,6 +81,26 @@ class LlamaWeights:
         freqs = pos[:, None] * inv_freq[None, :]
         self.cos, self.sin = freqs.cos().contiguous(), freqs.sin().contiguous()
         self.max_pos = cfg.max_position_embeddings
+
+    def folded(self):
+        """RMSNorm weights folded into the COLUMNS of the matrices that consume the normalised activations (decode megakernel
+        with fused norms: xn @ W^T = rstd * (x @ (W (.) g)^T)): per layer wqkv (.) n1 and wgu (.) n2, lm_head (.) final norm;
+        computed from the fp32 parameters, rounded once to the compute dtype.  Built on first use, cached per weight version."""
+        if self._folded is None:
+            hf = self._src()
+            if hf is None:
+                raise RuntimeError("the model these kernel-layout weights were packed from no longer exists")
+            layers = []
+            for lyr in hf.model.layers:
+                a, mlp = lyr.self_attn, lyr.mlp
+                n1 = lyr.input_layernorm.weight.detach().float()[None, :]
+                n2 = lyr.post_attention_layernorm.weight.detach().float()[None, :]
+                wqkv = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], dim=0).detach().float() * n1
+                wgu = torch.stack([mlp.gate_proj.weight, mlp.up_proj.weight], dim=1).reshape(2 * self.inter, self.hidden).detach().float() * n2
+                layers.append(dict(wqkv=_pack(wqkv, self.dtype), wgu=_pack(wgu, self.dtype)))
+            lm = hf.lm_head.weight.detach().float() * hf.model.norm.weight.detach().float()[None, :]
+            self._folded = dict(layers=layers, lm_head=_pack(lm, self.dtype))
+        return self._folded
 
     @staticmethod
     def signature(hf_model, dtype):
@@ -367,11 +390,17 @@ class LlamaEngine:
         nbytes = lib.ivgpt_mega_layer_bytes()
         host = (C.c_uint8 * (nbytes * w.layers_n + 64))()
         base_al = (C.addressof(host) + 63) // 64 * 64
+        # fused norms (gemm_mode 0 of this build): the matrices fed by a normalised activation carry the norm weight
+        fold = w.folded() if (mode == 0 and int(lib.ivgpt_mega_fused_norm()) == 1) else None
         for i, lw in enumerate(w.layers):
-            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(lw["wqkv"]), pack(lw["wo"]), pack(lw["wgu"], 1, bn_wide),
+            wqkv = fold["layers"][i]["wqkv"] if fold else lw["wqkv"]
+            wgu = fold["layers"][i]["wgu"] if fold else lw["wgu"]
+            _lib.check(lib.ivgpt_mega_fill_layer(base_al + i * nbytes, pack(wqkv), pack(lw["wo"]), pack(wgu, 1, bn_wide),
                                                  pack(lw["wd"], 0, bn_down), lw["n1"].data_ptr(), lw["n2"].data_ptr()),
                        "mega_fill_layer")
-        lm_head = pack(w.lm_head, 0, bn_wide)
+        lm_head = pack(fold["lm_head"] if fold else w.lm_head, 0, bn_wide)
+        if fold:
+            w._folded = None                       # the packed copies are what the kernel reads; drop the intermediates
         raw = bytes((C.c_uint8 * (nbytes * w.layers_n)).from_address(base_al))
         tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         cache[key] = (tab, lm_head, keep)
@@ -393,7 +422,8 @@ class LlamaEngine:
             o_s, d_s = self._mega_splits()
         kc, vc = self.kv_cache(B, Lmax)
         logits = self.buf("logits", (B, (w.vocab + 3) // 4 * 4), torch.float32)
-        sync = self.buf("mega_sync", (1024,), torch.int32)     # [0] barrier, [1] error, [64..] attention part counters
+        # ints: [0] barrier, [1] error, [512, 640) o-proj / down-proj tile counters, [1024, 2048) attention part counters
+        sync = self.buf("mega_sync", (2048,), torch.int32)
         sync.zero_()
         d = _lib.MegaDesc()
         d.B, d.hidden, d.inter, d.heads, d.layers, d.vocab, d.Lmax, d.steps = B, h, w.inter, w.heads, w.layers_n, w.vocab, Lmax, steps
@@ -422,8 +452,9 @@ class LlamaEngine:
         d.dseed = dseed.data_ptr()
         d.barrier = sync.data_ptr(); d.error = sync.data_ptr() + 4
         d.layers_dev = dev_tab.data_ptr(); d.lm_head_packed = lm_head_packed
-        d.attn_part = self.buf("mega_attn_part", (256 * 4 * 72,), torch.float32).data_ptr()
-        d.attn_cnt = sync.data_ptr() + 256
+        d.attn_part = self.buf("mega_attn_part", (8 * 160 * 72,), torch.float32).data_ptr()   # <= 8 parts x #CTAs records
+        d.attn_cnt = sync.data_ptr() + 4 * 1024
+        d.tile_cnt = sync.data_ptr() + 4 * 512                       # ints [512, 640): o-proj / down-proj tile counters
         d.attn_mode = int(getattr(self, "mega_attn_mode", int(os.environ.get("IVGPT_MEGA_ATTN", "0"))))
         d.a_bulk, d.mma_m64 = 1, 1
         if slot is not None:

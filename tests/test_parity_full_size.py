@@ -317,7 +317,8 @@ def test_megakernel_sampler_distribution(cuda):
     g = eng.generate(ids, None, 2, False, 0, 1.0, 0, use_mega=True, slot_cfg=force)
     assert bool((g[:, L] == first).all())
     lg = eng.buf("logits", (B, (1026 + 3) // 4 * 4), torch.float32)[:, :1026].float().cpu().clone()
-    assert float((lg - lg[0]).abs().max()) == 0.0, "identical rows must produce identical logits"
+    # identical rows: identical logits up to the attention phase's per-item schedule (whole items vs items merged from parts)
+    assert float((lg - lg[0]).abs().max()) < 1e-5 * float(lg.abs().max())
     p = _hf_topk_probs(lg[0], k, T)
     support = (p > 0).nonzero().flatten()
     draws = []
