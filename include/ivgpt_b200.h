@@ -135,6 +135,11 @@ int ivgpt_upsample2x(int dtype, const void* x, void* y, int N, int H, int W, int
 /* (de)patchify, compressive_vq_model.py:192-195 / :247-250.  inverse=0: [F,R,R,C] -> [F*(R/P)^2, P*P*C]. */
 int ivgpt_patchify(int dtype, const void* x, void* y, int F, int R, int C, int P, int inverse, void* stream);
 int ivgpt_convert(int src_dtype, const void* x, int dst_dtype, void* y, long long n, void* stream);
+/* The rest of diffusers VectorQuantizer.forward(beta, legacy=False) after the argmin (compressive_vq_model.py:297-301, the
+ * training / evaluation forward :332-369): zq[n,:] = codebook[idx[n],:] in `dtype` (may be NULL) and
+ * *loss = (beta + 1) * mean((zq - z)^2) -- the value of beta * mse(sg(zq), z) + mse(zq, sg(z)).  part_ws: fp32 [296] scratch. */
+int ivgpt_vq_commit(int dtype, const float* z, const float* codebook, const long long* idx, void* zq, long long N, int D,
+                    long long K, float beta, float* part_ws, float* loss, void* stream);
 
 /* token (de)serialisation, compressive_vq_model.py:205-220 / :227-245 */
 int ivgpt_tokens_serialise(const long long* idx_ctx, const long long* idx_dyn, long long* tokens, long long* labels,

@@ -106,6 +106,7 @@ SIGNATURES = {
     "ivgpt_upsample2x": [_I, _P, _P, _I, _I, _I, _I, _P],
     "ivgpt_patchify": [_I, _P, _P, _I, _I, _I, _I, _I, _P],
     "ivgpt_convert": [_I, _P, _I, _P, _L, _P],
+    "ivgpt_vq_commit": [_I, _P, _P, _P, _P, _L, _I, _L, _F, _P, _P, _P],
     "ivgpt_tokens_serialise": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P],
     "ivgpt_tokens_gather": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P, _P],
     "ivgpt_embed": [_P, _L, _I, _P, _P, _P, _L, _I, _L, _P],

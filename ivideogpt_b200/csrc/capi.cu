@@ -94,6 +94,8 @@ int conv_out3_launch(int, const void*, const float*, const float*, const float*,
                      int, int, int, int, int, int, int, int, cudaStream_t);
 int upsample2x_launch(int, const void*, void*, int, int, int, int, cudaStream_t);
 int patchify_launch(int, const void*, void*, int, int, int, int, int, cudaStream_t);
+int vq_commit_launch(int, const float*, const float*, const long long*, void*, long long, int, long long, float, float*, float*,
+                     cudaStream_t);
 int convert_launch(int, const void*, int, void*, long long, cudaStream_t);
 int serialise_launch(const long long*, const long long*, long long*, long long*, int, int, int, int, int, long long,
                      long long, cudaStream_t);
@@ -348,6 +350,10 @@ int ivgpt_upsample2x(int dtype, const void* x, void* y, int N, int H, int W, int
 }
 int ivgpt_patchify(int dtype, const void* x, void* y, int F, int R, int C, int P, int inverse, void* stream) {
   return patchify_launch(dtype, x, y, F, R, C, P, inverse, S(stream));
+}
+int ivgpt_vq_commit(int dtype, const float* z, const float* codebook, const long long* idx, void* zq, long long N, int D,
+                    long long K, float beta, float* part_ws, float* loss, void* stream) {
+  return vq_commit_launch(dtype, z, codebook, idx, zq, N, D, K, beta, part_ws, loss, S(stream));
 }
 int ivgpt_convert(int src_dtype, const void* x, int dst_dtype, void* y, long long n, void* stream) {
   return convert_launch(src_dtype, x, dst_dtype, y, n, S(stream));

@@ -787,4 +787,59 @@ int resize_aa_launch(int in_dtype, const void* in, long long st, long long sy, l
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// VectorQuantizer.forward beyond the argmin (diffusers VectorQuantizer(beta, legacy=False); reference call sites
+// compressive_vq_model.py:297-301 inside decode(), reached from forward() :332-369 -- tokenizer training / evaluation):
+//     z_q = E[idx]                                   (returned in the decoder's compute dtype; straight-through value)
+//     loss = beta * mean((sg(z_q) - z)^2) + mean((z_q - sg(z))^2)  =  (beta + 1) * mean((z_q - z)^2)   in value.
+// One pass: gather + squared difference, fixed-size grid of per-block partial sums, then a single-block ordered sum
+// (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int VQC_BLOCKS = 296;
+template <typename T>
+__global__ void vq_commit_partial_kernel(const float* __restrict__ z, const float* __restrict__ cb, const long long* __restrict__ idx,
+                                         T* __restrict__ zq, long long N, int D, long long K, float* __restrict__ part) {
+  __shared__ float s_red[8];
+  float acc = 0.f;
+  const long long total = N * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / D;
+    const int d = (int)(i - n * D);
+    long long id = idx[n];
+    id = id < 0 ? 0 : (id >= K ? K - 1 : id);
+    const float q = cb[id * D + d];
+    const float df = q - z[i];
+    acc = fmaf(df, df, acc);
+    if (zq != nullptr) zq[i] = from_f32<T>(q);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void vq_commit_final_kernel(const float* __restrict__ part, int nblocks, double scale, float* __restrict__ loss) {
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nblocks; ++i) t += (double)part[i];
+    *loss = (float)(t * scale);
+  }
+}
+int vq_commit_launch(int dtype, const float* z, const float* cb, const long long* idx, void* zq, long long N, int D, long long K,
+                     float beta, float* part_ws, float* loss, cudaStream_t st) {
+  IVG_CHECK(N >= 1 && D >= 1 && K >= 1, "vq_commit: bad shape N=%lld D=%d K=%lld", N, D, K);
+  if (dtype == DT_BF16)
+    vq_commit_partial_kernel<__nv_bfloat16><<<VQC_BLOCKS, 256, 0, st>>>(z, cb, idx, (__nv_bfloat16*)zq, N, D, K, part_ws);
+  else
+    vq_commit_partial_kernel<float><<<VQC_BLOCKS, 256, 0, st>>>(z, cb, idx, (float*)zq, N, D, K, part_ws);
+  vq_commit_final_kernel<<<1, 32, 0, st>>>(part_ws, VQC_BLOCKS, (double)(beta + 1.0f) / ((double)N * (double)D), loss);
+  count_launch(2);
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ivg

@@ -266,6 +266,21 @@ def convert(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return y
 
 
+def vq_commit(z: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, dtype: torch.dtype, beta: float = 1.0):
+    """(z_q [N, D] in `dtype`, loss 0-d fp32) = rows of the codebook picked by idx and (beta + 1) * mean((z_q - z)^2)."""
+    _cuda(z, codebook, idx)
+    assert z.dtype == torch.float32 and codebook.dtype == torch.float32 and idx.dtype == torch.int64
+    z, codebook, idx = z.contiguous(), codebook.contiguous(), idx.contiguous()
+    N, D = z.shape
+    zq = torch.empty(N, D, dtype=dtype, device=z.device)
+    part = torch.empty(296, dtype=torch.float32, device=z.device)
+    loss = torch.empty((), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.load().ivgpt_vq_commit(_dt(zq), z.data_ptr(), codebook.data_ptr(), idx.data_ptr(), zq.data_ptr(), N, D,
+                                           codebook.shape[0], float(beta), part.data_ptr(), loss.data_ptr(), _stream()),
+               "vq_commit")
+    return zq, loss
+
+
 def tokens_serialise(idx_ctx, idx_dyn, B, t, f, cr, dr, n_vq, n_dyn, want_labels=True):
     _cuda(idx_ctx, idx_dyn)
     L = t * (cr + 1) - 1 + f * (dr + 1)

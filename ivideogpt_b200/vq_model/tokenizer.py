@@ -5,7 +5,8 @@ tokenize :165-220, detokenize :223-277), none of its code.
 Differences that matter to a caller:  (1) it runs on CUDA sm_100a only and raises otherwise -- there is no
 PyTorch fallback;  (2) `diffusers` is not needed: from_pretrained / from_config / save_pretrained / .config
 are implemented in hub_io.py against the same on-disk layout (config.json + diffusion_pytorch_model.safetensors);
-(3) `forward()` (tokenizer *training*, reference :332-369) is out of scope for this hot path and raises.
+(3) `forward()` (the tokenizer training graph, reference :332-369) runs FORWARD ONLY (evaluation, validation losses);
+its backward is not built and raises.
 """
 from __future__ import annotations
 
@@ -33,6 +34,13 @@ def _default_compute_dtype(param_dtype: torch.dtype) -> torch.dtype:
     if param_dtype == torch.bfloat16 or torch.is_autocast_enabled():
         return torch.bfloat16
     return torch.float32
+
+
+class CompressiveVQDecoderOutput:
+    """Field-for-field the reference's output record (compressive_vq_model.py:16-30)."""
+
+    def __init__(self, sample, ref_sample=None, commit_loss=None, dyn_commit_loss=None):
+        self.sample, self.ref_sample, self.commit_loss, self.dyn_commit_loss = sample, ref_sample, commit_loss, dyn_commit_loss
 
 
 class CompressiveVQModel(HubMixin, nn.Module):
@@ -230,7 +238,60 @@ class CompressiveVQModel(HubMixin, nn.Module):
             return out, {"context_dec": out[:, :t].clone(), "cond_features": ctx_feats}
         return out
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError(
-            "CompressiveVQModel.forward (tokenizer training, reference compressive_vq_model.py:332-369) is outside "
-            "the B200 hot path of this package; use tokenize()/detokenize().")
+    # ---- forward (tokenizer training / evaluation graph, reference :332-369 + decode() :290-330) ---------------------------
+    @ops.device_scoped
+    def forward(self, sample: torch.FloatTensor, return_dict: bool = True, return_loss: bool = False,
+                segment_len: int = None, dyn_sample: torch.FloatTensor = None):
+        """sample [B*t, 3, H, W] context frames, dyn_sample [B*segment_len, 3, H, W] future frames ->
+        (dec [B*segment_len, 3, H, W], ref_dec [B*t, 3, H, W], commit_loss, dyn_commit_loss), the values the reference's
+        forward returns (encoder -> quant_conv -> VQ (straight-through value, commit loss) -> post_quant_conv -> decoder;
+        conditional encoder -> patchify -> quant_linear -> VQ -> post_quant_linear -> de-patchify -> conditional decoder).
+
+        FORWARD ONLY on the sm_100a kernels: this is what train_tokenizer.py's validation loop (:940-960) and any
+        no-grad evaluation need.  The backward pass (conv dgrad / wgrad, GroupNorm / attention backward, the codebook and
+        straight-through gradients) is not built: calling it with autograd recording and trainable parameters raises."""
+        if dyn_sample is None or segment_len is None:
+            raise NotImplementedError("CompressiveVQModel.forward: the ctx_vqgan form (sample=, dyn_sample=, segment_len=) "
+                                      "is the one train_tokenizer.py uses (:623-627) and the one implemented")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "CompressiveVQModel.forward: the backward pass of the tokenizer (reference train_tokenizer.py:734) is not "
+                "built on the sm_100a path; run the forward under torch.no_grad() (evaluation), or freeze the parameters")
+        self._require_cuda(sample, "forward")
+        with torch.no_grad():
+            plan = self._get_plan()
+            t, f, cr, dr = self.context_length, int(segment_len), _CTX_RES, _DYN_RES
+            assert sample.shape[0] % t == 0 and dyn_sample.shape[0] % f == 0 and sample.shape[0] // t == dyn_sample.shape[0] // f
+            B = sample.shape[0] // t
+            Cc, H, W = sample.shape[1:]
+            ctx = sample.to(torch.float32).contiguous().view(B, t, Cc, H, W)
+            fut = dyn_sample.to(torch.float32).contiguous().view(B, f, Cc, H, W)
+            # context branch
+            h, feats = plan.encode(ctx, self.encoder, 0, t, want_features=True)
+            wq, bq = plan.pw.linear(self.quant_conv.weight, self.quant_conv.bias, plan.dtype)
+            z_ctx = ops.gemm(h.view(-1, h.shape[-1]), wq, bq, out_dtype=torch.float32)
+            cb_c = self.quantize.embedding.weight.detach().float()
+            zq_c, commit = ops.vq_commit(z_ctx, cb_c, ops.vq_argmin(z_ctx, cb_c), plan.dtype, beta=1.0)
+            wpc, bpc = plan.pw.linear(self.post_quant_conv.weight, self.post_quant_conv.bias, plan.dtype)
+            lat_c = ops.gemm(zq_c, wpc, bpc).view(B * t, cr, cr, self.latent_channels)
+            ref_dec = torch.empty(B, t, self.config["out_channels"], H, W, dtype=torch.float32, device=sample.device)
+            dec_feats = plan.decode(lat_c, self.decoder, ref_dec, 0, t, want_features=True)
+            # dynamics branch
+            d = plan.encode(fut, self.cond_encoder, 0, f, ctx_feats=feats)
+            patches = ops.patchify(d, self.patch_size)
+            wl, bl = plan.pw.linear(self.quant_linear.weight, self.quant_linear.bias, plan.dtype)
+            z_dyn = ops.gemm(patches, wl, bl, out_dtype=torch.float32)
+            cb_d = self.dynamics_quantize.embedding.weight.detach().float()
+            zq_d, dyn_commit = ops.vq_commit(z_dyn, cb_d, ops.vq_argmin(z_dyn, cb_d), plan.dtype, beta=1.0)
+            wpl, bpl = plan.pw.linear(self.post_quant_linear.weight, self.post_quant_linear.bias, plan.dtype)
+            pd = ops.gemm(zq_d, wpl, bpl)
+            lat_d = ops.patchify(pd, self.patch_size, inverse=True, frames=B * f, res=cr, ch=self.latent_channels)
+            dec = torch.empty(B, f, self.config["out_channels"], H, W, dtype=torch.float32, device=sample.device)
+            plan.decode(lat_d, self.cond_decoder, dec, 0, f, ctx_feats=dec_feats)
+            dec = dec.view(B * f, -1, H, W)
+            ref_dec = ref_dec.view(B * t, -1, H, W)
+        if not return_dict:
+            return (dec, ref_dec, commit, dyn_commit) if return_loss else (dec,)
+        if return_loss:
+            return CompressiveVQDecoderOutput(sample=dec, ref_sample=ref_dec, commit_loss=commit, dyn_commit_loss=dyn_commit)
+        return CompressiveVQDecoderOutput(sample=dec)

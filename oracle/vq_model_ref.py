@@ -154,6 +154,16 @@ class RefVectorQuantizer(nn.Module):
         self.embedding = nn.Embedding(n_e, dim)
         self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
 
+    def forward(self, z_nchw, beta: float = 1.0):
+        """diffusers VectorQuantizer.forward(legacy=False): (straight-through z_q NCHW, loss, indices).  Differentiable."""
+        z = z_nchw.permute(0, 2, 3, 1).contiguous()
+        zf = z.view(-1, self.dim)
+        idx = torch.argmin(torch.cdist(zf, self.embedding.weight), dim=1)
+        z_q = self.embedding(idx).view(z.shape)
+        loss = beta * torch.mean((z_q.detach() - z) ** 2) + torch.mean((z_q - z.detach()) ** 2)
+        z_q = z + (z_q - z).detach()
+        return z_q.permute(0, 3, 1, 2).contiguous(), loss, idx
+
     def indices(self, z_nchw):
         zf = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, self.dim)
         return torch.argmin(torch.cdist(zf, self.embedding.weight), dim=1)
@@ -357,6 +367,30 @@ class RefCompressiveVQModel(nn.Module):
         zc = h.permute(0, 2, 3, 1).reshape(-1, self.vq_embed_dim)
         zd = d.reshape(-1, self.vq_embed_dim)
         return zc, zd
+
+    def forward_train(self, sample, dyn_sample, segment_len):
+        """compressive_vq_model.py:332-369 (forward) + :290-330 (decode): the tokenizer training graph, differentiable.
+        sample [B*t,3,H,W], dyn_sample [B*segment_len,3,H,W] -> (dec, ref_dec, commit_loss, dyn_commit_loss)."""
+        B = dyn_sample.shape[0] // segment_len
+        h, feats = self.encoder(sample, return_features=True)               # :340
+        h = self.quant_conv(h)                                              # :349
+        d = self.cond_encoder(dyn_sample, self._expand(feats, B, segment_len))      # :351
+        p = self.patch_size
+        d = d.permute(0, 2, 3, 1).unfold(1, p, p).unfold(2, p, p).permute(0, 1, 2, 4, 5, 3)
+        d = d.reshape(d.shape[0], d.shape[1] * d.shape[2], -1)
+        d = self.quant_linear(d)                                            # :355
+        quant, commit, _ = self.quantize(h)                                 # decode() :297
+        dq = d.transpose(-1, -2).unsqueeze(-1)                              # [B, L, D] -> [B, D, L, 1]   :299
+        quant_d, dyn_commit, _ = self.dynamics_quantize(dq)
+        quant_d = quant_d.squeeze(-1).transpose(-1, -2)
+        q2 = self.post_quant_conv(quant)
+        q2d = self.post_quant_linear(quant_d)
+        hh, c = q2.shape[-1], self.latent_channels
+        q2d = q2d.reshape(q2d.shape[0], hh // p, hh // p, p, p, c)
+        q2d = torch.einsum("nhwpqc->nchpwq", q2d).reshape(q2d.shape[0], c, hh, hh)
+        ref_dec, dfeats = self.decoder(q2, return_features=True)            # :311
+        dec = self.cond_decoder(q2d, self._expand(dfeats, B, segment_len))  # :321
+        return dec, ref_dec, commit, dyn_commit
 
     @torch.no_grad()
     def tokenize(self, pixel_values, context_length=0):

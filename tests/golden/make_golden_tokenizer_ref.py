@@ -63,6 +63,32 @@ def run(cfg, frames, res, seed, want_cache):
             out["recon_cached"] = step.numpy().astype(np.float32)
     diff = dict(tokens_equal=bool((tok == otok).all()), labels_equal=bool((lab == olab).all()),
                 recon_max_abs_diff=float((rec - orec).abs().max()))
+    if want_cache:
+        # the TRAINING graph (compressive_vq_model.py:332-369 forward + :290-330 decode): values and gradients of the reference's
+        # own forward() against the oracle's forward_train() -- straight-through VQ, both commit losses, both decoders
+        fut = frames - ctx
+        sample = px[0, :ctx].clone()
+        dyn = px[0, ctx:].clone()
+        ra = reference(sample=sample, dyn_sample=dyn, segment_len=fut, return_dict=False, return_loss=True)
+        oa = oracle.forward_train(sample, dyn, fut)
+        diff["train_forward_max_abs_diff"] = max(float((x - y).abs().max()) for x, y in zip(ra, oa))
+        for outs, model in ((ra, reference), (oa, oracle)):
+            for p in model.parameters():
+                p.grad = None
+            (sum(((x - 0.5) ** 2).mean() for x in outs[:2]) + outs[2] + outs[3]).backward()
+        og = dict(oracle.named_parameters())
+        gd = 0.0
+        for n_, p in reference.named_parameters():
+            if p.grad is not None:
+                gd = max(gd, float((p.grad - og[n_].grad).abs().max() / p.grad.abs().max().clamp_min(1e-12)))
+        diff["train_grad_max_rel_diff"] = gd
+        out["train_dec"] = ra[0].detach().numpy().astype(np.float32)
+        out["train_ref_dec"] = ra[1].detach().numpy().astype(np.float32)
+        out["train_losses"] = np.array([float(ra[2]), float(ra[3])], dtype=np.float64)
+        out["train_grad_norms"] = np.array([float(reference.quant_conv.weight.grad.norm()),
+                                            float(reference.cond_decoder.conv_out.weight.grad.norm()),
+                                            float(reference.quantize.embedding.weight.grad.norm()),
+                                            float(reference.encoder.conv_in.weight.grad.norm())], dtype=np.float64)
     return out, diff
 
 
@@ -77,4 +103,5 @@ if os.environ.get("WITH_256", "1") == "1":          # executed here, not stored 
     _, summary["cfg256_not_stored"] = run(load_cfg("ctx_vae256"), 3, 256, 13, False)
 print(json.dumps(summary, indent=1))
 assert all(d["tokens_equal"] and d["labels_equal"] and d["recon_max_abs_diff"] < 1e-5 for d in summary.values()), summary
+assert summary["tiny"]["train_forward_max_abs_diff"] < 1e-5 and summary["tiny"]["train_grad_max_rel_diff"] < 1e-4, summary
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tokenizer_refglue.npz"), summary=np.array(json.dumps(summary)), **fixture)

@@ -160,6 +160,18 @@ def test_oracle_reproduces_vectors_of_the_reference_own_tokenizer_code():
         assert np.array_equal(tok.numpy(), z[f"{name}_tokens"]) and np.array_equal(lab.numpy(), z[f"{name}_labels"]), name
         assert float(np.abs(rec.numpy() - z[f"{name}_recon"]).max()) < 1e-4, name
     assert z["tiny_recon_cached"].shape == (1, 3, 3, 64, 64)      # context (2) + the one future frame decoded from the cache
+    # the training graph (forward() :332-369 + decode() :290-330): values and gradients of the reference's own forward
+    assert summary["tiny"]["train_forward_max_abs_diff"] < 1e-5 and summary["tiny"]["train_grad_max_rel_diff"] < 1e-4
+    oracle = seeded_init_(RefCompressiveVQModel(**TINY_CFG).eval())
+    px = torch.from_numpy(z["tiny_pixels"])
+    outs = oracle.forward_train(px[0, :2].clone(), px[0, 2:].clone(), px.shape[1] - 2)
+    assert float(np.abs(outs[0].detach().numpy() - z["tiny_train_dec"]).max()) < 1e-4
+    assert float(np.abs(outs[1].detach().numpy() - z["tiny_train_ref_dec"]).max()) < 1e-4
+    assert np.allclose([float(outs[2]), float(outs[3])], z["tiny_train_losses"], rtol=1e-4)
+    (sum(((x - 0.5) ** 2).mean() for x in outs[:2]) + outs[2] + outs[3]).backward()
+    norms = [float(p.grad.norm()) for p in (oracle.quant_conv.weight, oracle.cond_decoder.conv_out.weight,
+                                            oracle.quantize.embedding.weight, oracle.encoder.conv_in.weight)]
+    assert np.allclose(norms, z["tiny_train_grad_norms"], rtol=1e-3)
 
 
 def test_legacy_checkpoint_keys_bin_fallback_and_mismatched_sizes(tmp_path):
@@ -224,3 +236,29 @@ def test_module_tree_equals_the_reference_own_class(config):
         sys.path.remove(stub)
         for k in [k for k in sys.modules if k == "diffusers" or k.startswith("diffusers.") or k.startswith("ref_vq_model_t")]:
             del sys.modules[k]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol,tol_loss", [(torch.float32, 4e-3, 2e-2), (torch.bfloat16, 4e-2, 1e-1)])
+def test_training_graph_forward_vs_reference_vectors(cuda, dtype, tol, tol_loss):
+    """Row f3 (forward half): CompressiveVQModel.forward(sample=, dyn_sample=, segment_len=) against vectors produced by the
+    REFERENCE'S OWN forward() (tests/golden/tokenizer_refglue.npz, made by make_golden_tokenizer_ref.py): both reconstructions
+    and both commit losses; the VQ indices feed the decoders, so an index flip on a near-tie shows up in the pixel error.
+    The backward half is not built: with autograd recording and trainable parameters the call raises."""
+    from oracle.vq_model_ref import TINY_CFG
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_refglue.npz"))
+    _, mine = _pair(TINY_CFG, cuda, dtype)
+    px = torch.from_numpy(z["tiny_pixels"]).to(cuda)
+    fut = px.shape[1] - 2
+    with torch.no_grad():
+        dec, ref_dec, commit, dyn_commit = mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut,
+                                                return_dict=False, return_loss=True)
+        rec = mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut, return_loss=True)
+    assert dec.shape == (fut, 3, 64, 64) and ref_dec.shape == (2, 3, 64, 64)
+    assert rel_err(dec, torch.from_numpy(z["tiny_train_dec"])) < tol
+    assert rel_err(ref_dec, torch.from_numpy(z["tiny_train_ref_dec"])) < tol
+    want = z["tiny_train_losses"]
+    assert abs(float(commit) - want[0]) / want[0] < tol_loss and abs(float(dyn_commit) - want[1]) / want[1] < tol_loss
+    assert torch.equal(rec.sample, dec) and torch.equal(rec.ref_sample, ref_dec) and float(rec.commit_loss) == float(commit)
+    with pytest.raises(NotImplementedError, match="backward"):
+        mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut)
