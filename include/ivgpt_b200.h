@@ -200,6 +200,14 @@ int ivgpt_slot_force(long long* tokens, long long tok_stride, const int* dpos, i
 int ivgpt_decode_attn_fused(int dtype, const void* qkv, void* k_cache, void* v_cache_t, void* out, int B, int heads,
                             int Lmax, int pos, const int* dpos, const float* cos_tab, const float* sin_tab,
                             float scale, void* stream);
+/* Fused attention of the prefill / teacher-forced pass (bf16, head_dim 64): out[b, i, h*64:(h+1)*64] =
+ * softmax(q_bh[i] . k_bh^T * scale (+ causal mask: key j visible iff j <= i + Lk - Lq)) . v_bh, scores and probabilities kept
+ * on chip (TMEM / shared memory).  Replaces the attention inside HF LlamaAttention (predict.py:64 via generate, train_gpt.py:792).
+ *   q  [B*heads][Lq][64] (batch pitch q_bstride elements), k [B*heads][Lk..][64] (pitch k_bstride),
+ *   vt [B*heads][64][vt_ld >= Lk] (V transposed, pitch vt_bstride), out [B*Lq][ldo] bf16, lse optional fp32 [B*heads][Lq]. */
+int ivgpt_flash_attn(const void* q, const void* k, const void* vt, void* out, float* lse, int B, int heads, int Lq, int Lk,
+                     long long q_bstride, long long k_bstride, long long vt_bstride, long long vt_ld, long long ldo, int causal,
+                     float scale, void* stream);
 /* ---- persistent decode megakernel (bf16): `steps` consecutive decode steps of HF generate in ONE cooperative launch
  * (embed -> layers x {qkv, RoPE+append+attention, o, norm, gate/up+SwiGLU, down, norm} -> lm_head -> sample -> append).
  * Weights are streamed as whole 16-row K-slabs by 1-D bulk copies, so every matrix (wqkv [3h,h], wo [h,h], wgu

@@ -133,6 +133,8 @@ int adamw_launch(float*, const float*, float*, float*, long long, float, float, 
                  cudaStream_t);
 int add_to_f32_launch(int, float*, const void*, long long, cudaStream_t);
 int dropout_launch(int, const void*, void*, long long, float, unsigned long long, cudaStream_t);
+int flash_attn_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, long long, long long, long long,
+                      long long, long long, int, float, int, cudaStream_t);
 int decode_attn_fused_launch(int, const void*, void*, void*, void*, int, int, int, int, const int*, const float*,
                              const float*, float, cudaStream_t);
 
@@ -505,6 +507,13 @@ int ivgpt_mega_fill_layer(void* host_layer, const void* wqkv, const void* wo, co
   L->wgu = (const __nv_bfloat16*)wgu; L->wd = (const __nv_bfloat16*)wd;
   L->n1 = n1; L->n2 = n2;
   return 0;
+}
+
+int ivgpt_flash_attn(const void* q, const void* k, const void* vt, void* out, float* lse, int B, int heads, int Lq, int Lk,
+                     long long q_bstride, long long k_bstride, long long vt_bstride, long long vt_ld, long long ldo, int causal,
+                     float scale, void* stream) {
+  return flash_attn_launch(q, k, vt, out, lse, B, heads, Lq, Lk, q_bstride, k_bstride, vt_bstride, vt_ld, ldo, causal, scale,
+                           num_sms(), S(stream));
 }
 
 int ivgpt_mega_fused_norm(void) { return ivg::mega_fused_norm(); }

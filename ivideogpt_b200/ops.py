@@ -335,6 +335,18 @@ def softmax(S, P, rows, Lq, Lk, lds, ldp, causal, causal_off=0):
                                          causal_off, _stream()), "softmax")
 
 
+def flash_attn(q, k, vt, out, B, heads, Lq, Lk, k_bstride, vt_bstride, vt_ld, causal=True, scale=0.125, lse=None):
+    """Fused causal attention (bf16, head_dim 64): q [B,heads,Lq,64], k rows [.., Lk, 64] with batch pitch k_bstride, vt = V^T
+    rows [.., 64, vt_ld] with batch pitch vt_bstride; out [B*Lq, heads*64].  Scores / probabilities never reach HBM."""
+    _cuda(q, k, vt, out, lse)
+    assert q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and vt.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    assert q.is_contiguous() and out.stride(-1) == 1
+    _lib.check(_lib.load().ivgpt_flash_attn(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), _ptr(lse), B, heads, Lq, Lk,
+                                            Lq * 64, k_bstride, vt_bstride, vt_ld, out.stride(0), int(causal), float(scale),
+                                            _stream()), "flash_attn")
+    return out
+
+
 def decode_attn(q, k_cache, v_cache_t, out, B, heads, Lmax, Lcur, dpos, scale):
     _lib.check(_lib.load().ivgpt_decode_attn(_dt(q), q.data_ptr(), k_cache.data_ptr(), v_cache_t.data_ptr(),
                                              out.data_ptr(), B, heads, Lmax, Lcur, _ptr(dpos), scale, _stream()),

@@ -114,6 +114,8 @@ class LlamaEngine:
         self.code = BF16 if self.dtype == torch.bfloat16 else F32
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        # bf16 prefill attention: fused kernel (default) or the round-1 materialised path (scores GEMM -> softmax -> PV GEMM)
+        self.use_flash = os.environ.get("IVGPT_FLASH_ATTN", "1") == "1"
 
     # ---- buffers ------------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -149,7 +151,10 @@ class LlamaEngine:
         vr = self.v_rows(B, Lmax)[li] if (prefill and dt == torch.bfloat16) else None
         ops.rope_kv(qkv, q, kc[li], vc[li], B, Lq, H, Lmax, pos0, dpos, w.cos, w.sin, v_rows=vr)
         ao = self.buf("attn_out", (M, h), dt)
-        if prefill:
+        if prefill and dt == torch.bfloat16 and self.use_flash:
+            # fused QK^T -> online softmax -> PV on tcgen05, S in TMEM, P through shared memory (csrc/flash_attn.cu)
+            ops.flash_attn(q, kc[li], vc[li], ao, B, H, Lq, pos0 + Lq, Lmax * 64, 64 * Lmax, Lmax, causal=True, scale=0.125)
+        elif prefill:
             Lk = pos0 + Lq
             ld = (Lk + 7) // 8 * 8
             s = self.buf("scores", (B * H, Lq, ld), torch.float32)

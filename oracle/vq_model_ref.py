@@ -154,11 +154,14 @@ class RefVectorQuantizer(nn.Module):
         self.embedding = nn.Embedding(n_e, dim)
         self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
 
-    def forward(self, z_nchw, beta: float = 1.0):
-        """diffusers VectorQuantizer.forward(legacy=False): (straight-through z_q NCHW, loss, indices).  Differentiable."""
+    def forward(self, z_nchw, beta: float = 1.0, idx=None):
+        """diffusers VectorQuantizer.forward(legacy=False): (straight-through z_q NCHW, loss, indices).  Differentiable.
+        idx (test aid, not in diffusers): use these indices instead of the argmin -- lets a test hold the discrete choice fixed
+        when comparing an implementation whose latents differ by rounding (an index may flip on a near-tie)."""
         z = z_nchw.permute(0, 2, 3, 1).contiguous()
         zf = z.view(-1, self.dim)
-        idx = torch.argmin(torch.cdist(zf, self.embedding.weight), dim=1)
+        if idx is None:
+            idx = torch.argmin(torch.cdist(zf, self.embedding.weight), dim=1)
         z_q = self.embedding(idx).view(z.shape)
         loss = beta * torch.mean((z_q.detach() - z) ** 2) + torch.mean((z_q - z.detach()) ** 2)
         z_q = z + (z_q - z).detach()
@@ -368,9 +371,10 @@ class RefCompressiveVQModel(nn.Module):
         zd = d.reshape(-1, self.vq_embed_dim)
         return zc, zd
 
-    def forward_train(self, sample, dyn_sample, segment_len):
+    def forward_train(self, sample, dyn_sample, segment_len, idx_ctx=None, idx_dyn=None):
         """compressive_vq_model.py:332-369 (forward) + :290-330 (decode): the tokenizer training graph, differentiable.
-        sample [B*t,3,H,W], dyn_sample [B*segment_len,3,H,W] -> (dec, ref_dec, commit_loss, dyn_commit_loss)."""
+        sample [B*t,3,H,W], dyn_sample [B*segment_len,3,H,W] -> (dec, ref_dec, commit_loss, dyn_commit_loss).
+        idx_ctx / idx_dyn: see RefVectorQuantizer.forward (test aid)."""
         B = dyn_sample.shape[0] // segment_len
         h, feats = self.encoder(sample, return_features=True)               # :340
         h = self.quant_conv(h)                                              # :349
@@ -379,9 +383,9 @@ class RefCompressiveVQModel(nn.Module):
         d = d.permute(0, 2, 3, 1).unfold(1, p, p).unfold(2, p, p).permute(0, 1, 2, 4, 5, 3)
         d = d.reshape(d.shape[0], d.shape[1] * d.shape[2], -1)
         d = self.quant_linear(d)                                            # :355
-        quant, commit, _ = self.quantize(h)                                 # decode() :297
+        quant, commit, _ = self.quantize(h, idx=idx_ctx)                    # decode() :297
         dq = d.transpose(-1, -2).unsqueeze(-1)                              # [B, L, D] -> [B, D, L, 1]   :299
-        quant_d, dyn_commit, _ = self.dynamics_quantize(dq)
+        quant_d, dyn_commit, _ = self.dynamics_quantize(dq, idx=idx_dyn)
         quant_d = quant_d.squeeze(-1).transpose(-1, -2)
         q2 = self.post_quant_conv(quant)
         q2d = self.post_quant_linear(quant_d)

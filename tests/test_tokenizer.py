@@ -239,26 +239,44 @@ def test_module_tree_equals_the_reference_own_class(config):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype,tol,tol_loss", [(torch.float32, 4e-3, 2e-2), (torch.bfloat16, 4e-2, 1e-1)])
-def test_training_graph_forward_vs_reference_vectors(cuda, dtype, tol, tol_loss):
-    """Row f3 (forward half): CompressiveVQModel.forward(sample=, dyn_sample=, segment_len=) against vectors produced by the
-    REFERENCE'S OWN forward() (tests/golden/tokenizer_refglue.npz, made by make_golden_tokenizer_ref.py): both reconstructions
-    and both commit losses; the VQ indices feed the decoders, so an index flip on a near-tie shows up in the pixel error.
+@pytest.mark.parametrize("dtype,tol,tol_loss", [(torch.float32, 4e-3, 1e-2), (torch.bfloat16, 4e-2, 6e-2)])
+def test_training_graph_forward_vs_oracle(cuda, dtype, tol, tol_loss):
+    """Row f3 (forward half): CompressiveVQModel.forward(sample=, dyn_sample=, segment_len=) against the oracle's forward_train
+    -- itself pinned, values AND gradients, to the reference's own forward() (tests/golden/tokenizer_refglue.npz).  The graph
+    contains two discrete choices (VQ argmin); rounding may flip one on a near-tie and a flipped code changes a whole latent
+    patch, so the comparison holds the choice fixed: the product's own indices (checked to differ from the oracle's only on
+    near-ties) are handed to the oracle, then both reconstructions and both commit losses must agree.
     The backward half is not built: with autograd recording and trainable parameters the call raises."""
+    from ivideogpt_b200 import ops
     from oracle.vq_model_ref import TINY_CFG
     z = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_refglue.npz"))
-    _, mine = _pair(TINY_CFG, cuda, dtype)
-    px = torch.from_numpy(z["tiny_pixels"]).to(cuda)
+    ref, mine = _pair(TINY_CFG, cuda, dtype)
+    px = torch.from_numpy(z["tiny_pixels"])
     fut = px.shape[1] - 2
+    sample, dyn = px[0, :2].contiguous(), px[0, 2:].contiguous()
     with torch.no_grad():
-        dec, ref_dec, commit, dyn_commit = mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut,
+        dec, ref_dec, commit, dyn_commit = mine(sample=sample.to(cuda), dyn_sample=dyn.to(cuda), segment_len=fut,
                                                 return_dict=False, return_loss=True)
-        rec = mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut, return_loss=True)
+        rec = mine(sample=sample.to(cuda), dyn_sample=dyn.to(cuda), segment_len=fut, return_loss=True)
+        zc, zd = mine.encode_latents(px.to(cuda))                      # the same arithmetic as inside forward()
+        idx_c = ops.vq_argmin(zc, mine.quantize.embedding.weight.detach().float()).cpu()
+        idx_d = ops.vq_argmin(zd, mine.dynamics_quantize.embedding.weight.detach().float()).cpu()
+        zc_ref, zd_ref = ref.encode_latents(px)
+        flips = 0
+        for z_ref, z_mine, idx, cb in ((zc_ref, zc, idx_c, ref.quantize.embedding.weight),
+                                       (zd_ref, zd, idx_d, ref.dynamics_quantize.embedding.weight)):
+            d = torch.cdist(z_ref.double(), cb.detach().double())
+            best = d.min(1).values
+            ours = d.gather(1, idx[:, None]).squeeze(1)
+            dz = (z_mine.cpu().double() - z_ref.double()).norm(dim=1)
+            assert bool((ours - best <= 2.0 * dz + 1e-9).all()), "a VQ index differs from the oracle's without a near-tie"
+            flips += int((idx != d.argmin(1)).sum())
+        want = ref.forward_train(sample, dyn, fut, idx_ctx=idx_c, idx_dyn=idx_d)
+    print(f"\n[train graph {dtype}] VQ indices differing from the oracle's (near-ties): {flips} of {idx_c.numel() + idx_d.numel()}")
     assert dec.shape == (fut, 3, 64, 64) and ref_dec.shape == (2, 3, 64, 64)
-    assert rel_err(dec, torch.from_numpy(z["tiny_train_dec"])) < tol
-    assert rel_err(ref_dec, torch.from_numpy(z["tiny_train_ref_dec"])) < tol
-    want = z["tiny_train_losses"]
-    assert abs(float(commit) - want[0]) / want[0] < tol_loss and abs(float(dyn_commit) - want[1]) / want[1] < tol_loss
+    assert rel_err(dec, want[0]) < tol and rel_err(ref_dec, want[1]) < tol
+    assert abs(float(commit) - float(want[2])) / float(want[2]) < tol_loss
+    assert abs(float(dyn_commit) - float(want[3])) / float(want[3]) < tol_loss
     assert torch.equal(rec.sample, dec) and torch.equal(rec.ref_sample, ref_dec) and float(rec.commit_loss) == float(commit)
     with pytest.raises(NotImplementedError, match="backward"):
-        mine(sample=px[0, :2].contiguous(), dyn_sample=px[0, 2:].contiguous(), segment_len=fut)
+        mine(sample=sample.to(cuda), dyn_sample=dyn.to(cuda), segment_len=fut)
