@@ -99,7 +99,15 @@ typedef struct ivgpt_conv_desc {
    * squares) per (frame, slab, group) written to gn_part [N][gn_slabs][gn_groups][2]; gn_slabs from ivgpt_conv3x3_plan,
    * finish with ivgpt_groupnorm_finalize.  NULL = off. */
   float* gn_part; int gn_groups;
+  /* optional fused GroupNorm (+ SiLU) of the INPUT -- the `norm -> nonlinearity -> conv` of diffusers ResnetBlock2D (reached
+   * from vae.py:133-137,236-294) and of the conv_norm_out -> conv_act -> conv_out tails (vae.py:188-193): the per-(frame,
+   * channel) affine coefficients in_scale / in_shift [N][Cin] (ivgpt_groupnorm_coeff) are applied to every operand tile in
+   * shared memory before the tensor core reads it; padding stays zero.  stride 1 only.  NULL = off. */
+  const float* in_scale; const float* in_shift; int in_silu;
 } ivgpt_conv_desc;
+/* scale = rstd * gamma, shift = beta - mean * scale per (sample, channel) from GroupNorm statistics [samples][G][2] */
+int ivgpt_groupnorm_coeff(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, int samples,
+                          int C, int G, void* stream);
 int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream);
 /* tile width the launcher would pick for this problem (set d->bn to it to pin the choice) and the number of
  * GroupNorm partial slabs per frame it implies. */

@@ -48,6 +48,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int),
         ("out", C.c_void_p), ("out_dtype", C.c_int),
         ("gn_part", C.c_void_p), ("gn_groups", C.c_int),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_silu", C.c_int),
     ]
 
 
@@ -99,6 +100,7 @@ SIGNATURES = {
     "ivgpt_conv3x3": [C.POINTER(ConvDesc), _P],
     "ivgpt_conv3x3_plan": [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ivgpt_groupnorm_finalize": [_P, _P, _I, _I, _I, C.c_double, _F, _P],
+    "ivgpt_groupnorm_coeff": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ivgpt_groupnorm_stats": [_I, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ivgpt_groupnorm_apply": [_I, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
     "ivgpt_conv_in": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -94,6 +94,7 @@ int conv_out3_launch(int, const void*, const float*, const float*, const float*,
                      int, int, int, int, int, int, int, int, cudaStream_t);
 int upsample2x_launch(int, const void*, void*, int, int, int, int, cudaStream_t);
 int patchify_launch(int, const void*, void*, int, int, int, int, int, cudaStream_t);
+int gn_coeff_launch(const float*, const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 int vq_commit_launch(int, const float*, const float*, const long long*, void*, long long, int, long long, float, float*, float*,
                      cudaStream_t);
 int convert_launch(int, const void*, int, void*, long long, cudaStream_t);
@@ -324,7 +325,16 @@ int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
     IVG_CHECK(d->gn_groups > 0 && d->gn_groups <= 32 && d->Cout % d->gn_groups == 0, "conv3x3: bad gn_groups %d", d->gn_groups);
     p.gn_part = d->gn_part; p.gn_groups = d->gn_groups;
   }
+  if (d->in_scale) {
+    IVG_CHECK(d->in_shift != nullptr && d->stride == 1, "conv3x3: fused input GroupNorm needs in_shift and stride 1");
+    p.xf_scale = d->in_scale; p.xf_shift = d->in_shift; p.xf_silu = d->in_silu; p.xf_cin = d->Cin;
+  }
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
+}
+
+int ivgpt_groupnorm_coeff(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, int samples,
+                          int C, int G, void* stream) {
+  return gn_coeff_launch(stats, gamma, beta, scale, shift, samples, C, G, S(stream));
 }
 
 int ivgpt_groupnorm_stats(int dtype, const void* x, float* part_ws, float* stats, int N, int rows, int C, int G,

@@ -152,6 +152,15 @@ __global__ void gn_coeff_kernel(const float* __restrict__ stats, const float* __
   shift[i] = beta[c] - st[0] * sc;
 }
 
+int gn_coeff_launch(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, int N, int C, int G,
+                    cudaStream_t st) {
+  IVG_CHECK(N >= 1 && C >= 1 && G >= 1 && C % G == 0, "groupnorm_coeff: bad shape N=%d C=%d G=%d", N, C, G);
+  gn_coeff_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(stats, gamma, beta, scale, shift, N, C, G);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
 // y = x * scale + shift ; optional SiLU ; optional + pos[(row % pos_rows)][C].
 // grid (row chunks, samples); a thread owns ONE 16-byte channel vector (its scale / shift live in registers) and walks the
 // chunk's rows with four loads in flight.  (Round-1 v1 was a flat grid-stride loop with two 64-bit divisions and four

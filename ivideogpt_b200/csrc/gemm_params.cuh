@@ -6,6 +6,7 @@ namespace ivg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS_XF = 320;   // + 4 operand-transform warps (GroupNorm + SiLU applied to the A tiles in shared memory)
 constexpr int GEMM_ROWB = 128;  // bytes of K per k-block row (one 128B swizzle atom)
 
 struct alignas(64) GemmMaps {
@@ -43,6 +44,12 @@ struct GemmParams {
   // ---- fused GroupNorm statistics of the OUTPUT (mode 1): per (image, tile, n-tile, epilogue warp) partial sums ----
   float* gn_part;    // [images][slabs][gn_groups][2] (sum, sum of squares), slabs = tiles_per_image * tiles_n * 4; or null
   int gn_groups;
+  // ---- fused GroupNorm (+ SiLU) of the INPUT (mode 1, stride 1): y = silu(x * xf_scale[img][c] + xf_shift[img][c]) is applied
+  //      to every A tile after it lands in shared memory and before the tensor core reads it; zero padding stays zero ----
+  const float* xf_scale;   // [images][Cin] or null
+  const float* xf_shift;
+  int xf_silu;
+  int xf_cin;
 };
 
 }  // namespace ivg

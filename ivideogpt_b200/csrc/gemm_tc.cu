@@ -39,8 +39,58 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 + 1024;  // + barrier block + GN accumulators + alignment slack
 };
 
-template <typename T, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// ---- operand transform: GroupNorm affine + SiLU on 8 bf16 / 4 fp32 channels of one pixel (one 16-byte chunk) ----
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_f32(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(y) = y * sigmoid(y) = h + h * tanh(h) with h = y / 2: ONE special-function op per element (per PAIR in bf16x2), where
+// y / (1 + exp(-y)) costs two -- the transform of a k-block must stay under the ~512 tensor cycles the same k-block takes
+template <typename T> struct XfChunk;
+template <> struct XfChunk<__nv_bfloat16> {
+  static constexpr int NCH = 8;
+  __device__ static __forceinline__ uint4 apply(uint4 v, const float* sc, const float* sh, bool silu) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      const float2 f = __bfloat1622float2(x2);
+      const float y0 = fmaf(f.x, sc[2 * i], sh[2 * i]), y1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
+      if (silu) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(0.5f * y0, 0.5f * y1);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const uint32_t tb = tanh_bf16x2(hb);
+        const __nv_bfloat162 o2 = __hfma2(h2, *reinterpret_cast<const __nv_bfloat162*>(&tb), h2);
+        w[i] = *reinterpret_cast<const uint32_t*>(&o2);
+      } else {
+        w[i] = pack_bf16x2(y0, y1);
+      }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct XfChunk<float> {
+  static constexpr int NCH = 4;
+  __device__ static __forceinline__ uint4 apply(uint4 v, const float* sc, const float* sh, bool silu) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float y = fmaf(__uint_as_float(w[i]), sc[i], sh[i]);
+      if (silu) { const float h = 0.5f * y; y = fmaf(h, tanh_f32(h), h); }
+      w[i] = __float_as_uint(y);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T, int BN, bool XF>
+__global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using SM = GemmSmem<BN>;
   constexpr bool TF32 = (sizeof(T) == 4);
@@ -54,7 +104,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* empty_bar = full_bar + SM::STAGES;
   uint64_t* tfull_bar = empty_bar + SM::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xf_bar = tempty_bar + 2;                      // [STAGES] A tile transformed (XF): 128 arrivals
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xf_bar + SM::STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,6 +115,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < SM::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 4); }
+    if (XF) for (int s = 0; s < SM::STAGES; ++s) mbar_init(xf_bar + s, 128);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_holder, TMEM_COLS); tmem_relinquish(); }
@@ -143,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + stage, phase);
+          if (XF) mbar_wait(xf_bar + stage, phase);       // the transform warps have rewritten the A tile in place
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128_kmajor(sa);
@@ -158,7 +211,72 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         umma_commit(tfull_bar + acc);      // accumulator complete -> epilogue
       }
     }
-  } else {
+  } else if (XF && warp >= 6) {
+    // =============================== operand-transform warps (fused GroupNorm + SiLU of the conv input) ===============================
+    // 128 threads; thread (c = tt & 7, rbase = tt >> 3) owns the 16-byte chunk of channels [chunk0 + c * NCH, + NCH) of rows
+    // rbase + 16 i: its per-(image, channel) coefficients stay in registers across the rows of a k-block and are prefetched one
+    // k-block ahead.  A quarter warp covers the 8 (permuted) chunks of one 128-byte row: bank-conflict free.
+    constexpr int NCH = XfChunk<T>::NCH;
+    const int tt = threadIdx.x - 192;
+    const int c = tt & 7, rbase = tt >> 3;
+    const int kb_taps = p.ntaps * p.cpb;
+    const bool silu = p.xf_silu != 0;
+    int rty[8], rtx[8];                                   // tile-relative pixel of this thread's 8 rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int r = rbase + 16 * i; rty[i] = r / p.tw; rtx[i] = r - rty[i] * p.tw; }
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int rem = tile % tiles_mn;
+      const int tm = rem / p.tiles_n;
+      const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
+      const int img = tm / tiles_img;
+      const int r2 = tm - img * tiles_img;
+      const int y0 = (r2 / tiles_x) * p.th, x0 = (r2 % tiles_x) * p.tw;
+      const float* scp = p.xf_scale + (size_t)img * p.xf_cin + c * NCH;
+      const float* shp = p.xf_shift + (size_t)img * p.xf_cin + c * NCH;
+      float sc[NCH], sh[NCH], nsc[NCH], nsh[NCH];
+#pragma unroll
+      for (int i = 0; i < NCH; i += 4) {
+        *reinterpret_cast<float4*>(nsc + i) = __ldg(reinterpret_cast<const float4*>(scp + i));
+        *reinterpret_cast<float4*>(nsh + i) = __ldg(reinterpret_cast<const float4*>(shp + i));
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const bool xf = kb < kb_taps;                       // k-blocks of the fused 1x1 shortcut source are left untouched
+        int tap = 0;
+        if (xf) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) { sc[i] = nsc[i]; sh[i] = nsh[i]; }
+          tap = kb / p.cpb;
+          const int nkb = kb + 1;
+          if (nkb < kb_taps) {                              // coefficients of the next k-block's channel chunk
+            const int chunk0 = (nkb - (nkb / p.cpb) * p.cpb) * (BK);
+#pragma unroll
+            for (int i = 0; i < NCH; i += 4) {
+              *reinterpret_cast<float4*>(nsc + i) = __ldg(reinterpret_cast<const float4*>(scp + chunk0 + i));
+              *reinterpret_cast<float4*>(nsh + i) = __ldg(reinterpret_cast<const float4*>(shp + chunk0 + i));
+            }
+          }
+        }
+        mbar_wait(full_bar + stage, phase);
+        if (xf) {
+          uint8_t* sa = smem + stage * SM::STAGE_BYTES;
+          const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rbase + 16 * i;
+            const int yy = y0 + rty[i] + dy, xx = x0 + rtx[i] + dx;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {            // padding pixels were zero-filled by TMA and stay zero
+              uint4* ptr = reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4));
+              *ptr = XfChunk<T>::apply(*ptr, sc, sh, silu);
+            }
+          }
+          fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core's reads
+        }
+        mbar_arrive(xf_bar + stage);
+        if (++stage == SM::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile owned by this thread
@@ -327,21 +445,30 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BN>
-static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+template <typename T, int BN, bool XF>
+static int launch_xf(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
   using SM = GemmSmem<BN>;
   static PerDeviceOnce attr_once;
   if (attr_once.pending()) {
-    IVG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    IVG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_once.mark();
   }
   long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
   int grid = (int)(total < num_sms ? total : num_sms);
   if (grid < 1) return 0;
-  IVG_CUDA(launch_k(gemm_tc_kernel<T, BN>, dim3(grid), dim3(GEMM_THREADS), (size_t)SM::TOTAL, stream, maps, p));
+  IVG_CUDA(launch_k(gemm_tc_kernel<T, BN, XF>, dim3(grid), dim3(XF ? GEMM_THREADS_XF : GEMM_THREADS), (size_t)SM::TOTAL, stream,
+                    maps, p));
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;
+}
+template <typename T, int BN>
+static int launch_one(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.xf_scale != nullptr) {
+    IVG_CHECK(p.mode == 1 && p.xf_shift != nullptr && p.xf_cin > 0, "gemm_tc: the operand transform belongs to stride-1 conv launches");
+    return launch_xf<T, BN, true>(maps, p, num_sms, stream);
+  }
+  return launch_xf<T, BN, false>(maps, p, num_sms, stream);
 }
 
 // ---- optional per-launch event timing (bench.py roofline leg) -----------------------------------------------

@@ -115,8 +115,10 @@ def gemm_raw(d: GemmDesc):
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1,
             x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-            out_dtype: Optional[torch.dtype] = None, bn: int = 0, gn_groups: int = 0) -> torch.Tensor:
+            out_dtype: Optional[torch.dtype] = None, bn: int = 0, gn_groups: int = 0, gn_in=None) -> torch.Tensor:
     """3x3 conv over NHWC x [N,H,W,Cin] with packed weights [Cout, 9*Cin (+C2)]; optional fused 1x1 source x2.
+    gn_in = (scale [N,Cin], shift [N,Cin], silu): the GroupNorm (+ SiLU) that precedes the conv, applied to the operand tiles
+    inside the kernel (groupnorm_coeff() makes the coefficients) -- the normalised activation never exists in HBM.
     gn_groups > 0: the epilogue also emits GroupNorm partial statistics of the output; they ride on the returned tensor
     as `out.gn_part = (partials [N, slabs, G, 2], slabs)` for groupnorm_stats_from_parts()."""
     _cuda(x, w_packed, bias, x2, residual)
@@ -142,6 +144,11 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
         d.residual = residual.data_ptr(); d.res_dtype = _dt(residual)
     d.act = act
     d.out = out.data_ptr(); d.out_dtype = _dt(out)
+    if gn_in is not None:
+        sc, sh, silu = gn_in
+        assert stride == 1 and sc.dtype == torch.float32 and sh.dtype == torch.float32 and sc.shape == (N, Cin) == sh.shape
+        assert sc.is_contiguous() and sh.is_contiguous()
+        d.in_scale = sc.data_ptr(); d.in_shift = sh.data_ptr(); d.in_silu = int(bool(silu))
     part = None
     if gn_groups > 0:
         bn_c, slabs_c = C.c_int(0), C.c_int(0)
@@ -185,6 +192,18 @@ def groupnorm_stats_from_parts(x: torch.Tensor, samples: int, groups: int, eps: 
     _lib.check(_lib.load().ivgpt_groupnorm_finalize(part.data_ptr(), stats.data_ptr(), samples, slabs * per, groups,
                                                     count, eps, _stream()), "groupnorm_finalize")
     return stats
+
+
+def groupnorm_coeff(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """(scale, shift) [samples, C] fp32 with y = x * scale + shift == GroupNorm(x) for statistics [samples, G, 2]."""
+    _cuda(stats, gamma, beta)
+    samples, groups = stats.shape[0], stats.shape[1]
+    Cc = gamma.numel()
+    scale = torch.empty(samples, Cc, dtype=torch.float32, device=stats.device)
+    shift = torch.empty(samples, Cc, dtype=torch.float32, device=stats.device)
+    _lib.check(_lib.load().ivgpt_groupnorm_coeff(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), scale.data_ptr(),
+                                                 shift.data_ptr(), samples, Cc, groups, _stream()), "groupnorm_coeff")
+    return scale, shift
 
 
 def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,

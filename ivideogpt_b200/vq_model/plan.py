@@ -110,6 +110,9 @@ class TokenizerPlan:
         # more than the separate statistics pass costs -- kept available (and unit-tested) but switched off until the
         # epilogue reduction is restructured (per-warp shared-memory transpose once per tile).
         self.fused_stats = groups if os.environ.get("IVGPT_FUSED_GN_STATS", "0") == "1" else 0
+        # GroupNorm + SiLU applied to the conv's operand tiles inside the conv kernel (no normalised copy of the activation in
+        # HBM: the read + write pass of gn_apply disappears).  IVGPT_FUSED_GN_APPLY=0 restores the separate pass (A/B, tests).
+        self.fused_apply = os.environ.get("IVGPT_FUSED_GN_APPLY", "1") == "1"
 
     # ---- building blocks --------------------------------------------------------------------------
     def _gn(self, x, norm, silu: bool, samples: Optional[int] = None, pos=None):
@@ -121,16 +124,31 @@ class TokenizerPlan:
         return ops.groupnorm_apply(x, stats, self.pw.f32(norm.weight), self.pw.f32(norm.bias), silu,
                                    None if pos is None else self.pw.f32(pos))
 
+    def _gn_coeff(self, x, norm):
+        """Coefficients of GroupNorm(x) for the conv that applies it on the fly: statistics pass (or the producing conv's
+        epilogue partials) + a tiny per-(frame, channel) kernel."""
+        n = x.shape[0]
+        if getattr(x, "gn_part", None) is not None and x.gn_part[0].shape[2] == norm.num_groups:
+            stats = ops.groupnorm_stats_from_parts(x, n, norm.num_groups, norm.eps)
+        else:
+            stats = ops.groupnorm_stats(x, n, norm.num_groups, norm.eps)
+        sc, sh = ops.groupnorm_coeff(stats, self.pw.f32(norm.weight), self.pw.f32(norm.bias))
+        return sc, sh, True
+
+    def gn_silu_conv(self, x, norm, w, b, **kw):
+        """conv3x3(silu(GroupNorm(x))) -- fused (default) or as two launches."""
+        if self.fused_apply:
+            return ops.conv3x3(x, w, b, gn_in=self._gn_coeff(x, norm), **kw)
+        return ops.conv3x3(self._gn(x, norm, True), w, b, **kw)
+
     def resnet(self, x, r: ResnetParams):
-        y = self._gn(x, r.norm1, True)
         w1, b1 = self.pw.conv3(r.conv1, self.dtype)
-        h = ops.conv3x3(y, w1, b1, gn_groups=self.fused_stats)
-        y2 = self._gn(h, r.norm2, True)
+        h = self.gn_silu_conv(x, r.norm1, w1, b1, gn_groups=self.fused_stats)
         if r.conv_shortcut is not None:
             w2, b2 = self.pw.conv3(r.conv2, self.dtype, shortcut=r.conv_shortcut)
-            return ops.conv3x3(y2, w2, b2, x2=x, gn_groups=self.fused_stats)
+            return self.gn_silu_conv(h, r.norm2, w2, b2, x2=x, gn_groups=self.fused_stats)
         w2, b2 = self.pw.conv3(r.conv2, self.dtype)
-        return ops.conv3x3(y2, w2, b2, residual=x, gn_groups=self.fused_stats)
+        return self.gn_silu_conv(h, r.norm2, w2, b2, residual=x, gn_groups=self.fused_stats)
 
     def attention(self, q_tok, kv_tok, wq, bq, wk, bk, wv, bv, heads: int, frames_per_clip: int):
         """q_tok [F, Lq, C], kv_tok [B, Lkv, C] (F = B*frames_per_clip) -> O [F*Lq, C] (before out-proj)."""
@@ -222,9 +240,8 @@ class TokenizerPlan:
             feats.append(x)
         x = self.mid(x, enc.mid_block)
         feats.append(x)
-        y = self._gn(x, enc.conv_norm_out, True)
         wo, bo = self.pw.conv3(enc.conv_out, self.dtype)
-        out = ops.conv3x3(y, wo, bo)
+        out = self.gn_silu_conv(x, enc.conv_norm_out, wo, bo)
         return (out, feats) if want_features else out
 
     # ---- decoders ---------------------------------------------------------------------------------

@@ -173,3 +173,54 @@ def test_conv3x3_fused_groupnorm_statistics(cuda, dtype, N, H, Cin, Cout, joint)
     want = ops.groupnorm_stats(out, samples, 32, 1e-6)
     assert rel_err(got[..., 0], want[..., 0]) < 1e-4 or float((got[..., 0] - want[..., 0]).abs().max()) < 1e-5
     assert rel_err(got[..., 1], want[..., 1]) < 1e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 8e-3), (torch.float32, 1.5e-3)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,C2,residual", [
+    (3, 16, 16, 128, 128, 0, True),       # 128-pixel tile spans 8 rows x 16 columns: every padding side is exercised
+    (2, 32, 32, 64, 256, 0, False),       # several tiles per frame, BN = 256
+    (2, 16, 16, 128, 64, 128, False),     # fused 1x1 shortcut k-blocks must NOT be normalised
+    (5, 8, 8, 256, 64, 0, False),         # two frames per 128-pixel tile is impossible (tw*th = 64 < 128): 8x8 -> tw=8, th=16? guarded below
+])
+def test_conv_with_fused_input_groupnorm_silu(cuda, dtype, tol, N, H, W, Cin, Cout, C2, residual):
+    """conv3x3(silu(GroupNorm(x))) with the normalisation applied to the operand tiles inside the conv kernel (the transform
+    warps of gemm_tc.cu) against fp64 math: F.conv2d(F.silu(F.group_norm(x))) on the same rounded x and weights.  The
+    tolerance covers the bf16 rounding of the normalised operand + tanh.approx (one rounding more than the two-launch path)."""
+    from ivideogpt_b200 import ops
+    if H * W < 128:
+        pytest.skip("a 128-pixel tile must fit inside one frame")
+    G = 32
+    x = _mk((N, H, W, Cin), dtype, 11, 1.3) + 0.4
+    x = x.to(torch.bfloat16) if dtype == torch.bfloat16 else tf32_round(x)
+    w = _mk((Cout, 3, 3, Cin), dtype, 12, 0.05)
+    gamma = 1.0 + 0.2 * torch.randn(Cin, generator=torch.Generator().manual_seed(13))
+    beta = 0.3 * torch.randn(Cin, generator=torch.Generator().manual_seed(14))
+    bias = torch.randn(Cout, generator=torch.Generator().manual_seed(15))
+    parts = [w.reshape(Cout, 9 * Cin)]
+    x2 = w2 = None
+    if C2:
+        x2 = _mk((N, H, W, C2), dtype, 16)
+        w2 = _mk((Cout, C2), dtype, 17, 0.05)
+        parts.append(w2)
+    wp = torch.cat(parts, dim=1).contiguous().to(cuda)
+    res = _mk((N, H, W, Cout), dtype, 18) if residual else None
+    xc = x.to(cuda)
+    stats = ops.groupnorm_stats(xc, N, G, 1e-6)
+    sc, sh = ops.groupnorm_coeff(stats, gamma.to(cuda), beta.to(cuda))
+    got = ops.conv3x3(xc, wp, bias.to(cuda), x2=None if x2 is None else x2.to(cuda), residual=None if res is None else res.to(cuda),
+                      out_dtype=torch.float32, gn_in=(sc, sh, True))
+    xd = x.double().permute(0, 3, 1, 2)
+    y = F.silu(F.group_norm(xd, G, gamma.double(), beta.double(), eps=1e-6))
+    want = F.conv2d(y, w.double().permute(0, 3, 1, 2), bias.double(), padding=1)
+    if C2:
+        want = want + F.conv2d(x2.double().permute(0, 3, 1, 2), w2.double()[:, :, None, None])
+    if res is not None:
+        want = want + res.double().permute(0, 3, 1, 2)
+    e = rel_err(got.permute(0, 3, 1, 2), want)
+    # and against the two-launch path (normalised copy in HBM, then the plain conv)
+    y2 = ops.groupnorm_apply(xc, stats, gamma.to(cuda), beta.to(cuda), True)
+    two = ops.conv3x3(y2, wp, bias.to(cuda), x2=None if x2 is None else x2.to(cuda), residual=None if res is None else res.to(cuda),
+                      out_dtype=torch.float32)
+    e2 = rel_err(two.permute(0, 3, 1, 2), want)
+    print(f"\n[fused GN conv {dtype}] rel err fused {e:.3e}, two launches {e2:.3e}")
+    assert e < tol, f"fused GroupNorm+SiLU conv rel err {e} (two-launch path: {e2})"
