@@ -6,7 +6,11 @@ namespace ivg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_THREADS_XF = 320;   // + 4 operand-transform warps (GroupNorm + SiLU applied to the A tiles in shared memory)
+#ifndef IVG_XF_WARPS
+#define IVG_XF_WARPS 8
+#endif
+constexpr int GEMM_XF_WARPS = IVG_XF_WARPS;                  // operand-transform warps (4, 8 or 16)
+constexpr int GEMM_THREADS_XF = 192 + 32 * GEMM_XF_WARPS;    // GroupNorm + SiLU applied to the A tiles in shared memory
 constexpr int GEMM_ROWB = 128;  // bytes of K per k-block row (one 128B swizzle atom)
 
 struct alignas(64) GemmMaps {

@@ -62,8 +62,8 @@ template <> struct XfChunk<__nv_bfloat16> {
       const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
       const float2 f = __bfloat1622float2(x2);
       const float y0 = fmaf(f.x, sc[2 * i], sh[2 * i]), y1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
-      if (silu) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(0.5f * y0, 0.5f * y1);
+      if (silu) {                                 // the caller passes HALVED coefficients: y0 / y1 are already h = y / 2
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
         const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
         const uint32_t tb = tanh_bf16x2(hb);
         const __nv_bfloat162 o2 = __hfma2(h2, *reinterpret_cast<const __nv_bfloat162*>(&tb), h2);
@@ -82,7 +82,7 @@ template <> struct XfChunk<float> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float y = fmaf(__uint_as_float(w[i]), sc[i], sh[i]);
-      if (silu) { const float h = 0.5f * y; y = fmaf(h, tanh_f32(h), h); }
+      if (silu) y = fmaf(y, tanh_f32(y), y);      // halved coefficients: y is h = (x * scale + shift) / 2
       w[i] = __float_as_uint(y);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
@@ -115,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < SM::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 4); }
-    if (XF) for (int s = 0; s < SM::STAGES; ++s) mbar_init(xf_bar + s, 128);
+    if (XF) for (int s = 0; s < SM::STAGES; ++s) mbar_init(xf_bar + s, 32 * GEMM_XF_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_holder, TMEM_COLS); tmem_relinquish(); }
@@ -212,18 +212,21 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else if (XF && warp >= 6) {
+    static_assert(GEMM_XF_WARPS == 4 || GEMM_XF_WARPS == 8 || GEMM_XF_WARPS == 16, "transform warps: 4, 8 or 16");
     // =============================== operand-transform warps (fused GroupNorm + SiLU of the conv input) ===============================
     // 128 threads; thread (c = tt & 7, rbase = tt >> 3) owns the 16-byte chunk of channels [chunk0 + c * NCH, + NCH) of rows
     // rbase + 16 i: its per-(image, channel) coefficients stay in registers across the rows of a k-block and are prefetched one
     // k-block ahead.  A quarter warp covers the 8 (permuted) chunks of one 128-byte row: bank-conflict free.
     constexpr int NCH = XfChunk<T>::NCH;
+    constexpr int XROWS = 128 / (4 * GEMM_XF_WARPS);       // rows per thread: 8 / 4 / 2
+    constexpr int XSTEP = 4 * GEMM_XF_WARPS;               // row stride between them
     const int tt = threadIdx.x - 192;
     const int c = tt & 7, rbase = tt >> 3;
     const int kb_taps = p.ntaps * p.cpb;
     const bool silu = p.xf_silu != 0;
-    int rty[8], rtx[8];                                   // tile-relative pixel of this thread's 8 rows
+    int rty[XROWS], rtx[XROWS];                           // tile-relative pixel of this thread's rows
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const int r = rbase + 16 * i; rty[i] = r / p.tw; rtx[i] = r - rty[i] * p.tw; }
+    for (int i = 0; i < XROWS; ++i) { const int r = rbase + XSTEP * i; rty[i] = r / p.tw; rtx[i] = r - rty[i] * p.tw; }
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int rem = tile % tiles_mn;
@@ -234,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const int y0 = (r2 / tiles_x) * p.th, x0 = (r2 % tiles_x) * p.tw;
       const float* scp = p.xf_scale + (size_t)img * p.xf_cin + c * NCH;
       const float* shp = p.xf_shift + (size_t)img * p.xf_cin + c * NCH;
+      const float cmul = silu ? 0.5f : 1.0f;               // silu(y) = h + h tanh(h), h = y / 2: fold the 1/2 into the affine map
       float sc[NCH], sh[NCH], nsc[NCH], nsh[NCH];
 #pragma unroll
       for (int i = 0; i < NCH; i += 4) {
@@ -245,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         int tap = 0;
         if (xf) {
 #pragma unroll
-          for (int i = 0; i < NCH; ++i) { sc[i] = nsc[i]; sh[i] = nsh[i]; }
+          for (int i = 0; i < NCH; ++i) { sc[i] = nsc[i] * cmul; sh[i] = nsh[i] * cmul; }
           tap = kb / p.cpb;
           const int nkb = kb + 1;
           if (nkb < kb_taps) {                              // coefficients of the next k-block's channel chunk
@@ -262,8 +266,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           uint8_t* sa = smem + stage * SM::STAGE_BYTES;
           const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rbase + 16 * i;
+          for (int i = 0; i < XROWS; ++i) {
+            const int r = rbase + XSTEP * i;
             const int yy = y0 + rty[i] + dy, xx = x0 + rtx[i] + dx;
             if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {            // padding pixels were zero-filled by TMA and stay zero
               uint4* ptr = reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4));

@@ -110,9 +110,12 @@ class TokenizerPlan:
         # more than the separate statistics pass costs -- kept available (and unit-tested) but switched off until the
         # epilogue reduction is restructured (per-warp shared-memory transpose once per tile).
         self.fused_stats = groups if os.environ.get("IVGPT_FUSED_GN_STATS", "0") == "1" else 0
-        # GroupNorm + SiLU applied to the conv's operand tiles inside the conv kernel (no normalised copy of the activation in
-        # HBM: the read + write pass of gn_apply disappears).  IVGPT_FUSED_GN_APPLY=0 restores the separate pass (A/B, tests).
-        self.fused_apply = os.environ.get("IVGPT_FUSED_GN_APPLY", "1") == "1"
+        # GroupNorm + SiLU applied to the conv's operand tiles inside the conv kernel (transform warps of gemm_tc.cu): no
+        # normalised copy of the activation in HBM.  MEASURED (profiles/r02/gn_fused_apply_ab.txt): the conv family goes from
+        # 45 to 82-104 ms per cfg64 step (4 / 8 / 16 transform warps: 104 / 84 / 82) -- every input pixel is re-normalised for
+        # each of the 9 taps and the extra shared-memory read + write per k-block, not the arithmetic, is the limit -- against
+        # ~17 ms of GroupNorm passes saved.  OFF by default; IVGPT_FUSED_GN_APPLY=1 selects it (parity-tested either way).
+        self.fused_apply = os.environ.get("IVGPT_FUSED_GN_APPLY", "0") == "1"
 
     # ---- building blocks --------------------------------------------------------------------------
     def _gn(self, x, norm, silu: bool, samples: Optional[int] = None, pos=None):
