@@ -279,6 +279,10 @@ typedef struct ivgpt_mega_desc {
                       barriers per step of a 12-layer model). */
 } ivgpt_mega_desc;
 int ivgpt_mega_fused_norm(void);   /* compile-time property of gemm_mode 0, see tile_cnt */
+/* GEMM / conv kernel: 0 (default) = two tcgen05.mma issuing warps accumulate alternate k-blocks into one accumulator (full
+ * tensor rate; the fp32 summation order, i.e. the last bits, may vary from run to run), 1 = one issuer (bit-reproducible,
+ * at most ~80 % of the tensor peak).  Also selectable with IVGPT_DETERMINISTIC=1 in the environment. */
+int ivgpt_set_deterministic(int on);
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);

@@ -2,6 +2,7 @@
 // thread-local error string, tensor-map construction through the driver entry point, GEMM/conv descriptors.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ivgpt_b200.h"
@@ -73,6 +74,17 @@ static int num_sms() {
     n = v > 0 ? v : 148;
   }
   return n;
+}
+
+// tcgen05.mma issuing warps of the GEMM / conv kernel: 2 (default: full tensor rate, summation order of the last bits not
+// fixed) or 1 (IVGPT_DETERMINISTIC=1 in the environment, or ivgpt_set_deterministic(1): bit-reproducible, <= 80 % of peak)
+static int g_issuers = 0;
+static int mma_issuers() {
+  if (!g_issuers) {
+    const char* e = getenv("IVGPT_DETERMINISTIC");
+    g_issuers = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return g_issuers;
 }
 
 // ---- forward declarations of launchers defined in the other translation units -----------------
@@ -233,6 +245,7 @@ int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream) {
   p.act = d->act; p.alpha = d->alpha;
   p.tiles_m = (int)tiles_m; p.tiles_n = (d->N + bn - 1) / bn;
   IVG_CHECK(d->act != IVGPT_ACT_SWIGLU || (d->N % 2 == 0 && d->residual == nullptr), "gemm: SwiGLU needs even N, no residual");
+  p.issuers = mma_issuers();
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
@@ -329,6 +342,7 @@ int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
     IVG_CHECK(d->in_shift != nullptr && d->stride == 1, "conv3x3: fused input GroupNorm needs in_shift and stride 1");
     p.xf_scale = d->in_scale; p.xf_shift = d->in_shift; p.xf_silu = d->in_silu; p.xf_cin = d->Cin;
   }
+  p.issuers = mma_issuers();
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
@@ -525,6 +539,8 @@ int ivgpt_flash_attn(const void* q, const void* k, const void* vt, void* out, fl
   return flash_attn_launch(q, k, vt, out, lse, B, heads, Lq, Lk, q_bstride, k_bstride, vt_bstride, vt_ld, ldo, causal, scale,
                            num_sms(), S(stream));
 }
+
+int ivgpt_set_deterministic(int on) { g_issuers = on ? 1 : 2; return 0; }
 
 int ivgpt_mega_fused_norm(void) { return ivg::mega_fused_norm(); }
 

@@ -5,12 +5,12 @@
 namespace ivg {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 224;      // warp 0 TMA producer, warp 1 + warp 6 tcgen05.mma issuers, warps 2-5 epilogue
 #ifndef IVG_XF_WARPS
 #define IVG_XF_WARPS 8
 #endif
 constexpr int GEMM_XF_WARPS = IVG_XF_WARPS;                  // operand-transform warps (4, 8 or 16)
-constexpr int GEMM_THREADS_XF = 192 + 32 * GEMM_XF_WARPS;    // GroupNorm + SiLU applied to the A tiles in shared memory
+constexpr int GEMM_THREADS_XF = GEMM_THREADS + 32 * GEMM_XF_WARPS;    // GroupNorm + SiLU applied to the A tiles in shared memory
 constexpr int GEMM_ROWB = 128;  // bytes of K per k-block row (one 128B swizzle atom)
 
 struct alignas(64) GemmMaps {
@@ -45,6 +45,7 @@ struct GemmParams {
   int act;           // 0 none, 1 SiLU, 2 SwiGLU over interleaved column pairs (out has N/2 columns)
   float alpha;
   int tiles_m, tiles_n;
+  int issuers;       // 1 or 2 tcgen05.mma issuing warps (2: alternate k-blocks, same accumulator; see gemm_tc.cu)
   // ---- fused GroupNorm statistics of the OUTPUT (mode 1): per (image, tile, n-tile, epilogue warp) partial sums ----
   float* gn_part;    // [images][slabs][gn_groups][2] (sum, sum of squares), slabs = tiles_per_image * tiles_n * 4; or null
   int gn_groups;

@@ -18,6 +18,13 @@
 // Structure (per CTA, 192 threads, 1 CTA/SM, grid = min(#tiles, #SMs), static tile striding):
 //   warp 0 (one elected lane) : TMA producer       -> smem ring of S stages {A 128x128B, B BNx128B}, SWIZZLE_128B
 //   warp 1 (one elected lane) : tcgen05.mma issuer -> 2 TMEM accumulator stages of BN fp32 columns each
+//   warp 6 (one elected lane) : SECOND tcgen05.mma issuer.  One thread issuing back to back sustains one 128 x 256 x 16 MMA per
+//                               ~160 cycles although the tensor core needs 128 (tools/probes/mma_probe.cu,
+//                               profiles/r02/mma_issue_and_ffma_probe.json): a single-issuer kernel is capped at 80 % of peak.
+//                               Two warps issuing ALTERNATE k-blocks into the SAME accumulator reach 127 cycles per MMA with exact
+//                               results (the probe checks every element).  The order in which the tensor core retires the two
+//                               streams is not fixed, so the fp32 summation order -- the last bits of the result -- may differ
+//                               from run to run; GemmParams::issuers = 1 (IVGPT_DETERMINISTIC=1) restores the single issuer.
 //   warps 2-5                 : epilogue, tcgen05.ld 32 lanes x 16 columns, bias/residual/activation, global stores
 // Operands are bf16 (kind::f16) or fp32 read as tf32 (kind::tf32); a k-block is always 128 bytes of K.
 #include <utility>
@@ -105,7 +112,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* tfull_bar = empty_bar + SM::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* xf_bar = tempty_bar + 2;                      // [STAGES] A tile transformed (XF): 128 arrivals
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xf_bar + SM::STAGES);
+  uint64_t* start_bar = xf_bar + SM::STAGES;              // [2] the accumulator-zeroing first k-block of a tile has retired
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(start_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < SM::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, (uint32_t)p.issuers); mbar_init(tempty_bar + s, 4); mbar_init(start_bar + s, 1); }
     if (XF) for (int s = 0; s < SM::STAGES; ++s) mbar_init(xf_bar + s, 32 * GEMM_XF_WARPS);
     fence_barrier_init();
   }
@@ -176,9 +184,14 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // =============================== MMA issuer ===============================
+  } else if (warp == 1 || warp == 6) {
+    const int iss = warp == 1 ? 0 : 1;
+    if (lane == 0 && iss < p.issuers) {
+      // =============================== MMA issuers ===============================
+      // issuer `iss` takes the k-blocks kb with kb % issuers == iss; both walk the same (stage, phase) sequence.  The first
+      // k-block of a tile (issuer 0) zeroes the accumulator: issuer 1 waits until it has retired (start_bar) before its
+      // first accumulating MMA of that tile.
+      const int NI = p.issuers;
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -193,25 +206,30 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        bool waited_start = iss == 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + stage, phase);
-          if (XF) mbar_wait(xf_bar + stage, phase);       // the transform warps have rewritten the A tile in place
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128_kmajor(sa);
-          const uint64_t bdesc = umma_desc_sw128_kmajor(sa + SM::A_BYTES);
+          if (NI == 1 || (kb & 1) == iss) {
+            if (!waited_start) { mbar_wait(start_bar + acc, acc_phase); waited_start = true; }
+            mbar_wait(full_bar + stage, phase);
+            if (XF) mbar_wait(xf_bar + stage, phase);       // the transform warps have rewritten the A tile in place
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+            const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(sa + SM::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per k-block
-            umma_ss<TF32>(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per k-block
+              umma_ss<TF32>(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
+            if (NI == 2 && kb == 0) umma_commit(start_bar + acc);
           }
-          umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
           if (++stage == SM::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + acc);      // accumulator complete -> epilogue
+        umma_commit(tfull_bar + acc);      // this issuer's share of the accumulator complete -> epilogue (NI arrivals)
       }
     }
-  } else if (XF && warp >= 6) {
+  } else if (XF && warp >= 7) {
     static_assert(GEMM_XF_WARPS == 4 || GEMM_XF_WARPS == 8 || GEMM_XF_WARPS == 16, "transform warps: 4, 8 or 16");
     // =============================== operand-transform warps (fused GroupNorm + SiLU of the conv input) ===============================
     // 128 threads; thread (c = tt & 7, rbase = tt >> 3) owns the 16-byte chunk of channels [chunk0 + c * NCH, + NCH) of rows
@@ -220,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     constexpr int NCH = XfChunk<T>::NCH;
     constexpr int XROWS = 128 / (4 * GEMM_XF_WARPS);       // rows per thread: 8 / 4 / 2
     constexpr int XSTEP = 4 * GEMM_XF_WARPS;               // row stride between them
-    const int tt = threadIdx.x - 192;
+    const int tt = threadIdx.x - GEMM_THREADS;
     const int c = tt & 7, rbase = tt >> 3;
     const int kb_taps = p.ntaps * p.cpb;
     const bool silu = p.xf_silu != 0;
@@ -280,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         if (++stage == SM::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 2 && warp < 6) {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile owned by this thread

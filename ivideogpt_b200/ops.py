@@ -378,6 +378,12 @@ def decode_attn_fused(qkv, k_cache, v_cache_t, out, B, heads, Lmax, pos, dpos, c
                                                    sin_tab.data_ptr(), scale, _stream()), "decode_attn_fused")
 
 
+def set_deterministic(on: bool):
+    """One tcgen05.mma issuing warp instead of two in the GEMM / conv kernel: bit-reproducible results at <= 80 % of the tensor
+    peak (two issuers accumulate into one accumulator in an order the hardware does not fix)."""
+    _lib.load().ivgpt_set_deterministic(int(bool(on)))
+
+
 def set_pdl(on: bool):
     _lib.load().ivgpt_set_pdl(int(on))
 
@@ -592,6 +598,6 @@ device_scoped = _device_guarded      # decorator for model-level methods (first 
 
 for _name, _fn in list(globals().items()):
     if isinstance(_fn, types.FunctionType) and not _name.startswith("_") and _fn.__module__ == __name__ and \
-            _name not in ("gemm_desc", "gemm_raw", "torch_dtype", "set_pdl", "on_device_of", "device_scoped"):
+            _name not in ("gemm_desc", "gemm_raw", "torch_dtype", "set_pdl", "set_deterministic", "on_device_of", "device_scoped"):
         globals()[_name] = _device_guarded(_fn)
 del _name, _fn

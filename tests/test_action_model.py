@@ -13,6 +13,7 @@ import torch
 from helpers import ROOT, rel_err
 
 GOLD = os.path.join(ROOT, "tests", "golden", "action_model_tiny.npz")
+pytestmark = pytest.mark.usefixtures("deterministic")      # greedy token sequences of two runs are compared exactly
 
 
 def _gold():

@@ -7,6 +7,22 @@ from helpers import rel_err, tf32_round, tf32_trunc
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=[2, 1], ids=["two-issuers", "one-issuer"], autouse=True)
+def mma_issuers(request):
+    """Every test of this module runs in both modes of the GEMM / conv kernel: two tcgen05.mma issuing warps on one accumulator
+    (default, what the bench runs) and the single bit-reproducible issuer."""
+    import torch
+    if not torch.cuda.is_available():
+        yield
+        return
+    from ivideogpt_b200 import ops
+    ops.set_deterministic(request.param == 1)
+    try:
+        yield
+    finally:
+        ops.set_deterministic(False)
+
 # Tolerances: inputs are pre-rounded to the operand format, so the only error left is fp32 accumulation order
 # (+ the kernel's truncation of unrounded fp32 A operands to tf32 where noted).
 TOL_EXACT_INPUTS = 2e-5

@@ -4,6 +4,11 @@ import torch
 
 from helpers import rel_err
 
+# Most tests of this module compare two runs of the same computation token for token / bit for bit (graph vs eager, megakernel
+# tile variants, reducer on/off): they run with one tcgen05.mma issuer.  The benchmarked two-issuer mode is covered by
+# tests/test_gemm_conv.py (both modes) and tests/test_parity_full_size.py (default mode, against HF / the oracle).
+pytestmark = pytest.mark.usefixtures("deterministic")
+
 
 def _pair(cfg, cuda, dtype, seed=4321, scale=1.0):
     from oracle.llama_ref import build_hf_llama

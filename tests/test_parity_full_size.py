@@ -56,6 +56,7 @@ def _tok_pair(cfg, cuda, dtype):
 # (a) megakernel vs HF, 138 M, teacher-forced
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.usefixtures("deterministic")      # rollouts of different lengths must share their prefix (the prefill GEMMs)
 def test_megakernel_138m_vs_hf_teacher_forced(cuda):
     from oracle.llama_ref import config_path
     torch.set_num_threads(min(32, os.cpu_count() or 8))
@@ -301,6 +302,7 @@ def test_topk_sample_kernel_distribution(cuda, k, temperature, ties):
 
 
 @pytest.mark.gpu
+@pytest.mark.usefixtures("deterministic")
 def test_megakernel_sampler_distribution(cuda):
     """The megakernel's own sampler (sample_row in decode_mega.cu).  Every row gets the SAME prompt and the first new token
     is FORCED (slot mechanism of the action-conditioned rollout), so all 64 rows x 160 seeds draw the second token from one

@@ -97,6 +97,7 @@ def test_tiny_tokenizer_vs_oracle(cuda, dtype, tol_lat, tol_px, min_match):
 
 
 @pytest.mark.gpu
+@pytest.mark.usefixtures("deterministic")      # tokenize() and tokenize_context() of the same clip are compared exactly
 def test_cfg64_tokenizer_vs_oracle(cuda):
     """BASELINE config ctx_vae64 (114 M), one 64x64x16 clip, TF32 path."""
     ref, mine = _pair(_cfg("ctx_vae64"), cuda, torch.float32)
@@ -117,6 +118,7 @@ def test_cfg64_tokenizer_vs_oracle(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.usefixtures("deterministic")
 def test_detokenize_batch_independence_and_cache(cuda):
     """Size-independent properties: clips are independent units (batching must not change any clip), and the
     cached-context path reproduces the uncached frames."""
@@ -240,6 +242,7 @@ def test_module_tree_equals_the_reference_own_class(config):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol,tol_loss", [(torch.float32, 4e-3, 1e-2), (torch.bfloat16, 4e-2, 6e-2)])
+@pytest.mark.usefixtures("deterministic")      # forward() twice and encode_latents(): identical VQ choices are assumed
 def test_training_graph_forward_vs_oracle(cuda, dtype, tol, tol_loss):
     """Row f3 (forward half): CompressiveVQModel.forward(sample=, dyn_sample=, segment_len=) against the oracle's forward_train
     -- itself pinned, values AND gradients, to the reference's own forward() (tests/golden/tokenizer_refglue.npz).  The graph
