@@ -279,10 +279,15 @@ typedef struct ivgpt_mega_desc {
                       barriers per step of a 12-layer model). */
 } ivgpt_mega_desc;
 int ivgpt_mega_fused_norm(void);   /* compile-time property of gemm_mode 0, see tile_cnt */
-/* GEMM / conv kernel: 0 (default) = two tcgen05.mma issuing warps accumulate alternate k-blocks into one accumulator (full
- * tensor rate; the fp32 summation order, i.e. the last bits, may vary from run to run), 1 = one issuer (bit-reproducible,
- * at most ~80 % of the tensor peak).  Also selectable with IVGPT_DETERMINISTIC=1 in the environment. */
+/* GEMM / conv kernel, tcgen05.mma issuing warps: 1 (default, bit-reproducible) or 2 (opt-in: IVGPT_MMA_ISSUERS=2 or
+ * ivgpt_set_mma_issuers(2)): two warps accumulate alternate k-blocks into one accumulator -- the full tensor rate in isolation,
+ * no gain in the operand-bound kernel, fp32 summation order (last bits) not fixed.  ivgpt_set_deterministic(1) forces 1. */
 int ivgpt_set_deterministic(int on);
+int ivgpt_set_mma_issuers(int n);
+/* 1: BN = 256 launches with enough tiles use 256 x 256 CTA tiles (two 128-row sub-tiles on one weight tile: a third less
+ * operand traffic, but the accumulator is no longer double-buffered across tiles).  Measured slower; default 0
+ * (IVGPT_GEMM_MH2=1 in the environment also enables it). */
+int ivgpt_set_gemm_mh2(int on);
 int ivgpt_mega_layer_bytes(void);
 long long ivgpt_mega_packed_elems(int rows, int cols);
 int ivgpt_mega_pack_weight(const void* w, void* out, int rows, int cols, void* stream);

@@ -149,6 +149,8 @@ SIGNATURES = {
     "ivgpt_decode_mega": [C.POINTER(MegaDesc), _P],
     "ivgpt_mega_fused_norm": [],
     "ivgpt_set_deterministic": [_I],
+    "ivgpt_set_mma_issuers": [_I],
+    "ivgpt_set_gemm_mh2": [_I],
     "ivgpt_flash_attn": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _I, _F, _P],
 }
 _RESTYPES = {"ivgpt_last_error": C.c_char_p, "ivgpt_launch_count": C.c_ulonglong,

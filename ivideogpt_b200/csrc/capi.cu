@@ -76,15 +76,28 @@ static int num_sms() {
   return n;
 }
 
-// tcgen05.mma issuing warps of the GEMM / conv kernel: 2 (default: full tensor rate, summation order of the last bits not
-// fixed) or 1 (IVGPT_DETERMINISTIC=1 in the environment, or ivgpt_set_deterministic(1): bit-reproducible, <= 80 % of peak)
+// tcgen05.mma issuing warps of the GEMM / conv kernel: 1 (default) or 2 (IVGPT_MMA_ISSUERS=2 / ivgpt_set_deterministic(0) after
+// opting in).  Two issuers reach the full tensor rate in isolation (tools/probes/mma_probe.cu) but changed nothing in the real
+// kernel, whose limit is operand supply from L2 (profiles/r02/gemm_issuers_and_tiles_ab.txt), and their summation order is not
+// fixed; together with the 256 x 256 CTA tiles they faulted on one launch shape, so those tiles always run with one issuer.
+static int g_issuers_optin = -1;
 static int g_issuers = 0;
 static int mma_issuers() {
-  if (!g_issuers) {
-    const char* e = getenv("IVGPT_DETERMINISTIC");
-    g_issuers = (e != nullptr && e[0] == '1') ? 1 : 2;
+  if (g_issuers_optin < 0) {
+    const char* e = getenv("IVGPT_MMA_ISSUERS");
+    g_issuers_optin = (e != nullptr && e[0] == '2') ? 1 : 0;
+    const char* d = getenv("IVGPT_DETERMINISTIC");
+    g_issuers = (g_issuers_optin && !(d != nullptr && d[0] == '1')) ? 2 : 1;
   }
   return g_issuers;
+}
+static int g_mh2 = -1;
+static int gemm_mh2() {
+  if (g_mh2 < 0) {
+    const char* e = getenv("IVGPT_GEMM_MH2");
+    g_mh2 = (e != nullptr && e[0] == '1') ? 1 : 0;      // opt-in: measured slower (profiles/r02/gemm_issuers_and_tiles_ab.txt)
+  }
+  return g_mh2;
 }
 
 // ---- forward declarations of launchers defined in the other translation units -----------------
@@ -245,7 +258,7 @@ int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream) {
   p.act = d->act; p.alpha = d->alpha;
   p.tiles_m = (int)tiles_m; p.tiles_n = (d->N + bn - 1) / bn;
   IVG_CHECK(d->act != IVGPT_ACT_SWIGLU || (d->N % 2 == 0 && d->residual == nullptr), "gemm: SwiGLU needs even N, no residual");
-  p.issuers = mma_issuers();
+  p.issuers = mma_issuers(); p.mh2 = gemm_mh2();
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
@@ -342,7 +355,7 @@ int ivgpt_conv3x3(const ivgpt_conv_desc* d, void* stream) {
     IVG_CHECK(d->in_shift != nullptr && d->stride == 1, "conv3x3: fused input GroupNorm needs in_shift and stride 1");
     p.xf_scale = d->in_scale; p.xf_shift = d->in_shift; p.xf_silu = d->in_silu; p.xf_cin = d->Cin;
   }
-  p.issuers = mma_issuers();
+  p.issuers = mma_issuers(); p.mh2 = gemm_mh2();
   return gemm_tc_dispatch(d->dtype, bn, maps, p, num_sms(), S(stream));
 }
 
@@ -540,7 +553,9 @@ int ivgpt_flash_attn(const void* q, const void* k, const void* vt, void* out, fl
                            num_sms(), S(stream));
 }
 
-int ivgpt_set_deterministic(int on) { g_issuers = on ? 1 : 2; return 0; }
+int ivgpt_set_deterministic(int on) { mma_issuers(); g_issuers = (on || !g_issuers_optin) ? 1 : 2; return 0; }
+int ivgpt_set_gemm_mh2(int on) { g_mh2 = on ? 1 : 0; return 0; }
+int ivgpt_set_mma_issuers(int n) { mma_issuers(); g_issuers_optin = n == 2 ? 1 : 0; g_issuers = n == 2 ? 2 : 1; return 0; }
 
 int ivgpt_mega_fused_norm(void) { return ivg::mega_fused_norm(); }
 

@@ -46,6 +46,7 @@ struct GemmParams {
   float alpha;
   int tiles_m, tiles_n;
   int issuers;       // 1 or 2 tcgen05.mma issuing warps (2: alternate k-blocks, same accumulator; see gemm_tc.cu)
+  int mh2;           // allow 256 x 256 CTA tiles (BN = 256 launches with enough tiles; opt-in with IVGPT_GEMM_MH2=1: measured slower than 128 x 256)
   // ---- fused GroupNorm statistics of the OUTPUT (mode 1): per (image, tile, n-tile, epilogue warp) partial sums ----
   float* gn_part;    // [images][slabs][gn_groups][2] (sum, sum of squares), slabs = tiles_per_image * tiles_n * 4; or null
   int gn_groups;

@@ -379,9 +379,18 @@ def decode_attn_fused(qkv, k_cache, v_cache_t, out, B, heads, Lmax, pos, dpos, c
 
 
 def set_deterministic(on: bool):
-    """One tcgen05.mma issuing warp instead of two in the GEMM / conv kernel: bit-reproducible results at <= 80 % of the tensor
-    peak (two issuers accumulate into one accumulator in an order the hardware does not fix)."""
+    """Force the single tcgen05.mma issuing warp (the default) even when two issuers were opted in."""
     _lib.load().ivgpt_set_deterministic(int(bool(on)))
+
+
+def set_gemm_mh2(on: bool):
+    """Opt in to 256 x 256 CTA tiles for BN = 256 launches (measured slower than 128 x 256; kept tested)."""
+    _lib.load().ivgpt_set_gemm_mh2(int(bool(on)))
+
+
+def set_mma_issuers(n: int):
+    """1 (default) or 2 tcgen05.mma issuing warps in the GEMM / conv kernel (2: summation order of the last bits not fixed)."""
+    _lib.load().ivgpt_set_mma_issuers(int(n))
 
 
 def set_pdl(on: bool):
@@ -598,6 +607,6 @@ device_scoped = _device_guarded      # decorator for model-level methods (first 
 
 for _name, _fn in list(globals().items()):
     if isinstance(_fn, types.FunctionType) and not _name.startswith("_") and _fn.__module__ == __name__ and \
-            _name not in ("gemm_desc", "gemm_raw", "torch_dtype", "set_pdl", "set_deterministic", "on_device_of", "device_scoped"):
+            _name not in ("gemm_desc", "gemm_raw", "torch_dtype", "set_pdl", "set_deterministic", "set_mma_issuers", "set_gemm_mh2", "on_device_of", "device_scoped"):
         globals()[_name] = _device_guarded(_fn)
 del _name, _fn

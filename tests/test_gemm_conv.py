@@ -10,18 +10,18 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=[2, 1], ids=["two-issuers", "one-issuer"], autouse=True)
 def mma_issuers(request):
-    """Every test of this module runs in both modes of the GEMM / conv kernel: two tcgen05.mma issuing warps on one accumulator
-    (default, what the bench runs) and the single bit-reproducible issuer."""
+    """Every test of this module runs in both modes of the GEMM / conv kernel: the single bit-reproducible tcgen05.mma issuer
+    (default, what the bench runs) and the opt-in second issuing warp on the same accumulator."""
     import torch
     if not torch.cuda.is_available():
         yield
         return
     from ivideogpt_b200 import ops
-    ops.set_deterministic(request.param == 1)
+    ops.set_mma_issuers(request.param)
     try:
         yield
     finally:
-        ops.set_deterministic(False)
+        ops.set_mma_issuers(1)
 
 # Tolerances: inputs are pre-rounded to the operand format, so the only error left is fp32 accumulation order
 # (+ the kernel's truncation of unrounded fp32 A operands to tf32 where noted).
@@ -240,3 +240,62 @@ def test_conv_with_fused_input_groupnorm_silu(cuda, dtype, tol, N, H, W, Cin, Co
     e2 = rel_err(two.permute(0, 3, 1, 2), want)
     print(f"\n[fused GN conv {dtype}] rel err fused {e:.3e}, two launches {e2:.3e}")
     assert e < tol, f"fused GroupNorm+SiLU conv rel err {e} (two-launch path: {e2})"
+
+
+@pytest.fixture
+def mh2():
+    """The opt-in 256 x 256 CTA tile path (measured slower than the default 128 x 256 tiles, profiles/r02) stays tested."""
+    from ivideogpt_b200 import ops
+    ops.set_gemm_mh2(True)
+    try:
+        yield
+    finally:
+        ops.set_gemm_mh2(False)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_256x256_cta_tiles(cuda, dtype, mh2):
+    """Enough 128-row tiles for the 256 x 256 CTA tile path (two M sub-tiles share one weight tile; BN = 256), with an odd
+    number of sub-tiles so that the last CTA tile has a phantom second half, bias + residual + SiLU epilogue included."""
+    from ivideogpt_b200 import ops
+    from ivideogpt_b200._lib import ACT_SILU
+    M, N, K = 2 * 300 * 128 + 128 + 57, 512, 192          # 601 full sub-tiles + a ragged one
+    a = _mk((M, K), dtype, 21).to(cuda)
+    w = _mk((N, K), dtype, 22, 0.1).to(cuda)
+    bias = torch.randn(N, device=cuda)
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, bn=256)
+    want = a.double() @ w.double().t() + bias.double()
+    assert rel_err(out, want) < TOL_EXACT_INPUTS
+    res = torch.randn(M, N, device=cuda)
+    out2 = ops.gemm(a, w, bias=bias, residual=res, act=ACT_SILU, out_dtype=torch.float32, bn=256)
+    assert rel_err(out2, F.silu(want + res.double())) < TOL_EXACT_INPUTS
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("stride,C2", [(1, 0), (1, 128), (2, 0)])
+def test_conv_256x256_cta_tiles(cuda, dtype, stride, C2, mh2):
+    """The decoder-sized conv launches (hundreds of 128-pixel tiles, Cout = 256) take the 256 x 256 CTA tile path: two spatial
+    tiles per CTA (possibly in different frames) against one weight tile; padding, stride 2 and the fused 1x1 shortcut."""
+    from ivideogpt_b200 import ops
+    N, H, W, Cin, Cout = 37, 64, 64, 128, 256              # 37 * 32 = 1184 tiles at stride 1 (odd count at stride 2: 296 / ...)
+    x = _mk((N, H, W, Cin), dtype, 31)
+    w = _mk((Cout, 3, 3, Cin), dtype, 32, 0.05)
+    bias = torch.randn(Cout, generator=torch.Generator().manual_seed(33))
+    parts = [w.reshape(Cout, 9 * Cin)]
+    Ho, Wo = H // stride, W // stride
+    x2 = w2 = None
+    if C2:
+        x2 = _mk((N, Ho, Wo, C2), dtype, 34)
+        w2 = _mk((Cout, C2), dtype, 35, 0.05)
+        parts.append(w2)
+    wp = torch.cat(parts, dim=1).contiguous().to(cuda)
+    got = ops.conv3x3(x.to(cuda), wp, bias.to(cuda), stride=stride, x2=None if x2 is None else x2.to(cuda), out_dtype=torch.float32)
+    xd = x.double().permute(0, 3, 1, 2)
+    if stride == 2:
+        xd = F.pad(xd, (0, 1, 0, 1))                       # diffusers Downsample2D: pad (0, 1, 0, 1), then stride-2 conv, padding 0
+        want = F.conv2d(xd, w.double().permute(0, 3, 1, 2), bias.double(), stride=2)
+    else:
+        want = F.conv2d(xd, w.double().permute(0, 3, 1, 2), bias.double(), padding=1)
+    if C2:
+        want = want + F.conv2d(x2.double().permute(0, 3, 1, 2), w2.double()[:, :, None, None])
+    assert rel_err(got.permute(0, 3, 1, 2), want) < TOL_EXACT_INPUTS
