@@ -453,13 +453,24 @@ def vq_argmin_leg(dev, N, peak_gbs, K=8192, D=64, iters=10):
         ts.append(a.elapsed_time(b))
     t = sorted(ts)[len(ts) // 2] * 1e-3
     byt = 4.0 * N * D + 4.0 * K * D + 8.0 * N
-    return {"N": N, "K": K, "D": D, "ms": t * 1e3, "algorithmic_GBps": byt / t / 1e9, "frac_of_hbm_peak": byt / t / 1e9 / peak_gbs,
-            "fp32_TFLOPs": 2.0 * N * K * D / t / 1e12, "l2_policy": "256 MB flush between iterations"}
+    out = {"N": N, "K": K, "D": D, "ms": t * 1e3, "algorithmic_GBps": byt / t / 1e9, "frac_of_hbm_peak": byt / t / 1e9 / peak_gbs,
+           "fp32_TFLOPs": 2.0 * N * K * D / t / 1e12, "l2_policy": "256 MB flush between iterations"}
+    # the kernel is bound by the fp32 FMA pipe: its fraction of the MEASURED FFMA peak of this pool's B200s
+    # (tools/probes/mma_probe.cu: 16 independent FFMA chains per thread, 2 x 1024 threads per SM; committed output)
+    probe = os.path.join(ROOT, "profiles", "r02", "mma_issue_and_ffma_probe.json")
+    if os.path.exists(probe):
+        with open(probe) as fh:
+            peak = json.load(fh)["ffma"]["reg_reg_tflops"]
+        out.update({"fp32_peak_TFLOPs": peak, "frac_of_fp32_peak": out["fp32_TFLOPs"] / peak,
+                    "fp32_peak_source": "profiles/r02/mma_issue_and_ffma_probe.json (FFMA micro-benchmark, 3-register form)"})
+    return out
 
 
 def mega_traffic():
     """`traffic` of the dominant kernel from the committed `ncu --set full` capture (bytes per launch), or None."""
-    path = os.path.join(ROOT, "profiles", "r01", "ncu_decode_mega_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02", "ncu_decode_mega_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01", "ncu_decode_mega_traffic.json")
     if os.path.exists(path):
         with open(path) as fh:
             return json.load(fh)
@@ -503,7 +514,7 @@ def build_roofline(args, dtype_name, nsteps, prof, total_ms, B, ctx, max_new, ll
         cap = mega_traffic()
         if cap:   # ncu --set full DRAM bytes of a shorter launch of the same kernel, scaled by its measured ratio to that launch's algorithmic bytes
             fam["mega"]["traffic"] = cap["ratio_to_algorithmic"] * per_launch
-            fam["mega"]["traffic_source"] = (f"profiles/r01/ncu_decode_mega_traffic.json: {cap['dram_bytes'] / 1e9:.2f} GB DRAM over a "
+            fam["mega"]["traffic_source"] = (f"{cap.get('source', 'profiles/r01/ncu_decode_mega_traffic.json')}: {cap['dram_bytes'] / 1e9:.2f} GB DRAM over a "
                                              f"{cap['decode_steps']}-step launch = {cap['ratio_to_algorithmic']:.3f} x algorithmic, scaled to {steps} steps")
     dom = max(fam, key=lambda k: fam[k]["kernel_ms_per_step"])
     roofline = dict(fam[dom])

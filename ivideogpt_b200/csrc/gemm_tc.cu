@@ -395,8 +395,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       {
         const int es_o = p.out_dtype == DT_BF16 ? 2 : 4, es_r = p.res_dtype == DT_BF16 ? 2 : 4;
         const long long obase = (long long)o_b * p.out_bstride + ocol0, rbase_ = (long long)o_b * p.res_bstride + ocol0;
-        bool fast = !gn_on && p.act != 2 && !(p.bias && p.bias_along_m) &&
-                    ((reinterpret_cast<uintptr_t>(p.out) + (uintptr_t)(obase * es_o)) & 15) == 0 && (p.ldo * es_o) % 16 == 0;
+        // SwiGLU halves the column index of the output: (ocol0 + c) / 2 stays 8-element aligned for c % 16 == 0
+        const long long obase_al = p.act == 2 ? ((long long)o_b * p.out_bstride + (ocol0 >> 1)) : obase;
+        bool fast = !gn_on && !(p.bias && p.bias_along_m) && (p.act != 2 || (ocol0 & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(p.out) + (uintptr_t)(obase_al * es_o)) & 15) == 0 && (p.ldo * es_o) % 16 == 0;
         if (p.residual) fast = fast && ((reinterpret_cast<uintptr_t>(p.residual) + (uintptr_t)(rbase_ * es_r)) & 15) == 0 && (p.ldr * es_r) % 16 == 0;
         if (fast) {
           const int ncols = (p.N - n0) < BN ? (p.N - n0) : BN;
@@ -438,6 +440,21 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                   if (p.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+                  }
+                  if (p.act == 2) {               // interleaved (gate, up) pairs -> 8 outputs at column (ocol0 + c + 16 i) / 2
+                    float o8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o8[j] = silu_f(v[2 * j]) * v[2 * j + 1];
+                    const long long so = obase_al + orow * p.ldo + ((c + 16 * i) >> 1);
+                    if (p.out_dtype == DT_BF16) {
+                      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + so) =
+                          make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]), pack_bf16x2(o8[6], o8[7]));
+                    } else {
+                      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + so);
+                      op[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                      op[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                    }
+                    continue;
                   }
                   if (p.out_dtype == DT_BF16) {
                     uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + 16 * i);
