@@ -51,7 +51,11 @@ struct GemmSmem {
   static constexpr int STAGES = MH == 2 ? 3 : ((BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8));
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int GN_OFFSET = BAR_OFFSET + 256;     // 4 warps x 32 groups x (sum, sumsq) fp32 = 1 KB
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 + 1024;  // + barrier block + GN accumulators + alignment slack
+  // fast-epilogue GroupNorm statistics: per-row partials [128 rows][17 (16 slots, padded)] float2, per-16-row-block sums
+  // [8][16] float2, per-tile group sums [32] float2
+  static constexpr int GNR_OFFSET = GN_OFFSET + 1024;
+  static constexpr int GNR_BYTES = 128 * 17 * 8 + 8 * 16 * 8 + 32 * 8;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 + GNR_BYTES + 1024;  // + barrier block + GN scratch + alignment slack
 };
 
 // ---- operand transform: GroupNorm affine + SiLU on 8 bf16 / 4 fp32 channels of one pixel (one 16-byte chunk) ----
@@ -390,14 +394,19 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
       if (gn_on) { gn_acc[lane] = 0.f; gn_acc[lane + 32] = 0.f; __syncwarp(); }
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      // ---- fast path (warp-uniform conditions): no epilogue statistics, no SwiGLU, no per-row bias, 16-byte aligned rows ----
+      // ---- fast path (warp-uniform conditions): no per-row bias, 16-byte aligned rows ----
       int c_done = 0;
+      bool gn_fast_done = false;
       {
         const int es_o = p.out_dtype == DT_BF16 ? 2 : 4, es_r = p.res_dtype == DT_BF16 ? 2 : 4;
         const long long obase = (long long)o_b * p.out_bstride + ocol0, rbase_ = (long long)o_b * p.res_bstride + ocol0;
         // SwiGLU halves the column index of the output: (ocol0 + c) / 2 stays 8-element aligned for c % 16 == 0
         const long long obase_al = p.act == 2 ? ((long long)o_b * p.out_bstride + (ocol0 >> 1)) : obase;
-        bool fast = !gn_on && !(p.bias && p.bias_along_m) && (p.act != 2 || (ocol0 & 15) == 0) &&
+        const int ncols_t = (p.N - n0) < BN ? (p.N - n0) : BN;
+        // epilogue statistics ride on the fast path when the tile is made of whole 64-column windows and a window holds at
+        // most 16 groups (>= 4 channels per group)
+        const bool gn_fast_ok = !gn_on || (ncols_t % 64 == 0 && gn_cpg >= 4 && p.gn_groups <= 32 && p.act != 2 && p.out_dtype == DT_BF16);
+        bool fast = gn_fast_ok && !(p.bias && p.bias_along_m) && (p.act != 2 || (ocol0 & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(p.out) + (uintptr_t)(obase_al * es_o)) & 15) == 0 && (p.ldo * es_o) % 16 == 0;
         if (p.residual) fast = fast && ((reinterpret_cast<uintptr_t>(p.residual) + (uintptr_t)(rbase_ * es_r)) & 15) == 0 && (p.ldr * es_r) % 16 == 0;
         if (fast) {
@@ -411,6 +420,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const bool use_res = rrow != nullptr && row_ok;
             EpiRes<GC, RB> cur, nxt;
             if (use_res) cur.load(rrow);                      // before the accumulator is complete
+            // ---- epilogue GroupNorm statistics of the values being written (GC == 64 only) ----
+            float2* gn_rows = reinterpret_cast<float2*>(smem + SM::GNR_OFFSET);         // [128][17]
+            float2* gn_blk = gn_rows + 128 * 17;                                        // [8][16]
+            float2* gn_tile = gn_blk + 8 * 16;                                          // [32]
+            const int et = (int)threadIdx.x - 64;                                       // 0..127 over the four epilogue warps
+            if (gn_on) {
+              if (et < 32) gn_tile[et] = make_float2(0.f, 0.f);
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -421,7 +439,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               for (int i = 0; i < GC / 16; ++i) tmem_ld_32x32b_x16(taddr + (uint32_t)(c + 16 * i), r[i]);
               if (use_res && gi + 1 < ngroups) nxt.load(rrow + (size_t)(c + GC) * es_r);
               tmem_ld_wait();
-              if (row_ok) {
+              // statistics: running (sum, sum of squares) of the current GroupNorm group, flushed to this row's slot when the
+              // column index crosses a group boundary (comparisons only, no division per element)
+              const int g_first = gn_on ? (n0 + c) / gn_cpg : 0;
+              int g_cur = g_first, g_next_col = (g_first + 1) * gn_cpg;
+              float gs = 0.f, gq = 0.f;
+              if (row_ok || gn_on) {
                 const long long ooff = obase + orow * p.ldo + c;
 #pragma unroll
                 for (int i = 0; i < GC / 16; ++i) {
@@ -440,6 +463,19 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                   if (p.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+                  }
+                  if (gn_on) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const int col = n0 + c + 16 * i + j;
+                      if (col == g_next_col) {
+                        gn_rows[row * 17 + (g_cur - g_first)] = make_float2(gs, gq);
+                        gs = 0.f; gq = 0.f; ++g_cur; g_next_col += gn_cpg;
+                      }
+                      const float x = row_ok ? v[j] : 0.f;
+                      gs += x; gq = fmaf(x, x, gq);
+                    }
+                    if (!row_ok) continue;
                   }
                   if (p.act == 2) {               // interleaved (gate, up) pairs -> 8 outputs at column (ocol0 + c + 16 i) / 2
                     float o8[8];
@@ -467,7 +503,48 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                   }
                 }
               }
+              if (gn_on) {
+                // this window's slots: rows -> 16-row blocks -> window total, fixed orders (bit-reproducible), then into the tile's
+                // per-group sums; three named barriers over the four epilogue warps per 64 columns
+                gn_rows[row * 17 + (g_cur - g_first)] = make_float2(gs, gq);
+                const int ns = g_cur - g_first + 1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                {
+                  const int slot = et & 15, rb = et >> 4;
+                  if (slot < ns) {
+                    float s = 0.f, qv = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) { const float2 t = gn_rows[(rb * 16 + rr) * 17 + slot]; s += t.x; qv += t.y; }
+                    gn_blk[rb * 16 + slot] = make_float2(s, qv);
+                  }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et < ns && g_first + et < 32) {
+                  float s = 0.f, qv = 0.f;
+#pragma unroll
+                  for (int rb = 0; rb < 8; ++rb) { const float2 t = gn_blk[rb * 16 + et]; s += t.x; qv += t.y; }
+                  float2 acc2 = gn_tile[g_first + et];
+                  acc2.x += s; acc2.y += qv;
+                  gn_tile[g_first + et] = acc2;
+                }
+              }
               if (use_res) cur = nxt;
+            }
+            if (gn_on) {
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (tm < p.tiles_m) {
+                const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
+                const int img = tm / tiles_img, t_in = tm - img * tiles_img;
+                const int slabs = tiles_img * p.tiles_n * 4;
+                const int sub = et >> 5, ln = et & 31;                    // slab layout keeps 4 sub-records per (tile, n-tile)
+                float* dst = p.gn_part + (((size_t)img * slabs) + ((size_t)t_in * p.tiles_n + tn) * 4 + sub) * p.gn_groups * 2;
+                if (ln < p.gn_groups) {
+                  const float2 t = sub == 0 ? gn_tile[ln] : make_float2(0.f, 0.f);
+                  dst[2 * ln] = t.x; dst[2 * ln + 1] = t.y;
+                }
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              gn_fast_done = true;
             }
             c_done = ngroups * GC;
           };
@@ -586,7 +663,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + acc);
-      if (gn_on && tm < p.tiles_m) {
+      if (gn_on && !gn_fast_done && tm < p.tiles_m) {
         const int tiles_x = p.W / p.tw, tiles_img = tiles_x * (p.H / p.th);
         const int img = tm / tiles_img, t_in = tm - img * tiles_img;
         const int slabs = tiles_img * p.tiles_n * 4;

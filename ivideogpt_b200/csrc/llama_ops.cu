@@ -129,10 +129,87 @@ __global__ void rope_kv_kernel(const T* __restrict__ qkv, T* __restrict__ qout, 
   }
 }
 
+// Prefill-sized variant (round 2): one CTA per (clip, head, 64 positions).  The scalar kernel above moves 2 bytes per access and
+// scatters V^T with a stride of Lmax elements: 245 us per layer at B = 64 (350 MB: 1.4 TB/s).  Here every global access is an
+// 8-byte vector along the head dimension (q, K, the row-major V copy) and V^T goes through a shared-memory tile so that its
+// rows (64 consecutive positions of one dimension) are written as 4-byte pairs, contiguous per warp.  bf16 only (the dtype of
+// the benchmarked prefill); same arithmetic, same rounding as the scalar kernel.
+__global__ void __launch_bounds__(256) rope_kv_tiled_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ qout,
+                                                            __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache,
+                                                            __nv_bfloat16* __restrict__ vrows, int Lq, int heads, int Lmax, int pos0,
+                                                            const float* __restrict__ cos_tab, const float* __restrict__ sin_tab) {
+  __shared__ __nv_bfloat16 vt[64][66];                      // [d][l], padded: conflict-free transposed reads
+  const int l0 = blockIdx.x * 64, hh = blockIdx.y, b = blockIdx.z;
+  const int Hd = heads * 64;
+  const int t = threadIdx.x;
+  const int iq = (t & 7) * 4;                               // dims iq..iq+3 and iq+32..iq+35
+  // ---- q, k: rotate; v: copy + stash ----
+  for (int l = t >> 3; l < 64; l += 32) {
+    const int lq = l0 + l;
+    if (lq >= Lq) break;
+    const int pos = pos0 + lq;
+    const __nv_bfloat16* row = qkv + ((size_t)b * Lq + lq) * (3 * Hd) + hh * 64;
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_tab + (size_t)pos * 32 + iq));
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_tab + (size_t)pos * 32 + iq));
+    const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {               // 0: q, 1: k
+      const __nv_bfloat16* src = row + which * Hd;
+      const uint2 lo = *reinterpret_cast<const uint2*>(src + iq), hi = *reinterpret_cast<const uint2*>(src + iq + 32);
+      const __nv_bfloat16* lo_h = reinterpret_cast<const __nv_bfloat16*>(&lo);
+      const __nv_bfloat16* hi_h = reinterpret_cast<const __nv_bfloat16*>(&hi);
+      __nv_bfloat16 olo[4], ohi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x0 = __bfloat162float(lo_h[j]), x1 = __bfloat162float(hi_h[j]);
+        olo[j] = __float2bfloat16_rn(x0 * c4[j] - x1 * s4[j]);
+        ohi[j] = __float2bfloat16_rn(x1 * c4[j] + x0 * s4[j]);
+      }
+      __nv_bfloat16* dst = which == 0 ? qout + (((size_t)b * heads + hh) * Lq + lq) * 64
+                                      : kcache + (((size_t)b * heads + hh) * Lmax + pos) * 64;
+      *reinterpret_cast<uint2*>(dst + iq) = *reinterpret_cast<const uint2*>(olo);
+      *reinterpret_cast<uint2*>(dst + iq + 32) = *reinterpret_cast<const uint2*>(ohi);
+    }
+    const uint2 vlo = *reinterpret_cast<const uint2*>(row + 2 * Hd + iq), vhi = *reinterpret_cast<const uint2*>(row + 2 * Hd + iq + 32);
+    if (vrows) {
+      __nv_bfloat16* vr = vrows + (((size_t)b * heads + hh) * Lmax + pos) * 64;
+      *reinterpret_cast<uint2*>(vr + iq) = vlo;
+      *reinterpret_cast<uint2*>(vr + iq + 32) = vhi;
+    }
+    const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(&vlo);
+    const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(&vhi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { vt[iq + j][l] = vl[j]; vt[iq + 32 + j][l] = vh[j]; }
+  }
+  __syncthreads();
+  // ---- V^T rows: dimension d, positions l0 .. l0+63 (pairs of positions per lane) ----
+  const int nl = (Lq - l0) < 64 ? (Lq - l0) : 64;
+  for (int d = t >> 5; d < 64; d += 8) {
+    const int l = (t & 31) * 2;
+    __nv_bfloat16* vo = vcache + (((size_t)b * heads + hh) * 64 + d) * Lmax + pos0 + l0;
+    if (l + 1 < nl && (((pos0 + l0) & 1) == 0)) {
+      __nv_bfloat162 pr;
+      pr.x = vt[d][l]; pr.y = vt[d][l + 1];
+      *reinterpret_cast<__nv_bfloat162*>(vo + l) = pr;
+    } else {
+      if (l < nl) vo[l] = vt[d][l];
+      if (l + 1 < nl) vo[l + 1] = vt[d][l + 1];
+    }
+  }
+}
+
 int rope_kv_launch(int dtype, const void* qkv, void* qout, void* kcache, void* vcache, void* vrows, int B, int Lq,
                    int heads, int Lmax, int pos0, const int* dpos, const float* cos_tab, const float* sin_tab, cudaStream_t st) {
   IVG_CHECK(pos0 + Lq <= Lmax, "rope_kv: pos0+Lq=%d exceeds cache length %d", pos0 + Lq, Lmax);
   if (B == 0 || Lq == 0) return 0;
+  if (dtype == DT_BF16 && dpos == nullptr && Lq >= 64 && B <= 65535 && heads <= 65535) {      // prefill / teacher-forced pass
+    rope_kv_tiled_kernel<<<dim3((Lq + 63) / 64, heads, B), 256, 0, st>>>(
+        (const __nv_bfloat16*)qkv, (__nv_bfloat16*)qout, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, (__nv_bfloat16*)vrows, Lq,
+        heads, Lmax, pos0, cos_tab, sin_tab);
+    count_launch();
+    IVG_LAUNCH_CHECK();
+    return 0;
+  }
   long long work = (long long)B * Lq * heads * 32;
   int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
   if (dtype == DT_BF16)

@@ -207,13 +207,14 @@ def groupnorm_coeff(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
 
 
 def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,
-                    pos: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _cuda(x, stats, gamma, beta, pos)
+                    pos: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, stats, gamma, beta, pos, out)
     assert x.is_contiguous()
     Cc = x.shape[-1]
     samples, groups = stats.shape[0], stats.shape[1]
     total_rows = x.numel() // Cc
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_contiguous() and y.shape == x.shape and y.dtype == x.dtype
     pos_rows = 0
     if pos is not None:
         assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[1] == Cc

@@ -105,11 +105,15 @@ class TokenizerPlan:
         self.groups = groups
         self.dtype = compute_dtype
         self.pw = PackedWeights()
-        # GroupNorm statistics can be emitted by the producing conv's epilogue (ops.conv3x3(gn_groups=...)).  Measured
-        # round 1: the per-chunk warp-shuffle reduction in that epilogue slowed the conv kernel from 963 to 583 TFLOP/s,
-        # more than the separate statistics pass costs -- kept available (and unit-tested) but switched off until the
-        # epilogue reduction is restructured (per-warp shared-memory transpose once per tile).
+        # GroupNorm statistics CAN be emitted by the producing conv's epilogue (ops.conv3x3(gn_groups=...)): per-row running sums
+        # per group -> shared-memory partials -> fixed-order reduction once per 64-column window.  Correct, and MEASURED slower
+        # again (round 2: conv family 39.9 -> 46.4 ms per cfg64 step, 127 -> 158 ms at cfg256, for a ~7 / ~15 ms statistics pass
+        # saved): the epilogue is the stage the conv kernel can least afford to load.  OFF; IVGPT_FUSED_GN_STATS=1 selects it.
         self.fused_stats = groups if os.environ.get("IVGPT_FUSED_GN_STATS", "0") == "1" else 0
+        # The statistics pass and the apply pass of a GroupNorm read the same tensor; running them over chunks of frames small
+        # enough for the apply's read to hit the 126 MB L2 was MEASURED slower (detokenize 65 -> 75 / 96 ms with 24 / 12 MB chunks
+        # at cfg64: hundreds of small launches, the host falls behind).  0 = whole tensor at once (default).
+        self.gn_chunk_bytes = int(os.environ.get("IVGPT_GN_CHUNK_MB", "0")) << 20
         # GroupNorm + SiLU applied to the conv's operand tiles inside the conv kernel (transform warps of gemm_tc.cu): no
         # normalised copy of the activation in HBM.  MEASURED (profiles/r02/gn_fused_apply_ab.txt): the conv family goes from
         # 45 to 82-104 ms per cfg64 step (4 / 8 / 16 transform warps: 104 / 84 / 82) -- every input pixel is re-normalised for
@@ -120,12 +124,25 @@ class TokenizerPlan:
     # ---- building blocks --------------------------------------------------------------------------
     def _gn(self, x, norm, silu: bool, samples: Optional[int] = None, pos=None):
         n = x.shape[0] if samples is None else samples
+        gamma, beta = self.pw.f32(norm.weight), self.pw.f32(norm.bias)
+        posf = None if pos is None else self.pw.f32(pos)
         if getattr(x, "gn_part", None) is not None and x.gn_part[0].shape[2] == norm.num_groups:
             stats = ops.groupnorm_stats_from_parts(x, n, norm.num_groups, norm.eps)   # fused in the producing conv
-        else:
+            return ops.groupnorm_apply(x, stats, gamma, beta, silu, posf)
+        per = x.numel() * x.element_size() // max(n, 1)                   # bytes per sample
+        step = n if (self.gn_chunk_bytes <= 0 or per * n <= self.gn_chunk_bytes) else max(1, self.gn_chunk_bytes // per)
+        if step >= n:
             stats = ops.groupnorm_stats(x, n, norm.num_groups, norm.eps)
-        return ops.groupnorm_apply(x, stats, self.pw.f32(norm.weight), self.pw.f32(norm.bias), silu,
-                                   None if pos is None else self.pw.f32(pos))
+            return ops.groupnorm_apply(x, stats, gamma, beta, silu, posf)
+        # statistics + apply per chunk of samples: the second read of a chunk comes from L2 instead of HBM
+        fps = x.shape[0] // n                                            # frames per sample (joint norms merge frames)
+        y = torch.empty_like(x)
+        for s0 in range(0, n, step):
+            s1 = min(n, s0 + step)
+            xc = x[s0 * fps: s1 * fps]
+            stats = ops.groupnorm_stats(xc, s1 - s0, norm.num_groups, norm.eps)
+            ops.groupnorm_apply(xc, stats, gamma, beta, silu, posf, out=y[s0 * fps: s1 * fps])
+        return y
 
     def _gn_coeff(self, x, norm):
         """Coefficients of GroupNorm(x) for the conv that applies it on the fly: statistics pass (or the producing conv's

@@ -97,3 +97,30 @@ def test_token_serialise_roundtrip(cuda):
     qc, qd = ops.tokens_gather(tok, cb_c.to(cuda), cb_d.to(cuda), t, f, 256, 16, torch.float32)
     assert torch.equal(qc.cpu(), cb_c[ic.reshape(-1)])
     assert torch.equal(qd.cpu(), cb_d[idd.reshape(-1)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,Lq,Lmax,pos0", [(2, 3, 130, 136, 0), (1, 2, 64, 72, 0), (2, 2, 70, 200, 65)])
+def test_rope_kv_tiled_prefill_kernel_matches_the_scalar_one(cuda, B, H, Lq, Lmax, pos0):
+    """The prefill-sized RoPE + cache-append kernel (64-position tiles, vector accesses, V^T through shared memory; bf16) against
+    the scalar kernel run in fp32 on the same bf16-exact values: q, K, V^T and the row-major V copy must agree to one bf16
+    rounding of the same fp32 arithmetic (partial last tile, odd cache offset included)."""
+    from ivideogpt_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + Lq)
+    qkv = torch.randn(B * Lq, 3 * H * 64, generator=g).to(torch.bfloat16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    fr = torch.arange(Lmax).float()[:, None] * inv[None, :]
+    cos, sin = fr.cos().contiguous().to(cuda), fr.sin().contiguous().to(cuda)
+    outs = {}
+    for dt in (torch.bfloat16, torch.float32):
+        q = torch.zeros(B, H, Lq, 64, dtype=dt, device=cuda)
+        k = torch.zeros(B, H, Lmax, 64, dtype=dt, device=cuda)
+        vt = torch.zeros(B, H, 64, Lmax, dtype=dt, device=cuda)
+        vr = torch.zeros(B, H, Lmax, 64, dtype=dt, device=cuda)
+        ops.rope_kv(qkv.to(dt).to(cuda), q, k, vt, B, Lq, H, Lmax, pos0, None, cos, sin, v_rows=vr)
+        outs[dt] = [t.float().cpu() for t in (q, k, vt, vr)]
+    for a, b in zip(outs[torch.bfloat16], outs[torch.float32]):
+        want = b.to(torch.bfloat16).float()
+        assert float((a - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) + 1e-6     # one bf16 ulp at the largest magnitude
+        assert float((a != want).float().mean()) < 0.02                                        # fma contraction may flip a last bit
+    assert float(outs[torch.bfloat16][2][..., :pos0].abs().max()) == 0.0 if pos0 else True   # nothing written before the offset
