@@ -192,14 +192,14 @@ def run_reference(args):
     t = statistics.median(times)
     fps = args.cpu_clips * (seg - ctx) / t
     sample = f"{args.cpu_clips} clip(s) {res}x{res}x{seg}, greedy, fp32, {cores} threads (oracle tokenizer + HF Llama)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "predicted_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.cpu_clips, res),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config(args, batch, res):
@@ -430,7 +430,7 @@ def run_b200(args):
                         "sample": f"8 clips {res}x{res}x{ctx + 2} (2 predicted frames each), greedy, fp32, {t8:.1f} s"}
             out["cpu_baseline_b8"] = leg("cpu_baseline_b8", cpu_b8)
     if out is not None:
-        print(json.dumps(out))
+        emit(out)
     D.close()
 
 
@@ -627,12 +627,29 @@ def run_train(args):
     D = Dist()
     rec = train_record(args, D, args.workload, args.steps, args.warmup)
     if rec is not None:
-        print(json.dumps(rec))
+        emit(rec)
     D.close()
 
 
+def emit(rec):
+    """The one JSON line, on the process's real stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(rec) + "\n").encode())
+
+
+def _quiet_stdout():
+    """NCCL (NCCL_DEBUG=VERSION on some boxes) and library banners write to fd 1; the contract is ONE line on stdout, so fd 1
+    is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    _quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
     elif a.workload.startswith("train"):
