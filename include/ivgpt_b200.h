@@ -321,6 +321,26 @@ int ivgpt_add_to_f32(int dtype, float* y, const void* x, long long n, void* stre
  * scripts/pretrain/oxe-64-act-free.sh:31 uses 0.1): y[i] = keep(seed, i) ? x[i] / (1 - p) : 0, counter-based so that the
  * backward pass regenerates the forward mask from the seed.  y may alias x. */
 int ivgpt_dropout(int dtype, const void* x, void* y, long long n, float p, unsigned long long seed, void* stream);
+/* ---- tokenizer training: backward of CompressiveVQModel.forward (reference train_tokenizer.py:734 through
+ * compressive_vq_model.py:332-369, vae.py:141-195,298-371, conditional_vae.py:38-55,108-132,186-212).  The contractions (conv
+ * dgrad = ivgpt_conv3x3 on flipped weights, conv wgrad = dY^T x im2col(X)^T, Linear / attention products) are ivgpt_gemm /
+ * ivgpt_conv3x3 calls; these are the fp32 NHWC kernels around them. */
+int ivgpt_colsum(const float* x, long long M, int C, long long ld, float* part_ws /* part_rows*C */, int part_rows, float* out,
+                 int accumulate, void* stream);
+int ivgpt_groupnorm_bwd_chunks(int samples, int rows);   /* workspace sizing: ws = samples*(chunks+1)*C*2 + samples*G*2 floats */
+int ivgpt_groupnorm_bwd(const float* x, const float* dy, const float* stats, const float* gamma, const float* beta, int silu,
+                        int samples, int rows, int C, int G, float* ws, float* dx, int dx_accumulate, float* dgamma,
+                        float* dbeta, int param_accumulate, void* stream);
+int ivgpt_im2col3x3_t(const float* x, float* colT /* [k_rows][N*Ho*Wo] */, int N, int H, int W, int C, int stride, int k_rows,
+                      void* stream);
+int ivgpt_zero_insert2x(const float* dy, float* out, int N, int h, int w, int C, void* stream);
+int ivgpt_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+int ivgpt_silu(const float* x, const float* dy /* null: forward */, float* out, long long n, void* stream);
+int ivgpt_axpby(const float* x, const float* y /* may be null */, float* out, float a, float b, long long n, void* stream);
+int ivgpt_reduce_mid(const float* x, float* out, long long outer, int mid, long long inner, int accumulate, void* stream);
+int ivgpt_nchw_to_nhwc(const float* x, float* y, long long N, int Cs, int Cd, long long HW, void* stream);
+int ivgpt_vq_bwd(const float* z, const float* zq, const float* dout /* may be null */, const float* gloss /* device scalar or null */,
+                 float beta, long long n, float* dz, float* de_rows, void* stream);
 /* Programmatic dependent launch for the kernels of the decode step (prologue overlap inside CUDA graphs). */
 int ivgpt_set_pdl(int on);
 

@@ -136,6 +136,17 @@ SIGNATURES = {
     "ivgpt_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "ivgpt_add_to_f32": [_I, _P, _P, _L, _P],
     "ivgpt_dropout": [_I, _P, _P, _L, _F, _U, _P],
+    "ivgpt_colsum": [_P, _L, _I, _L, _P, _I, _P, _I, _P],
+    "ivgpt_groupnorm_bwd_chunks": [_I, _I],
+    "ivgpt_groupnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P],
+    "ivgpt_im2col3x3_t": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ivgpt_zero_insert2x": [_P, _P, _I, _I, _I, _I, _P],
+    "ivgpt_upsample2x_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "ivgpt_silu": [_P, _P, _P, _L, _P],
+    "ivgpt_axpby": [_P, _P, _P, _F, _F, _L, _P],
+    "ivgpt_reduce_mid": [_P, _P, _L, _I, _L, _I, _P],
+    "ivgpt_nchw_to_nhwc": [_P, _P, _L, _I, _I, _L, _P],
+    "ivgpt_vq_bwd": [_P, _P, _P, _P, _F, _L, _P, _P, _P],
     "ivgpt_vq_set_order": [_I],
     "ivgpt_vq_get_order": [],
     "ivgpt_mega_layer_bytes": [],

@@ -573,6 +573,140 @@ def preprocess_resize(frames: torch.Tensor, size_hw, channels_last: bool = True,
 
 
 # ------------------------------------------------------------------------------------------------
+# tokenizer training (backward) pieces -- fp32 NHWC (csrc/tok_train.cu)
+# ------------------------------------------------------------------------------------------------
+def _f32c(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """out[c] (+)= sum over rows of x [M, C] (fp32, last dim contiguous): bias gradients."""
+    _cuda(x, out)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    M, Cc = x.shape
+    if out is None:
+        assert not accumulate
+        out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    nb = 592
+    part = torch.empty(nb * Cc, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_colsum(x.data_ptr(), M, Cc, x.stride(0), part.data_ptr(), nb, out.data_ptr(),
+                                        int(accumulate), _stream()), "colsum")
+    return out
+
+
+def groupnorm_bwd(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  silu: bool, want_dx: bool = True):
+    """Backward of y = act(GroupNorm(x)) for x viewed [samples, rows, C] with statistics [samples, G, 2]:
+    returns (dx or None, dgamma [C], dbeta [C])."""
+    _cuda(x, dy, stats, gamma, beta)
+    _f32c(x, dy, stats, gamma, beta)
+    assert dy.shape == x.shape
+    Cc = x.shape[-1]
+    samples, groups = stats.shape[0], stats.shape[1]
+    rows = x.numel() // (samples * Cc)
+    lib = _lib.load()
+    chunks = lib.ivgpt_groupnorm_bwd_chunks(samples, rows)
+    ws = torch.empty(samples * (chunks + 1) * Cc * 2 + samples * groups * 2, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if want_dx else None
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    _lib.check(lib.ivgpt_groupnorm_bwd(x.data_ptr(), dy.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                       int(silu), samples, rows, Cc, groups, ws.data_ptr(), _ptr(dx), 0, dgamma.data_ptr(),
+                                       dbeta.data_ptr(), 0, _stream()), "groupnorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def im2col3x3_t(x: torch.Tensor, stride: int = 1, k_rows: Optional[int] = None) -> torch.Tensor:
+    """colT [k_rows, N*Ho*Wo] fp32 with colT[tap*C + c][pixel] = the input pixel tap (a, b) of that output pixel sees
+    (zero padding as the forward conv; rows beyond 9*C are zero): the K-major operand of the conv weight gradient."""
+    _cuda(x)
+    _f32c(x)
+    N, H, W, Cc = x.shape
+    k_rows = 9 * Cc if k_rows is None else k_rows
+    P = N * (H // stride) * (W // stride)
+    assert P % 4 == 0
+    colT = torch.empty(k_rows, P, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_im2col3x3_t(x.data_ptr(), colT.data_ptr(), N, H, W, Cc, stride, k_rows, _stream()),
+               "im2col3x3_t")
+    return colT
+
+
+def zero_insert2x(dy: torch.Tensor) -> torch.Tensor:
+    """[N,h,w,C] -> [N,2h,2w,C] with out[2i+1, 2j+1] = dy[i, j]: the operand of the stride-2 conv's data gradient."""
+    _cuda(dy)
+    _f32c(dy)
+    N, h, w, Cc = dy.shape
+    out = torch.empty(N, 2 * h, 2 * w, Cc, dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.load().ivgpt_zero_insert2x(dy.data_ptr(), out.data_ptr(), N, h, w, Cc, _stream()), "zero_insert2x")
+    return out
+
+
+def upsample2x_bwd(dy: torch.Tensor) -> torch.Tensor:
+    _cuda(dy)
+    _f32c(dy)
+    N, H2, W2, Cc = dy.shape
+    dx = torch.empty(N, H2 // 2, W2 // 2, Cc, dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.load().ivgpt_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), N, H2 // 2, W2 // 2, Cc, _stream()),
+               "upsample2x_bwd")
+    return dx
+
+
+def silu(x: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """forward: silu(x); with dy: dy * silu'(x)."""
+    _cuda(x, dy)
+    _f32c(x, dy)
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().ivgpt_silu(x.data_ptr(), _ptr(dy), out.data_ptr(), x.numel(), _stream()), "silu")
+    return out
+
+
+def axpby(x: torch.Tensor, y: Optional[torch.Tensor], a: float, b: float = 0.0, out: Optional[torch.Tensor] = None):
+    _cuda(x, y, out)
+    _f32c(x, y, out)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().ivgpt_axpby(x.data_ptr(), _ptr(y), out.data_ptr(), float(a), float(b), x.numel(), _stream()),
+               "axpby")
+    return out
+
+
+def reduce_mid(x: torch.Tensor, outer: int, mid: int, out: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """x viewed [outer, mid, inner] -> out [outer, inner] (+)= sum over mid."""
+    _cuda(x, out)
+    _f32c(x, out)
+    inner = x.numel() // (outer * mid)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(outer, inner, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_reduce_mid(x.data_ptr(), out.data_ptr(), outer, mid, inner, int(accumulate), _stream()),
+               "reduce_mid")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """[N, Cs, H, W] fp32 -> [N, H, W, c_pad] (channels beyond Cs zero)."""
+    _cuda(x)
+    _f32c(x)
+    N, Cs, H, W = x.shape
+    Cd = Cs if c_pad is None else c_pad
+    y = torch.empty(N, H, W, Cd, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ivgpt_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), N, Cs, Cd, H * W, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def vq_bwd(z: torch.Tensor, zq: torch.Tensor, dout: Optional[torch.Tensor], gloss: Optional[torch.Tensor], beta: float):
+    """(dz, de_rows): straight-through + commitment gradients of the VQ layer; de_rows are scattered onto the codebook
+    with embed_bwd(idx, de_rows, dE).  gloss: 0-d fp32 CUDA tensor (gradient of the returned loss) or None."""
+    _cuda(z, zq, dout, gloss)
+    _f32c(z, zq, dout, gloss)
+    dz, de = torch.empty_like(z), torch.empty_like(z)
+    _lib.check(_lib.load().ivgpt_vq_bwd(z.data_ptr(), zq.data_ptr(), _ptr(dout), _ptr(gloss), float(beta), z.numel(),
+                                        dz.data_ptr(), de.data_ptr(), _stream()), "vq_bwd")
+    return dz, de
+
+
+# ------------------------------------------------------------------------------------------------
 # device guard: every launch above goes to torch.cuda.current_stream() of the CURRENT device, and the C side keeps
 # per-device state keyed by cudaGetDevice().  A tensor living on another GPU (model on cuda:1 while cuda:0 is current)
 # therefore switches the current device for the duration of the call.

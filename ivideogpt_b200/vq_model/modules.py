@@ -91,6 +91,7 @@ class CrossAttnParams(_NoForward):
     def __init__(self, ch: int, res: int, kv_frames: int, groups: int = 32, heads: int = 4):
         super().__init__()
         self.ch, self.res, self.heads = ch, res, heads
+        self.dropout = 0.1   # attention-probability and residual dropout of the reference block (train mode only; :17,24-25)
         self.kv_frames = kv_frames
         self.att = _MHAParams(ch)
         self.kv_norm = nn.GroupNorm(groups, ch)  # eps 1e-5 (torch default), unlike the resnet norms

@@ -85,6 +85,33 @@ class PackedWeights:
             self._cache[key] = p.detach().float().contiguous()
         return self._cache[key]
 
+    def derived(self, tag, params, make):
+        """Any other kernel-layout copy of `params` (training: flipped / transposed weights for the data gradients),
+        rebuilt when a parameter's version changes."""
+        key = self._key(tag, params, torch.float32)
+        if key not in self._cache:
+            self._cache[key] = make()
+        return self._cache[key]
+
+    def conv3_dgrad(self, conv, cout_pad: int = 0) -> torch.Tensor:
+        """[Cin, 9*Cout] K-major weights of the conv's data gradient: dX = conv3x3(dY, this) with the taps flipped
+        (Wd[ci, (a, b), co] = W[co, ci, 2-a, 2-b]); cout_pad > Cout appends zero output channels (the 3-channel conv_out)."""
+        def make():
+            w = conv.weight.detach().float()
+            if cout_pad > w.shape[0]:
+                w = torch.cat([w, w.new_zeros(cout_pad - w.shape[0], *w.shape[1:])], dim=0)
+            return _round_tf32(w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous())
+        return self.derived(("conv3_dgrad", cout_pad), [conv.weight], make)
+
+    def linear_t(self, weight, lo: Optional[int] = None, hi: Optional[int] = None) -> torch.Tensor:
+        """[K, N] = rows lo:hi of a Linear / 1x1-conv weight, transposed (the B operand of dX = dY @ W)."""
+        def make():
+            w = weight.detach().float().reshape(weight.shape[0], -1)
+            if lo is not None:
+                w = w[lo:hi]
+            return _round_tf32(w.t().contiguous())
+        return self.derived(("lin_t", lo, hi), [weight], make)
+
     def conv_in27(self, conv):
         key = self._key("cin", [conv.weight, conv.bias], torch.float32)
         if key not in self._cache:

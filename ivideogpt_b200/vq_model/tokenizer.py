@@ -247,16 +247,26 @@ class CompressiveVQModel(HubMixin, nn.Module):
         forward returns (encoder -> quant_conv -> VQ (straight-through value, commit loss) -> post_quant_conv -> decoder;
         conditional encoder -> patchify -> quant_linear -> VQ -> post_quant_linear -> de-patchify -> conditional decoder).
 
-        FORWARD ONLY on the sm_100a kernels: this is what train_tokenizer.py's validation loop (:940-960) and any
-        no-grad evaluation need.  The backward pass (conv dgrad / wgrad, GroupNorm / attention backward, the codebook and
-        straight-through gradients) is not built: calling it with autograd recording and trainable parameters raises."""
+        With autograd recording and trainable parameters this is the TRAINING graph (reference train_tokenizer.py:734
+        `accelerator.backward(loss)`): the forward keeps a tape and `loss.backward()` runs the conv dgrad / wgrad, GroupNorm,
+        attention, codebook and straight-through gradients on the sm_100a kernels (vq_model/train_plan.py; fp32 storage /
+        TF32 tensor cores).  Under torch.no_grad(), or with frozen parameters, it is the evaluation forward of
+        train_tokenizer.py's validation loop (:940-960) in the configured compute dtype."""
         if dyn_sample is None or segment_len is None:
             raise NotImplementedError("CompressiveVQModel.forward: the ctx_vqgan form (sample=, dyn_sample=, segment_len=) "
                                       "is the one train_tokenizer.py uses (:623-627) and the one implemented")
+        self._require_cuda(sample, "forward")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "CompressiveVQModel.forward: the backward pass of the tokenizer (reference train_tokenizer.py:734) is not "
-                "built on the sm_100a path; run the forward under torch.no_grad() (evaluation), or freeze the parameters")
+            from .train_plan import forward_train
+            t, f = self.context_length, int(segment_len)
+            assert sample.shape[0] % t == 0 and dyn_sample.shape[0] % f == 0 and sample.shape[0] // t == dyn_sample.shape[0] // f
+            (dec, ref_dec, commit, dyn_commit), self._last_train_graph = forward_train(
+                self, self._get_plan(), sample, dyn_sample, f, getattr(self, "_vq_index_override", None))
+            if not return_dict:
+                return (dec, ref_dec, commit, dyn_commit) if return_loss else (dec,)
+            if return_loss:
+                return CompressiveVQDecoderOutput(sample=dec, ref_sample=ref_dec, commit_loss=commit, dyn_commit_loss=dyn_commit)
+            return CompressiveVQDecoderOutput(sample=dec)
         self._require_cuda(sample, "forward")
         with torch.no_grad():
             plan = self._get_plan()

@@ -12,7 +12,7 @@ B=ivideogpt_b200/csrc/build
 for def in ${VARIANT_DEFS}; do
   name=${def%%=*}; flags=${def#*=}
   ( $NVCC $FLAGS ${flags//,/ } -c ivideogpt_b200/csrc/decode_mega.cu -o ab/build/dm_$name.o &&
-    $NVCC -shared -o ab/build/lib_$name.so $B/capi.o $B/vq_argmin.o $B/gemm_tc.o $B/elementwise.o $B/llama_ops.o ab/build/dm_$name.o $B/llama_train.o $B/flash_attn.o -lcudart ) &
+    $NVCC -shared -o ab/build/lib_$name.so $B/capi.o $B/vq_argmin.o $B/gemm_tc.o $B/elementwise.o $B/llama_ops.o ab/build/dm_$name.o $B/llama_train.o $B/flash_attn.o $B/tok_train.o -lcudart ) &
 done
 wait
 OLD=${OLD:-aceeb50}
