@@ -38,6 +38,10 @@ WORKLOADS = {
     # master weights) -> gradient all-reduce over ranks -> fused AdamW.  per-device batch 16 (oxe-64-act-free.sh:26)
     "train64": ("ctx_vae64", "llama_138m", 64, 16),
     "train-tiny": (None, None, 64, 2),
+    # tokenizer training step (row f3; the reconstruction + commitment part of train_tokenizer.py's generator step):
+    # CompressiveVQModel.forward (train mode) -> MSE of both reconstructions + commit losses -> backward -> fused AdamW
+    "train-tokenizer64": ("ctx_vae64", "llama_138m", 64, 8),
+    "train-tokenizer-tiny": (None, None, 64, 1),
 }
 
 
@@ -56,7 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=1)
     ap.add_argument("--quick", action="store_true", help="profiling aid: exact --warmup, no e2e / cpu legs")
-    ap.add_argument("--no-legs", action="store_true", help="skip the nested tf32 / cfg256 / cfg64_medium / train64 legs")
+    ap.add_argument("--no-legs", action="store_true", help="skip the nested tf32 / cfg256 / cfg64_medium / train64 / train_tokenizer64 legs")
     return ap.parse_args()
 
 
@@ -409,6 +413,9 @@ def run_b200(args):
         r = leg("train64", lambda: train_record(args, D, "train64", 3, 3))
         if out is not None:
             out["train64"] = r
+        r = leg("train_tokenizer64", lambda: tok_train_record(args, D, "train-tokenizer64", 3, 3))
+        if out is not None:
+            out["train_tokenizer64"] = r
     if out is not None and ref_tok is not None:
         cores = host_threads()
         torch.set_num_threads(cores)
@@ -623,8 +630,107 @@ def train_record(args, D, workload, steps, warmup):
     return rec
 
 
+def tok_train_record(args, D, workload, steps, warmup):
+    """One tokenizer training step per bench step (reference train_tokenizer.py:620-740 without the LPIPS / GAN terms, which are
+    out of scope): forward in train mode, loss = MSE(dec, target) + MSE(ref_dec, context) + commit + dyn_commit, backward on
+    the sm_100a kernels, gradient all-reduce (N > 1), clip_grad_norm_, fused AdamW.  metric = clips/s."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from ivideogpt_b200 import _lib
+    from ivideogpt_b200.optim import FusedAdamW
+    world, rank, dev = D.world, D.rank, D.dev
+    base = "tiny" if workload.endswith("tiny") else "cfg64"
+    _, _, res, default_b = WORKLOADS[workload]
+    B = args.batch or default_b
+    ctx, seg = args.context_length, args.segment_length
+    tok, llm, ref_tok, _ = build_b200_models(base, dev, torch.float32)
+    del llm
+    tok.train()
+    params = [p for p in tok.parameters()]
+    opt = FusedAdamW(params, lr=1e-4, betas=(0.5, 0.9), weight_decay=0.0, grad_scale=1.0 / world)   # train_tokenizer.py:466-472
+    clips = synthetic_clips(B, seg, res, seed=rank).to(dev)
+    sample = clips[:, :ctx].reshape(B * ctx, 3, res, res).contiguous()
+    target = clips[:, ctx:].reshape(B * (seg - ctx), 3, res, res).contiguous()
+
+    def step():
+        dec, ref_dec, commit, dyn_commit = tok(sample=sample, dyn_sample=target, return_dict=False, return_loss=True,
+                                               segment_len=seg - ctx)
+        loss = F.mse_loss(dec, target) + F.mse_loss(ref_dec, sample) + commit + dyn_commit
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                if p.grad is not None:
+                    n = p.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    sampler = ClockSampler(D.local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    D.barrier()
+    n0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    losses = [step() for _ in range(steps)]
+    b.record()
+    D.barrier()
+    ms_step = D.max_ms(a.elapsed_time(b)) / steps
+    clocks = sampler.finish() if sampler else None
+    rec = None
+    if rank == 0:
+        mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        rec = {
+            "metric": "tokenizer_train_clips_per_sec", "value": world * B / (ms_step / 1e3), "unit": "clips/s", "n_gpus": world,
+            "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": f"{workload}: CompressiveVQModel.forward (train mode) + backward + AdamW, {B} clips/GPU of "
+                                   f"{res}x{res}x{seg} (context {ctx}), loss = MSE + commit (no LPIPS / GAN terms)",
+                       "per_gpu_batch": B, "parallelism": f"dp{world}"},
+            "loss_first_last": [float(losses[0]), float(losses[-1])], "gpu_launches": _lib.launch_count() - n0,
+            "peak_memory_gib": mem, "clocks": clocks,
+        }
+        # the same step on the host cores: the oracle's differentiable forward_train + torch autograd + torch AdamW, 1 clip
+        try:
+            cores = host_threads()
+            torch.set_num_threads(cores)
+            ref_tok = ref_tok.train()
+            for m in ref_tok.modules():                    # the oracle restates the eval-mode block: keep its dropouts off
+                if isinstance(m, torch.nn.MultiheadAttention):
+                    m.dropout = 0.0
+            o = torch.optim.AdamW(ref_tok.parameters(), lr=1e-4, betas=(0.5, 0.9), weight_decay=0.0)
+            c1 = synthetic_clips(1, seg, res)
+            s1, t1 = c1[0, :ctx].contiguous(), c1[0, ctx:].contiguous()
+            t0 = time.perf_counter()
+            out = ref_tok.forward_train(s1, t1, seg - ctx)
+            (F.mse_loss(out[0], t1) + F.mse_loss(out[1], s1) + out[2] + out[3]).backward()
+            o.step()
+            t_cpu = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
+                                   "sample": f"1 clip {res}x{res}x{seg}, oracle forward_train + torch autograd + AdamW, fp32, {t_cpu:.1f} s"}
+        except Exception as e:     # noqa: BLE001
+            rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
+    del tok, opt, params
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_train(args):
     D = Dist()
+    if args.workload.startswith("train-tokenizer"):
+        rec = tok_train_record(args, D, args.workload, args.steps, args.warmup)
+        if rec is not None:
+            emit(rec)
+        D.close()
+        return
     rec = train_record(args, D, args.workload, args.steps, args.warmup)
     if rec is not None:
         emit(rec)

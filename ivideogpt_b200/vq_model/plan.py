@@ -39,12 +39,23 @@ class PackedWeights:
 
     def __init__(self):
         self._cache: Dict[tuple, torch.Tensor] = {}
+        self._latest: Dict[tuple, tuple] = {}
 
     def clear(self):
         self._cache.clear()
+        self._latest.clear()
 
     def _key(self, tag, params, dtype):
-        return (tag, dtype) + tuple((p.data_ptr(), p._version) for p in params)
+        """Cache key.  The parameter VERSIONS are part of it, and entries of older versions of the same parameters are dropped
+        when a new version is packed: during training every optimizer step bumps every version, and a cache that kept the
+        stale copies would grow by one full set of packed weights per step."""
+        ident = (tag, dtype) + tuple(p.data_ptr() for p in params)
+        key = ident + tuple(p._version for p in params)
+        old = self._latest.get(ident)
+        if old is not None and old != key:
+            self._cache.pop(old, None)
+        self._latest[ident] = key
+        return key
 
     def _cast(self, w: torch.Tensor, dtype):
         w = w.detach().to(torch.float32)

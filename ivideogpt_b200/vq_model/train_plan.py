@@ -42,7 +42,8 @@ class TokenizerTrainGraph:
             raise NotImplementedError("tokenizer training runs in fp32 storage / TF32 tensor cores; "
                                       "call set_compute_dtype(torch.float32) (bf16 is an inference arithmetic here)")
         self.m, self.plan, self.pw = model, plan, plan.pw
-        self.tape: List = []
+        self.tape: List = []          # (closure, parameters whose gradient the closure produces)
+        self.vars: List[Var] = []
         self.pgrads: Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]] = {}
         self.vq_indices: Dict[str, torch.Tensor] = {}
         self.idx_override: Dict[str, torch.Tensor] = {}
@@ -53,6 +54,14 @@ class TokenizerTrainGraph:
         self._drop_sites = 0
 
     # ---- gradient slots ---------------------------------------------------------------------------------
+    def _var(self, v: torch.Tensor, needs: bool = True) -> Var:
+        var = Var(v, needs)
+        self.vars.append(var)
+        return var
+
+    def _push(self, bwd, outs, *params):
+        self.tape.append((bwd, tuple(p for p in params if p is not None), outs))
+
     def _acc(self, var: Optional[Var], g: torch.Tensor, own: bool):
         """own: g was produced for this slot alone (it may be kept and later added into in place)."""
         if var is None or not var.needs:
@@ -68,6 +77,9 @@ class TokenizerTrainGraph:
             return
         key = id(p)
         if key not in self.pgrads:
+            if lo is None and g.numel() == p.numel() and g.is_contiguous() and g._base is None:
+                self.pgrads[key] = (p, g.view(p.shape))        # fresh tensor produced for this parameter: keep it
+                return
             self.pgrads[key] = (p, torch.zeros(p.shape, dtype=torch.float32, device=g.device))
         buf = self.pgrads[key][1]
         tgt = buf if lo is None else buf[lo: lo + g.shape[0]]
@@ -77,12 +89,12 @@ class TokenizerTrainGraph:
 
     # ---- ops ----------------------------------------------------------------------------------------------
     def view(self, x: Var, shape) -> Var:
-        out = Var(x.v.view(shape), x.needs)
+        out = self._var(x.v.view(shape), x.needs)
 
         def bwd():
             if out.g is not None:
                 self._acc(x, out.g, own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     @staticmethod
@@ -112,7 +124,7 @@ class TokenizerTrainGraph:
         w, b = self.pw.conv3(conv, torch.float32, shortcut=shortcut)
         y = ops.conv3x3(x.v, w, b, stride=stride, x2=None if x2 is None else x2.v,
                         residual=None if residual is None else residual.v)
-        out = Var(y)
+        out = self._var(y)
 
         def bwd():
             dy = out.g
@@ -126,7 +138,7 @@ class TokenizerTrainGraph:
                 db = ops.colsum(dy2)
                 self._pacc(conv.bias, db)
                 if shortcut is not None:
-                    self._pacc(shortcut.bias, db)
+                    self._pacc(shortcut.bias, db.clone())        # two parameters must not share one gradient tensor
             need_sw = shortcut is not None and shortcut.weight.requires_grad
             dyT = ops.transpose(dy2) if (conv.weight.requires_grad or need_sw) else None      # [Co, P]
             if conv.weight.requires_grad:
@@ -143,7 +155,7 @@ class TokenizerTrainGraph:
             if x.needs:
                 src = ops.zero_insert2x(dy) if stride == 2 else dy
                 self._acc(x, ops.conv3x3(src, self.pw.conv3_dgrad(conv), None), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,), conv.weight, conv.bias, *((shortcut.weight, shortcut.bias) if shortcut is not None else ()))
         return out
 
     def gn(self, x: Var, norm, silu: bool, samples: Optional[int] = None, pos=None) -> Var:
@@ -151,7 +163,7 @@ class TokenizerTrainGraph:
         gamma, beta = self.pw.f32(norm.weight), self.pw.f32(norm.bias)
         stats = ops.groupnorm_stats(x.v, n, norm.num_groups, norm.eps)
         y = ops.groupnorm_apply(x.v, stats, gamma, beta, silu, None if pos is None else self.pw.f32(pos))
-        out = Var(y)
+        out = self._var(y)
 
         def bwd():
             dy = out.g
@@ -164,7 +176,7 @@ class TokenizerTrainGraph:
                 self._pacc(pos, ops.reduce_mid(dy, 1, dy.numel() // pos.numel()).view(pos.shape))
             if x.needs:
                 self._acc(x, dx, own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,), norm.weight, norm.bias, pos)
         return out
 
     def linear(self, x: Var, weight, bias, lo: Optional[int] = None, hi: Optional[int] = None,
@@ -175,7 +187,7 @@ class TokenizerTrainGraph:
         else:
             w, b = self.pw.rows(weight, bias, lo, hi, torch.float32, tag)
         y = ops.gemm(x.v, w, b, residual=None if residual is None else residual.v)
-        out = Var(y)
+        out = self._var(y)
 
         def bwd():
             dy = out.g
@@ -190,7 +202,7 @@ class TokenizerTrainGraph:
                 self._acc(residual, dy, own=False)
             if x.needs:
                 self._acc(x, ops.gemm(dy, self.pw.linear_t(weight, lo, hi)), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,), weight, bias)
         return out
 
     def _next_seed(self) -> int:
@@ -201,31 +213,31 @@ class TokenizerTrainGraph:
         if p <= 0.0:
             return x
         seed = self._next_seed()
-        out = Var(ops.dropout(x.v, p, seed))
+        out = self._var(ops.dropout(x.v, p, seed))
 
         def bwd():
             if out.g is not None:
                 self._acc(x, ops.dropout(out.g, p, seed), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def add(self, a: Var, b: Var) -> Var:
-        out = Var(ops.axpby(a.v, b.v, 1.0, 1.0))
+        out = self._var(ops.axpby(a.v, b.v, 1.0, 1.0))
 
         def bwd():
             if out.g is not None:
                 self._acc(a, out.g, own=False)
                 self._acc(b, out.g, own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def silu(self, x: Var) -> Var:
-        out = Var(ops.silu(x.v))
+        out = self._var(ops.silu(x.v))
 
         def bwd():
             if out.g is not None:
                 self._acc(x, ops.silu(x.v, out.g), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     # attention products: the two descriptor forms of plan.TokenizerPlan.attention
@@ -275,7 +287,7 @@ class TokenizerTrainGraph:
         del s
         seed = self._next_seed() if p_drop > 0.0 else 0
         pd = ops.dropout(p, p_drop, seed) if p_drop > 0.0 else p
-        out = Var(self._values(pd, ops.transpose(v.v), heads, bdiv))
+        out = self._var(self._values(pd, ops.transpose(v.v), heads, bdiv))
 
         def bwd():
             do = out.g
@@ -295,35 +307,35 @@ class TokenizerTrainGraph:
             if k.needs:
                 dkf = self._values(ops.transpose(ds), ops.transpose(q.v), heads, 1)
                 self._acc(k, dkf if bdiv == 1 else ops.reduce_mid(dkf, Fk, bdiv), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def upsample(self, x: Var) -> Var:
-        out = Var(ops.upsample2x(x.v))
+        out = self._var(ops.upsample2x(x.v))
 
         def bwd():
             if out.g is not None:
                 self._acc(x, ops.upsample2x_bwd(out.g), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def patchify(self, x: Var, p: int) -> Var:
         F_, R, _, Cc = x.v.shape
-        out = Var(ops.patchify(x.v, p))
+        out = self._var(ops.patchify(x.v, p))
 
         def bwd():
             if out.g is not None:
                 self._acc(x, ops.patchify(out.g, p, inverse=True, frames=F_, res=R, ch=Cc), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def unpatchify(self, x: Var, p: int, frames: int, res: int, ch: int) -> Var:
-        out = Var(ops.patchify(x.v, p, inverse=True, frames=frames, res=res, ch=ch))
+        out = self._var(ops.patchify(x.v, p, inverse=True, frames=frames, res=res, ch=ch))
 
         def bwd():
             if out.g is not None:
                 self._acc(x, ops.patchify(out.g, p), own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,))
         return out
 
     def vq(self, z: Var, codebook, name: str, beta: float = 1.0) -> Tuple[Var, Var]:
@@ -334,7 +346,7 @@ class TokenizerTrainGraph:
             idx = ops.vq_argmin(z.v, cb)
         self.vq_indices[name] = idx
         zq, loss = ops.vq_commit(z.v, cb, idx, torch.float32, beta=beta)
-        out, lossv = Var(zq), Var(loss)
+        out, lossv = self._var(zq), self._var(loss)
 
         def bwd():
             if out.g is None and lossv.g is None:
@@ -345,14 +357,14 @@ class TokenizerTrainGraph:
                 ops.embed_bwd(idx, de, dE)
                 self._pacc(codebook.embedding.weight, dE)
             self._acc(z, dz, own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out, lossv), codebook.embedding.weight)
         return out, lossv
 
     def conv_in(self, px: torch.Tensor, conv) -> Var:
         """px [N,3,H,W] fp32 (no gradient) -> [N,H,W,C0]."""
         N, _, H, W = px.shape
         w27, b27 = self.pw.conv_in27(conv)
-        out = Var(ops.conv_in(px.view(1, N, 3, H, W), w27, b27, torch.float32, 0, N))
+        out = self._var(ops.conv_in(px.view(1, N, 3, H, W), w27, b27, torch.float32, 0, N))
 
         def bwd():
             dy = out.g
@@ -366,7 +378,7 @@ class TokenizerTrainGraph:
                 colT = ops.im2col3x3_t(ops.nchw_to_nhwc(px), 1, k_rows=32)             # rows (tap, ci), padded 27 -> 32
                 dW = self._wgrad(ops.transpose(dy2), colT)[:, :27]
                 self._pacc(conv.weight, dW.reshape(Co, 3, 3, 3).permute(0, 3, 1, 2))
-        self.tape.append(bwd)
+        self._push(bwd, (out,), conv.weight, conv.bias)
         return out
 
     def conv_out(self, x: Var, norm, conv, out_nchw: torch.Tensor) -> Var:
@@ -376,7 +388,7 @@ class TokenizerTrainGraph:
         stats = ops.groupnorm_stats(x.v, N, norm.num_groups, norm.eps)
         w3, b3 = self.pw.conv_out3(conv)
         ops.conv_out3(x.v, stats, gamma, beta, w3, b3, out_nchw.view(1, N, 3, H, W), 0, N)
-        out = Var(out_nchw)
+        out = self._var(out_nchw)
 
         def bwd():
             d = out.g
@@ -397,7 +409,7 @@ class TokenizerTrainGraph:
             self._pacc(norm.bias, db)
             if x.needs:
                 self._acc(x, dx, own=True)
-        self.tape.append(bwd)
+        self._push(bwd, (out,), conv.weight, conv.bias, norm.weight, norm.bias)
         return out
 
     # ---- blocks (mirror plan.TokenizerPlan) ------------------------------------------------------------
@@ -462,7 +474,7 @@ class TokenizerTrainGraph:
         feats.append(x)
         return self.conv(self.gn(x, enc.conv_norm_out, True), enc.conv_out), feats
 
-    def decode(self, latent: Var, dec, out_nchw: torch.Tensor, ctx_feats: Optional[List[Var]] = None, clips: int = 0):
+    def decode(self, latent: Var, dec, out_nchw: Optional[torch.Tensor], ctx_feats: Optional[List[Var]] = None, clips: int = 0):
         x = self.conv(latent, dec.conv_in)
         feats = [x]
         x = self.mid(x, dec.mid_block)
@@ -477,11 +489,15 @@ class TokenizerTrainGraph:
             if ctx_feats is not None and x.v.shape[2] <= dec.max_att_resolution:
                 x = self.cross_attention(x, ctx_feats[i + 2], dec.cross_att_blocks[i + 1], clips)
             feats.append(x)
+        if out_nchw is None:        # the caller runs GroupNorm + SiLU + conv_out as a separate autograd node (see forward_train)
+            return x, feats
         return self.conv_out(x, dec.conv_norm_out, dec.conv_out, out_nchw), feats
 
     # ---- the whole graph -----------------------------------------------------------------------------------
     def forward(self, sample: torch.Tensor, dyn_sample: torch.Tensor, segment_len: int):
-        """compressive_vq_model.py:332-369 / :290-330.  Returns Vars (dec, ref_dec, commit_loss, dyn_commit_loss)."""
+        """compressive_vq_model.py:332-369 / :290-330.  Returns Vars (x_last, ref_dec, commit_loss, dyn_commit_loss) where x_last
+        is the input of the conditional decoder's last layer (conv_norm_out -> SiLU -> conv_out): that layer is a separate
+        autograd node (head()), so that a gradient asked w.r.t. it alone does not sweep the whole tape."""
         m = self.m
         t, f, cr = m.context_length, int(segment_len), _CTX_RES
         B = sample.shape[0] // t
@@ -499,52 +515,137 @@ class TokenizerTrainGraph:
         zq_d, dyn_commit = self.vq(z_dyn, m.dynamics_quantize, "dyn")
         pd = self.linear(zq_d, m.post_quant_linear.weight, m.post_quant_linear.bias)
         lat_d = self.unpatchify(pd, m.patch_size, B * f, cr, m.latent_channels)
-        dec, _ = self.decode(lat_d, m.cond_decoder, torch.empty(B * f, m.config["out_channels"], H, W, dtype=torch.float32, device=dev),
-                             ctx_feats=dec_feats, clips=B)
-        self.outputs = (dec, ref_dec, commit, dyn_commit)
+        x_last, _ = self.decode(lat_d, m.cond_decoder, None, ctx_feats=dec_feats, clips=B)
+        self.outputs = (x_last, ref_dec, commit, dyn_commit)
         return self.outputs
 
-    def backward(self, d_dec, d_ref_dec, d_commit, d_dyn_commit) -> Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]]:
-        """Seeds the four outputs (None = no gradient) and runs the tape once; returns {id(param): (param, grad fp32)}."""
-        for var, g in zip(self.outputs, (d_dec, d_ref_dec, d_commit, d_dyn_commit)):
+    def head(self, x_last: torch.Tensor) -> Var:
+        """The conditional decoder's last layer on a detached activation: (input Var, output Var)."""
+        m = self.m
+        N, H, W, _ = x_last.shape
+        self.head_in = self._var(x_last)
+        out = self.conv_out(self.head_in, m.cond_decoder.conv_norm_out, m.cond_decoder.conv_out,
+                            torch.empty(N, m.config["out_channels"], H, W, dtype=torch.float32, device=x_last.device))
+        self.outputs = (out,)
+        return out
+
+    # The closures capture the graph, and the graph owning its tape would be a reference cycle: the activations of a finished
+    # step would then live until the cyclic garbage collector runs (measured: 56 GiB held and a 4x slower step at 4 clips).
+    # The autograd node owns the tape instead (ctx.tape) and lends it back for the duration of a backward sweep, so everything
+    # a step saved is released by reference counting the moment autograd drops the node.
+    def detach_tape(self):
+        t = (self.tape, self.vars)
+        self.tape, self.vars = [], []
+        return t
+
+    def attached(self, t):
+        import contextlib
+
+        @contextlib.contextmanager
+        def lend():
+            self.tape, self.vars = t
+            try:
+                yield
+            finally:
+                self.tape, self.vars = [], []
+        return lend()
+
+    def backward_from(self, seeds, needed=None, want=()) -> Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]]:
+        """seeds: [(Var, gradient tensor)].  Runs the tape in reverse and returns {id(param): (param, grad fp32)}.  The tape is
+        kept: the graph can be differentiated again (train_tokenizer.py:706-707 takes torch.autograd.grad(..., retain_graph=
+        True) of two losses w.r.t. the last decoder layer before the real backward; that layer is its own autograd node, see
+        forward_train).  `needed` (ids of the parameters whose gradient is wanted) stops the sweep at the earliest op that
+        touches one of them; `want`: Vars whose gradient is kept in self.wanted."""
+        for var in self.vars:
+            var.g = None
+        self.pgrads = {}
+        for var, g in seeds:
             if g is not None:
                 var.g = g.detach().to(torch.float32).contiguous().view(var.v.shape).clone()
-        tape, self.tape = self.tape, []
-        while tape:
-            tape.pop()()                    # closures (and the activations they hold) are released as the sweep proceeds
+        lo = 0
+        if needed is not None:
+            hit = [i for i, (_, ps, _) in enumerate(self.tape) if any(id(p) in needed for p in ps)]
+            lo = min(hit) if hit else len(self.tape)
+        for fn, _, outs in reversed(self.tape[lo:]):
+            fn()
+            for var in outs:              # this op's output gradient has been consumed: release it now, not at the end
+                var.g = None
+        self.wanted = [var.g for var in want]
+        for var in self.vars:
+            var.g = None
         return self.pgrads
+
+    def backward(self, d_dec, d_ref_dec, d_commit, d_dyn_commit, needed=None):
+        return self.backward_from(list(zip(self.outputs, (d_dec, d_ref_dec, d_commit, d_dyn_commit))), needed)
 
 
 class _TokenizerTrainFn(torch.autograd.Function):
-    """autograd boundary: (dec, ref_dec, commit_loss, dyn_commit_loss) = f(parameters); the inputs are pixels (no gradient)."""
+    """autograd boundary of the body: (x_last, ref_dec, commit_loss, dyn_commit_loss) = f(parameters); the inputs are pixels."""
 
     @staticmethod
     def forward(ctx, graph: TokenizerTrainGraph, sample, dyn_sample, segment_len, *params):
         with torch.no_grad():
-            dec, ref_dec, commit, dyn_commit = graph.forward(sample, dyn_sample, segment_len)
+            x_last, ref_dec, commit, dyn_commit = graph.forward(sample, dyn_sample, segment_len)
         ctx.graph, ctx.params = graph, params
-        return dec.v, ref_dec.v, commit.v, dyn_commit.v
+        ctx.tape = graph.detach_tape()
+        ctx.set_materialize_grads(False)
+        # fresh tensor objects: autograd hangs grad_fn (-> this node -> the tape) on what is returned, and the graph keeps its
+        # own Vars -- returning those very objects would tie graph -> tensor -> node -> graph into a cycle that no collector
+        # sees through (measured: one step's activations leaked per step)
+        return x_last.v.detach(), ref_dec.v.detach(), commit.v.detach(), dyn_commit.v.detach()
 
     @staticmethod
-    def backward(ctx, d_dec, d_ref_dec, d_commit, d_dyn_commit):
+    def backward(ctx, d_x_last, d_ref_dec, d_commit, d_dyn_commit):
         graph = ctx.graph
-        if graph is None or not graph.tape:
-            raise RuntimeError("CompressiveVQModel.forward: the tokenizer training graph can be differentiated once "
-                               "(its tape is consumed by the backward pass, like autograd without retain_graph)")
-        with torch.no_grad(), torch.cuda.device(graph.outputs[0].v.device):
-            pg = graph.backward(d_dec, d_ref_dec, d_commit, d_dyn_commit)
+        with torch.no_grad(), torch.cuda.device(graph.outputs[0].v.device), graph.attached(ctx.tape):
+            pg = graph.backward(d_x_last, d_ref_dec, d_commit, d_dyn_commit)
         grads = []
-        for p in ctx.params:
-            e = pg.get(id(p))
+        for p, need in zip(ctx.params, ctx.needs_input_grad[4:]):
+            e = pg.get(id(p)) if need else None
             grads.append(None if e is None else e[1].to(p.dtype))
-        ctx.graph = None
+        graph.pgrads = {}
         return (None, None, None, None, *grads)
 
 
+class _TokenizerHeadFn(torch.autograd.Function):
+    """dec = conv_out(silu(conv_norm_out(x_last))) of the conditional decoder as its own node: torch.autograd.grad(loss,
+    cond_decoder.conv_out.weight, retain_graph=True) (train_tokenizer.py:706-707, the adaptive GAN weight) runs this node only."""
+
+    @staticmethod
+    def forward(ctx, graph: TokenizerTrainGraph, x_last, *params):
+        with torch.no_grad():
+            out = graph.head(x_last.detach())
+        ctx.graph, ctx.params = graph, params
+        ctx.tape = graph.detach_tape()
+        ctx.set_materialize_grads(False)
+        return out.v.detach()
+
+    @staticmethod
+    def backward(ctx, d_dec):
+        graph = ctx.graph
+        if d_dec is None:
+            return (None, None) + (None,) * len(ctx.params)
+        with torch.no_grad(), torch.cuda.device(graph.outputs[0].v.device), graph.attached(ctx.tape):
+            pg = graph.backward_from([(graph.outputs[0], d_dec)], want=(graph.head_in,))
+        grads = []
+        for p, need in zip(ctx.params, ctx.needs_input_grad[2:]):
+            e = pg.get(id(p)) if need else None
+            grads.append(None if e is None else e[1].to(p.dtype))
+        graph.pgrads = {}
+        dx, graph.wanted = (graph.wanted[0] if ctx.needs_input_grad[1] else None), []
+        return (None, dx, *grads)
+
+
 def forward_train(model, plan: TokenizerPlan, sample, dyn_sample, segment_len, idx_override=None):
+    """(dec, ref_dec, commit_loss, dyn_commit_loss) with autograd history, and the body graph (for its VQ indices)."""
     graph = TokenizerTrainGraph(model, plan)
     if idx_override:
         graph.idx_override = dict(idx_override)
-    params = [p for p in model.parameters() if p.requires_grad]
-    out = _TokenizerTrainFn.apply(graph, sample, dyn_sample, segment_len, *params)
-    return out, graph
+    cd = model.cond_decoder
+    head_params = [cd.conv_norm_out.weight, cd.conv_norm_out.bias, cd.conv_out.weight, cd.conv_out.bias]
+    head_ids = {id(p) for p in head_params}
+    params = [p for p in model.parameters() if p.requires_grad and id(p) not in head_ids]
+    x_last, ref_dec, commit, dyn_commit = _TokenizerTrainFn.apply(graph, sample, dyn_sample, segment_len, *params)
+    head = TokenizerTrainGraph(model, plan)
+    dec = _TokenizerHeadFn.apply(head, x_last, *head_params)
+    return (dec, ref_dec, commit, dyn_commit), graph

@@ -23,11 +23,7 @@ def _graph():
 
 
 def _run(graph, out, dout):
-    graph.outputs = (out,)
-    out.g = dout.clone()
-    tape, graph.tape = graph.tape, []
-    while tape:
-        tape.pop()()
+    graph.backward_from([(out, dout)])
     return {k: v[1] for k, v in graph.pgrads.items()}
 
 
@@ -259,11 +255,7 @@ def test_vq_bwd_vs_oracle_quantizer(cuda):
     out, lossv = gr.vq(zv, cb, "ctx")
     assert torch.equal(gr.vq_indices["ctx"].cpu(), idx)
     assert abs(float(lossv.v) - float(loss)) < 1e-5 * float(loss)
-    gr.outputs = (out, lossv)
-    out.g, lossv.g = dout.to(cuda), torch.tensor(0.7, device=cuda)
-    tape, gr.tape = gr.tape, []
-    while tape:
-        tape.pop()()
+    gr.backward_from([(out, dout.to(cuda)), (lossv, torch.tensor(0.7, device=cuda))])
     assert rel_err(zv.g, zr.grad) < 1e-5
     assert rel_err(gr.pgrads[id(cb.embedding.weight)][1], ref.embedding.weight.grad) < 1e-5
 

@@ -305,7 +305,17 @@ def test_training_graph_backward_vs_oracle(cuda):
     out = mine(sample=sample.to(cuda), dyn_sample=dyn.to(cuda), segment_len=fut, return_loss=True)
     assert out.sample.requires_grad and out.commit_loss.requires_grad
     loss = F.mse_loss(out.sample, dyn.to(cuda)) + F.mse_loss(out.ref_sample, sample.to(cuda)) + out.commit_loss + 0.5 * out.dyn_commit_loss
+    # train_tokenizer.py:706-707 (grad_layer_wrt_loss): gradient of ONE loss term w.r.t. the last decoder layer, graph retained.
+    # The sweep stops at the earliest op touching that layer -- the last op of the forward -- so it costs a handful of launches.
+    from ivideogpt_b200 import _lib
+    n0 = _lib.launch_count()
+    probe = torch.autograd.grad(F.mse_loss(out.sample, dyn.to(cuda)), mine.cond_decoder.conv_out.weight, retain_graph=True)[0]
+    probe_launches = _lib.launch_count() - n0
+    n0 = _lib.launch_count()
     loss.backward()
+    full_launches = _lib.launch_count() - n0
+    print(f"\n[train graph backward] launches: last-layer probe {probe_launches}, full backward {full_launches}")
+    assert probe_launches < 40 and full_launches > 500
     idx = {k: v.cpu() for k, v in mine._last_train_graph.vq_indices.items()}
     # float64 oracle (the product computes in TF32: compare against the exact gradient, not another rounded one)
     ref = ref.double()
@@ -334,5 +344,43 @@ def test_training_graph_backward_vs_oracle(cuda):
             print(f"   {e:9.5f}  {n}  |g_ref|={float(dict(ref.named_parameters())[n].grad.norm()):.3e}")
     assert not missing, missing[:8]
     assert worst[0][0] < 1e-2, worst[:8]          # measured: 5.6e-3 worst of 316 tensors
-    with pytest.raises(RuntimeError):          # the tape is consumed by the first backward
+    want2 = ref.forward_train(sample64, dyn64, fut, idx_ctx=idx["ctx"], idx_dyn=idx["dyn"])
+    probe_ref = torch.autograd.grad(F.mse_loss(want2[0], dyn64), ref.cond_decoder.conv_out.weight)[0]
+    assert rel_err(probe, probe_ref) < 5e-3
+
+
+@pytest.mark.gpu
+def test_tokenizer_optimizer_steps_reduce_the_loss(cuda):
+    """The reconstruction part of train_tokenizer.py's generator step, end to end on the sm_100a kernels: forward in train mode
+    (cross-attention dropouts active) -> loss.backward() -> clip_grad_norm_ -> FusedAdamW.step(), repeated: the loss falls,
+    every parameter that has a gradient moves, and the packed weight copies follow the updates (version counters)."""
+    import torch.nn.functional as F
+    from ivideogpt_b200.optim import FusedAdamW
+    from oracle.vq_model_ref import TINY_CFG
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_refglue.npz"))
+    _, mine = _pair(TINY_CFG, cuda, torch.float32)
+    mine.train()
+    px = torch.from_numpy(z["tiny_pixels"]).to(cuda)
+    fut = px.shape[1] - 2
+    sample, dyn = px[0, :2].contiguous(), px[0, 2:].contiguous()
+    opt = FusedAdamW(mine.parameters(), lr=2e-4, betas=(0.9, 0.99), weight_decay=0.0)
+    before = {n: p.detach().clone() for n, p in mine.named_parameters()}
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(6):
+        dec, ref_dec, commit, dyn_commit = mine(sample=sample, dyn_sample=dyn, return_dict=False, return_loss=True, segment_len=fut)
+        loss = F.mse_loss(dec, dyn) + F.mse_loss(ref_dec, sample) + 0.25 * (commit + dyn_commit)
         loss.backward()
+        with_grad = {n for n, p in mine.named_parameters() if p.grad is not None}
+        torch.nn.utils.clip_grad_norm_(mine.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+    print("\n[tokenizer training] losses:", [round(l, 4) for l in losses])
+    assert losses[-1] < 0.8 * losses[0], losses
+    moved = [n for n, p in mine.named_parameters() if not torch.equal(p.detach(), before[n])]
+    assert set(moved) == with_grad and len(with_grad) >= 316, sorted(with_grad ^ set(moved))[:8]
+    with torch.no_grad():                      # the evaluation forward sees the updated weights (no stale packed copies)
+        mine.eval()
+        dec_eval = mine(sample=sample, dyn_sample=dyn, segment_len=fut).sample
+    assert float(F.mse_loss(dec_eval, dyn)) < float(F.mse_loss(torch.zeros_like(dyn), dyn))
