@@ -374,7 +374,9 @@ class RefCompressiveVQModel(nn.Module):
     def forward_train(self, sample, dyn_sample, segment_len, idx_ctx=None, idx_dyn=None):
         """compressive_vq_model.py:332-369 (forward) + :290-330 (decode): the tokenizer training graph, differentiable.
         sample [B*t,3,H,W], dyn_sample [B*segment_len,3,H,W] -> (dec, ref_dec, commit_loss, dyn_commit_loss).
-        idx_ctx / idx_dyn: see RefVectorQuantizer.forward (test aid)."""
+        idx_ctx / idx_dyn: see RefVectorQuantizer.forward (test aid).
+        Call it in eval(): RefCrossAttention restates the reference block with its dropouts as identity, but the
+        nn.MultiheadAttention inside still carries dropout=0.1 and would randomise values and gradients in train()."""
         B = dyn_sample.shape[0] // segment_len
         h, feats = self.encoder(sample, return_features=True)               # :340
         h = self.quant_conv(h)                                              # :349
