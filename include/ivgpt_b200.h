@@ -333,6 +333,11 @@ int ivgpt_groupnorm_bwd(const float* x, const float* dy, const float* stats, con
                         float* dbeta, int param_accumulate, void* stream);
 int ivgpt_im2col3x3_t(const float* x, float* colT /* [k_rows][N*Ho*Wo] */, int N, int H, int W, int C, int stride, int k_rows,
                       void* stream);
+/* out[c][n*img_stride + (y+1)*Wp + (x+1) - shift] = x[n][y][x][c] (out pre-zeroed by the caller, row pitch ld_out; Wp >= W+2, a
+ * multiple of 4; shift in {-1,0,1}): the K-major operands of the 3x3 stride-1 weight gradient -- tap (a, b) reads the copy
+ * written with shift = b-1 at K offset (a-1)*Wp (TMA boxes must start on 16-byte boundaries of the innermost dimension). */
+int ivgpt_transpose_pad(const float* x, float* out, int N, int H, int W, int C, int Wp, int shift, long long img_stride,
+                        long long ld_out, void* stream);
 int ivgpt_zero_insert2x(const float* dy, float* out, int N, int h, int w, int C, void* stream);
 int ivgpt_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int ivgpt_silu(const float* x, const float* dy /* null: forward */, float* out, long long n, void* stream);

@@ -140,6 +140,7 @@ SIGNATURES = {
     "ivgpt_groupnorm_bwd_chunks": [_I, _I],
     "ivgpt_groupnorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P],
     "ivgpt_im2col3x3_t": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ivgpt_transpose_pad": [_P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "ivgpt_zero_insert2x": [_P, _P, _I, _I, _I, _I, _P],
     "ivgpt_upsample2x_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "ivgpt_silu": [_P, _P, _P, _L, _P],

@@ -224,6 +224,11 @@ int ivgpt_gemm(const ivgpt_gemm_desc* d, void* stream) {
   IVG_CHECK(d->batch % heads == 0, "gemm: batch %d not a multiple of heads %d", d->batch, heads);
   IVG_CHECK(heads == 1 || d->K % BK == 0 || (d->a_khead == 0 && d->b_khead == 0),
             "gemm: per-head K offsets need K %% %d == 0 (K=%d)", BK, d->K);
+  // a TMA box must start on a 16-byte boundary of the innermost (K) dimension: an odd element offset is not a wrong answer
+  // but an illegal instruction on sm_100a (measured), so it is refused here
+  IVG_CHECK((d->a_kbase * es) % 16 == 0 && (d->a_khead * es) % 16 == 0 && (d->b_kbase * es) % 16 == 0 && (d->b_khead * es) % 16 == 0,
+            "gemm: K offsets (a_kbase=%d a_khead=%d b_kbase=%d b_khead=%d) must be multiples of %d elements", d->a_kbase,
+            d->a_khead, d->b_kbase, d->b_khead, 16 / es);
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   GemmParams p;

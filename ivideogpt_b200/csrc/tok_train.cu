@@ -4,7 +4,8 @@
 // products) runs on the tcgen05 GEMM / conv kernel of gemm_tc.cu; this file holds what surrounds them, all fp32 NHWC:
 //   colsum            bias gradients                           out[c] (+)= sum_m x[m][c]
 //   groupnorm_bwd     GroupNorm (+ SiLU) backward              4 small kernels, fixed summation order
-//   im2col3x3_t       K-major operand of the weight gradient   colT[tap*C + c][pixel]  (transposed while gathering)
+//   transpose_pad     K-major operands of the 3x3 weight gradient: channel-major copies with a zero frame per image
+//   im2col3x3_t       the same for stride-2 / 3-channel convs   colT[tap*C + c][pixel]  (transposed while gathering)
 //   zero_insert2x     operand of the stride-2 conv dgrad       out[2i+1][2j+1] = dy[i][j], zeros elsewhere
 //   upsample2x_bwd    nearest-neighbour 2x backward            sum of the 4 children
 //   silu / silu_bwd, axpby, reduce_mid (sum over a middle axis), nchw <-> nhwc with channel padding, vq_bwd
@@ -175,6 +176,35 @@ __global__ void im2col_t_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// NHWC -> channel-major with a zero frame around every image:
+//   out[c][n*img_stride + (y+1)*Wp + (x+1) - shift] = x[n][y][x][c]        (Wp >= W+2, a multiple of 4)
+// (the caller zero-fills `out`; this kernel writes the interior only).  In this layout the input pixel that tap (a, b) of a
+// 3x3 / stride-1 / pad-1 conv pairs with output pixel q sits at q + (a-1)*Wp + (b-1): the weight gradient becomes nine
+// GEMMs over the pixel axis whose B operand is the same array read at a constant K offset, and image borders need no
+// masking because dY is zero on the frame.  A TMA box must start on a 16-byte boundary of the innermost dimension
+// (measured: an odd element offset is an illegal instruction), so the row term (a-1)*Wp is a box coordinate and the
+// column term b-1 is baked into three copies written with shift = b-1.  Replaces the 9x im2col copy by 3x + 1x.
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_pad_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int C, int Wp, int shift,
+                                     long long img_stride, long long ld_out, int xtiles) {
+  __shared__ float tile[32][33];
+  const int xt = blockIdx.x % xtiles;
+  const long long ny = blockIdx.x / xtiles;       // n*H + y
+  const int y = (int)(ny % H);
+  const long long n = ny / H;
+  const int x0 = xt * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int xx = x0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (xx < W && c < C) ? x[((n * H + y) * W + xx) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, xx = x0 + threadIdx.x;
+    if (c < C && xx < W) out[(long long)c * ld_out + n * img_stride + (long long)(y + 1) * Wp + xx + 1 - shift] = tile[threadIdx.x][j];
+  }
+}
+
 __global__ void zero_insert2x_kernel(const float* __restrict__ dy, float* __restrict__ out, int h, int w, int C, long long total) {
   // out [N, 2h, 2w, C]
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -313,6 +343,21 @@ int ivgpt_im2col3x3_t(const float* x, float* colT, int N, int H, int W, int C, i
   IVG_CHECK((P + 31) / 32 < 2147483647LL, "im2col3x3_t: too many pixels");
   dim3 grid((unsigned)((P + 31) / 32), (k_rows + 31) / 32);
   im2col_t_kernel<<<grid, dim3(32, 8), 0, S(stream)>>>(x, colT, H, W, C, stride, Ho, Wo, P, k_rows);
+  count_launch();
+  IVG_LAUNCH_CHECK();
+  return 0;
+}
+
+int ivgpt_transpose_pad(const float* x, float* out, int N, int H, int W, int C, int Wp, int shift, long long img_stride,
+                        long long ld_out, void* stream) {
+  IVG_CHECK(Wp >= W + 2 && Wp % 4 == 0 && shift >= -1 && shift <= 1, "transpose_pad: Wp=%d (W=%d) shift=%d", Wp, W, shift);
+  IVG_CHECK(img_stride >= (long long)(H + 2) * Wp + 4 && ld_out >= N * img_stride, "transpose_pad: strides too small");
+  if (N <= 0) return 0;
+  const int xtiles = (W + 31) / 32;
+  const long long gx = (long long)N * H * xtiles;
+  IVG_CHECK(gx < 2147483647LL, "transpose_pad: too many rows");
+  transpose_pad_kernel<<<dim3((unsigned)gx, (C + 31) / 32), dim3(32, 8), 0, S(stream)>>>(x, out, H, W, C, Wp, shift, img_stride,
+                                                                                          ld_out, xtiles);
   count_launch();
   IVG_LAUNCH_CHECK();
   return 0;

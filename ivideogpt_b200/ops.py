@@ -633,6 +633,26 @@ def im2col3x3_t(x: torch.Tensor, stride: int = 1, k_rows: Optional[int] = None) 
     return colT
 
 
+def transpose_pad(x: torch.Tensor, copies: int = 1) -> torch.Tensor:
+    """[N,H,W,C] fp32 -> [copies*C, N*img_stride]: channel-major with a zero frame around every image, row pitch Wp = W+2
+    rounded up to 4, img_stride = (H+2)*Wp + 4 rounded up to 64.  copies=1: out[c, n*img_stride + (y+1)*Wp + (x+1)];
+    copies=3: rows [b*C, (b+1)*C) hold the same data shifted by b-1 columns (out index minus (b-1))."""
+    _cuda(x)
+    _f32c(x)
+    assert copies in (1, 3)
+    N, H, W, Cc = x.shape
+    Wp = (W + 2 + 3) // 4 * 4
+    img_stride = ((H + 2) * Wp + 4 + 63) // 64 * 64
+    ld = N * img_stride
+    out = torch.zeros(copies * Cc, ld, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    for b in range(copies):
+        shift = b - 1 if copies == 3 else 0
+        _lib.check(lib.ivgpt_transpose_pad(x.data_ptr(), out.data_ptr() + b * Cc * ld * 4, N, H, W, Cc, Wp, shift, img_stride,
+                                           ld, _stream()), "transpose_pad")
+    return out
+
+
 def zero_insert2x(dy: torch.Tensor) -> torch.Tensor:
     """[N,h,w,C] -> [N,2h,2w,C] with out[2i+1, 2j+1] = dy[i, j]: the operand of the stride-2 conv's data gradient."""
     _cuda(dy)

@@ -17,6 +17,7 @@ Nothing here falls back to torch arithmetic: torch allocates, views and zero-fil
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -49,6 +50,9 @@ class TokenizerTrainGraph:
         self.idx_override: Dict[str, torch.Tensor] = {}
         # train mode: the cross-attention dropouts of conditional_vae.py:24-25,52 are active (counter-based masks; the seed
         # comes from torch's CPU generator, so torch.manual_seed() fixes a run)
+        # 3x3 weight gradients from padded channel-major copies (see _wgrad_conv3); IVGPT_TOK_WGRAD_IM2COL=1 selects the
+        # explicit transposed im2col instead (9x the activation; measured 35 % of the step's kernel time)
+        self.wgrad_no_im2col = os.environ.get("IVGPT_TOK_WGRAD_IM2COL", "0") != "1"
         self.training = bool(model.training) if model is not None else False
         self.base_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.training else 0
         self._drop_sites = 0
@@ -119,6 +123,39 @@ class TokenizerTrainGraph:
             out=part.data_ptr(), ldo=N, out_bstride=M * N, out_dtype=F32))
         return ops.reduce_mid(part, 1, ks).view(M, N)
 
+    @staticmethod
+    def _wgrad_conv3(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """Weight gradient [Cout, 9*Cin] of a 3x3 / stride-1 / pad-1 conv from dY [N,H,W,Cout] and X [N,H,W,Cin] WITHOUT an
+        im2col copy: both tensors are transposed into channel-major arrays with a zero frame around every image
+        (ops.transpose_pad, row pitch Wp); tap (a, b) is then the GEMM dY^T x X^T over the pixel axis with X^T read at the
+        constant K offset (a-1)*Wp + (b-1), and the frame of zeros in dY^T makes the image borders come out right.  The row
+        part of the offset is a TMA box coordinate (out-of-range columns read as zeros); the column part cannot be -- a box
+        must start on a 16-byte boundary of the innermost dimension -- so X^T is written three times, shifted by b-1.
+        Three launches (one per kernel row a; the column taps ride the descriptor's head index: B rows h*Cin of the stacked
+        copies, output columns h*Cin), the pixel axis cut into whole-image slices as the batch so that every launch has
+        enough tiles, partials added in fixed order."""
+        N, H, W, Co = dy.shape
+        Ci = x.shape[-1]
+        dyT, xT3 = ops.transpose_pad(dy), ops.transpose_pad(x, copies=3)
+        Pp = dyT.shape[1]
+        simg = Pp // N
+        Wp = (W + 2 + 3) // 4 * 4
+        tiles = ((Co + 127) // 128) * ((Ci + 127) // 128) * 3
+        ks = 1
+        for d in range(1, N + 1):                       # largest divisor of N that keeps the launch within ~2 waves
+            if N % d == 0 and d * tiles <= 296:
+                ks = d
+        Kc = (N // ks) * simg
+        part = torch.empty(ks, Co, 9 * Ci, dtype=torch.float32, device=dy.device)
+        for a in range(3):
+            ops.gemm_raw(ops.gemm_desc(
+                dtype=F32, a=dyT.data_ptr(), lda=Pp, a_bstride=Kc, a_rows=Co, a_cols=Kc, a_batches=ks,
+                b=xT3.data_ptr(), ldb=Pp, b_bstride=Kc, b_rows=3 * Ci, b_cols=Kc, b_batches=ks,
+                M=Co, N=Ci, K=Kc, batch=ks * 3, heads=3, a_bsel=1, a_bdiv=1, b_bsel=1, b_bdiv=1, o_bsel=1,
+                b_kbase=(a - 1) * Wp, b_nhead=Ci, o_nhead=Ci,
+                out=part.data_ptr() + a * 3 * Ci * 4, ldo=9 * Ci, out_bstride=Co * 9 * Ci, out_dtype=F32))
+        return part[0] if ks == 1 else ops.reduce_mid(part, 1, ks).view(Co, 9 * Ci)
+
     def conv(self, x: Var, conv, stride: int = 1, shortcut=None, x2: Optional[Var] = None,
              residual: Optional[Var] = None) -> Var:
         w, b = self.pw.conv3(conv, torch.float32, shortcut=shortcut)
@@ -140,9 +177,10 @@ class TokenizerTrainGraph:
                 if shortcut is not None:
                     self._pacc(shortcut.bias, db.clone())        # two parameters must not share one gradient tensor
             need_sw = shortcut is not None and shortcut.weight.requires_grad
-            dyT = ops.transpose(dy2) if (conv.weight.requires_grad or need_sw) else None      # [Co, P]
+            fast = stride == 1 and self.wgrad_no_im2col
+            dyT = ops.transpose(dy2) if ((conv.weight.requires_grad and not fast) or need_sw) else None      # [Co, P]
             if conv.weight.requires_grad:
-                dWp = self._wgrad(dyT, ops.im2col3x3_t(x.v, stride))                            # [Co, 9*Ci]
+                dWp = self._wgrad_conv3(dy, x.v) if fast else self._wgrad(dyT, ops.im2col3x3_t(x.v, stride))   # [Co, 9*Ci]
                 self._pacc(conv.weight, dWp.view(Co, 3, 3, Ci).permute(0, 3, 1, 2))
             if shortcut is not None:
                 C2 = x2.v.shape[-1]
@@ -400,7 +438,7 @@ class TokenizerTrainGraph:
                 self._pacc(conv.bias, ops.colsum(dy2)[:3])
             if conv.weight.requires_grad:
                 y = ops.groupnorm_apply(x.v, stats, gamma, beta, True)                   # recomputed, not kept from the forward
-                dWp = self._wgrad(ops.transpose(dy2), ops.im2col3x3_t(y, 1))             # [32, 9*C]
+                dWp = self._wgrad_conv3(dy32, y) if self.wgrad_no_im2col else self._wgrad(ops.transpose(dy2), ops.im2col3x3_t(y, 1))   # [32, 9*C]
                 del y
                 self._pacc(conv.weight, dWp[:3].reshape(3, 3, 3, Cc).permute(0, 3, 1, 2))
             dyn = ops.conv3x3(dy32, self.pw.conv3_dgrad(conv, cout_pad=32), None)        # gradient of the normalised input

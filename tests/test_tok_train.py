@@ -344,3 +344,38 @@ def test_residual_dropout_site(cuda):
     assert rel_err(u.v, zt + a * mask) < FP32
     _run(gr, u, du.to(cuda))
     assert rel_err(av.g, du * mask) < FP32 and torch.equal(zv.g.cpu(), du)
+
+
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(4, 32, 32, 64, 128), (6, 16, 16, 128, 64), (2, 64, 64, 32, 32)])
+def test_wgrad_conv3_without_im2col(cuda, N, H, W, Ci, Co):
+    """Weight gradient from the padded channel-major copies (nine K-offset GEMMs) == the explicit-im2col route == float64."""
+    from ivideogpt_b200 import ops
+    from ivideogpt_b200.vq_model.train_plan import TokenizerTrainGraph
+    g = torch.Generator().manual_seed(12)
+    x, dy = torch.randn(N, H, W, Ci, generator=g), torch.randn(N, H, W, Co, generator=g)
+    cols = F.unfold(x.permute(0, 3, 1, 2).double(), 3, padding=1)                                # [N, Ci*9, HW]
+    want = torch.einsum("npo,nkp->ok", dy.double().view(N, H * W, Co), cols.view(N, Ci * 9, H * W))
+    want = want.view(Co, Ci, 9).permute(0, 2, 1).reshape(Co, 9 * Ci)                              # (tap, ci) column order
+    got = TokenizerTrainGraph._wgrad_conv3(dy.to(cuda), x.to(cuda))
+    assert rel_err(got, want) < TF32
+    old = TokenizerTrainGraph._wgrad(ops.transpose(dy.view(-1, Co).to(cuda)), ops.im2col3x3_t(x.to(cuda), 1))
+    assert rel_err(got, old) < 1e-4
+
+
+def test_transpose_pad_layout(cuda):
+    from ivideogpt_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    N, H, W, Cc = 3, 16, 16, 40
+    x = torch.randn(N, H, W, Cc, generator=g)
+    Wp = 20
+    pad = F.pad(x.permute(3, 0, 1, 2), (1, Wp - W - 1, 1, 1))                                     # [C, N, H+2, Wp]
+    out = ops.transpose_pad(x.to(cuda)).cpu()
+    simg = out.shape[1] // N
+    assert simg % 64 == 0 and simg >= (H + 2) * Wp + 4
+    want = torch.zeros(Cc, N, simg)
+    want[:, :, : (H + 2) * Wp] = pad.reshape(Cc, N, -1)
+    assert torch.equal(out, want.view(Cc, -1))
+    out3 = ops.transpose_pad(x.to(cuda), copies=3).cpu().view(3, Cc, N * simg)
+    flat = want.view(Cc, -1)
+    for b in range(3):                      # copy b read at q gives the unshifted array at q + (b - 1)
+        assert torch.equal(out3[b], torch.roll(flat, -(b - 1), 1))
