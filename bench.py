@@ -40,7 +40,7 @@ WORKLOADS = {
     "train-tiny": (None, None, 64, 2),
     # tokenizer training step (row f3; the reconstruction + commitment part of train_tokenizer.py's generator step):
     # CompressiveVQModel.forward (train mode) -> MSE of both reconstructions + commit losses -> backward -> fused AdamW
-    "train-tokenizer64": ("ctx_vae64", "llama_138m", 64, 8),
+    "train-tokenizer64": ("ctx_vae64", "llama_138m", 64, 16),
     "train-tokenizer-tiny": (None, None, 64, 1),
 }
 
