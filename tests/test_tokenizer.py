@@ -384,3 +384,29 @@ def test_tokenizer_optimizer_steps_reduce_the_loss(cuda):
         mine.eval()
         dec_eval = mine(sample=sample, dyn_sample=dyn, segment_len=fut).sample
     assert float(F.mse_loss(dec_eval, dyn)) < float(F.mse_loss(torch.zeros_like(dyn), dyn))
+
+
+def test_packed_weight_cache_drops_stale_versions():
+    """Training bumps every parameter version every step; the kernel-layout cache must follow the update (new copy) and must
+    not keep the copies of older versions (it would grow by a full set of packed weights per optimizer step)."""
+    import torch.nn as nn
+    from ivideogpt_b200.vq_model.plan import PackedWeights
+    pw = PackedWeights()
+    conv, sc, lin = nn.Conv2d(32, 64, 3, padding=1), nn.Conv2d(32, 64, 1), nn.Linear(64, 64)
+    sizes = []
+    for step in range(4):
+        w, b = pw.conv3(conv, torch.float32, shortcut=sc)
+        wd = pw.conv3_dgrad(conv)
+        wl, bl = pw.linear(lin.weight, lin.bias, torch.float32)
+        wt = pw.linear_t(lin.weight)
+        assert w.shape == (64, 9 * 32 + 32) and wd.shape == (32, 9 * 64) and wt.shape == (64, 64)
+        # the packed copies reflect the CURRENT values (tf32-rounded)
+        assert torch.allclose(w[:, : 9 * 32], conv.weight.detach().permute(0, 2, 3, 1).reshape(64, -1), rtol=1e-3, atol=1e-6)
+        assert torch.allclose(wd.view(32, 3, 3, 64)[:, 0, 0], conv.weight.detach()[:, :, 2, 2].t(), rtol=1e-3, atol=1e-6)
+        assert torch.allclose(wt, lin.weight.detach().t(), rtol=1e-3, atol=1e-6)
+        assert pw.conv3(conv, torch.float32, shortcut=sc)[0] is w          # unchanged parameters: cached
+        sizes.append(len(pw._cache))
+        with torch.no_grad():                                               # an optimizer step: in-place update, version bump
+            for p in list(conv.parameters()) + list(sc.parameters()) + list(lin.parameters()):
+                p.add_(0.01)
+    assert len(set(sizes)) == 1, sizes
