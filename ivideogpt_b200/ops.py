@@ -460,7 +460,9 @@ def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad_to: int =
         lead, bs_in = (), 0
     Rp = (R + pad_to - 1) // pad_to * pad_to
     if out is None:
-        out = torch.zeros(*lead, Cc, Rp, dtype=x.dtype, device=x.device)
+        # the pad columns [R, Rp) are read by the consumer GEMM as part of its K range and must be zero; with no pad columns
+        # the zero fill would be a wasted pass (5 % of the train64 step's kernel time in profiles/r02/launches_train64.txt)
+        out = (torch.empty if Rp == R else torch.zeros)(*lead, Cc, Rp, dtype=x.dtype, device=x.device)
     _lib.check(_lib.load().ivgpt_transpose(_dt(x), x.data_ptr(), out.data_ptr(), batch, R, Cc, x.stride(-2), Rp, bs_in,
                                            Cc * Rp, _stream()), "transpose")
     return out[..., :R]

@@ -46,7 +46,9 @@ class LlamaTrainEngine:
     def _t2(self, x: torch.Tensor) -> torch.Tensor:
         """[R, C] -> [C, R] (row pitch padded to 8), returned as the [C, :R] view."""
         R, Cc = x.shape
-        out = torch.zeros(Cc, _r8(R), dtype=x.dtype, device=x.device)
+        # pad columns (if any) are outside the consumer's tensor-map extent ([:, :R] is what is passed on): TMA never reads
+        # them, so nothing needs zero-filling (the fills were 5 % of the step's kernel time, profiles/r02/launches_train64.txt)
+        out = torch.empty(Cc, _r8(R), dtype=x.dtype, device=x.device)
         ops.transpose_raw(x, 0, out, 1, R, Cc, x.stride(0), out.stride(0), 0, 0)
         return out[:, :R]
 
@@ -174,11 +176,11 @@ class LlamaTrainEngine:
             dS = torch.empty(B * H, L, Lp, dtype=dt, device=dev)
             ops.softmax_bwd(P, dP, dS, B * H * L, L, L, Lp, True, 0.125)
             del dP
-            Pt = torch.zeros(B * H, L, Lp, dtype=dt, device=dev)
+            Pt = torch.empty(B * H, L, Lp, dtype=dt, device=dev)       # read through maps of extent L: the pad column is never touched
             Pd = ops.dropout(P, p_drop, layer_seed(li)) if p_drop > 0.0 else P      # dV = P'^T . dO
             ops.transpose_raw(Pd, 0, Pt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
             del Pd
-            d_aoT = torch.zeros(B, h, Lp, dtype=dt, device=dev)
+            d_aoT = torch.empty(B, h, Lp, dtype=dt, device=dev)       # read through maps of extent L: the pad column is never touched
             ops.transpose_raw(d_ao, 0, d_aoT, B, L, h, h, Lp, L * h, h * Lp)
             dV = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
             ops.gemm_raw(ops.gemm_desc(      # dV[b,h] = P^T . dO_h
@@ -187,7 +189,7 @@ class LlamaTrainEngine:
                 M=L, N=64, K=L, batch=B * H, heads=H, a_bsel=2, b_bsel=1, b_bdiv=1, o_bsel=2, b_nhead=64,
                 out=dV.data_ptr(), ldo=64, out_bstride=L * 64, out_dtype=F32))
             del Pt
-            kT = torch.zeros(B * H, 64, Lp, dtype=dt, device=dev)
+            kT = torch.empty(B * H, 64, Lp, dtype=dt, device=dev)       # read through maps of extent L: the pad column is never touched
             ops.transpose_raw(s["k"], 0, kT, B * H, L, 64, 64, Lp, Lp * 64, 64 * Lp)
             dQ = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
             ops.gemm_raw(ops.gemm_desc(      # dQ'[b,h] = dS . K'
@@ -195,9 +197,9 @@ class LlamaTrainEngine:
                 b=kT.data_ptr(), ldb=Lp, b_bstride=64 * Lp, b_rows=64, b_cols=L, b_batches=B * H,
                 M=L, N=64, K=L, batch=B * H, heads=1, a_bsel=2, b_bsel=2, o_bsel=2,
                 out=dQ.data_ptr(), ldo=64, out_bstride=L * 64, out_dtype=F32))
-            dSt = torch.zeros(B * H, L, Lp, dtype=dt, device=dev)
+            dSt = torch.empty(B * H, L, Lp, dtype=dt, device=dev)       # read through maps of extent L: the pad column is never touched
             ops.transpose_raw(dS, 0, dSt, B * H, L, L, Lp, Lp, L * Lp, L * Lp)
-            qT = torch.zeros(B * H, 64, Lp, dtype=dt, device=dev)
+            qT = torch.empty(B * H, 64, Lp, dtype=dt, device=dev)       # read through maps of extent L: the pad column is never touched
             ops.transpose_raw(s["q"], 0, qT, B * H, L, 64, 64, Lp, L * 64, 64 * Lp)
             dK = torch.empty(B, H, L, 64, dtype=torch.float32, device=dev)
             ops.gemm_raw(ops.gemm_desc(      # dK'[b,h] = dS^T . Q'
