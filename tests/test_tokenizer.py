@@ -410,3 +410,18 @@ def test_packed_weight_cache_drops_stale_versions():
             for p in list(conv.parameters()) + list(sc.parameters()) + list(lin.parameters()):
                 p.add_(0.01)
     assert len(set(sizes)) == 1, sizes
+
+
+def test_training_forward_refuses_cpu_and_bf16():
+    """No fallback: the training graph on CPU tensors raises (there is no torch / CPU path behind it), and a bf16 compute dtype is
+    refused for training instead of being silently promoted."""
+    from oracle.vq_model_ref import TINY_CFG
+    _, mine = _pair(TINY_CFG)
+    mine.train()
+    s, d = torch.rand(2, 3, 64, 64), torch.rand(2, 3, 64, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mine(sample=s, dyn_sample=d, segment_len=2, return_loss=True)
+    from ivideogpt_b200.vq_model.plan import TokenizerPlan
+    from ivideogpt_b200.vq_model.train_plan import TokenizerTrainGraph
+    with pytest.raises(NotImplementedError, match="fp32"):
+        TokenizerTrainGraph(mine, TokenizerPlan(32, torch.bfloat16))
