@@ -179,6 +179,66 @@ def cpu_rollout(ref_tok, ref_llm, clips, ctx, seg, greedy=True):
     return time.perf_counter() - t0, frames
 
 
+def cpu_tokenizer_train_step(ref_tok, clips, ctx, seg):
+    """The reconstruction + commitment part of train_tokenizer.py's generator step on host cores: oracle forward_train + torch
+    autograd + torch AdamW.  Returns seconds for one step over `clips`."""
+    import torch
+    import torch.nn.functional as F
+    ref_tok = ref_tok.train()
+    for m in ref_tok.modules():                    # the oracle restates the eval-mode block: keep its dropouts off
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    opt = torch.optim.AdamW(ref_tok.parameters(), lr=1e-4, betas=(0.5, 0.9), weight_decay=0.0)
+    B, T = clips.shape[:2]
+    s = clips[:, :ctx].reshape(B * ctx, *clips.shape[2:]).contiguous()
+    t = clips[:, ctx:].reshape(B * (T - ctx), *clips.shape[2:]).contiguous()
+    t0 = time.perf_counter()
+    out = ref_tok.forward_train(s, t, seg - ctx)
+    (F.mse_loss(out[0], t) + F.mse_loss(out[1], s) + out[2] + out[3]).backward()
+    opt.step()
+    return time.perf_counter() - t0
+
+
+def cpu_llm_train_step(ref_tok, ref_llm, clips, ctx):
+    """One train_gpt.py step (:776-803) on host cores: oracle tokenizer (frozen) -> HF Llama forward(labels) + backward -> AdamW."""
+    import torch
+    ref_llm = ref_llm.train()
+    opt = torch.optim.AdamW(ref_llm.parameters(), lr=1e-4, weight_decay=0.01)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        tokens, labels = ref_tok.tokenize(clips, ctx)
+    ref_llm(input_ids=tokens, labels=labels).loss.backward()
+    opt.step()
+    return time.perf_counter() - t0
+
+
+def run_reference_train(args):
+    """--impl reference for the training workloads: the same step on the host cores, bounded to --cpu-clips clips."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    _, _, res, _ = WORKLOADS[args.workload]
+    _, ref_tok, ref_llm = build_oracle_models("tiny" if args.workload.endswith("tiny") else "cfg64")
+    ctx, seg = args.context_length, args.segment_length
+    clips = synthetic_clips(args.cpu_clips, seg, res)
+    tokenizer = args.workload.startswith("train-tokenizer")
+    step = (lambda: cpu_tokenizer_train_step(ref_tok, clips, ctx, seg)) if tokenizer else (lambda: cpu_llm_train_step(ref_tok, ref_llm, clips, ctx))
+    for _ in range(max(args.warmup, 0) and 1):
+        step()
+    t = statistics.median([step() for _ in range(max(args.steps, 1))])
+    v = args.cpu_clips / t
+    what = "oracle forward_train + torch autograd + AdamW" if tokenizer else "oracle tokenizer + HF Llama forward/backward + AdamW"
+    sample = f"{args.cpu_clips} clip(s) {res}x{res}x{seg}, fp32, {cores} threads ({what})"
+    emit({"impl": "reference", "metric": "tokenizer_train_clips_per_sec" if tokenizer else "train_clips_per_sec", "value": v,
+          "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"{args.workload}: {sample}", "per_gpu_batch": args.cpu_clips},
+          "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+          "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -542,7 +602,7 @@ def train_record(args, D, workload, steps, warmup):
     _, _, res, default_b = WORKLOADS[workload]
     B = args.batch or default_b
     ctx, seg = args.context_length, args.segment_length
-    tok, llm, _, _ = build_b200_models(base, dev, torch.bfloat16)
+    tok, llm, ref_tok, ref_llm = build_b200_models(base, dev, torch.bfloat16)
     tok.set_compute_dtype(torch.float32)          # train_gpt.py runs the frozen tokenizer in fp32 (TF32 convs)
     llm.train()
     p_drop = float(os.environ.get("IVGPT_TRAIN_ATTN_DROPOUT", "0.0"))    # 0.1 = as scripted (oxe-64-act-free.sh:31); 0 = parity config
@@ -625,6 +685,15 @@ def train_record(args, D, workload, steps, warmup):
                          "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": f"bf16_tflops_sustained ({src})",
                          "traffic": None, "note": "model-FLOPs utilisation (MFU) of the transformer fwd+bwd only, per GPU"},
         }
+        # the same step on the host cores (bounded: 1 clip): oracle tokenizer + HF Llama forward/backward + torch AdamW
+        try:
+            cores = host_threads()
+            torch.set_num_threads(cores)
+            t_cpu = cpu_llm_train_step(ref_tok, ref_llm, synthetic_clips(1, seg, res), ctx)
+            rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
+                                   "sample": f"1 clip {res}x{res}x{seg}, oracle tokenizer + HF Llama fwd/bwd + AdamW, fp32, {t_cpu:.1f} s"}
+        except Exception as e:     # noqa: BLE001
+            rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
     del tok, llm, opt, params
     torch.cuda.empty_cache()
     return rec
@@ -702,18 +771,7 @@ def tok_train_record(args, D, workload, steps, warmup):
         try:
             cores = host_threads()
             torch.set_num_threads(cores)
-            ref_tok = ref_tok.train()
-            for m in ref_tok.modules():                    # the oracle restates the eval-mode block: keep its dropouts off
-                if isinstance(m, torch.nn.MultiheadAttention):
-                    m.dropout = 0.0
-            o = torch.optim.AdamW(ref_tok.parameters(), lr=1e-4, betas=(0.5, 0.9), weight_decay=0.0)
-            c1 = synthetic_clips(1, seg, res)
-            s1, t1 = c1[0, :ctx].contiguous(), c1[0, ctx:].contiguous()
-            t0 = time.perf_counter()
-            out = ref_tok.forward_train(s1, t1, seg - ctx)
-            (F.mse_loss(out[0], t1) + F.mse_loss(out[1], s1) + out[2] + out[3]).backward()
-            o.step()
-            t_cpu = time.perf_counter() - t0
+            t_cpu = cpu_tokenizer_train_step(ref_tok, synthetic_clips(1, seg, res), ctx, seg)
             rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
                                    "sample": f"1 clip {res}x{res}x{seg}, oracle forward_train + torch autograd + AdamW, fp32, {t_cpu:.1f} s"}
         except Exception as e:     # noqa: BLE001
@@ -757,7 +815,7 @@ if __name__ == "__main__":
     a = parse()
     _quiet_stdout()
     if a.impl == "reference":
-        run_reference(a)
+        (run_reference_train if a.workload.startswith("train") else run_reference)(a)
     elif a.workload.startswith("train"):
         run_train(a)
     else:

@@ -54,3 +54,19 @@ def test_launch_list_summariser(tmp_path):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarise_launches.py"), str(csv)],
                          capture_output=True, text=True, check=True).stdout
     assert "launches 3" in out and "60.00%" in out and "2 x" in out
+
+
+@pytest.mark.parametrize("workload,metric", [("train-tokenizer-tiny", "tokenizer_train_clips_per_sec"), ("train-tiny", "train_clips_per_sec")])
+def test_reference_arm_of_the_training_workloads(workload, metric):
+    """`bench.py --impl reference --workload train*`: the same training step on the host cores (oracle tokenizer / HF Llama +
+    torch autograd + torch AdamW), ONE JSON line on stdout with the reference-arm keys of the contract."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1",
+                          "--warmup", "0", "--cpu-clips", "1", "--segment-length", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["metric"] == metric and rec["unit"] == "clips/s" and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["value"] == rec["value"]
+    assert rec["e2e"] == {"value": rec["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
