@@ -591,7 +591,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     if out is None:
         assert not accumulate
         out = torch.empty(Cc, dtype=torch.float32, device=x.device)
-    nb = 592
+    nb = 256          # row slabs of the first stage; the second stage adds them serially per column (592 was 37 us per call)
     part = torch.empty(nb * Cc, dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().ivgpt_colsum(x.data_ptr(), M, Cc, x.stride(0), part.data_ptr(), nb, out.data_ptr(),
                                         int(accumulate), _stream()), "colsum")
