@@ -470,10 +470,10 @@ def run_b200(args):
             r = leg(key, lambda wl=wl, dt=dt: short(wl, dt))
             if out is not None:
                 out[key] = r
-        r = leg("train64", lambda: train_record(args, D, "train64", 3, 3))
+        r = leg("train64", lambda: train_record(args, D, "train64", 3, 3, cpu_arm=False))
         if out is not None:
             out["train64"] = r
-        r = leg("train_tokenizer64", lambda: tok_train_record(args, D, "train-tokenizer64", 3, 3))
+        r = leg("train_tokenizer64", lambda: tok_train_record(args, D, "train-tokenizer64", 3, 3, cpu_arm=False))
         if out is not None:
             out["train_tokenizer64"] = r
     if out is not None and ref_tok is not None:
@@ -496,6 +496,20 @@ def run_b200(args):
                 return {"value": 8 * 2 / t8, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"8 clips {res}x{res}x{ctx + 2} (2 predicted frames each), greedy, fp32, {t8:.1f} s"}
             out["cpu_baseline_b8"] = leg("cpu_baseline_b8", cpu_b8)
+            # the training legs' own CPU arms (1 clip each), last: they update the oracle models' weights
+            def cpu_train(kind):
+                c1 = synthetic_clips(1, seg, res)
+                if kind == "train64":
+                    t1 = cpu_llm_train_step(ref_tok, ref_llm, c1, ctx)
+                    what = "oracle tokenizer + HF Llama fwd/bwd + AdamW"
+                else:
+                    t1 = cpu_tokenizer_train_step(ref_tok, c1, ctx, seg)
+                    what = "oracle forward_train + torch autograd + AdamW"
+                return {"value": 1.0 / t1, "unit": "clips/s", "cores": cores, "kind": "port",
+                        "sample": f"1 clip {res}x{res}x{seg}, {what}, fp32, {t1:.1f} s"}
+            for kind in ("train64", "train_tokenizer64"):
+                if isinstance(out.get(kind), dict) and "error" not in out[kind]:
+                    out[kind]["cpu_baseline"] = leg(kind + ".cpu_baseline", lambda kind=kind: cpu_train(kind))
     if out is not None:
         emit(out)
     D.close()
@@ -590,7 +604,7 @@ def build_roofline(args, dtype_name, nsteps, prof, total_ms, B, ctx, max_new, ll
     return roofline
 
 
-def train_record(args, D, workload, steps, warmup):
+def train_record(args, D, workload, steps, warmup, cpu_arm=True):
     """One training step of reference train_gpt.py:766-804 per bench step; metric = clips/s.
     All ranks call it together; rank 0 returns the record."""
     import torch
@@ -686,20 +700,22 @@ def train_record(args, D, workload, steps, warmup):
                          "traffic": None, "note": "model-FLOPs utilisation (MFU) of the transformer fwd+bwd only, per GPU"},
         }
         # the same step on the host cores (bounded: 1 clip): oracle tokenizer + HF Llama forward/backward + torch AdamW
-        try:
-            cores = host_threads()
-            torch.set_num_threads(cores)
-            t_cpu = cpu_llm_train_step(ref_tok, ref_llm, synthetic_clips(1, seg, res), ctx)
-            rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
-                                   "sample": f"1 clip {res}x{res}x{seg}, oracle tokenizer + HF Llama fwd/bwd + AdamW, fp32, {t_cpu:.1f} s"}
-        except Exception as e:     # noqa: BLE001
-            rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
+        # (nested legs of a default run get it at the very end of the run instead: CPU work between GPU legs perturbs them)
+        if cpu_arm:
+            try:
+                cores = host_threads()
+                torch.set_num_threads(cores)
+                t_cpu = cpu_llm_train_step(ref_tok, ref_llm, synthetic_clips(1, seg, res), ctx)
+                rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
+                                       "sample": f"1 clip {res}x{res}x{seg}, oracle tokenizer + HF Llama fwd/bwd + AdamW, fp32, {t_cpu:.1f} s"}
+            except Exception as e:     # noqa: BLE001
+                rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
     del tok, llm, opt, params
     torch.cuda.empty_cache()
     return rec
 
 
-def tok_train_record(args, D, workload, steps, warmup):
+def tok_train_record(args, D, workload, steps, warmup, cpu_arm=True):
     """One tokenizer training step per bench step (reference train_tokenizer.py:620-740 without the LPIPS / GAN terms, which are
     out of scope): forward in train mode, loss = MSE(dec, target) + MSE(ref_dec, context) + commit + dyn_commit, backward on
     the sm_100a kernels, gradient all-reduce (N > 1), clip_grad_norm_, fused AdamW.  metric = clips/s."""
@@ -768,14 +784,15 @@ def tok_train_record(args, D, workload, steps, warmup):
             "peak_memory_gib": mem, "clocks": clocks,
         }
         # the same step on the host cores: the oracle's differentiable forward_train + torch autograd + torch AdamW, 1 clip
-        try:
-            cores = host_threads()
-            torch.set_num_threads(cores)
-            t_cpu = cpu_tokenizer_train_step(ref_tok, synthetic_clips(1, seg, res), ctx, seg)
-            rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
-                                   "sample": f"1 clip {res}x{res}x{seg}, oracle forward_train + torch autograd + AdamW, fp32, {t_cpu:.1f} s"}
-        except Exception as e:     # noqa: BLE001
-            rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
+        if cpu_arm:
+            try:
+                cores = host_threads()
+                torch.set_num_threads(cores)
+                t_cpu = cpu_tokenizer_train_step(ref_tok, synthetic_clips(1, seg, res), ctx, seg)
+                rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "clips/s", "cores": cores, "kind": "port",
+                                       "sample": f"1 clip {res}x{res}x{seg}, oracle forward_train + torch autograd + AdamW, fp32, {t_cpu:.1f} s"}
+            except Exception as e:     # noqa: BLE001
+                rec["cpu_baseline"] = {"value": None, "unit": "clips/s", "kind": "port", "sample": f"failed: {repr(e)[:200]}"}
     del tok, opt, params
     torch.cuda.empty_cache()
     return rec
