@@ -425,3 +425,36 @@ def test_training_forward_refuses_cpu_and_bf16():
     from ivideogpt_b200.vq_model.train_plan import TokenizerTrainGraph
     with pytest.raises(NotImplementedError, match="fp32"):
         TokenizerTrainGraph(mine, TokenizerPlan(32, torch.bfloat16))
+
+
+def test_wgrad_index_algebra_of_the_zero_framed_layout():
+    """The algebra behind TokenizerTrainGraph._wgrad_conv3, on the CPU in float64: with dY and X written channel-major with a zero
+    frame around every image (row pitch Wp), the 3x3 / stride-1 / pad-1 weight gradient of tap (a, b) is the plain product
+    dY^T . shift(X^T, (a-1)*Wp + (b-1))^T over the padded pixel axis -- no masking at the image borders, and columns shifted in
+    from outside a slice of whole images may be read as zeros (what the TMA does for out-of-range box columns)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    N, H, W, Ci, Co = 3, 6, 10, 4, 5
+    x, dy = torch.randn(N, H, W, Ci, generator=g).double(), torch.randn(N, H, W, Co, generator=g).double()
+    Wp = (W + 2 + 3) // 4 * 4
+    simg = ((H + 2) * Wp + 4 + 63) // 64 * 64
+
+    def framed(t):                                     # [N,H,W,C] -> [C, N*simg]
+        p = F.pad(t.permute(3, 0, 1, 2), (1, Wp - W - 1, 1, 1)).reshape(t.shape[-1], N, -1)
+        return F.pad(p, (0, simg - p.shape[-1])).reshape(t.shape[-1], N * simg)
+    dyT, xT = framed(dy), framed(x)
+    cols = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1).view(N, Ci, 9, H * W)
+    want = torch.einsum("npo,nctp->otc", dy.view(N, H * W, Co), cols)                 # [Co, tap, Ci]
+    for ks in (1, N):                                  # one slice, or one slice per image (out-of-slice columns read as zeros)
+        Kc = (N // ks) * simg
+        got = torch.zeros(Co, 9, Ci, dtype=torch.float64)
+        for a in range(3):
+            for b in range(3):
+                s = (a - 1) * Wp + (b - 1)
+                for k in range(ks):
+                    A = dyT[:, k * Kc:(k + 1) * Kc]
+                    Bm = torch.zeros(Ci, Kc, dtype=torch.float64)
+                    lo, hi = max(0, -s), min(Kc, Kc - s)
+                    Bm[:, lo:hi] = xT[:, k * Kc + lo + s: k * Kc + hi + s]
+                    got[:, 3 * a + b] += A @ Bm.t()
+        assert torch.allclose(got, want, rtol=1e-12, atol=1e-12), ks
