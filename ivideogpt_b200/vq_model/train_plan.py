@@ -48,11 +48,11 @@ class TokenizerTrainGraph:
         self.pgrads: Dict[int, Tuple[torch.nn.Parameter, torch.Tensor]] = {}
         self.vq_indices: Dict[str, torch.Tensor] = {}
         self.idx_override: Dict[str, torch.Tensor] = {}
-        # train mode: the cross-attention dropouts of conditional_vae.py:24-25,52 are active (counter-based masks; the seed
-        # comes from torch's CPU generator, so torch.manual_seed() fixes a run)
         # 3x3 weight gradients from padded channel-major copies (see _wgrad_conv3); IVGPT_TOK_WGRAD_IM2COL=1 selects the
         # explicit transposed im2col instead (9x the activation; measured 35 % of the step's kernel time)
         self.wgrad_no_im2col = os.environ.get("IVGPT_TOK_WGRAD_IM2COL", "0") != "1"
+        # train mode: the cross-attention dropouts of conditional_vae.py:24-25,52 are active (counter-based masks; the seed
+        # comes from torch's CPU generator, so torch.manual_seed() fixes a run)
         self.training = bool(model.training) if model is not None else False
         self.base_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.training else 0
         self._drop_sites = 0
