@@ -723,6 +723,7 @@ def tok_train_record(args, D, workload, steps, warmup, cpu_arm=True):
     import torch.distributed as dist
     import torch.nn.functional as F
     from ivideogpt_b200 import _lib
+    from ivideogpt_b200.grad_reduce import allreduce_grads_flat
     from ivideogpt_b200.optim import FusedAdamW
     world, rank, dev = D.world, D.rank, D.dev
     base = "tiny" if workload.endswith("tiny") else "cfg64"
@@ -743,15 +744,7 @@ def tok_train_record(args, D, workload, steps, warmup, cpu_arm=True):
                                                segment_len=seg - ctx)
         loss = F.mse_loss(dec, target) + F.mse_loss(ref_dec, sample) + commit + dyn_commit
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                if p.grad is not None:
-                    n = p.numel()
-                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                    off += n
+        allreduce_grads_flat(params)              # SUM over ranks (no-op at N = 1); the mean is AdamW's grad_scale = 1/world
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss.detach()

@@ -73,3 +73,24 @@ class BucketedGradReducer:
                 off += cnt
         self._pending = []
         return grads
+
+
+def allreduce_grads_flat(params, group: Optional[dist.ProcessGroup] = None) -> int:
+    """One flat all-reduce (SUM) of every existing `.grad` of `params` after the backward -- the simple exchange used by the
+    tokenizer training step (reference train_tokenizer.py:734 under DDP), where one autograd node produces all gradients at
+    once and there is nothing to overlap with yet.  Parameters without a gradient are skipped (all ranks must agree on which,
+    as under DDP).  Returns the bytes exchanged; a single process is a no-op."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    gs = [p.grad for p in params if p.grad is not None]
+    if not gs:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in gs])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in gs:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * flat.element_size()
+

@@ -66,3 +66,39 @@ def test_reducer_single_process_is_identity():
         red.on_grads(grads, names)
     red.finish(grads)
     assert all(torch.equal(grads[k], want[k]) and grads[k].is_contiguous() for k in want)
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ivideogpt_b200.grad_reduce import allreduce_grads_flat
+    g = torch.Generator().manual_seed(7 + rank)
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 2, 3))]
+    params[0].grad = torch.randn(3, 5, generator=g)
+    params[2].grad = torch.randn(2, 3, 2, generator=g).permute(0, 2, 1)      # a non-contiguous gradient; params[1] has none
+    nbytes = allreduce_grads_flat(params)
+    out.put((rank, [None if p.grad is None else p.grad.contiguous().numpy().copy() for p in params], nbytes))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_exchange_gloo():
+    """The tokenizer training step's exchange (bench.py train_tokenizer64 leg): one flat SUM over the existing gradients."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    [p.join(30) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+
+    def local(rank):
+        g = torch.Generator().manual_seed(7 + rank)
+        return torch.randn(3, 5, generator=g), torch.randn(2, 3, 2, generator=g).permute(0, 2, 1)
+    w0, w2 = local(0)[0] + local(1)[0], local(0)[1] + local(1)[1]
+    for rank, grads, nbytes in res:
+        assert nbytes == (15 + 12) * 4 and grads[1] is None
+        assert torch.equal(torch.from_numpy(grads[0]), w0) and torch.equal(torch.from_numpy(grads[2]), w2.contiguous())
+    from ivideogpt_b200.grad_reduce import allreduce_grads_flat
+    p = torch.nn.Parameter(torch.zeros(2)); p.grad = torch.ones(2)
+    assert allreduce_grads_flat([p]) == 0 and torch.equal(p.grad, torch.ones(2))        # single process: untouched
